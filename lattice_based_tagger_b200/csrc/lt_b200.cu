@@ -1,0 +1,669 @@
+// lt_b200.cu — C ABI (include/lt_b200.h): host-side table compiler, batch workspace, launches.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -shared
+//        -Xcompiler -fPIC  (see __graft_entry__.build()).  -fmad=false keeps every fp64
+// multiply and add of the score arithmetic separately rounded, as in the reference's Python.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/lt_b200.h"
+#include "beam.cuh"
+#include "hash.cuh"
+#include "lattice.cuh"
+#include "scan.cuh"
+#include "tables.cuh"
+
+using namespace lt;
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_error;
+
+static int fail(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_error = buf;
+    return code;
+}
+
+#define CU(call)                                                                                  \
+    do {                                                                                          \
+        cudaError_t _e = (call);                                                                  \
+        if (_e != cudaSuccess)                                                                    \
+            return fail(LT_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+extern "C" const char* lt_last_error(void) { return g_error.c_str(); }
+extern "C" int lt_abi_version(void) { return LT_ABI_VERSION; }
+
+// ------------------------------------------------------------------------------------------------
+// tables
+// ------------------------------------------------------------------------------------------------
+struct lt_tables {
+    int device = 0;
+    DevTables dev{};
+    std::vector<void*> allocations;
+    int64_t bytes = 0;
+    int sm_count = 0;
+};
+
+static H2 hash_units(const uint16_t* p, int64_t n) {
+    H2 h{0, 0};
+    for (int64_t i = 0; i < n; ++i) h = h2_push(h, p[i]);
+    return h;
+}
+
+static uint64_t next_pow2(uint64_t x) {
+    uint64_t p = 16;
+    while (p < x) p <<= 1;
+    return p;
+}
+
+template <typename T>
+static int upload(lt_tables* t, const std::vector<T>& host, const T** out) {
+    void* d = nullptr;
+    size_t bytes = std::max<size_t>(host.size(), 1) * sizeof(T);
+    CU(cudaMalloc(&d, bytes));
+    t->allocations.push_back(d);
+    t->bytes += (int64_t)bytes;
+    if (!host.empty()) CU(cudaMemcpy(d, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice));
+    *out = reinterpret_cast<const T*>(d);
+    return LT_OK;
+}
+
+extern "C" void lt_tables_destroy(lt_tables* t) {
+    if (!t) return;
+    cudaSetDevice(t->device);
+    for (void* p : t->allocations) cudaFree(p);
+    delete t;
+}
+
+extern "C" int64_t lt_tables_device_bytes(const lt_tables* t) { return t ? t->bytes : 0; }
+
+static int build_tables(const lt_tables_desc* d, lt_tables* t) {
+    DevTables& D = t->dev;
+    if (d->abi_version != LT_ABI_VERSION) return fail(LT_ERR_INVALID, "abi_version %d != %d", d->abi_version, LT_ABI_VERSION);
+    if (d->n_tags < LT_TAG_UNK + 1 || d->n_tags > LT_MAX_TAGS) return fail(LT_ERR_INVALID, "n_tags %d out of range", d->n_tags);
+    if (d->n_tag_order < 0 || d->n_tag_order > LT_MAX_TAGS) return fail(LT_ERR_INVALID, "n_tag_order out of range");
+    if (d->n_funcs < 0 || d->n_funcs > LT_MAX_FUNCS) return fail(LT_ERR_INVALID, "at most %d score functions", LT_MAX_FUNCS);
+    D.n_tags = d->n_tags;
+    D.n_tag_order = d->n_tag_order;
+    D.max_len = d->max_len;
+    for (int i = 0; i < d->n_tag_order; ++i) D.tag_order[i] = d->tag_order[i];
+
+    // ---- powers of the hash bases ----
+    int64_t max_str = 8;
+    for (int64_t i = 0; i < d->n_dict; ++i) max_str = std::max(max_str, d->dict_off[i + 1] - d->dict_off[i]);
+    const int n_pows = 65536 + 64;
+    std::vector<H2> pows(n_pows);
+    pows[0] = H2{1, 1};
+    for (int i = 1; i < n_pows; ++i) pows[i] = H2{pows[i - 1].a * kBaseA, pows[i - 1].b * kBaseB};
+    D.n_pows = n_pows;
+    if (int rc = upload(t, pows, &D.pows)) return rc;
+
+    // ---- dictionary ----
+    {
+        const uint64_t slots = next_pow2((uint64_t)d->n_dict * (d->n_dict < (1 << 22) ? 4 : 2));
+        std::vector<DictSlot> table(slots, DictSlot{0, 0, 0});
+        std::vector<uint64_t> slot_h(slots, 0);
+        for (int64_t i = 0; i < d->n_dict; ++i) {
+            const int64_t len = d->dict_off[i + 1] - d->dict_off[i];
+            if (len < 0 || len > 65535) return fail(LT_ERR_INVALID, "dictionary entry %lld has length %lld", (long long)i, (long long)len);
+            const H2 h = hash_units(d->dict_chars + d->dict_off[i], len);
+            const uint64_t fp = dict_fp(h, (uint32_t)len);
+            const uint64_t sh = dict_slot_hash(h, (uint32_t)len);
+            uint64_t s = sh & (slots - 1);
+            while (table[s].fp != 0) {
+                if (table[s].fp == fp && slot_h[s] == sh)
+                    return fail(LT_ERR_COLLISION, "dictionary entries collide on the 128-bit key (entry %lld)", (long long)i);
+                s = (s + 1) & (slots - 1);
+            }
+            table[s].fp = fp;
+            table[s].tagmask = d->dict_tagmask[i];
+            table[s].lemma = d->dict_lemma[i];
+            slot_h[s] = sh;
+        }
+        D.dict_mask = slots - 1;
+        if (int rc = upload(t, table, &D.dict)) return rc;
+    }
+
+    // ---- rules ----
+    {
+        std::vector<RuleRec> recs((size_t)d->n_rules);
+        for (int64_t r = 0; r < d->n_rules; ++r) {
+            const int64_t s0 = d->rule_stem_off[r], e0 = d->rule_eomi_off[r], s1 = d->rule_stem_off[r + 1];
+            if (!(s0 <= e0 && e0 <= s1)) return fail(LT_ERR_INVALID, "rule %lld has inconsistent offsets", (long long)r);
+            recs[r].stem = hash_units(d->rule_chars + s0, e0 - s0);
+            recs[r].eomi = hash_units(d->rule_chars + e0, s1 - e0);
+            recs[r].stem_len = (uint32_t)(e0 - s0);
+            recs[r].eomi_len = (uint32_t)(s1 - e0);
+        }
+        if (int rc = upload(t, recs, &D.rrec)) return rc;
+        const uint64_t slots = next_pow2((uint64_t)d->n_rule_keys * 4);
+        std::vector<RuleSlot> table(slots, RuleSlot{0, 0, 0});
+        for (int64_t k = 0; k < d->n_rule_keys; ++k) {
+            const uint32_t len = d->rule_key_len[k];
+            if (len < 1 || len > 3) return fail(LT_ERR_INVALID, "rule key %lld has length %u (1..3 expected)", (long long)k, len);
+            const uint16_t* c = d->rule_key_chars + 3 * k;
+            const uint64_t key = rule_key(c[0], len > 1 ? c[1] : 0, len > 2 ? c[2] : 0, len);
+            const int64_t first = d->rule_first[k], count = d->rule_first[k + 1] - first;
+            if (count < 0 || count > 0xFFFF) return fail(LT_ERR_INVALID, "rule key %lld has %lld rules", (long long)k, (long long)count);
+            uint64_t s = fmix64(key) & (slots - 1);
+            while (table[s].key != 0) {
+                if (table[s].key == key) return fail(LT_ERR_INVALID, "duplicate rule key %lld", (long long)k);
+                s = (s + 1) & (slots - 1);
+            }
+            table[s].key = key;
+            table[s].first = (uint32_t)first;
+            table[s].count = (uint32_t)count | (d->rule_k3_first[k] ? 0x80000000u : 0u);
+        }
+        D.rule_mask = slots - 1;
+        D.has_rules = d->n_rule_keys > 0;
+        if (int rc = upload(t, table, &D.rules)) return rc;
+    }
+
+    // ---- score program ----
+    D.n_funcs = d->n_funcs;
+    D.n_tri = 0;
+    for (int f = 0; f < d->n_funcs; ++f) {
+        D.funcs[f] = d->funcs[f];
+        D.func_dense[f] = -1;
+        switch (d->funcs[f].kind) {
+            case LT_FUNC_REG: case LT_FUNC_MPREF: case LT_FUNC_WPREF: break;
+            case LT_FUNC_TRIGRAM: D.func_dense[f] = (int8_t)D.n_tri++; break;
+            default: return fail(LT_ERR_INVALID, "score function %d has unknown kind %d", f, d->funcs[f].kind);
+        }
+    }
+
+    // ---- feature strings ----
+    std::vector<H2> fstr((size_t)d->n_fstr);
+    for (int64_t i = 0; i < d->n_fstr; ++i)
+        fstr[i] = hash_units(d->fstr_chars + d->fstr_off[i], d->fstr_off[i + 1] - d->fstr_off[i]);
+    auto str_hash = [&](int32_t id, H2* out) -> bool {
+        if (id < 0) { *out = H2{0, 0}; return true; }
+        if (id >= d->n_fstr) return false;
+        *out = fstr[id];
+        return true;
+    };
+
+    // ---- dense blocks + hashed feature table ----
+    const int NT = d->n_tags;
+    const size_t blk = (size_t)dense_block_bytes(NT);
+    std::vector<unsigned char> dense(std::max<size_t>(1, (size_t)D.n_tri * blk), 0);
+    struct Pending { FKey key; double w; };
+    std::vector<Pending> pending;
+    pending.reserve((size_t)(d->n_feat + d->n_pref));
+    for (int64_t i = 0; i < d->n_feat; ++i) {
+        const int f = d->feat_func[i];
+        if (f >= d->n_funcs || D.func_dense[f] < 0) return fail(LT_ERR_INVALID, "feature %lld belongs to scorer %d which is not a trigram scorer", (long long)i, f);
+        const int tmpl = d->feat_template[i];
+        const int32_t* s = d->feat_s + 3 * i;
+        const int32_t* a = d->feat_a + 2 * i;
+        const double w = d->feat_weight[i];
+        unsigned char* base = dense.data() + (size_t)D.func_dense[f] * blk;
+        double* t3 = reinterpret_cast<double*>(base);
+        double* t4 = t3 + NT * NT;
+        double* t6 = t4 + kT4Dense;
+        uint32_t* m3 = reinterpret_cast<uint32_t*>(t6 + 16);
+        uint32_t* m4 = m3 + NT;
+        uint32_t* m6 = m4 + 2;
+        if (tmpl == 3) {
+            if (a[0] < 0 || a[0] >= NT || a[1] < 0 || a[1] >= NT) return fail(LT_ERR_INVALID, "feature %lld: tag id out of range", (long long)i);
+            t3[a[0] * NT + a[1]] = w;
+            m3[a[0]] |= 1u << a[1];
+            continue;
+        }
+        if (tmpl == 4 && a[0] >= 0 && a[0] < kT4Dense) {
+            t4[a[0]] = w;
+            m4[a[0] >> 5] |= 1u << (a[0] & 31);
+            continue;
+        }
+        if (tmpl == 6) {
+            if (a[0] < 0 || a[0] > 8) continue;          // min(8, len) never exceeds 8
+            t6[a[0]] = w;
+            m6[0] |= 1u << a[0];
+            continue;
+        }
+        if (tmpl < 0 || tmpl > 8) return fail(LT_ERR_INVALID, "feature %lld: template %d", (long long)i, tmpl);
+        if (a[0] < 0 || a[1] < 0 || a[0] >= (1 << 24) || a[1] >= (1 << 24)) continue;   // cannot equal a generated tuple
+        H2 h0, h1, h2;
+        if (!str_hash(s[0], &h0) || !str_hash(s[1], &h1) || !str_hash(s[2], &h2))
+            return fail(LT_ERR_INVALID, "feature %lld: string id out of range", (long long)i);
+        pending.push_back(Pending{feature_key((uint32_t)tmpl, (uint32_t)f, h0, h1, h2, (uint32_t)a[0], (uint32_t)a[1]), w});
+    }
+    for (int64_t i = 0; i < d->n_pref; ++i) {
+        const int f = d->pref_func[i];
+        if (f >= d->n_funcs) return fail(LT_ERR_INVALID, "preference %lld: scorer index", (long long)i);
+        const int kind = d->funcs[f].kind;
+        if (kind != LT_FUNC_MPREF && kind != LT_FUNC_WPREF) return fail(LT_ERR_INVALID, "preference %lld belongs to a non-preference scorer", (long long)i);
+        H2 h0;
+        if (!str_hash(d->pref_s[i], &h0)) return fail(LT_ERR_INVALID, "preference %lld: string id out of range", (long long)i);
+        pending.push_back(Pending{feature_key(kind == LT_FUNC_MPREF ? kKindMPref : kKindWPref, (uint32_t)f, h0, H2{0, 0}, H2{0, 0},
+                                              d->pref_tag[i], 0), d->pref_value[i]});
+    }
+    {
+        const uint64_t n = pending.size();
+        const uint64_t slots = next_pow2(n * (n < (1u << 22) ? 4 : 2));
+        std::vector<FeatSlot> table(slots, FeatSlot{0, 0.0});
+        std::vector<uint64_t> slot_k1(slots, 0);
+        for (const Pending& p : pending) {
+            uint64_t s = p.key.k1 & (slots - 1);
+            while (table[s].fp != 0) {
+                if (table[s].fp == p.key.k2 && slot_k1[s] == p.key.k1)
+                    return fail(LT_ERR_COLLISION, "two feature keys share the 128-bit hash (or a key was given twice)");
+                s = (s + 1) & (slots - 1);
+            }
+            table[s].fp = p.key.k2;
+            table[s].w = p.w;
+            slot_k1[s] = p.key.k1;
+        }
+        D.feat_mask = slots - 1;
+        if (int rc = upload(t, table, &D.feat)) return rc;
+    }
+    if (int rc = upload(t, dense, &D.dense)) return rc;
+
+    const uint16_t bos[3] = {'B', 'O', 'S'};
+    D.bos = hash_units(bos, 3);
+    return LT_OK;
+}
+
+extern "C" int lt_tables_create(const lt_tables_desc* desc, int device, lt_tables** out) {
+    if (!desc || !out) return fail(LT_ERR_INVALID, "null argument");
+    *out = nullptr;
+    CU(cudaSetDevice(device));
+    lt_tables* t = new lt_tables();
+    t->device = device;
+    cudaDeviceProp prop;
+    cudaError_t e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) { delete t; return fail(LT_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e)); }
+    t->sm_count = prop.multiProcessorCount;
+    int rc = build_tables(desc, t);
+    if (rc != LT_OK) { lt_tables_destroy(t); return rc; }
+    *out = t;
+    return LT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// batch workspace
+// ------------------------------------------------------------------------------------------------
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+struct lt_batch {
+    lt_tables* tables = nullptr;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t last_stream = nullptr;
+    // inputs (host entry point) and per-unit / per-sentence arrays
+    DevBuf text, sent_off, end_cnt, beg_cnt, end_off, scan_tmp;
+    DevBuf sent_len, sent_edges, status, path_len, path_off, scores;
+    DevBuf edges, trail, path_tmp, path_out, counters, queue;
+    const uint16_t* d_text = nullptr;
+    const int32_t* d_sent_off = nullptr;
+    int32_t n_sent = 0;
+    int64_t n_units = 0;
+    int32_t lcap = 0;
+    int64_t n_edges = 0;
+    int32_t beam = 0;
+    bool have_lattice = false, have_paths = false;
+    cudaEvent_t ev[10]{};
+    bool timed = false;
+    lt_timings timings{};
+};
+
+static int ensure(DevBuf& b, size_t bytes) {
+    if (bytes <= b.cap) return LT_OK;
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) {
+        e = cudaMalloc(&b.p, bytes);
+        want = bytes;
+    }
+    if (e != cudaSuccess) return fail(LT_ERR_CUDA, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    b.cap = want;
+    return LT_OK;
+}
+
+extern "C" int lt_batch_create(lt_tables* tables, lt_batch** out) {
+    if (!tables || !out) return fail(LT_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(tables->device));
+    lt_batch* b = new lt_batch();
+    b->tables = tables;
+    CU(cudaStreamCreateWithFlags(&b->own_stream, cudaStreamNonBlocking));
+    for (auto& e : b->ev) CU(cudaEventCreate(&e));
+    *out = b;
+    return LT_OK;
+}
+
+extern "C" void lt_batch_destroy(lt_batch* b) {
+    if (!b) return;
+    cudaSetDevice(b->tables->device);
+    DevBuf* bufs[] = {&b->text, &b->sent_off, &b->end_cnt, &b->beg_cnt, &b->end_off, &b->scan_tmp, &b->sent_len,
+                      &b->sent_edges, &b->status, &b->path_len, &b->path_off, &b->scores, &b->edges, &b->trail,
+                      &b->path_tmp, &b->path_out, &b->counters, &b->queue};
+    for (DevBuf* x : bufs)
+        if (x->p) cudaFree(x->p);
+    for (auto& e : b->ev)
+        if (e) cudaEventDestroy(e);
+    if (b->own_stream) cudaStreamDestroy(b->own_stream);
+    delete b;
+}
+
+static int scan_u32(lt_batch* b, const uint32_t* in, uint32_t* out, int64_t n, cudaStream_t st) {
+    const int64_t tiles = (n + kScanTile - 1) / kScanTile;
+    if (int rc = ensure(b->scan_tmp, (size_t)tiles * 4)) return rc;
+    uint32_t* sums = static_cast<uint32_t*>(b->scan_tmp.p);
+    scan_tile_sums<<<(unsigned)tiles, kScanThreads, 0, st>>>(in, n, sums);
+    scan_sums<<<1, kScanThreads, 0, st>>>(sums, tiles);
+    scan_apply<<<(unsigned)tiles, kScanThreads, 0, st>>>(in, out, n, sums);
+    CU(cudaGetLastError());
+    return LT_OK;
+}
+
+static const size_t kSmemBudget = 200 * 1024;
+
+extern "C" int lt_lattice(lt_batch* b, const uint16_t* d_text, const int32_t* d_sent_off, int32_t n_sent,
+                          int64_t n_units, int32_t max_sent_units, void* stream) {
+    if (!b || n_sent < 0 || n_units < 0) return fail(LT_ERR_INVALID, "bad argument");
+    lt_tables* t = b->tables;
+    CU(cudaSetDevice(t->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    b->last_stream = st;
+    b->d_text = d_text;
+    b->d_sent_off = d_sent_off;
+    b->n_sent = n_sent;
+    b->n_units = n_units;
+    b->have_lattice = b->have_paths = false;
+    const int lcap = std::max(8, (max_sent_units + 7) & ~7);
+    b->lcap = lcap;
+    if (lcap > 65528) return fail(LT_ERR_INVALID, "a sentence has %d code units; at most 65528 are supported", max_sent_units);
+    const size_t warp_smem = lattice_warp_smem(lcap);
+    int warps = (int)std::min<size_t>(kLatWarps, kSmemBudget / warp_smem);
+    if (warps < 1) return fail(LT_ERR_INVALID, "a sentence of %d code units does not fit the lattice kernel's shared memory", max_sent_units);
+
+    const size_t nu = (size_t)n_units + 1;
+    if (int rc = ensure(b->end_cnt, nu * 4)) return rc;
+    if (int rc = ensure(b->beg_cnt, nu * 4)) return rc;
+    if (int rc = ensure(b->end_off, nu * 4)) return rc;
+    if (int rc = ensure(b->sent_len, (size_t)std::max(1, n_sent) * 4)) return rc;
+    if (int rc = ensure(b->sent_edges, (size_t)std::max(1, n_sent) * 4)) return rc;
+    if (int rc = ensure(b->status, (size_t)std::max(1, n_sent) * 4)) return rc;
+    if (int rc = ensure(b->counters, 8 * sizeof(unsigned long long))) return rc;
+    if (int rc = ensure(b->queue, 4 * sizeof(unsigned int))) return rc;
+
+    CU(cudaMemsetAsync(b->counters.p, 0, 8 * sizeof(unsigned long long), st));
+    CU(cudaMemsetAsync(b->queue.p, 0, 4 * sizeof(unsigned int), st));
+    CU(cudaMemsetAsync(b->beg_cnt.p, 0, nu * 4, st));
+    CU(cudaMemsetAsync(static_cast<uint32_t*>(b->end_cnt.p) + n_units, 0, 4, st));
+
+    LatticeArgs A{};
+    A.text = d_text;
+    A.sent_off = d_sent_off;
+    A.n_sent = n_sent;
+    A.lcap = lcap;
+    A.end_cnt = static_cast<uint32_t*>(b->end_cnt.p);
+    A.beg_cnt = static_cast<uint32_t*>(b->beg_cnt.p);
+    A.end_off = static_cast<const uint32_t*>(b->end_off.p);
+    A.edges = nullptr;
+    A.sent_len = static_cast<int32_t*>(b->sent_len.p);
+    A.sent_edges = static_cast<int32_t*>(b->sent_edges.p);
+    A.status = static_cast<int32_t*>(b->status.p);
+    A.counters = static_cast<unsigned long long*>(b->counters.p);
+    A.queue = static_cast<unsigned int*>(b->queue.p) + 0;
+
+    const size_t smem = warp_smem * warps;
+    CU(cudaFuncSetAttribute(lattice_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU(cudaFuncSetAttribute(lattice_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 1;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lattice_kernel<false>, warps * 32, smem));
+    per_sm = std::max(1, per_sm);
+    const int64_t want_blocks = ((int64_t)n_sent + warps - 1) / warps;
+    const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(want_blocks, (int64_t)t->sm_count * per_sm));
+
+    if (b->timed) CU(cudaEventRecord(b->ev[0], st));
+    if (n_sent > 0) lattice_kernel<false><<<grid, warps * 32, smem, st>>>(t->dev, A);
+    CU(cudaGetLastError());
+    if (b->timed) CU(cudaEventRecord(b->ev[1], st));
+    if (int rc = scan_u32(b, A.end_cnt, static_cast<uint32_t*>(b->end_off.p), (int64_t)nu, st)) return rc;
+    if (b->timed) CU(cudaEventRecord(b->ev[2], st));
+
+    // total edge count decides the size of the edge array
+    uint32_t total = 0;
+    CU(cudaMemcpyAsync(&total, static_cast<uint32_t*>(b->end_off.p) + n_units, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    b->n_edges = total;
+    if (int rc = ensure(b->edges, std::max<size_t>(1, total) * sizeof(lt_edge))) return rc;
+
+    A.edges = static_cast<lt_edge*>(b->edges.p);
+    A.queue = static_cast<unsigned int*>(b->queue.p) + 1;
+    if (b->timed) CU(cudaEventRecord(b->ev[3], st));
+    if (n_sent > 0 && total > 0) lattice_kernel<true><<<grid, warps * 32, smem, st>>>(t->dev, A);
+    CU(cudaGetLastError());
+    if (b->timed) CU(cudaEventRecord(b->ev[4], st));
+    b->have_lattice = true;
+    return LT_OK;
+}
+
+extern "C" int lt_beam(lt_batch* b, int32_t beam_size, void* stream) {
+    if (!b || !b->have_lattice) return fail(LT_ERR_INVALID, "lt_beam needs a lattice: call lt_lattice first");
+    if (beam_size < 1 || beam_size > LT_MAX_BEAM) return fail(LT_ERR_INVALID, "beam_size must be in 1..%d", LT_MAX_BEAM);
+    lt_tables* t = b->tables;
+    CU(cudaSetDevice(t->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    b->last_stream = st;
+    b->beam = beam_size;
+    const int n_sent = b->n_sent;
+    const size_t nu = (size_t)b->n_units + 1;
+
+    if (int rc = ensure(b->trail, nu * (size_t)beam_size * 8)) return rc;
+    if (int rc = ensure(b->path_tmp, nu * sizeof(lt_edge))) return rc;
+    if (int rc = ensure(b->path_out, nu * sizeof(lt_edge))) return rc;
+    if (int rc = ensure(b->path_len, (size_t)(n_sent + 1) * 4)) return rc;
+    if (int rc = ensure(b->path_off, (size_t)(n_sent + 1) * 4)) return rc;
+    if (int rc = ensure(b->scores, (size_t)std::max(1, n_sent) * 8)) return rc;
+
+    const size_t dense_bytes = ((size_t)t->dev.n_tri * dense_block_bytes(t->dev.n_tags) + 15) & ~(size_t)15;
+    const size_t warp_smem = beam_warp_smem(b->lcap, beam_size);
+    if (dense_bytes + warp_smem > kSmemBudget)
+        return fail(LT_ERR_INVALID, "sentence length %d with beam %d does not fit the beam kernel's shared memory", b->lcap, beam_size);
+    int warps = (int)std::min<size_t>(8, (kSmemBudget - dense_bytes) / warp_smem);
+    // keep several CTAs per SM resident when the per-warp footprint allows it
+    while (warps > 2 && (dense_bytes + warp_smem * warps) > 48 * 1024) warps >>= 1;
+    const size_t smem = dense_bytes + warp_smem * warps;
+
+    BeamArgs A{};
+    A.text = b->d_text;
+    A.sent_off = b->d_sent_off;
+    A.n_sent = n_sent;
+    A.lcap = b->lcap;
+    A.beam = beam_size;
+    A.warps = warps;
+    A.end_off = static_cast<const uint32_t*>(b->end_off.p);
+    A.edges = static_cast<const lt_edge*>(b->edges.p);
+    A.status = static_cast<const int32_t*>(b->status.p);
+    A.trail = static_cast<uint64_t*>(b->trail.p);
+    A.path_tmp = static_cast<lt_edge*>(b->path_tmp.p);
+    A.path_len = static_cast<int32_t*>(b->path_len.p);
+    A.scores = static_cast<double*>(b->scores.p);
+    A.counters = static_cast<unsigned long long*>(b->counters.p);
+    A.queue = static_cast<unsigned int*>(b->queue.p) + 2;
+
+    CU(cudaFuncSetAttribute(beam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 1;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, beam_kernel, warps * 32, smem));
+    per_sm = std::max(1, per_sm);
+    const int64_t want_blocks = ((int64_t)n_sent + warps - 1) / warps;
+    const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(want_blocks, (int64_t)t->sm_count * per_sm));
+
+    CU(cudaMemsetAsync(static_cast<unsigned int*>(b->queue.p) + 2, 0, sizeof(unsigned int), st));
+    CU(cudaMemsetAsync(static_cast<unsigned long long*>(b->counters.p) + 3, 0, 4 * sizeof(unsigned long long), st));
+    CU(cudaMemsetAsync(static_cast<int32_t*>(b->path_len.p) + n_sent, 0, 4, st));
+    if (b->timed) CU(cudaEventRecord(b->ev[5], st));
+    if (n_sent > 0) beam_kernel<<<grid, warps * 32, smem, st>>>(t->dev, A);
+    CU(cudaGetLastError());
+    if (b->timed) CU(cudaEventRecord(b->ev[6], st));
+    if (int rc = scan_u32(b, reinterpret_cast<const uint32_t*>(b->path_len.p), static_cast<uint32_t*>(b->path_off.p),
+                          (int64_t)n_sent + 1, st))
+        return rc;
+    if (n_sent > 0) {
+        const unsigned pgrid = (unsigned)std::min<int64_t>(((int64_t)n_sent + 7) / 8, (int64_t)t->sm_count * 8);
+        pack_paths<<<pgrid, 256, 0, st>>>(static_cast<const lt_edge*>(b->path_tmp.p), b->d_sent_off,
+                                          static_cast<const uint32_t*>(b->path_off.p), n_sent,
+                                          static_cast<lt_edge*>(b->path_out.p));
+        CU(cudaGetLastError());
+    }
+    if (b->timed) CU(cudaEventRecord(b->ev[7], st));
+    b->have_paths = true;
+    return LT_OK;
+}
+
+extern "C" int lt_lattice_size(lt_batch* b, int64_t* n_edges) {
+    if (!b || !b->have_lattice || !n_edges) return fail(LT_ERR_INVALID, "no lattice");
+    *n_edges = b->n_edges;
+    return LT_OK;
+}
+
+extern "C" int lt_lattice_fetch(lt_batch* b, lt_edge* edges, int64_t edge_cap, int64_t* end_off) {
+    if (!b || !b->have_lattice) return fail(LT_ERR_INVALID, "no lattice");
+    CU(cudaSetDevice(b->tables->device));
+    if (edge_cap < b->n_edges) return fail(LT_ERR_CAPACITY, "edge buffer holds %lld, need %lld", (long long)edge_cap, (long long)b->n_edges);
+    CU(cudaStreamSynchronize(b->last_stream));
+    if (b->n_edges) CU(cudaMemcpy(edges, b->edges.p, (size_t)b->n_edges * sizeof(lt_edge), cudaMemcpyDeviceToHost));
+    if (end_off) {
+        std::vector<uint32_t> tmp((size_t)b->n_units + 1);
+        CU(cudaMemcpy(tmp.data(), b->end_off.p, tmp.size() * 4, cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < tmp.size(); ++i) end_off[i] = tmp[i];
+    }
+    return LT_OK;
+}
+
+extern "C" int lt_paths_size(lt_batch* b, int64_t* n_words) {
+    if (!b || !b->have_paths || !n_words) return fail(LT_ERR_INVALID, "no paths");
+    CU(cudaSetDevice(b->tables->device));
+    uint32_t total = 0;
+    CU(cudaMemcpyAsync(&total, static_cast<uint32_t*>(b->path_off.p) + b->n_sent, 4, cudaMemcpyDeviceToHost, b->last_stream));
+    CU(cudaStreamSynchronize(b->last_stream));
+    *n_words = total;
+    return LT_OK;
+}
+
+static int fetch_paths(lt_batch* b, int32_t* path_off, lt_edge* path_edges, int64_t path_cap, double* scores,
+                       int32_t* status, cudaStream_t st) {
+    const int n = b->n_sent;
+    if (n == 0) {
+        if (path_off) path_off[0] = 0;
+        return LT_OK;
+    }
+    CU(cudaMemcpyAsync(path_off, b->path_off.p, (size_t)(n + 1) * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(scores, b->scores.p, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(status, b->status.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    // every path has at most one word per syllable, so n_units records always suffice
+    const int64_t words_max = std::min<int64_t>(b->n_units, path_cap);
+    if (path_cap >= b->n_units) {
+        // one-shot copy without waiting for the word count: copy what can exist
+        CU(cudaStreamSynchronize(st));
+        const int64_t total = path_off[n];
+        if (total) CU(cudaMemcpyAsync(path_edges, b->path_out.p, (size_t)total * sizeof(lt_edge), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    } else {
+        CU(cudaStreamSynchronize(st));
+        const int64_t total = path_off[n];
+        if (total > path_cap) return fail(LT_ERR_CAPACITY, "path buffer holds %lld records, need %lld", (long long)path_cap, (long long)total);
+        if (total) CU(cudaMemcpyAsync(path_edges, b->path_out.p, (size_t)total * sizeof(lt_edge), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    (void)words_max;
+    return LT_OK;
+}
+
+extern "C" int lt_paths_fetch(lt_batch* b, int32_t* path_off, lt_edge* path_edges, int64_t path_cap, double* scores,
+                              int32_t* status) {
+    if (!b || !b->have_paths) return fail(LT_ERR_INVALID, "no paths");
+    CU(cudaSetDevice(b->tables->device));
+    return fetch_paths(b, path_off, path_edges, path_cap, scores, status, b->last_stream);
+}
+
+extern "C" int lt_tag_batch_host(lt_batch* b, const uint16_t* text, const int32_t* sent_off, int32_t n_sent,
+                                 int32_t beam_size, int32_t* path_off, lt_edge* path_edges, int64_t path_cap,
+                                 double* scores, int32_t* status) {
+    if (!b || !sent_off || n_sent < 0) return fail(LT_ERR_INVALID, "bad argument");
+    CU(cudaSetDevice(b->tables->device));
+    cudaStream_t st = b->own_stream;
+    const int64_t n_units = sent_off[n_sent];
+    int32_t max_units = 0;
+    for (int32_t i = 0; i < n_sent; ++i) {
+        const int32_t len = sent_off[i + 1] - sent_off[i];
+        if (len < 0) return fail(LT_ERR_INVALID, "sent_off is not monotone at %d", i);
+        max_units = std::max(max_units, len);
+    }
+    if (int rc = ensure(b->text, (size_t)std::max<int64_t>(1, n_units) * 2)) return rc;
+    if (int rc = ensure(b->sent_off, (size_t)(n_sent + 1) * 4)) return rc;
+    const bool timed = b->timed;
+    if (timed) CU(cudaEventRecord(b->ev[8], st));
+    if (n_units) CU(cudaMemcpyAsync(b->text.p, text, (size_t)n_units * 2, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(b->sent_off.p, sent_off, (size_t)(n_sent + 1) * 4, cudaMemcpyHostToDevice, st));
+    if (int rc = lt_lattice(b, static_cast<const uint16_t*>(b->text.p), static_cast<const int32_t*>(b->sent_off.p), n_sent,
+                            n_units, max_units, st))
+        return rc;
+    if (int rc = lt_beam(b, beam_size, st)) return rc;
+    if (int rc = fetch_paths(b, path_off, path_edges, path_cap, scores, status, st)) return rc;
+    if (timed) {
+        CU(cudaEventRecord(b->ev[9], st));
+        CU(cudaEventSynchronize(b->ev[9]));
+    }
+    return LT_OK;
+}
+
+extern "C" int lt_batch_counters(lt_batch* b, lt_counters* out) {
+    if (!b || !out) return fail(LT_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(b->tables->device));
+    unsigned long long c[8] = {0};
+    if (b->counters.p) {
+        CU(cudaStreamSynchronize(b->last_stream));
+        CU(cudaMemcpy(c, b->counters.p, sizeof c, cudaMemcpyDeviceToHost));
+    }
+    out->sentences = (uint64_t)b->n_sent;
+    out->L = c[0]; out->P = c[1]; out->E = c[2]; out->T = c[3]; out->F = c[4]; out->Bk = c[5]; out->W = c[6];
+    return LT_OK;
+}
+
+// timings: enabled by the first call (so that un-timed batches record no events)
+extern "C" int lt_batch_timings(lt_batch* b, lt_timings* out) {
+    if (!b || !out) return fail(LT_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(b->tables->device));
+    memset(out, 0, sizeof *out);
+    if (!b->timed) {
+        b->timed = true;      // subsequent batches are timed
+        return LT_OK;
+    }
+    if (!b->have_paths) return LT_OK;
+    CU(cudaStreamSynchronize(b->last_stream));
+    auto ms = [&](int a, int c, float* dst) {
+        float v = 0.f;
+        if (cudaEventElapsedTime(&v, b->ev[a], b->ev[c]) == cudaSuccess) *dst = v;
+        else cudaGetLastError();
+    };
+    ms(0, 1, &out->ms_lattice_count);
+    ms(1, 2, &out->ms_scan);
+    ms(3, 4, &out->ms_lattice_emit);
+    ms(5, 6, &out->ms_beam);
+    ms(6, 7, &out->ms_pack);
+    ms(8, 0, &out->ms_h2d);
+    ms(7, 9, &out->ms_d2h);
+    ms(8, 9, &out->ms_total);
+    return LT_OK;
+}

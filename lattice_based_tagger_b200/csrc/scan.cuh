@@ -1,0 +1,106 @@
+// scan.cuh — device exclusive scan of 32-bit counts (CSR offsets of the lattice, path offsets)
+// and the kernel that packs the per-sentence best paths into one contiguous output array.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/lt_b200.h"
+
+namespace lt {
+
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 8;
+constexpr int kScanTile = kScanThreads * kScanItems;
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* warp_sums, uint32_t& block_total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t incl = v;
+    #pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if (lane >= d) incl += t;
+    }
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = (lane < kScanThreads / 32) ? warp_sums[lane] : 0u;
+        uint32_t wi = w;
+        #pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t t = __shfl_up_sync(0xFFFFFFFFu, wi, d);
+            if (lane >= d) wi += t;
+        }
+        if (lane < kScanThreads / 32) warp_sums[lane] = wi - w;
+        if (lane == kScanThreads / 32 - 1) warp_sums[kScanThreads / 32] = wi;
+    }
+    __syncthreads();
+    block_total = warp_sums[kScanThreads / 32];
+    uint32_t r = warp_sums[warp] + incl - v;
+    __syncthreads();
+    return r;
+}
+
+// pass 1: per-tile sums
+__global__ void __launch_bounds__(kScanThreads) scan_tile_sums(const uint32_t* __restrict__ in, int64_t n, uint32_t* __restrict__ sums) {
+    __shared__ uint32_t ws[kScanThreads / 32 + 1];
+    const int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
+    uint32_t local = 0;
+    #pragma unroll
+    for (int i = 0; i < kScanItems; ++i)
+        if (base + i < n) local += in[base + i];
+    uint32_t total;
+    block_exclusive_scan(local, ws, total);
+    if (threadIdx.x == 0) sums[blockIdx.x] = total;
+}
+
+// pass 2: exclusive scan of the tile sums by one block
+__global__ void __launch_bounds__(kScanThreads) scan_sums(uint32_t* __restrict__ sums, int64_t n_tiles) {
+    __shared__ uint32_t ws[kScanThreads / 32 + 1];
+    uint32_t carry = 0;
+    for (int64_t base = 0; base < n_tiles; base += kScanThreads) {
+        const int64_t i = base + threadIdx.x;
+        uint32_t v = (i < n_tiles) ? sums[i] : 0u;
+        uint32_t total;
+        uint32_t ex = block_exclusive_scan(v, ws, total);
+        if (i < n_tiles) sums[i] = carry + ex;
+        carry += total;
+    }
+}
+
+// pass 3: exclusive scan inside each tile + tile offset
+__global__ void __launch_bounds__(kScanThreads) scan_apply(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int64_t n,
+                                                          const uint32_t* __restrict__ sums) {
+    __shared__ uint32_t ws[kScanThreads / 32 + 1];
+    const int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
+    uint32_t v[kScanItems];
+    uint32_t local = 0;
+    #pragma unroll
+    for (int i = 0; i < kScanItems; ++i) {
+        v[i] = (base + i < n) ? in[base + i] : 0u;
+        local += v[i];
+    }
+    uint32_t total;
+    uint32_t run = block_exclusive_scan(local, ws, total) + sums[blockIdx.x];
+    #pragma unroll
+    for (int i = 0; i < kScanItems; ++i) {
+        if (base + i < n) out[base + i] = run;
+        run += v[i];
+    }
+}
+
+// best paths: reversed per-sentence scratch -> contiguous forward order
+__global__ void pack_paths(const lt_edge* __restrict__ tmp, const int32_t* __restrict__ sent_off,
+                           const uint32_t* __restrict__ path_off, int32_t n_sent, lt_edge* __restrict__ out) {
+    const int warps_per_block = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31;
+    for (int s = blockIdx.x * warps_per_block + (threadIdx.x >> 5); s < n_sent; s += gridDim.x * warps_per_block) {
+        const uint32_t o0 = path_off[s], o1 = path_off[s + 1];
+        const int W = (int)(o1 - o0);
+        const int s0 = sent_off[s];
+        const uint4* src = reinterpret_cast<const uint4*>(tmp + s0);
+        uint4* dst = reinterpret_cast<uint4*>(out + o0);
+        for (int i = lane; i < W; i += 32) dst[i] = src[W - 1 - i];
+    }
+}
+
+}  // namespace lt

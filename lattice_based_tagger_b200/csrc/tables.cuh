@@ -1,0 +1,158 @@
+// tables.cuh — layout of the device-resident tables and the probe routines the kernels use.
+//
+// HBM layout (all built once by lt_tables_create, read-only afterwards):
+//   dict   open-addressing table, 16 B slots {fp, tagmask, lemma bits}; key = (string, length)
+//   rules  open-addressing table, 16 B slots {exact 1..3-syllable key, first rule, count|k3_first}
+//   rrec   one 40 B record per (stem, eomi) rule: hashes and lengths of both strings
+//   feat   open-addressing table, 16 B slots {fp, fp64 weight}; key = feature tuple / preference
+//   dense  per trigram scorer: tag x tag matrix (template 3), length vectors (templates 4, 6)
+//          with presence masks — staged into shared memory by the beam kernel
+//   pows   base^n pairs for composing polynomial hashes
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/lt_b200.h"
+#include "hash.cuh"
+
+namespace lt {
+
+struct DictSlot {
+    uint64_t fp;        // 0 = empty
+    uint32_t tagmask;   // bit t: string is in tag t's set
+    uint32_t lemma;     // bit0 verbs, bit1 adjectives, bit2 eomis
+};
+static_assert(sizeof(DictSlot) == 16, "DictSlot");
+
+constexpr uint32_t kLemVerb = 1u, kLemAdj = 2u, kLemEomi = 4u;
+
+struct RuleSlot {
+    uint64_t key;       // rule_key(); 0 = empty (len field is never 0 for a real key)
+    uint32_t first;     // index of the key's first rule record
+    uint32_t count;     // low 16 bits: number of rules; bit 31: k3_first
+};
+static_assert(sizeof(RuleSlot) == 16, "RuleSlot");
+
+struct RuleRec {
+    H2 stem, eomi;
+    uint32_t stem_len, eomi_len;
+};
+static_assert(sizeof(RuleRec) == 40, "RuleRec");
+
+struct FeatSlot {
+    uint64_t fp;        // 0 = empty
+    double w;
+};
+static_assert(sizeof(FeatSlot) == 16, "FeatSlot");
+
+constexpr int kT4Dense = 64;   // template-4 lengths below this are looked up densely
+
+// Dense block of one trigram scorer, in doubles, for n_tags = NT:
+//   [0, NT*NT)            template 3 weights, row = tj, col = tk
+//   [NT*NT, +kT4Dense)    template 4 weights by len
+//   [.., +16)             template 6 weights by min(8, len) (0..8 used)
+// followed (as raw 32-bit words, 2 per double slot) by presence masks:
+//   NT words   template 3 row masks (bit tk)
+//   2 words    template 4 presence (bits 0..63)
+//   1 word     template 6 presence (bits 0..8)
+__host__ __device__ inline int dense_doubles(int nt) { return nt * nt + kT4Dense + 16; }
+__host__ __device__ inline int dense_mask_words(int nt) { return nt + 3; }
+__host__ __device__ inline int dense_block_bytes(int nt) {
+    return (dense_doubles(nt) * 8 + dense_mask_words(nt) * 4 + 7) & ~7;
+}
+
+struct DevTables {
+    const DictSlot* dict;
+    uint64_t dict_mask;
+    const RuleSlot* rules;
+    uint64_t rule_mask;
+    const RuleRec* rrec;
+    const FeatSlot* feat;
+    uint64_t feat_mask;
+    const unsigned char* dense;   // n_tri blocks of dense_block_bytes(n_tags)
+    const H2* pows;
+    int32_t n_pows;
+    int32_t n_tags;
+    int32_t n_tag_order;
+    int32_t max_len;
+    int32_t n_funcs;
+    int32_t n_tri;                // number of LT_FUNC_TRIGRAM scorers
+    int32_t has_rules;
+    int32_t reserved;
+    uint8_t tag_order[LT_MAX_TAGS];
+    lt_func funcs[LT_MAX_FUNCS];
+    int8_t  func_dense[LT_MAX_FUNCS];   // dense block index of a trigram scorer, -1 otherwise
+    H2 bos;                        // hash of the literal 'BOS' (beam.py:21)
+};
+
+#if defined(__CUDACC__)
+
+__device__ __forceinline__ uint4 ldg16(const void* p) {
+    return __ldg(reinterpret_cast<const uint4*>(p));
+}
+
+// dictionary probe: returns the 64-bit payload (tagmask | lemma << 32), 0 when absent
+__device__ __forceinline__ uint64_t dict_probe(const DevTables& T, H2 h, uint32_t len) {
+    uint64_t i = dict_slot_hash(h, len) & T.dict_mask;
+    const uint64_t fp = dict_fp(h, len);
+    while (true) {
+        uint4 s = ldg16(T.dict + i);
+        uint64_t sfp = (uint64_t)s.x | ((uint64_t)s.y << 32);
+        if (sfp == fp) return (uint64_t)s.z | ((uint64_t)s.w << 32);
+        if (sfp == 0) return 0;
+        i = (i + 1) & T.dict_mask;
+    }
+}
+
+// rule probe: (first, count|flag) of an exact 1..3 syllable key; count = 0 when absent
+__device__ __forceinline__ uint2 rule_probe(const DevTables& T, uint64_t key) {
+    if (!T.has_rules) return make_uint2(0u, 0u);
+    uint64_t i = fmix64(key) & T.rule_mask;
+    while (true) {
+        uint4 s = ldg16(T.rules + i);
+        uint64_t skey = (uint64_t)s.x | ((uint64_t)s.y << 32);
+        if (skey == key) return make_uint2(s.z, s.w);
+        if (skey == 0) return make_uint2(0u, 0u);
+        i = (i + 1) & T.rule_mask;
+    }
+}
+
+__device__ __forceinline__ RuleRec rule_load(const DevTables& T, uint32_t idx) {
+    const uint64_t* p = reinterpret_cast<const uint64_t*>(T.rrec + idx);
+    RuleRec r;
+    r.stem.a = __ldg(p + 0);
+    r.stem.b = __ldg(p + 1);
+    r.eomi.a = __ldg(p + 2);
+    r.eomi.b = __ldg(p + 3);
+    uint64_t l = __ldg(p + 4);
+    r.stem_len = (uint32_t)l;
+    r.eomi_len = (uint32_t)(l >> 32);
+    return r;
+}
+
+// feature probe, split in two so that callers can put several first-slot loads in flight
+__device__ __forceinline__ uint4 feat_first(const DevTables& T, FKey k) {
+    return ldg16(T.feat + (k.k1 & T.feat_mask));
+}
+__device__ __forceinline__ bool feat_resolve(const DevTables& T, FKey k, uint4 s, double& w) {
+    uint64_t i = k.k1 & T.feat_mask;
+    while (true) {
+        uint64_t sfp = (uint64_t)s.x | ((uint64_t)s.y << 32);
+        if (sfp == k.k2) {
+            w = __hiloint2double((int)s.w, (int)s.z);
+            return true;
+        }
+        if (sfp == 0) return false;
+        i = (i + 1) & T.feat_mask;
+        s = ldg16(T.feat + i);
+    }
+}
+
+__device__ __forceinline__ H2 pow_at(const DevTables& T, uint32_t n) {
+    const uint64_t* p = reinterpret_cast<const uint64_t*>(T.pows + n);
+    return H2{__ldg(p), __ldg(p + 1)};
+}
+
+#endif  // __CUDACC__
+
+}  // namespace lt

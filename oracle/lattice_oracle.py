@@ -182,8 +182,9 @@ def eojeol_lookup(eojeol, view, offset, counters=None):
     # stage 2: sub-word scan, b starts at 1 so is_l is never set (:259-277)
     standalones = DEFAULT_STANDALONES
     noun_end = [False] * (n + 1)
+    max_len = view.max_len if view.max_len > 0 else n            # :229-230
     for b in range(1, n):
-        for e in range(b + 1, min(b + view.max_len, n) + 1):
+        for e in range(b + 1, min(b + max_len, n) + 1):
             sub = eojeol[b:e]
             examined.add((b, e))
             for tag in standalones:

@@ -1,0 +1,93 @@
+"""GPU parity: the CUDA path (through the C ABI) against the oracle and the golden fixtures."""
+
+import pytest
+
+import lattice_based_tagger_b200 as pkg
+from oracle import lattice_oracle as lo
+from tests import _cases, _golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _lattice_key(edges):
+    """reference order -> the order the device emits: stable by (end, begin)"""
+    return sorted(edges, key=lambda w: (w[7], w[6]))
+
+
+@pytest.mark.parametrize('name', _golden.names())
+def test_golden_fixtures(name):
+    payload = _golden.load(name)
+    case = payload['case']
+    dictionary, funcs = _cases.build_objects(case, pkg)
+    tagger = pkg.Tagger(dictionary, score_funcs=funcs, k3_first=payload['k3_first'])
+    sents = case['sentences']
+    # lattice
+    for sent, entry, (words, bindex) in zip(sents, payload['expected'], tagger.lattice_batch(sents)):
+        want = _lattice_key([_golden.edge(w) for w in entry['lattice']])
+        assert [tuple(w) for w in words[1:-1]] == want, sent
+    # best path for every recorded beam size
+    beams = sorted({int(k) for entry in payload['expected'] for k in entry['beams']})
+    for k in beams:
+        got = tagger.tag_batch(sents, beam_size=k, errors='none')
+        for sent, entry, seq in zip(sents, payload['expected'], got):
+            want = _golden.expected_survivors(entry, k)
+            if want is None:
+                assert seq is None, sent
+                continue
+            words, score, num_unk = want[0]
+            assert [tuple(w) for w in seq.sequences] == words, (sent, k)
+            assert seq.score == score, (sent, k)
+            assert seq.num_unk == num_unk
+
+
+@pytest.mark.parametrize('seed', range(2000, 2030))
+def test_random_cases_against_oracle(seed):
+    case = _cases.random_case(seed, n_sent=24, features=True, prefs=(seed % 2 == 0), max_sent_len=60)
+    _cases.add_features(case, _cases.observed_features(case, lo, seed=seed), seed)
+    dictionary, funcs = _cases.build_objects(case, pkg)
+    tagger = pkg.Tagger(dictionary, score_funcs=funcs)
+    oracle = lo.OracleTagger(dictionary, funcs)
+    sents = case['sentences']
+    lat_counters = lo.Counters()
+    for sent, (words, bindex) in zip(sents, tagger.lattice_batch(sents)):
+        assert [tuple(w) for w in words[1:-1]] == _lattice_key(oracle.lattice(sent, lat_counters)), sent
+    for k in (1, 2, 5, 10, 33, 64):
+        got = tagger.tag_batch(sents, beam_size=k, errors='none')
+        counters = lo.Counters()
+        for sent, seq in zip(sents, got):
+            try:
+                want = oracle.tag(sent, k, counters)
+            except IndexError:
+                assert seq is None, sent
+                continue
+            assert [tuple(w) for w in seq.sequences] == want.words, (sent, k)
+            assert seq.score == want.score, (sent, k)
+        dev = tagger.counters()
+        # the device counts the work of the reference's control flow
+        for name in ('T', 'F', 'Bk', 'W'):
+            assert dev[name] == getattr(counters, name), (name, k)
+        assert dev['E'] == lat_counters.E and dev['P'] == lat_counters.P
+
+
+def test_error_behaviour():
+    dictionary = pkg.dictionary.DemoMorphemeDictionary()
+    funcs = pkg.beam.BeamScoreFunctions(pkg.beam.RegularizationScore())
+    tagger = pkg.Tagger(dictionary, score_funcs=funcs)
+    with pytest.raises(IndexError):
+        tagger.tag('가나다라')                      # no dictionary hit at all
+    empty = tagger.tag('')
+    assert [w.word for w in empty.sequences] == ['BOS', 'EOS'] and empty.score == 0
+    with pytest.raises(ValueError):
+        tagger.tag('노래\t입니다')
+    with pytest.raises(ValueError):
+        pkg.Tagger(dictionary, score_funcs=pkg.beam.BeamScoreFunctions(object()))
+
+
+def test_demo_known_answer():
+    dictionary = pkg.dictionary.DemoMorphemeDictionary()
+    funcs = pkg.beam.BeamScoreFunctions(pkg.beam.RegularizationScore(unknown_penalty=-.1, known_preference=0.5))
+    best = pkg.Tagger(dictionary, score_funcs=funcs).tag('너무너무너무는 아이오아이의 노래 입니다')
+    assert best.score == 15.5
+    assert [(w.word, w.tag0, w.len) for w in best.sequences[1:-1]] == [
+        ('너무너무너무', 'Noun', 7), ('는', 'Josa', 7), ('아이오아이', 'Noun', 6), ('의', 'Josa', 6),
+        ('노래', 'Noun', 2), ('입니다', 'Adjective', 3)]

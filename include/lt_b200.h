@@ -45,12 +45,12 @@ extern "C" {
 
 #define LT_WINDOW   8        /* beam_search max_len, beam/beam.py:5                              */
 #define LT_MAX_BEAM 64
-#define LT_MAX_TAGS 32
+#define LT_MAX_TAGS 29       /* tag sets are 29-bit masks next to 3 lemmatizer bits */
 #define LT_MAX_FUNCS 8
 #define LT_NO_TAG   0xFF
 #define LT_NO_RULE  0xFFFFFFFFu
 
-/* fixed tag ids (lattice_tagger/tagset.py:1-15); dictionaries may add ids 13..31 */
+/* fixed tag ids (lattice_tagger/tagset.py:1-15); dictionaries may add ids 13..28 */
 enum { LT_TAG_NOUN = 0, LT_TAG_PRONOUN, LT_TAG_NUMBER, LT_TAG_JOSA, LT_TAG_ADJECTIVE, LT_TAG_VERB,
        LT_TAG_EOMI, LT_TAG_ADVERB, LT_TAG_DETERMINER, LT_TAG_EXCLAMATION, LT_TAG_BOS, LT_TAG_EOS,
        LT_TAG_UNK };
@@ -116,9 +116,8 @@ typedef struct lt_tables_desc {
     const int64_t*  rule_first;     /* n_rule_keys + 1: rules of key i = [first[i], first[i+1]) */
     int64_t         n_rules;
     const uint16_t* rule_chars;     /* stems and eomis, concatenated                            */
-    const int64_t*  rule_stem_off;  /* n_rules + 1 is NOT used: stem i = [stem_off[i], eomi_off[i]) */
-    const int64_t*  rule_eomi_off;  /*             eomi i = [eomi_off[i], stem_off[i+1]);
-                                       both arrays have n_rules + 1 entries                     */
+    const int64_t*  rule_stem_off;  /* n_rules + 1 entries: stem i = [stem_off[i], eomi_off[i])    */
+    const int64_t*  rule_eomi_off;  /* n_rules entries:     eomi i = [eomi_off[i], stem_off[i+1])  */
 
     /* score program */
     int32_t         n_funcs;
@@ -164,7 +163,7 @@ typedef struct lt_counters {
 
 /* Device-time of the last batch, measured with CUDA events on the batch's stream. */
 typedef struct lt_timings {
-    float ms_h2d, ms_lattice_count, ms_scan, ms_lattice_emit, ms_beam, ms_pack, ms_d2h, ms_total;
+    float ms_h2d, ms_lattice, ms_reserved0, ms_reserved1, ms_beam, ms_pack, ms_d2h, ms_total;
 } lt_timings;
 
 typedef struct lt_tables lt_tables;   /* immutable device tables; shareable between batches */

@@ -61,7 +61,7 @@ class lt_counters(ctypes.Structure):
 
 
 class lt_timings(ctypes.Structure):
-    _fields_ = [(name, ctypes.c_float) for name in ('ms_h2d', 'ms_lattice_count', 'ms_scan', 'ms_lattice_emit',
+    _fields_ = [(name, ctypes.c_float) for name in ('ms_h2d', 'ms_lattice', 'ms_reserved0', 'ms_reserved1',
                                                     'ms_beam', 'ms_pack', 'ms_d2h', 'ms_total')]
 
     def as_dict(self):

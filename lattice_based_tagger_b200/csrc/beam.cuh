@@ -4,19 +4,23 @@
 // (beam/score_funcs.py:18-144) with their feature templates (features/feature.py:76-121).
 //
 // One warp per sentence (atomic work queue).  Hypotheses are back-pointer entries in a shared-
-// memory ring of the last 9 end positions (window 8, beam.py:30): score, the hashes of the last
-// two words and of the contextual morpheme, and a few tag bits — everything the next transition's
-// features depend on.  Per end position e the warp
-//   1. reads the CSR bucket of e and counts edges per begin (the bucket is sorted by begin);
-//   2. enumerates candidates in the reference's generation order — begin ascending, parent rank
-//      ascending, edge order ascending (beam.py:30-48) — 32 at a time, one per lane;
-//   3. scores each lane's transition: the score program in BeamScoreFunctions order, every fp64
-//      add in the reference's association, feature weights gathered from the
-//      HBM feature table by hashed key with all first-slot loads in flight together, the tag x tag
-//      matrix and the length vectors from shared memory;
-//   4. keeps the best `beam` candidates in a sorted shared-memory list; insertion is strict
-//      (a later equal score never displaces an earlier one), which is exactly the stable sort of
-//      Beam.append (beam.py:83-86);
+// memory ring of the last 9 end positions (window 8, beam.py:30).  An entry holds its score and the
+// hash products of its last two words that the NEXT transition's feature keys are sums of
+// (hash.cuh: keys are additive), so a transition costs additions, not string hashing.
+//
+// Per end position e the warp
+//   1. reads the CSR bucket of e (sorted by begin) and counts edges per span;
+//   2. EDGE PREP, lanes = edges: per edge the word/morpheme hash products and everything of the
+//      score that depends on the edge alone — RegularizationScore, the preference scorers,
+//      templates 4 and 5 — into a shared-memory edge cache;
+//   3. enumerates candidates in the reference's generation order — begin ascending, parent rank
+//      ascending, edge order ascending (beam.py:30-48) — 32 at a time, one per lane, and scores
+//      each: score program in BeamScoreFunctions order, every fp64 add in the reference's
+//      association; templates 0,1,2,7,8 are gathered from the HBM feature table
+//      with all first-slot loads in flight together, template 3/6 come from shared memory;
+//   4. keeps the best `beam` candidates: repeated warp arg-max (redux.sync on the order-preserving
+//      integer image of the fp64 score) with ties resolved towards the earlier candidate, which is
+//      exactly the stable sort of Beam.append (beam.py:83-86);
 //   5. writes the survivors as new ring entries and one 8-byte back-pointer each to the HBM trail.
 // The best path is recovered from the trail and written as 16-byte edge records.
 #pragma once
@@ -26,6 +30,8 @@
 namespace lt {
 
 constexpr int kRing = LT_WINDOW + 1;
+constexpr int kECache = 24;                   // cached window edges per position (+ 8 unknown spans)
+constexpr int kECacheAll = kECache + LT_WINDOW;
 constexpr uint32_t kCtxMask = (1u << LT_TAG_NOUN) | (1u << LT_TAG_ADVERB) | (1u << LT_TAG_ADJECTIVE) | (1u << LT_TAG_VERB);
 
 // entry meta bits
@@ -41,9 +47,10 @@ struct BeamArgs {
     int32_t lcap;
     int32_t beam;
     int32_t warps;              // warps per CTA
-    const uint32_t* end_off;
+    const uint2* pos;           // [n_units] (first edge, edge count) per (sentence, end position)
     const lt_edge* edges;
     const int32_t* status;      // from the lattice pass
+    const uint32_t* flags;      // lattice overflow flags (lattice.cuh)
     uint64_t* trail;            // [(n_units) * beam] back-pointers
     lt_edge* path_tmp;          // [n_units] best path, reversed, at the sentence's offset
     int32_t* path_len;          // [n_sent]
@@ -52,15 +59,30 @@ struct BeamArgs {
     unsigned int* queue;
 };
 
-__host__ __device__ inline size_t beam_warp_smem(int lcap, int beam) {
+// per-edge cache entry (shared memory, struct of arrays)
+struct EdgeCache {
+    H2* e0;            // word hash   * M0
+    H2* g0;            // morph0 hash * M0
+    double* kval;      // kRingVals doubles per edge: score-program values that depend on the edge only
+    uint32_t* meta;    // tag0 | len << 8 (16 bits) | flags << 24
+    uint32_t* eref;    // global edge index (kTrailUnk for unknown words)
+    uint32_t* present; // bit f*2: template 4 present, bit f*2+1: template 5 present (per scorer f)
+};
+
+// doubles per edge in kval (stride 2 * n_funcs): for scorer f: [2f] = REG / MPREF / WPREF value or
+// template-4 weight, [2f+1] = template-5 weight
+
+__host__ __device__ inline size_t beam_warp_smem(int lcap, int beam, int n_funcs) {
     size_t units = (size_t)lcap + 8;
-    size_t bytes = units * 8 * 2;                    // ha, hb
-    bytes += (size_t)kRing * beam * (8 + 48);        // score, wj, wi, mc
-    bytes += (size_t)beam * 8;                       // list keys
-    bytes += units * 2;                              // chars
-    bytes += (size_t)kRing * beam * 4;               // meta
-    bytes += (size_t)beam * 4;                       // list payloads
-    bytes += 16;                                     // ring sizes
+    size_t bytes = units * 8 * 2;                          // ha, hb
+    bytes += units * 8;                                    // pos (uint2)
+    bytes += (size_t)kRing * beam * (8 + 64);              // score, p1, pp, j2, c1
+    bytes += (size_t)kECacheAll * (16 + 16 + 16 * (n_funcs > 0 ? n_funcs : 1));   // e0, g0, kval
+    bytes += units * 2;                                    // chars
+    bytes = (bytes + 7) & ~(size_t)7;
+    bytes += (size_t)kRing * beam * 4;                     // meta
+    bytes += (size_t)kECacheAll * 12;                      // cache meta, eref, present
+    bytes += 64 * 4;                                       // per-span tables + ring sizes
     return (bytes + 15) & ~(size_t)15;
 }
 
@@ -108,24 +130,33 @@ __device__ __forceinline__ double numpy_order_sum9(const double (&v)[9], uint32_
     return s;
 }
 
-struct ParentView {
-    double score;
-    H2 wj, wi, mc;
-    uint32_t meta;
-};
-
 struct EdgeView {
     int b, e;
     uint32_t len, tag0, tag1, rule, split, flags;
     H2 wk, mk, m1;      // hashes of word, morph0, morph1
-    uint32_t m1_valid;
 };
 
-__device__ __forceinline__ void edge_hashes(const DevTables& T, const SentView& v, EdgeView& k, bool need_m1) {
+__device__ __forceinline__ void unpack_edge(uint4 raw, EdgeView& k) {
+    k.b = (int)(raw.x & 0xFFFFu);
+    k.e = (int)(raw.x >> 16);
+    k.len = raw.y & 0xFFFFu;
+    k.tag0 = (raw.y >> 16) & 0xFFu;
+    k.tag1 = (raw.y >> 24) & 0xFFu;
+    k.rule = raw.z;
+    k.split = raw.w & 0xFFFFu;
+    k.flags = (raw.w >> 16) & 0xFFu;
+}
+
+__device__ __forceinline__ void unknown_edge(int b, int e, EdgeView& k) {
+    k.b = b; k.e = e;
+    k.len = (uint32_t)(e - b); k.tag0 = LT_TAG_UNK; k.tag1 = LT_NO_TAG; k.rule = LT_NO_RULE;
+    k.split = 0; k.flags = LT_EDGE_UNK;
+}
+
+__device__ __noinline__ void edge_hashes(const DevTables& T, const SentView& v, EdgeView& k, bool need_m1) {
     k.wk = sub_hash(T, v, k.b, k.e);
     k.mk = k.wk;
     k.m1 = H2{0, 0};
-    k.m1_valid = 0;
     if (k.flags & LT_EDGE_LEMMA) {
         const int p = k.b + (int)k.split;
         if (k.rule == LT_NO_RULE) {
@@ -143,96 +174,72 @@ __device__ __forceinline__ void edge_hashes(const DevTables& T, const SentView& 
                 k.m1 = h2_concat(rec.eomi, suf, pow_at(T, sl));
             }
         }
-        k.m1_valid = 1;
     }
 }
 
-// increment of one transition: BeamScoreFunctions.score (score_funcs.py:50-54)
-__device__ __forceinline__ double transition_increment(const DevTables& T, const unsigned char* dense_smem,
-                                                       const ParentView& P, const EdgeView& k, uint32_t& nfeat) {
-    double inc = 0.0;
-    const uint32_t tj = P.meta & kMetaTagMask;
+// Everything of a transition's score that depends on the edge alone, for scorer f:
+//   REG / MPREF / WPREF: a = the scorer's value;  TRIGRAM: a = template 4 weight, b2 = template 5
+//   weight, presence bits 0 / 1.
+__device__ __noinline__ uint32_t edge_score(const DevTables& T, const unsigned char* dense_smem, const EdgeView& k,
+                                            H2 e0, H2 g0, int f, double& a, double& b2) {
+    uint32_t present = 0;
     const uint32_t tk = k.tag0;
-    const H2 zero{0, 0};
-    for (int f = 0; f < T.n_funcs; ++f) {
-        const lt_func& fn = T.funcs[f];
-        double val;
-        if (fn.kind == LT_FUNC_REG) {
-            // score_funcs.py:65-73
-            if (tk == LT_TAG_UNK) val = __dmul_rn(fn.p[0], __dadd_rn((double)k.len, 0.1));
-            else val = __dmul_rn(fn.p[1], (double)k.len);
-            val = __dadd_rn(0.0, val);
-            if (k.len == 1 && tk == LT_TAG_NOUN) val = __dadd_rn(val, fn.p[2]);
-        } else if (fn.kind == LT_FUNC_MPREF) {
-            // score_funcs.py:84-88
-            FKey k0 = feature_key(kKindMPref, f, k.mk, zero, zero, tk, 0);
-            uint4 s0 = feat_first(T, k0);
-            double a = 0.0, b2 = 0.0;
-            if (k.tag1 != LT_NO_TAG) {
-                FKey k1 = feature_key(kKindMPref, f, k.m1, zero, zero, k.tag1, 0);
-                uint4 s1 = feat_first(T, k1);
-                feat_resolve(T, k1, s1, b2);
-            }
-            feat_resolve(T, k0, s0, a);
-            val = (k.tag1 != LT_NO_TAG) ? __dadd_rn(a, b2) : a;
-        } else if (fn.kind == LT_FUNC_WPREF) {
-            // score_funcs.py:99-100
-            FKey k0 = feature_key(kKindWPref, f, k.wk, zero, zero, tk, 0);
-            uint4 s0 = feat_first(T, k0);
-            val = 0.0;
-            feat_resolve(T, k0, s0, val);
-        } else {
-            // SimpleTrigramFeatureScore.score (score_funcs.py:137-144) over trigram_encoder's templates
-            const DenseView D = dense_view(dense_smem + (size_t)T.func_dense[f] * dense_block_bytes(T.n_tags), T.n_tags);
-            double v[9];
-            uint32_t present = 0;
-            const bool has_i = (P.meta & kMetaHasI) != 0;
-            const bool j_unk = (tj == LT_TAG_UNK);
-            const bool ctx8 = ((kCtxMask >> tk) & 1u) && (tk < 32) && (P.meta & kMetaHasCtx);
-            const bool t4_hashed = k.len >= (uint32_t)kT4Dense;
-            nfeat += 6u + (j_unk ? 1u : 0u) + (has_i ? 1u : 0u) + (ctx8 ? 1u : 0u);
-            // keys
-            FKey q0 = feature_key(0, f, P.wj, k.wk, zero, tk, 0);
-            FKey q1 = feature_key(1, f, P.wj, zero, zero, tk, 0);
-            FKey q2 = feature_key(2, f, k.wk, zero, zero, tj, tk);
-            FKey q5 = feature_key(5, f, k.wk, zero, zero, tk, (k.flags & LT_EDGE_IS_L) ? 1u : 0u);
-            FKey q7 = feature_key(7, f, P.wi, P.wj, k.wk, 0, 0);
-            FKey q8 = feature_key(8, f, P.mc, k.mk, zero, 0, 0);
-            FKey q4 = feature_key(4, f, zero, zero, zero, k.len, 0);
-            // all first-slot loads in flight before any is consumed
-            uint4 s0 = feat_first(T, q0);
-            uint4 s1 = feat_first(T, q1);
-            uint4 s2 = feat_first(T, q2);
-            uint4 s5 = feat_first(T, q5);
-            uint4 s7 = has_i ? feat_first(T, q7) : make_uint4(0, 0, 0, 0);
-            uint4 s8 = ctx8 ? feat_first(T, q8) : make_uint4(0, 0, 0, 0);
-            uint4 s4 = t4_hashed ? feat_first(T, q4) : make_uint4(0, 0, 0, 0);
-            #pragma unroll
-            for (int i = 0; i < 9; ++i) v[i] = 0.0;
-            if (feat_resolve(T, q0, s0, v[0])) present |= 1u << 0;
-            if (feat_resolve(T, q1, s1, v[1])) present |= 1u << 1;
-            if (feat_resolve(T, q2, s2, v[2])) present |= 1u << 2;
-            if ((D.m3[tj] >> tk) & 1u) { v[3] = D.t3[tj * T.n_tags + tk]; present |= 1u << 3; }
-            if (t4_hashed) {
-                if (feat_resolve(T, q4, s4, v[4])) present |= 1u << 4;
-            } else if ((D.m4[k.len >> 5] >> (k.len & 31)) & 1u) {
-                v[4] = D.t4[k.len]; present |= 1u << 4;
-            }
-            if (feat_resolve(T, q5, s5, v[5])) present |= 1u << 5;
-            if (j_unk) {
-                const uint32_t ul = (P.meta >> kMetaUnkLenShift) & 0xFu;
-                if ((D.m6[0] >> ul) & 1u) { v[6] = D.t6[ul]; present |= 1u << 6; }
-            }
-            if (has_i && feat_resolve(T, q7, s7, v[7])) present |= 1u << 7;
-            if (ctx8 && feat_resolve(T, q8, s8, v[8])) present |= 1u << 8;
-            val = present ? numpy_order_sum9(v, present) : 0.0;
+    const lt_func& fn = T.funcs[f];
+    a = 0.0;
+    b2 = 0.0;
+    if (fn.kind == LT_FUNC_REG) {
+        // score_funcs.py:65-73
+        if (tk == LT_TAG_UNK) a = __dmul_rn(fn.p[0], __dadd_rn((double)k.len, 0.1));
+        else a = __dmul_rn(fn.p[1], (double)k.len);
+        a = __dadd_rn(0.0, a);
+        if (k.len == 1 && tk == LT_TAG_NOUN) a = __dadd_rn(a, fn.p[2]);
+    } else if (fn.kind == LT_FUNC_MPREF) {
+        // score_funcs.py:84-88
+        FKey k0 = feature_key_sum(T.seeds[f][9], feature_head(tk, 0), g0);
+        uint4 s0 = feat_first(T, k0);
+        if (k.tag1 != LT_NO_TAG) {
+            FKey k1 = feature_key_sum(T.seeds[f][9], feature_head(k.tag1, 0), h2_mul(k.m1, kM0a, kM0b));
+            uint4 s1 = feat_first(T, k1);
+            feat_resolve(T, k1, s1, b2);
         }
-        inc = __dadd_rn(inc, val);
+        feat_resolve(T, k0, s0, a);
+        if (k.tag1 != LT_NO_TAG) a = __dadd_rn(a, b2);
+        b2 = 0.0;
+    } else if (fn.kind == LT_FUNC_WPREF) {
+        // score_funcs.py:99-100
+        FKey k0 = feature_key_sum(T.seeds[f][9], feature_head(tk, 0), e0);
+        uint4 s0 = feat_first(T, k0);
+        feat_resolve(T, k0, s0, a);
+    } else {
+        // templates 4 (wk.len) and 5 (wk.word, wk.tag0, wk.is_l), features/feature.py:100,104
+        const DenseView D = dense_view(dense_smem + (size_t)T.func_dense[f] * dense_block_bytes(T.n_tags), T.n_tags);
+        FKey q5 = feature_key_sum(T.seeds[f][5], feature_head(tk, (k.flags & LT_EDGE_IS_L) ? 1u : 0u), e0);
+        uint4 s5 = feat_first(T, q5);
+        if (k.len >= (uint32_t)kT4Dense) {
+            FKey q4 = feature_key_sum(T.seeds[f][4], feature_head(k.len, 0), H2{0, 0});
+            uint4 s4 = feat_first(T, q4);
+            if (feat_resolve(T, q4, s4, a)) present |= 1u;
+        } else if ((D.m4[k.len >> 5] >> (k.len & 31)) & 1u) {
+            a = D.t4[k.len];
+            present |= 1u;
+        }
+        if (feat_resolve(T, q5, s5, b2)) present |= 2u;
     }
-    return inc;
+    return present;
 }
 
-__global__ void __launch_bounds__(256) beam_kernel(const DevTables T, const BeamArgs A) {
+// order-preserving integer image of an fp64 score (larger score -> larger key); 0 is "no candidate"
+__device__ __forceinline__ uint64_t sortable(double s) {
+    uint64_t bits = (uint64_t)__double_as_longlong(s);
+    return bits ^ ((bits >> 63) ? 0xFFFFFFFFFFFFFFFFull : 0x8000000000000000ull);
+}
+__device__ __forceinline__ double unsortable(uint64_t key) {
+    uint64_t bits = key ^ ((key >> 63) ? 0x8000000000000000ull : 0xFFFFFFFFFFFFFFFFull);
+    return __longlong_as_double((long long)bits);
+}
+
+template <int KR>   // KR = ceil(beam / 32): kept entries per lane
+__global__ void __launch_bounds__(256) beam_kernel(const __grid_constant__ DevTables T, const __grid_constant__ BeamArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -245,26 +252,39 @@ __global__ void __launch_bounds__(256) beam_kernel(const DevTables T, const Beam
     for (size_t i = threadIdx.x * 4; i < (size_t)T.n_tri * dense_block_bytes(NT); i += blockDim.x * 4)
         *reinterpret_cast<uint32_t*>(dense_smem + i) = *reinterpret_cast<const uint32_t*>(T.dense + i);
     __syncthreads();
+    if (A.flags[kFlagEdgeOverflow] | A.flags[kFlagStageOverflow]) return;   // lattice incomplete: the host grows the buffer and reruns
 
     const size_t units = (size_t)A.lcap + 8;
-    unsigned char* wbase = smem_raw + dense_bytes + (size_t)warp * beam_warp_smem(A.lcap, K);
+    unsigned char* wbase = smem_raw + dense_bytes + (size_t)warp * beam_warp_smem(A.lcap, K, T.n_funcs);
     uint64_t* ha = reinterpret_cast<uint64_t*>(wbase);
     uint64_t* hb = ha + units;
-    double* e_score = reinterpret_cast<double*>(hb + units);
-    H2* e_wj = reinterpret_cast<H2*>(e_score + kRing * K);
-    H2* e_wi = e_wj + kRing * K;
-    H2* e_mc = e_wi + kRing * K;
-    double* l_key = reinterpret_cast<double*>(e_mc + kRing * K);
-    uint16_t* ch = reinterpret_cast<uint16_t*>(l_key + K);
-    uint32_t* e_meta = reinterpret_cast<uint32_t*>(ch + units);
-    uint32_t* l_pay = e_meta + kRing * K;
-    uint32_t* ring_n = l_pay + K;      // kRing entries used (as u8-in-u32: keep simple)
-    // ring_n needs kRing words; beam_warp_smem reserves 16 bytes -> use bytes
-    uint8_t* nbeam = reinterpret_cast<uint8_t*>(ring_n);
+    uint2* spos = reinterpret_cast<uint2*>(hb + units);
+    double* e_score = reinterpret_cast<double*>(spos + units);
+    H2* e_p1 = reinterpret_cast<H2*>(e_score + kRing * K);     // wj * M1
+    H2* e_pp = e_p1 + kRing * K;                                // wj * M1 + wi * M2
+    H2* e_j2 = e_pp + kRing * K;                                // wj * M2
+    H2* e_c1 = e_j2 + kRing * K;                                // contextual morph * M1
+    EdgeCache C;
+    C.e0 = e_c1 + kRing * K;
+    C.g0 = C.e0 + kECacheAll;
+    C.kval = reinterpret_cast<double*>(C.g0 + kECacheAll);
+    const int kvs = 2 * (T.n_funcs > 0 ? T.n_funcs : 1);   // kval stride
+    uint16_t* ch = reinterpret_cast<uint16_t*>(C.kval + (size_t)kECacheAll * kvs);
+    uintptr_t after = (reinterpret_cast<uintptr_t>(ch + units) + 7) & ~(uintptr_t)7;
+    uint32_t* e_meta = reinterpret_cast<uint32_t*>(after);
+    C.meta = e_meta + kRing * K;
+    C.eref = C.meta + kECacheAll;
+    C.present = C.eref + kECacheAll;
+    uint32_t* s_cnt = C.present + kECacheAll;       // [9] edges per span
+    uint32_t* s_gstart = s_cnt + 16;                // [9] first bucket-local index of the span's group
+    uint32_t* s_ncand = s_gstart + 16;              // [9] candidates of the span
+    uint32_t* s_nbeam = s_ncand + 16;               // [kRing] entries per ring slot
 
     unsigned long long acc_T = 0, acc_F = 0, acc_B = 0, acc_W = 0;
+
     bool need_m1 = false;
     for (int f = 0; f < T.n_funcs; ++f) need_m1 |= (T.funcs[f].kind == LT_FUNC_MPREF);
+    const int nf = T.n_funcs;
 
     while (true) {
         unsigned int s = 0;
@@ -277,7 +297,7 @@ __global__ void __launch_bounds__(256) beam_kernel(const DevTables T, const Beam
             if (lane == 0) { A.path_len[s] = 0; A.scores[s] = 0.0; }
             continue;
         }
-        // ---- stage syllables + prefix hashes (same arithmetic as the lattice kernel) ----
+        // ---- stage syllables, prefix hashes and the sentence's CSR row ----
         int L = 0;
         for (int base = s0; base < s1; base += 32) {
             int idx = base + lane;
@@ -290,6 +310,7 @@ __global__ void __launch_bounds__(256) beam_kernel(const DevTables T, const Beam
             L += __popc(km);
         }
         __syncwarp();
+        for (int i = lane; i < L; i += 32) spos[i] = __ldg(A.pos + s0 + i);
         prefix_hashes(ch, L, lane, ha, hb);
         SentView v{ch, ha, hb, nullptr};
 
@@ -301,50 +322,116 @@ __global__ void __launch_bounds__(256) beam_kernel(const DevTables T, const Beam
         // beam[0] = [BOS] (beam.py:21-23)
         if (lane == 0) {
             e_score[0] = 0.0;
-            e_wj[0] = T.bos;
-            e_wi[0] = H2{0, 0};
-            e_mc[0] = H2{0, 0};
+            e_p1[0] = h2_mul(T.bos, kM1a, kM1b);
+            e_j2[0] = h2_mul(T.bos, kM2a, kM2b);
+            e_pp[0] = H2{0, 0};
+            e_c1[0] = H2{0, 0};
             e_meta[0] = (uint32_t)LT_TAG_BOS;
-            nbeam[0] = 1;
+            s_nbeam[0] = 1;
         }
         __syncwarp();
 
         for (int e = 1; e <= L; ++e) {
             const int slot_e = e % kRing;
-            const uint32_t es = __ldg(A.end_off + s0 + e - 1), ee = __ldg(A.end_off + s0 + e);
+            const uint2 bucket = spos[e - 1];
+            const uint32_t es = bucket.x, ne = bucket.y;
             const int jmax = (e < LT_WINDOW) ? e : LT_WINDOW;
-            // edges per span (bucket sorted by begin ascending = span descending)
-            uint32_t cnt[LT_WINDOW + 1];
-            #pragma unroll
-            for (int j = 0; j <= LT_WINDOW; ++j) cnt[j] = 0;
-            for (uint32_t base = es; base < ee; base += 32) {
+
+            // ---- 1. edges per span (bucket sorted by begin ascending = span descending) ----
+            uint32_t my_cnt = 0;            // lane j (1..8) counts span j
+            uint4 raw0 = make_uint4(0, 0, 0, 0);
+            for (uint32_t base = 0; base < ne; base += 32) {
                 uint32_t idx = base + lane;
                 int span = 0;
-                if (idx < ee) {
-                    uint32_t be = __ldg(reinterpret_cast<const uint32_t*>(A.edges + idx));
-                    span = (int)(be >> 16) - (int)(be & 0xFFFFu);
+                if (idx < ne) {
+                    uint4 raw = ldg16(A.edges + es + idx);
+                    if (base == 0) raw0 = raw;
+                    span = (int)(raw.x >> 16) - (int)(raw.x & 0xFFFFu);
                 }
                 #pragma unroll
-                for (int j = 1; j <= LT_WINDOW; ++j) cnt[j] += __popc(__ballot_sync(kFull, span == j));
+                for (int j = 1; j <= LT_WINDOW; ++j) {
+                    uint32_t c = __popc(__ballot_sync(kFull, span == j));
+                    if (lane == j) my_cnt += c;
+                }
             }
-            // group starts and candidate counts, spans from jmax down to 1 (begin ascending)
-            uint32_t gstart[LT_WINDOW + 1], ncand[LT_WINDOW + 1];
-            uint32_t in_window = 0;
-            #pragma unroll
-            for (int j = 1; j <= LT_WINDOW; ++j) in_window += cnt[j];
-            uint32_t run = ee - in_window;          // first edge inside the window
+            // lane j: group start = ne - sum_{j' <= j} cnt[j'] ... spans descend along the bucket
+            {
+                uint32_t c = (lane >= 1 && lane <= LT_WINDOW) ? my_cnt : 0u;
+                uint32_t incl = c;      // inclusive prefix over lanes 1..j
+                #pragma unroll
+                for (int d = 1; d < 16; d <<= 1) {
+                    uint32_t t = __shfl_up_sync(kFull, incl, d);
+                    if (lane >= d) incl += t;
+                }
+                if (lane >= 1 && lane <= LT_WINDOW) {
+                    s_cnt[lane] = c;
+                    s_gstart[lane] = ne - incl;                 // bucket-local index of the group's first edge
+                    uint32_t np = (lane <= jmax) ? s_nbeam[(e - lane) % kRing] : 0u;
+                    s_ncand[lane] = np * (c ? c : 1u);
+                }
+            }
+            __syncwarp();
+            const uint32_t in_window = ne - s_gstart[LT_WINDOW] ;   // = sum of cnt[1..8]
+            const uint32_t first_in = ne - in_window;               // bucket-local index of the first window edge
             uint32_t N = 0;
             #pragma unroll
-            for (int j = LT_WINDOW; j >= 1; --j) {
-                gstart[j] = run;
-                run += cnt[j];
-                uint32_t np = (j <= jmax) ? (uint32_t)nbeam[(e - j) % kRing] : 0u;
-                uint32_t nedge = cnt[j] ? cnt[j] : 1u;
-                ncand[j] = np * nedge;
-                N += ncand[j];
-            }
+            for (int j = 1; j <= LT_WINDOW; ++j) N += s_ncand[j];
 
-            int nl = 0;     // entries in the sorted list (warp-uniform)
+            // ---- 2. edge prep into the cache: window edges, then the unknown word of every empty span ----
+            {
+                const uint32_t n_cached = in_window < (uint32_t)kECache ? in_window : (uint32_t)kECache;
+                for (uint32_t base = 0; base < n_cached + LT_WINDOW; base += 32) {
+                    const uint32_t ci = base + lane;
+                    bool active = false;
+                    EdgeView k;
+                    uint32_t slot = 0, eref = kTrailUnk;
+                    // the first 32 bucket entries are still in the registers of lane (bucket index)
+                    const uint32_t bidx = first_in + ci;
+                    uint4 r0;
+                    r0.x = __shfl_sync(kFull, raw0.x, bidx & 31);
+                    r0.y = __shfl_sync(kFull, raw0.y, bidx & 31);
+                    r0.z = __shfl_sync(kFull, raw0.z, bidx & 31);
+                    r0.w = __shfl_sync(kFull, raw0.w, bidx & 31);
+                    if (ci < n_cached) {
+                        unpack_edge((bidx < 32) ? r0 : ldg16(A.edges + es + bidx), k);
+                        slot = ci;
+                        eref = es + bidx;
+                        active = true;
+                    } else {
+                        const int j = (int)(ci - n_cached) + 1;
+                        if (j <= jmax && s_cnt[j] == 0) {
+                            unknown_edge(e - j, e, k);
+                            slot = (uint32_t)(kECache + j - 1);
+                            active = true;
+                        }
+                    }
+                    if (active) {
+                        edge_hashes(T, v, k, need_m1);
+                        const H2 e0 = h2_mul(k.wk, kM0a, kM0b), g0 = h2_mul(k.mk, kM0a, kM0b);
+                        uint32_t present = 0;
+                        #pragma unroll 1
+                        for (int f = 0; f < nf; ++f) {
+                            double a, b2;
+                            present |= edge_score(T, dense_smem, k, e0, g0, f, a, b2) << (2 * f);
+                            C.kval[slot * kvs + 2 * f] = a;
+                            C.kval[slot * kvs + 2 * f + 1] = b2;
+                        }
+                        C.e0[slot] = e0;
+                        C.g0[slot] = g0;
+                        C.meta[slot] = k.tag0 | (k.len << 8) | (k.flags << 24);
+                        C.eref[slot] = eref;
+                        C.present[slot] = present;
+                    }
+                }
+            }
+            __syncwarp();
+
+            // ---- 3 + 4. candidates in generation order, running top-K ----
+            uint64_t keep_key[KR];
+            uint32_t keep_pay[KR];
+            #pragma unroll
+            for (int r = 0; r < KR; ++r) { keep_key[r] = 0; keep_pay[r] = 0; }
+
             for (uint32_t c0 = 0; c0 < N; c0 += 32) {
                 uint32_t c = c0 + lane;
                 bool valid = c < N;
@@ -354,134 +441,201 @@ __global__ void __launch_bounds__(256) beam_kernel(const DevTables T, const Beam
                     #pragma unroll
                     for (int jj = LT_WINDOW; jj >= 1; --jj) {
                         if (j == 0) {
-                            if (rem < ncand[jj]) j = jj; else rem -= ncand[jj];
+                            const uint32_t nc = s_ncand[jj];
+                            if (rem < nc) j = jj; else rem -= nc;
                         }
                     }
                 }
-                double newscore = 0.0;
-                uint32_t pay = 0;
+                uint64_t ckey = 0;
+                uint32_t cpay = 0;
                 if (valid) {
-                    // select by dynamic j without local-memory arrays
-                    uint32_t cj = 0, gs = 0;
-                    #pragma unroll
-                    for (int jj = 1; jj <= LT_WINDOW; ++jj)
-                        if (jj == j) { cj = cnt[jj]; gs = gstart[jj]; }
+                    const uint32_t cj = s_cnt[j];
                     const bool unk_edge = (cj == 0);
                     const uint32_t nedge = unk_edge ? 1u : cj;
                     const uint32_t prank = rem / nedge, eidx = rem - prank * nedge;
                     const int pslot = ((e - j) % kRing) * K + (int)prank;
-                    ParentView P;
-                    P.score = e_score[pslot];
-                    P.wj = e_wj[pslot];
-                    P.wi = e_wi[pslot];
-                    P.mc = e_mc[pslot];
-                    P.meta = e_meta[pslot];
-                    EdgeView k;
-                    k.b = e - j; k.e = e;
-                    uint32_t eref;
-                    if (unk_edge) {
-                        k.len = (uint32_t)j; k.tag0 = LT_TAG_UNK; k.tag1 = LT_NO_TAG; k.rule = LT_NO_RULE;
-                        k.split = 0; k.flags = LT_EDGE_UNK;
-                        eref = kTrailUnk;
+                    const uint32_t pmeta = e_meta[pslot];
+                    const uint32_t tj = pmeta & kMetaTagMask;
+                    // cache slot of the edge
+                    const uint32_t widx = s_gstart[j] - first_in + eidx;     // index among window edges
+                    uint32_t slot = unk_edge ? (uint32_t)(kECache + j - 1) : widx;
+                    H2 e0, g0;
+                    uint32_t emeta, epresent = 0;
+                    const bool uncached = !unk_edge && widx >= (uint32_t)kECache;
+                    EdgeView kfly;
+                    if (uncached) {
+                        // bucket larger than the cache: prepare this edge on the fly
+                        unpack_edge(ldg16(A.edges + es + s_gstart[j] + eidx), kfly);
+                        edge_hashes(T, v, kfly, need_m1);
+                        e0 = h2_mul(kfly.wk, kM0a, kM0b);
+                        g0 = h2_mul(kfly.mk, kM0a, kM0b);
+                        emeta = kfly.tag0 | (kfly.len << 8) | (kfly.flags << 24);
                     } else {
-                        eref = gs + eidx;
-                        uint4 raw = ldg16(A.edges + eref);
-                        k.len = raw.y & 0xFFFFu;
-                        k.tag0 = (raw.y >> 16) & 0xFFu;
-                        k.tag1 = (raw.y >> 24) & 0xFFu;
-                        k.rule = raw.z;
-                        k.split = raw.w & 0xFFFFu;
-                        k.flags = (raw.w >> 16) & 0xFFu;
+                        e0 = C.e0[slot];
+                        g0 = C.g0[slot];
+                        emeta = C.meta[slot];
+                        epresent = C.present[slot];
                     }
+                    const uint32_t tk = emeta & 0xFFu;
                     // two unknown words in a row are only allowed from the window's first begin (beam.py:44-45)
-                    const bool parent_unk = (P.meta & kMetaTagMask) == LT_TAG_UNK;
-                    if (parent_unk && k.tag0 == LT_TAG_UNK && j < jmax) {
+                    if (tj == LT_TAG_UNK && tk == LT_TAG_UNK && j < jmax) {
                         valid = false;
                     } else {
-                        edge_hashes(T, v, k, need_m1);
-                        uint32_t nfeat = 0;
-                        double inc = transition_increment(T, dense_smem, P, k, nfeat);
-                        newscore = __dadd_rn(P.score, inc);            // Sequence.add, beam.py:115
-                        newscore = __dadd_rn(newscore, 0.0);           // -0.0 sorts as 0.0
-                        pay = (unk_edge ? 0x80000000u : 0u) | ((uint32_t)j << 27) | (prank << 20) | (unk_edge ? 0u : (eref - es));
+                        const double pscore = e_score[pslot];
+                        const H2 p1 = e_p1[pslot];
+                        const bool has_i = (pmeta & kMetaHasI) != 0;
+                        const bool j_unk = (tj == LT_TAG_UNK);
+                        const bool ctx8 = ((kCtxMask >> tk) & 1u) && (pmeta & kMetaHasCtx);
+                        double inc = 0.0;
+                        #pragma unroll 1
+                        for (int f = 0; f < nf; ++f) {
+                            double val, val5;
+                            if (uncached) {
+                                epresent |= edge_score(T, dense_smem, kfly, e0, g0, f, val, val5) << (2 * f);
+                            } else {
+                                val = C.kval[slot * kvs + 2 * f];
+                                val5 = C.kval[slot * kvs + 2 * f + 1];
+                            }
+                            if (T.funcs[f].kind == LT_FUNC_TRIGRAM) {
+                                // SimpleTrigramFeatureScore.score (score_funcs.py:137-144)
+                                const DenseView D = dense_view(dense_smem + (size_t)T.func_dense[f] * dense_block_bytes(NT), NT);
+                                acc_F += 6u + (j_unk ? 1u : 0u) + (has_i ? 1u : 0u) + (ctx8 ? 1u : 0u);
+                                const H2 sum0 = h2_add(e0, p1);
+                                FKey q0 = feature_key_sum(T.seeds[f][0], feature_head(tk, 0), sum0);
+                                FKey q1 = feature_key_sum(T.seeds[f][1], feature_head(tk, 0), p1);
+                                FKey q2 = feature_key_sum(T.seeds[f][2], feature_head(tj, tk), e0);
+                                uint4 s0 = feat_first(T, q0);
+                                uint4 s1 = feat_first(T, q1);
+                                uint4 s2 = feat_first(T, q2);
+                                FKey q7, q8;
+                                uint4 s7 = make_uint4(0, 0, 0, 0), s8 = make_uint4(0, 0, 0, 0);
+                                if (has_i) {
+                                    q7 = feature_key_sum(T.seeds[f][7], 0, h2_add(e0, e_pp[pslot]));
+                                    s7 = feat_first(T, q7);
+                                }
+                                if (ctx8) {
+                                    q8 = feature_key_sum(T.seeds[f][8], 0, h2_add(g0, e_c1[pslot]));
+                                    s8 = feat_first(T, q8);
+                                }
+                                double w[9];
+                                uint32_t present = 0;
+                                #pragma unroll
+                                for (int i = 0; i < 9; ++i) w[i] = 0.0;
+                                if (feat_resolve(T, q0, s0, w[0])) present |= 1u << 0;
+                                if (feat_resolve(T, q1, s1, w[1])) present |= 1u << 1;
+                                if (feat_resolve(T, q2, s2, w[2])) present |= 1u << 2;
+                                if ((D.m3[tj] >> tk) & 1u) { w[3] = D.t3[tj * NT + tk]; present |= 1u << 3; }
+                                if ((epresent >> (2 * f)) & 1u) { w[4] = val; present |= 1u << 4; }
+                                if ((epresent >> (2 * f + 1)) & 1u) { w[5] = val5; present |= 1u << 5; }
+                                if (j_unk) {
+                                    const uint32_t ul = (pmeta >> kMetaUnkLenShift) & 0xFu;
+                                    if ((D.m6[0] >> ul) & 1u) { w[6] = D.t6[ul]; present |= 1u << 6; }
+                                }
+                                if (has_i && feat_resolve(T, q7, s7, w[7])) present |= 1u << 7;
+                                if (ctx8 && feat_resolve(T, q8, s8, w[8])) present |= 1u << 8;
+                                val = present ? numpy_order_sum9(w, present) : 0.0;
+                            }
+                            inc = __dadd_rn(inc, val);          // score += f(...), score_funcs.py:51-53
+                        }
+                        double newscore = __dadd_rn(pscore, inc);        // Sequence.add, beam.py:115
+                        newscore = __dadd_rn(newscore, 0.0);             // -0.0 sorts as 0.0
+                        ckey = sortable(newscore);
+                        cpay = (unk_edge ? 0x80000000u : 0u) | ((uint32_t)j << 27) | (prank << 20) | (s_gstart[j] + eidx);
                         acc_T += 1;
-                        acc_F += nfeat;
                     }
                 }
-                // ---- strict insertion into the sorted top-K list, lanes in generation order ----
-                bool want = valid && (nl < K || newscore > l_key[K - 1]);
-                unsigned m = __ballot_sync(kFull, want);
-                while (m) {
-                    const int src = __ffs(m) - 1;
-                    m &= m - 1;
-                    const double key = __shfl_sync(kFull, newscore, src);
-                    const uint32_t kp = __shfl_sync(kFull, pay, src);
-                    if (nl == K && !(key > l_key[K - 1])) continue;
-                    // position = number of entries with key >= new key (equal keys stay in front)
-                    int pos = 0;
-                    for (int i0 = 0; i0 < nl; i0 += 32) {
-                        int i = i0 + lane;
-                        bool ge = (i < nl) && (l_key[i] >= key);
-                        pos += __popc(__ballot_sync(kFull, ge));
+                // ---- top-K of (kept so far) U (this chunk): K rounds of warp arg-max ----
+                // Priority on equal keys: kept entries (earlier candidates) by rank, then chunk lanes in order.
+                uint64_t new_key[KR];
+                uint32_t new_pay[KR];
+                #pragma unroll
+                for (int r = 0; r < KR; ++r) { new_key[r] = 0; new_pay[r] = 0; }
+                uint64_t pool_key[KR + 1];
+                #pragma unroll
+                for (int r = 0; r < KR; ++r) pool_key[r] = keep_key[r];
+                pool_key[KR] = ckey;
+                for (int round = 0; round < K; ++round) {
+                    // lane-local best: lower pool index wins ties
+                    uint64_t best = pool_key[0];
+                    int cls = 0;
+                    #pragma unroll
+                    for (int r = 1; r <= KR; ++r)
+                        if (pool_key[r] > best) { best = pool_key[r]; cls = r; }
+                    const uint32_t hi = (uint32_t)(best >> 32), lo = (uint32_t)best;
+                    const uint32_t mhi = __reduce_max_sync(kFull, hi);
+                    if (mhi == 0) break;                                    // pool exhausted
+                    const bool c1 = (hi == mhi);
+                    const uint32_t mlo = __reduce_max_sync(kFull, c1 ? lo : 0u);
+                    const bool c2 = c1 && (lo == mlo);
+                    int win_cls = 0;
+                    unsigned wm = 0;
+                    #pragma unroll
+                    for (int r = 0; r <= KR; ++r) {
+                        unsigned m = __ballot_sync(kFull, c2 && cls == r);
+                        if (wm == 0 && m != 0) { wm = m; win_cls = r; }
                     }
-                    const int last = (nl < K) ? nl : K - 1;     // index that receives the shifted tail
-                    // shift [pos, last) one step down
-                    double mk0 = 0.0, mk1 = 0.0;
-                    uint32_t mp0 = 0, mp1 = 0;
-                    const int i_a = pos + 1 + lane, i_b = pos + 33 + lane;
-                    if (i_a <= last) { mk0 = l_key[i_a - 1]; mp0 = l_pay[i_a - 1]; }
-                    if (i_b <= last) { mk1 = l_key[i_b - 1]; mp1 = l_pay[i_b - 1]; }
-                    __syncwarp();
-                    if (i_a <= last) { l_key[i_a] = mk0; l_pay[i_a] = mp0; }
-                    if (i_b <= last) { l_key[i_b] = mk1; l_pay[i_b] = mp1; }
-                    if (lane == 0) { l_key[pos] = key; l_pay[pos] = kp; }
-                    if (nl < K) ++nl;
-                    __syncwarp();
+                    const int src = __ffs(wm) - 1;
+                    uint32_t pay_mine = cpay;
+                    #pragma unroll
+                    for (int r = 0; r < KR; ++r)
+                        if (win_cls == r) pay_mine = keep_pay[r];
+                    const uint32_t wpay = __shfl_sync(kFull, pay_mine, src);
+                    const uint64_t wkey = ((uint64_t)mhi << 32) | mlo;
+                    if (lane == (round & 31)) {
+                        #pragma unroll
+                        for (int r = 0; r < KR; ++r)
+                            if ((round >> 5) == r) { new_key[r] = wkey; new_pay[r] = wpay; }
+                    }
+                    if (lane == src) {
+                        #pragma unroll
+                        for (int r = 0; r <= KR; ++r)
+                            if (win_cls == r) pool_key[r] = 0;
+                    }
                 }
+                #pragma unroll
+                for (int r = 0; r < KR; ++r) { keep_key[r] = new_key[r]; keep_pay[r] = new_pay[r]; }
             }
 
-            // ---- survivors -> ring entries + trail ----
-            for (int r0 = 0; r0 < nl; r0 += 32) {
-                const int r = r0 + lane;
-                if (r < nl) {
-                    const uint32_t kp = l_pay[r];
+            // ---- 5. survivors -> ring entries + trail ----
+            int nl = 0;
+            #pragma unroll
+            for (int r = 0; r < KR; ++r) {
+                const unsigned m = __ballot_sync(kFull, keep_key[r] != 0);
+                nl += __popc(m);
+                if (keep_key[r] != 0) {
+                    const int rank = r * 32 + lane;
+                    const uint32_t kp = keep_pay[r];
                     const int j = (int)((kp >> 27) & 0xFu);
                     const uint32_t prank = (kp >> 20) & 0x7Fu;
                     const bool unk_edge = (kp >> 31) != 0;
                     const int pslot = ((e - j) % kRing) * K + (int)prank;
                     EdgeView k;
-                    k.b = e - j; k.e = e;
                     uint32_t eref = kTrailUnk;
                     if (unk_edge) {
-                        k.len = (uint32_t)j; k.tag0 = LT_TAG_UNK; k.tag1 = LT_NO_TAG; k.rule = LT_NO_RULE;
-                        k.split = 0; k.flags = LT_EDGE_UNK;
+                        unknown_edge(e - j, e, k);
                     } else {
                         eref = es + (kp & 0xFFFFFu);
-                        uint4 raw = ldg16(A.edges + eref);
-                        k.len = raw.y & 0xFFFFu;
-                        k.tag0 = (raw.y >> 16) & 0xFFu;
-                        k.tag1 = (raw.y >> 24) & 0xFFu;
-                        k.rule = raw.z;
-                        k.split = raw.w & 0xFFFFu;
-                        k.flags = (raw.w >> 16) & 0xFFu;
+                        unpack_edge(ldg16(A.edges + eref), k);
                     }
                     edge_hashes(T, v, k, false);
                     const uint32_t pmeta = e_meta[pslot];
                     const uint32_t tj = pmeta & kMetaTagMask;
                     const bool k_ctx = (k.tag0 < 32) && ((kCtxMask >> k.tag0) & 1u);
                     const bool j_ctx = (tj < 32) && ((kCtxMask >> tj) & 1u);
-                    const int dst = slot_e * K + r;
-                    e_score[dst] = l_key[r];
-                    e_wj[dst] = k.wk;
-                    e_wi[dst] = e_wj[pslot];
-                    e_mc[dst] = k_ctx ? k.mk : (j_ctx ? e_mc[pslot] : H2{0, 0});
+                    const int dst = slot_e * K + rank;
+                    const H2 wk1 = h2_mul(k.wk, kM1a, kM1b);
+                    e_score[dst] = unsortable(keep_key[r]);
+                    e_p1[dst] = wk1;
+                    e_pp[dst] = h2_add(wk1, e_j2[pslot]);
+                    e_j2[dst] = h2_mul(k.wk, kM2a, kM2b);
+                    e_c1[dst] = k_ctx ? h2_mul(k.mk, kM1a, kM1b) : (j_ctx ? e_c1[pslot] : H2{0, 0});
                     uint32_t ul = k.len < 8u ? k.len : 8u;
                     e_meta[dst] = k.tag0 | kMetaHasI | ((k_ctx || j_ctx) ? kMetaHasCtx : 0u) | (ul << kMetaUnkLenShift);
-                    A.trail[(size_t)(s0 + e - 1) * K + r] =
+                    A.trail[(size_t)(s0 + e - 1) * K + rank] =
                         (uint64_t)eref | ((uint64_t)j << 32) | ((uint64_t)prank << 40);
                 }
             }
-            if (lane == 0) nbeam[slot_e] = (uint8_t)nl;
+            if (lane == 0) s_nbeam[slot_e] = (uint32_t)nl;
             acc_B += (lane == 0) ? (unsigned long long)nl : 0ull;
             __syncwarp();
         }

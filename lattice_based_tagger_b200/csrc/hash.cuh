@@ -67,22 +67,49 @@ LT_HD uint64_t rule_key(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t len) {
 // kind: 0..8 trigram templates; 16 morpheme preference; 17 word preference.  func: index of the
 // owning scorer in the score program.  s0..s2: component strings (zero H2 when unused);
 // a0, a1: small integers (tag ids, lengths, flags).
+//
+// The key is ADDITIVE in its components:
+//     ka = seed_a(kind, func) + head * Ta + s0.a * M0a + s1.a * M1a + s2.a * M2a      (mod 2^64)
+//     kb = seed_b(kind, func) + head * Tb + s0.b * M0b + s1.b * M1b + s2.b * M2b
+// so the beam kernel keeps the products of a word's hashes with the slot multipliers (once per
+// lattice edge, once per surviving hypothesis) and forms a transition's keys with additions only.
+// ka picks the slot by multiply-shift (top bits of ka * kSlotMul), kb is the stored fingerprint.
 struct FKey {
-    uint64_t k1, k2;
+    uint64_t k1, k2;     // k1 = ka (slot source), k2 = kb (fingerprint, never 0)
 };
 
-LT_HD FKey feature_key(uint32_t kind, uint32_t func, H2 s0, H2 s1, H2 s2, uint32_t a0, uint32_t a1) {
-    uint64_t head = ((uint64_t)kind << 56) | ((uint64_t)func << 48) | ((uint64_t)a0 << 24) | (uint64_t)a1;
-    uint64_t ka = head * 0x8CB92BA72F3D8DD7ull + s0.a * 0xE7037ED1A0B428DBull +
-                  s1.a * 0x1D8E4E27C47D124Full + s2.a * 0xEB44ACCAB455D165ull;
-    uint64_t kb = head * 0xA0761D6478BD642Full + s0.b * 0x2D358DCCAA6C78A5ull +
-                  s1.b * 0x8BB84B93962EACC9ull + s2.b * 0x4B33A62ED433D4A3ull;
+constexpr uint64_t kM0a = 0xE7037ED1A0B428DBull, kM1a = 0x1D8E4E27C47D124Full, kM2a = 0xEB44ACCAB455D165ull;
+constexpr uint64_t kM0b = 0x2D358DCCAA6C78A5ull, kM1b = 0x8BB84B93962EACC9ull, kM2b = 0x4B33A62ED433D4A3ull;
+constexpr uint64_t kTa = 0x8CB92BA72F3D8DD7ull, kTb = 0xA0761D6478BD642Full;
+constexpr uint64_t kSlotMul = 0x9E3779B97F4A7C15ull;
+
+LT_HD H2 h2_mul(H2 h, uint64_t ma, uint64_t mb) { return H2{h.a * ma, h.b * mb}; }
+LT_HD H2 h2_add(H2 x, H2 y) { return H2{x.a + y.a, x.b + y.b}; }
+
+LT_HD H2 feature_seed(uint32_t kind, uint32_t func) {
+    const uint64_t t = ((uint64_t)kind << 8) | (uint64_t)func;
+    return H2{fmix64(t * 0xD1B54A32D192ED03ull + 0x589965CC75374CC3ull),
+              fmix64(t * 0xAEF17502108EF2D9ull + 0x1B03738712FAD5C9ull)};
+}
+
+LT_HD uint64_t feature_head(uint32_t a0, uint32_t a1) { return ((uint64_t)a0 << 24) | (uint64_t)a1; }
+
+// key from an already summed component part `sum` = s0*M0 + s1*M1 + s2*M2 (pairwise)
+LT_HD FKey feature_key_sum(H2 seed, uint64_t head, H2 sum) {
     FKey k;
-    k.k1 = fmix64(ka);
-    k.k2 = fmix64(kb ^ 0x589965CC75374CC3ull);
+    k.k1 = seed.a + head * kTa + sum.a;
+    k.k2 = seed.b + head * kTb + sum.b;
     if (k.k2 == 0) k.k2 = 1;
     return k;
 }
+
+LT_HD FKey feature_key(uint32_t kind, uint32_t func, H2 s0, H2 s1, H2 s2, uint32_t a0, uint32_t a1) {
+    H2 sum{s0.a * kM0a + s1.a * kM1a + s2.a * kM2a, s0.b * kM0b + s1.b * kM1b + s2.b * kM2b};
+    return feature_key_sum(feature_seed(kind, func), feature_head(a0, a1), sum);
+}
+
+// slot of a key in a table of 2^bits slots
+LT_HD uint64_t feature_slot(uint64_t k1, uint32_t bits) { return (k1 * kSlotMul) >> (64 - bits); }
 
 constexpr uint32_t kKindMPref = 16;
 constexpr uint32_t kKindWPref = 17;

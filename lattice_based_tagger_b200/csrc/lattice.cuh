@@ -6,23 +6,26 @@
 // (dictionary/lookup.py:344-369, :7-62, :99-132, :212-279, :171-210; dictionary/dictionary.py:304-315;
 // dictionary/lemmatizer.py:5-112).
 //
-// One warp per sentence, sentences pulled from an atomic work queue.  The warp stages the
-// sentence in shared memory: space-stripped syllables, eojeol starts, two prefix-hash arrays
-// (warp scan) and, per syllable, the conjugation-rule lists of the 1/2/3-syllable keys that start
-// there.  Every dictionary test is then one probe of the hashed dictionary with a substring hash
-// composed from the prefix arrays (and rule stem/eomi hashes) — no characters are compared.
-//
-// Output is CSR keyed by END position: edges of sentence s that end at syllable e are
-// edges[end_off[sent_off[s]+e-1] .. end_off[sent_off[s]+e]), ordered by begin position and, within
-// one (b, e) span, in the reference's emission order (the only order beam_search can observe,
-// SURVEY App. A Q5).  The kernel runs twice: COUNT fills end_cnt / beg_cnt, a device scan turns
-// end_cnt into end_off, EMIT writes the 16-byte edge records.
-//
-// Work decomposition per eojeol (offset o, n syllables):
-//   stage 1 (lr_lookup): lanes = tasks {whole, left_i, right_i}; a left task owns bucket o+i, the
-//     whole + right tasks share bucket o+n in begin order, offsets from beg_cnt.
-//   stage 2 (sub-word scan, only when stage 1 found nothing): lanes = end positions; each lane
-//     walks its begins in ascending order, so its bucket is written sequentially.
+// One warp per sentence, sentences pulled from an atomic work queue, ONE launch per batch.
+//   1. stage: space-stripped syllables, eojeol starts and two prefix-hash arrays (warp scan) in
+//      shared memory; every string the reference would build is a hash composed from these.
+//   2. rule lists of the 1/2/3-syllable keys starting at every syllable (3 probes per syllable).
+//   3. SUBSTRING TABLE: the dictionary payload (tag set + lemmatizer bits) of every substring of
+//      at most `max_str` syllables (no longer string is in the dictionary) — one wave of
+//      independent probes.  All plain dictionary tests of the enumeration below (the large majority
+//      of the reference's string probes) are then shared-memory reads.
+//   4. per eojeol, lanes = (task, split position) items in a flat index space, so lanes stay busy:
+//        stage 1 (lr_lookup): tasks {whole, left_i, right_i}, n items per pair -> n*n items
+//        stage 2 (sub-word scan, only when stage 1 found nothing): (begin, span, split) items
+//      an item tests its plain split in the table and probes the dictionary only for conjugation-rule
+//      candidates (prefix + stem, eomi + suffix).  Hits are staged in shared memory with a sort key
+//      (end, begin, class, split, candidate order) that encodes the reference's emission order.
+//   5. the eojeol's hits are filtered (lr_lookup keeps a split only when both sides are non-empty,
+//      lookup.py:205-209) and ranked by key; staged edges go to HBM at their rank with one atomic
+//      reservation per flush (normally one per sentence).
+// Output is CSR keyed by END position: pos[sent_off[s]+e-1] = (first edge, count) of the edges of
+// sentence s ending at syllable e, ordered by begin and, within one (b, e) span, in the reference's
+// emission order (the only order beam_search can observe).
 #pragma once
 #include "tables.cuh"
 
@@ -30,17 +33,24 @@ namespace lt {
 
 constexpr int kLatWarps = 4;                 // warps per CTA of the lattice kernel
 constexpr unsigned kFull = 0xFFFFFFFFu;
-constexpr uint32_t kStage2Flag = 0x80000000u;
+
+// flags[] written by the lattice kernel, read by the beam kernel and the host
+constexpr int kFlagEdgeOverflow = 0;         // edge buffer too small (cursor holds the needed size)
+constexpr int kFlagStageOverflow = 1;        // an eojeol's hits did not fit the staging buffer
 
 struct LatticeArgs {
     const uint16_t* text;       // raw UTF-16 units, spaces included
     const int32_t* sent_off;    // n_sent + 1
     int32_t n_sent;
     int32_t lcap;               // max raw units of one sentence (shared-memory sizing)
-    uint32_t* end_cnt;          // [n_units + 1]  edges per (sentence, end position)
-    uint32_t* beg_cnt;          // [n_units + 1]  stage-1 counts of the eojeol-end bucket by begin
-    const uint32_t* end_off;    // exclusive scan of end_cnt (EMIT only)
-    lt_edge* edges;             // EMIT only
+    int32_t hcap;               // staging capacity (hits) per warp
+    int32_t max_str;            // longest dictionary string (syllables), >= 1
+    uint2* pos;                 // [n_units] out: (first edge, count) per (sentence, end position)
+    lt_edge* edges;             // out
+    uint32_t edge_cap;
+    uint32_t reserved;
+    uint32_t* cursor;           // edge allocation cursor
+    uint32_t* flags;
     int32_t* sent_len;          // [n_sent] syllables
     int32_t* sent_edges;        // [n_sent] dictionary edges
     int32_t* status;            // [n_sent]
@@ -48,12 +58,19 @@ struct LatticeArgs {
     unsigned int* queue;        // work-queue cursor
 };
 
-__host__ __device__ inline size_t lattice_warp_smem(int lcap) {
-    // chars u16, eoj u16, nend u8 (+pad), ha u64, hb u64, rref uint2[3], cnt u32
+__host__ __device__ inline size_t lattice_warp_smem(int lcap, int hcap, int max_str) {
     size_t units = (size_t)lcap + 8;
-    size_t bytes = units * 2 + units * 2 + units * 1;
-    bytes = (bytes + 15) & ~(size_t)15;
-    bytes += units * 8 * 2 + units * 8 * 3 + units * 4;
+    size_t bytes = units * 8 * 2;                  // ha, hb
+    bytes += units * 8 * 3;                        // rref
+    bytes += (size_t)hcap * 8;                     // staged keys
+    bytes += (size_t)hcap * 16;                    // staged edge records
+    bytes += units * 4 * (size_t)max_str;          // substring table
+    bytes += units * 4 * 2;                        // pstart, pcnt
+    bytes += units * 4 * 2;                        // tcnt (2 tasks per syllable of an eojeol)
+    bytes += (size_t)hcap * 4;                     // staged task id, later final rank
+    bytes += units * 2 * 2;                        // chars, eojeol starts
+    bytes += units;                                // nend
+    bytes += 64;                                   // counters
     return (bytes + 15) & ~(size_t)15;
 }
 
@@ -158,155 +175,196 @@ __device__ __forceinline__ int stage_sentence(const uint16_t* __restrict__ text,
     return L;
 }
 
-// ---- lemmatizer ---------------------------------------------------------------------------------
 
-// One (stem, eomi) candidate: the eomi must be a known Eomi; an Adjective stem is reported before
-// a Verb stem (lemmatizer.py:44-50).  Returns the number of edges (0..2).
-template <bool EMIT>
-__device__ __forceinline__ int lemma_candidate(const DevTables& T, H2 stem, uint32_t stem_len, H2 eomi,
-                                               uint32_t eomi_len, lt_edge proto, lt_edge*& out) {
-    uint64_t pe = dict_probe(T, eomi, eomi_len);
-    if (!((uint32_t)(pe >> 32) & kLemEomi)) return 0;
-    uint32_t ps = (uint32_t)(dict_probe(T, stem, stem_len) >> 32);
-    int n = 0;
-    if (ps & kLemAdj) {
-        if (EMIT) { proto.tag0 = LT_TAG_ADJECTIVE; *out++ = proto; }
-        ++n;
-    }
-    if (ps & kLemVerb) {
-        if (EMIT) { proto.tag0 = LT_TAG_VERB; *out++ = proto; }
-        ++n;
-    }
-    return n;
+// ---- enumeration state ---------------------------------------------------------------------------
+
+// substring payload: bits 0..28 tag set, bit 29 in .verbs, bit 30 in .adjectives, bit 31 in .eomis
+constexpr uint32_t kSubTagMask = 0x1FFFFFFFu;
+constexpr uint32_t kSubVerb = 1u << 29, kSubAdj = 1u << 30, kSubEomi = 1u << 31;
+
+struct Enum {
+    const uint32_t* sub;     // [L * max_str]
+    int max_str;
+    // staging
+    uint64_t* hkey;
+    lt_edge* hrec;
+    uint32_t* htask;         // task id while an eojeol is enumerated, final rank afterwards
+    uint32_t* tcnt;          // hits per task of the current eojeol
+    uint32_t* nh;            // staged entries (shared counter)
+    int hcap;
+};
+
+__device__ __forceinline__ uint32_t sub_get(const Enum& E, int x, int y) {
+    const int len = y - x;
+    if (len <= 0 || len > E.max_str) return 0u;
+    return E.sub[x * E.max_str + (len - 1)];
 }
 
-// Rules of one key applied at split position p of the word [b, e): stem = word[:p-b] + rule.stem,
-// eomi = rule.eomi + word[suffix_from - b:]  (lemmatizer.py:100-102, :107-111).
-template <bool EMIT>
-__device__ __forceinline__ int apply_rules(const DevTables& T, const SentView& v, uint2 ref, int b, int p, int e,
-                                           int suffix_from, H2 pre, lt_edge proto, lt_edge*& out) {
-    int count = (int)(ref.y & 0xFFFFu);
-    if (count == 0) return 0;
+// sort key: end | begin | class (0 tag hits, 1 lemma hits) | split | order within the split
+__device__ __forceinline__ uint64_t hit_key(int e, int b, uint32_t cls, uint32_t split, uint32_t k) {
+    return ((uint64_t)e << 48) | ((uint64_t)b << 32) | ((uint64_t)cls << 31) | ((uint64_t)(split & 0xFFFu) << 19) |
+           (uint64_t)(k & 0x7FFFFu);
+}
+
+__device__ __forceinline__ void stage_hit(const Enum& E, const lt_edge& rec, uint64_t key, uint32_t task) {
+    const uint32_t slot = atomicAdd(E.nh, 1u);
+    if (slot < (uint32_t)E.hcap) {
+        E.hrec[slot] = rec;
+        E.hkey[slot] = key;
+        E.htask[slot] = task;
+    }
+    atomicAdd(&E.tcnt[task], 1u);
+}
+
+// One (stem, eomi) lemma candidate whose strings are COMPOSED (a rule applied): the eomi must be a
+// known Eomi; an Adjective stem is reported before a Verb stem (lemmatizer.py:44-50).  With
+// reps > 1 the same candidate recurs at candidate indices cand + rep * rep_stride.
+__device__ __forceinline__ void rule_candidate(const DevTables& T, const Enum& E, H2 stem, uint32_t stem_len, H2 eomi,
+                                               uint32_t eomi_len, lt_edge proto, uint32_t split, uint32_t cand,
+                                               uint32_t reps, uint32_t rep_stride, uint32_t task) {
+    if (eomi_len > (uint32_t)E.max_str || stem_len > (uint32_t)E.max_str) return;    // longer than any entry
+    const uint64_t pe = dict_probe(T, eomi, eomi_len);
+    if (!((uint32_t)(pe >> 32) & kLemEomi)) return;
+    const uint32_t ps = (uint32_t)(dict_probe(T, stem, stem_len) >> 32);
+    if (!(ps & (kLemAdj | kLemVerb))) return;
+    for (uint32_t rep = 0; rep < reps; ++rep) {
+        const uint32_t k = (cand + rep * rep_stride) * 2u;
+        if (ps & kLemAdj) {
+            proto.tag0 = LT_TAG_ADJECTIVE;
+            stage_hit(E, proto, hit_key(proto.e, proto.b, 1, split, k), task);
+        }
+        if (ps & kLemVerb) {
+            proto.tag0 = LT_TAG_VERB;
+            stage_hit(E, proto, hit_key(proto.e, proto.b, 1, split, k + 1), task);
+        }
+    }
+}
+
+// Rules of one key applied at split p of the word [b, e): stem = word[:p-b] + rule.stem,
+// eomi = rule.eomi + word[suffix_from - b:]  (lemmatizer.py:100-102, :107-111).  `cand0` is the
+// candidate index of the key's first rule inside this split; with reps > 1 the whole list repeats
+// (the nested duplicate loop of lemmatizer.py:100-102) at stride `count`.
+__device__ __noinline__ void apply_rules(const DevTables& T, const SentView& v, const Enum& E, uint2 ref, int b, int p,
+                                         int e, int suffix_from, lt_edge proto, uint32_t cand0, uint32_t reps,
+                                         uint32_t task) {
+    const uint32_t count = ref.y & 0xFFFFu;
+    if (count == 0) return;
     H2 suf{0, 0};
     uint32_t suf_len = 0;
     if (suffix_from < e) {
         suf = sub_hash(T, v, suffix_from, e);
         suf_len = (uint32_t)(e - suffix_from);
     }
-    H2 pw_suf = pow_at(T, suf_len);
-    int n = 0;
-    for (int r = 0; r < count; ++r) {
-        RuleRec rec = rule_load(T, ref.x + r);
-        H2 stem = h2_concat(pre, rec.stem, pow_at(T, rec.stem_len));
-        H2 eomi = h2_concat(rec.eomi, suf, pw_suf);
+    const H2 pre = (p > b) ? sub_hash(T, v, b, p) : H2{0, 0};
+    const H2 pw_suf = pow_at(T, suf_len);
+    for (uint32_t r = 0; r < count; ++r) {
+        const RuleRec rec = rule_load(T, ref.x + r);
+        const H2 stem = h2_concat(pre, rec.stem, pow_at(T, rec.stem_len));
+        const H2 eomi = h2_concat(rec.eomi, suf, pw_suf);
         proto.rule = ref.x + r;
-        n += lemma_candidate<EMIT>(T, stem, (uint32_t)(p - b) + rec.stem_len, eomi, rec.eomi_len + suf_len, proto, out);
+        rule_candidate(T, E, stem, (uint32_t)(p - b) + rec.stem_len, eomi, rec.eomi_len + suf_len, proto,
+                       (uint32_t)(p - b), cand0 + r, reps, count, task);
     }
-    return n;
 }
 
-// All lemma edges of the word [b, e) in get_lemma_candidates order.  `ncand` accumulates the number
-// of candidates the reference generates (2 dictionary probes each in the P counter).
-template <bool EMIT>
-__device__ int lemma_scan(const DevTables& T, const SentView& v, int b, int e, lt_edge proto, lt_edge*& out,
-                          uint32_t& ncand) {
-    int total = 0;
+// Lemma candidates of the word [b, e) at split position p, in get_lemma_candidates order
+// (lemmatizer.py:90-112).  Returns the number of candidates the reference generates there.
+__device__ __forceinline__ uint32_t lemma_item(const DevTables& T, const SentView& v, const Enum& E, int b, int e, int p,
+                                               lt_edge proto, uint32_t task) {
+    uint32_t ncand = 0;
     proto.tag1 = LT_TAG_EOMI;
-    for (int p = b; p < e; ++p) {
-        proto.split = (uint16_t)(p - b);
-        // plain split (not at the last syllable)
-        if (p < e - 1) {
+    proto.split = (uint16_t)(p - b);
+    const uint8_t base_flags = proto.flags & LT_EDGE_IS_L;
+    // plain split (not at the last syllable): both strings are sentence substrings -> table
+    if (p < e - 1) {
+        ++ncand;
+        if (sub_get(E, p + 1, e) & kSubEomi) {
+            const uint32_t ps = sub_get(E, b, p + 1);
             proto.rule = LT_NO_RULE;
-            proto.flags = (proto.flags & LT_EDGE_IS_L) | LT_EDGE_LEMMA;
-            H2 stem = sub_hash(T, v, b, p + 1);
-            H2 eomi = sub_hash(T, v, p + 1, e);
-            total += lemma_candidate<EMIT>(T, stem, (uint32_t)(p + 1 - b), eomi, (uint32_t)(e - p - 1), proto, out);
-            ++ncand;
-        }
-        uint2 r1 = v.rref[3 * p + 0];
-        uint2 r2 = (p + 2 <= e) ? v.rref[3 * p + 1] : make_uint2(0u, 0u);
-        uint2 r3 = (p + 3 <= e) ? v.rref[3 * p + 2] : make_uint2(0u, 0u);
-        int c1 = (int)(r1.y & 0xFFFFu);
-        if (!(c1 | (r2.y & 0xFFFFu) | (r3.y & 0xFFFFu))) continue;
-        H2 pre = (p > b) ? sub_hash(T, v, b, p) : H2{0, 0};
-        // one-syllable key: the whole rule list once per rule of the key (lemmatizer.py:100-102)
-        if (c1) {
-            proto.flags = (proto.flags & LT_EDGE_IS_L) | LT_EDGE_LEMMA;
-            if (EMIT) {
-                for (int rep = 0; rep < c1; ++rep) total += apply_rules<true>(T, v, r1, b, p, e, p + 1, pre, proto, out);
-            } else {
-                total += c1 * apply_rules<false>(T, v, r1, b, p, e, p + 1, pre, proto, out);
+            proto.flags = base_flags | LT_EDGE_LEMMA;
+            if (ps & kSubAdj) {
+                proto.tag0 = LT_TAG_ADJECTIVE;
+                stage_hit(E, proto, hit_key(e, b, 1, (uint32_t)(p - b), 0), task);
             }
-            ncand += (uint32_t)(c1 * c1);
-        }
-        // {word[i:i+2], word[i:i+3]} in set order; the eomi continues at word[i+2:] for both
-        proto.flags = (proto.flags & LT_EDGE_IS_L) | LT_EDGE_LEMMA | LT_EDGE_SKIP2;
-        if (p == e - 1) {
-            // both slices are the last syllable itself: its rules once more, empty suffix
-            if (c1) {
-                total += apply_rules<EMIT>(T, v, r1, b, p, e, e, pre, proto, out);
-                ncand += (uint32_t)c1;
+            if (ps & kSubVerb) {
+                proto.tag0 = LT_TAG_VERB;
+                stage_hit(E, proto, hit_key(e, b, 1, (uint32_t)(p - b), 1), task);
             }
-        } else {
-            bool k3_first = (r3.y >> 31) != 0;
-            uint2 first = k3_first ? r3 : r2;
-            uint2 second = k3_first ? r2 : r3;
-            total += apply_rules<EMIT>(T, v, first, b, p, e, p + 2, pre, proto, out);
-            total += apply_rules<EMIT>(T, v, second, b, p, e, p + 2, pre, proto, out);
-            ncand += (first.y & 0xFFFFu) + (second.y & 0xFFFFu);
         }
     }
-    return total;
+    const uint2 r1 = v.rref[3 * p + 0];
+    const uint2 r2 = (p + 2 <= e) ? v.rref[3 * p + 1] : make_uint2(0u, 0u);
+    const uint2 r3 = (p + 3 <= e) ? v.rref[3 * p + 2] : make_uint2(0u, 0u);
+    const uint32_t c1 = r1.y & 0xFFFFu, c2 = r2.y & 0xFFFFu, c3 = r3.y & 0xFFFFu;
+    if (!(c1 | c2 | c3)) return ncand;
+    // one-syllable key: the whole rule list once per rule of the key (lemmatizer.py:100-102)
+    if (c1) {
+        proto.flags = base_flags | LT_EDGE_LEMMA;
+        apply_rules(T, v, E, r1, b, p, e, p + 1, proto, 1u, c1, task);
+        ncand += c1 * c1;
+    }
+    // {word[i:i+2], word[i:i+3]} in set order; the eomi continues at word[i+2:] for both
+    proto.flags = base_flags | LT_EDGE_LEMMA | LT_EDGE_SKIP2;
+    const uint32_t after1 = 1u + c1 * c1;
+    if (p == e - 1) {
+        // both slices are the last syllable itself: its rules once more, empty suffix
+        if (c1) {
+            apply_rules(T, v, E, r1, b, p, e, e, proto, after1, 1u, task);
+            ncand += c1;
+        }
+    } else {
+        const bool k3_first = (r3.y >> 31) != 0;
+        const uint2 first = k3_first ? r3 : r2;
+        const uint2 second = k3_first ? r2 : r3;
+        apply_rules(T, v, E, first, b, p, e, p + 2, proto, after1, 1u, task);
+        apply_rules(T, v, E, second, b, p, e, p + 2, proto, after1 + (first.y & 0xFFFFu), 1u, task);
+        ncand += c2 + c3;
+    }
+    return ncand;
 }
 
-// MorphemeDictionary.lookup on [b, e): tag hits in dictionary order, then lemma edges
-// (dictionary.py:304-312).  `tagmask` is the dictionary payload of the substring.
-template <bool EMIT>
-__device__ int full_lookup(const DevTables& T, const SentView& v, int b, int e, bool is_l, uint32_t tagmask,
-                           lt_edge*& out, uint32_t& ncand) {
-    lt_edge proto;
-    proto.b = (uint16_t)b;
-    proto.e = (uint16_t)e;
-    proto.len = (uint16_t)(e - b);
-    proto.tag0 = 0;
-    proto.tag1 = LT_NO_TAG;
-    proto.rule = LT_NO_RULE;
-    proto.split = 0;
-    proto.flags = is_l ? LT_EDGE_IS_L : 0;
-    proto.reserved = 0;
-    int n = __popc(tagmask);
-    if (EMIT && tagmask) {
-        for (int k = 0; k < T.n_tag_order; ++k) {
-            uint32_t t = T.tag_order[k];
-            if ((tagmask >> t) & 1u) {
-                proto.tag0 = (uint8_t)t;
-                *out++ = proto;
-            }
-        }
-    }
-    n += lemma_scan<EMIT>(T, v, b, e, proto, out, ncand);
-    return n;
+__device__ __forceinline__ lt_edge edge_proto(int b, int e, uint32_t len, bool is_l) {
+    lt_edge p;
+    p.b = (uint16_t)b;
+    p.e = (uint16_t)e;
+    p.len = (uint16_t)len;
+    p.tag0 = 0;
+    p.tag1 = LT_NO_TAG;
+    p.rule = LT_NO_RULE;
+    p.split = 0;
+    p.flags = is_l ? LT_EDGE_IS_L : 0;
+    p.reserved = 0;
+    return p;
 }
 
 // ---- the kernel -----------------------------------------------------------------------------------
 
-template <bool EMIT>
-__global__ void __launch_bounds__(kLatWarps * 32) lattice_kernel(const DevTables T, const LatticeArgs A) {
+__global__ void __launch_bounds__(kLatWarps * 32) lattice_kernel(const __grid_constant__ DevTables T,
+                                                                const __grid_constant__ LatticeArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const size_t units = (size_t)A.lcap + 8;
-    unsigned char* base = smem_raw + (size_t)warp * lattice_warp_smem(A.lcap);
-    uint16_t* ch = reinterpret_cast<uint16_t*>(base);
-    uint16_t* eoj = ch + units;
-    uint8_t* nend = reinterpret_cast<uint8_t*>(eoj + units);
-    size_t off = (units * 5 + 15) & ~(size_t)15;
-    uint64_t* ha = reinterpret_cast<uint64_t*>(base + off);
+    const int HC = A.hcap;
+    const int DM = A.max_str;
+    unsigned char* base = smem_raw + (size_t)warp * lattice_warp_smem(A.lcap, HC, DM);
+    uint64_t* ha = reinterpret_cast<uint64_t*>(base);
     uint64_t* hb = ha + units;
     uint2* rref = reinterpret_cast<uint2*>(hb + units);
-    uint32_t* cnt = reinterpret_cast<uint32_t*>(rref + 3 * units);
+    uint64_t* hkey = reinterpret_cast<uint64_t*>(rref + 3 * units);
+    lt_edge* hrec = reinterpret_cast<lt_edge*>(hkey + HC);
+    uint32_t* sub = reinterpret_cast<uint32_t*>(hrec + HC);
+    uint32_t* pstart = sub + units * DM;
+    uint32_t* pcnt = pstart + units;
+    uint32_t* tcnt = pcnt + units;
+    uint32_t* htask = tcnt + 2 * units;
+    uint16_t* ch = reinterpret_cast<uint16_t*>(htask + HC);
+    uint16_t* eoj = ch + units;
+    uint8_t* nend = reinterpret_cast<uint8_t*>(eoj + units);
+    uint32_t* nh = reinterpret_cast<uint32_t*>((reinterpret_cast<uintptr_t>(nend + units) + 3) & ~(uintptr_t)3);
 
     unsigned long long acc_L = 0, acc_P = 0, acc_E = 0;
+    const int n_order = T.n_tag_order;
 
     while (true) {
         unsigned int s = 0;
@@ -318,6 +376,7 @@ __global__ void __launch_bounds__(kLatWarps * 32) lattice_kernel(const DevTables
         bool bad;
         const int L = stage_sentence(A.text, s0, s1, lane, ch, eoj, ha, hb, n_eoj, bad);
         SentView v{ch, ha, hb, rref};
+        Enum E{sub, DM, hkey, hrec, htask, tcnt, nh, HC};
 
         // conjugation-rule lists of the keys starting at every syllable
         for (int p = lane; p < L; p += 32) {
@@ -326,209 +385,225 @@ __global__ void __launch_bounds__(kLatWarps * 32) lattice_kernel(const DevTables
             rref[3 * p + 1] = (p + 1 < L) ? rule_probe(T, rule_key(c0, c1, 0, 2)) : make_uint2(0u, 0u);
             rref[3 * p + 2] = (p + 2 < L) ? rule_probe(T, rule_key(c0, c1, c2, 3)) : make_uint2(0u, 0u);
         }
-        if (!EMIT) {
-            for (int p = lane; p < s1 - s0 + 1; p += 32) cnt[p] = 0;
+        // substring table: every substring of at most max_str syllables, one wave of probes
+        for (int q = lane; q < L * DM; q += 32) {
+            const int x = q / DM, len = q - x * DM + 1;
+            uint32_t payload = 0;
+            if (x + len <= L) {
+                const uint64_t pl = dict_probe(T, sub_hash(T, v, x, x + len), (uint32_t)len);
+                payload = ((uint32_t)pl & kSubTagMask) | (((uint32_t)(pl >> 32) & 7u) << 29);
+            }
+            sub[q] = payload;
         }
+        for (int p = lane; p < s1 - s0; p += 32) { pstart[p] = 0xFFFFFFFFu; pcnt[p] = 0; }
+        if (lane == 0) *nh = 0;
         __syncwarp();
 
-        uint32_t sent_total = 0;
-        uint32_t ncand = 0;      // lemma candidates (lane-local)
+        uint32_t ncand = 0;      // lemma candidates the reference generates (lane-local)
         uint32_t nsub = 0;       // distinct substrings examined (lane 0 only)
+        uint32_t slots = 0;      // staged entries, dead ones included (warp-uniform copy of *nh)
+        uint32_t alive = 0;      // staged entries that survive = next free rank (warp-uniform)
+        uint32_t sent_total = 0;
+        bool overflow = false;
 
-        for (int w = 0; w < n_eoj; ++w) {
+        // write the staged survivors to HBM at (reservation + rank); CSR bookkeeping in shared memory
+        auto flush = [&]() {
+            if (alive > 0) {
+                uint32_t gbase = 0;
+                if (lane == 0) gbase = atomicAdd(A.cursor, alive);
+                gbase = __shfl_sync(kFull, gbase, 0);
+                const bool fits = (gbase + alive <= A.edge_cap) && (gbase + alive >= gbase);
+                if (!fits && lane == 0) atomicOr(A.flags + kFlagEdgeOverflow, 1u);
+                for (uint32_t i = lane; i < slots; i += 32) {
+                    const uint32_t rank = htask[i];
+                    if (rank == 0xFFFFFFFFu) continue;
+                    const lt_edge rec = hrec[i];
+                    if (fits) A.edges[gbase + rank] = rec;
+                    atomicAdd(&pcnt[rec.e - 1], 1u);
+                    atomicMin(&pstart[rec.e - 1], gbase + rank);
+                }
+            }
+            __syncwarp();
+            slots = 0;
+            alive = 0;
+            if (lane == 0) *nh = 0;
+            __syncwarp();
+        };
+
+        for (int w = 0; w < n_eoj && !overflow; ++w) {
             const int o = eoj[w];
             const int n = eoj[w + 1] - o;
             const int oe = o + n;
-            bool stage2;
-            if (!EMIT) {
-                // ---------------- stage 1, COUNT ----------------
-                uint32_t total = 0;
-                for (int ub = 0; ub < 2 * n; ub += 32) {
-                    const int u = ub + lane;
-                    const bool valid = (u < 2 * n) && (u != 1);
-                    int b = o, e = oe;
-                    if (u >= 2) {
-                        if (u & 1) b = o + (u >> 1); else e = o + (u >> 1);
-                    }
-                    uint32_t tagmask = 0;
-                    if (valid) tagmask = (uint32_t)dict_probe(T, sub_hash(T, v, b, e), (uint32_t)(e - b));
-                    const uint32_t pmask = __shfl_xor_sync(kFull, tagmask, 1);
-                    const bool left = !(u & 1);
-                    bool special = false;
-                    if (valid && u >= 2) {
-                        special = left ? ((tagmask >> LT_TAG_NOUN) & 1u) && ((pmask >> LT_TAG_JOSA) & 1u)
-                                       : ((pmask >> LT_TAG_NOUN) & 1u) && ((tagmask >> LT_TAG_JOSA) & 1u);
-                    }
-                    uint32_t c_full = 0;
-                    if (valid && !special) {
-                        lt_edge* none = nullptr;
-                        c_full = (uint32_t)full_lookup<false>(T, v, b, e, b == o, tagmask, none, ncand);
-                    }
-                    const uint32_t pc = __shfl_xor_sync(kFull, c_full, 1);
-                    uint32_t c = 0;
-                    if (valid) {
-                        if (u == 0) c = c_full;
-                        else c = special ? 1u : ((c_full > 0 && pc > 0) ? c_full : 0u);
-                    }
-                    if (valid && c) {
-                        if (u >= 2 && left) cnt[e - 1] = c;          // bucket o+i: this task only
-                        else {
-                            atomicAdd(&cnt[oe - 1], c);              // bucket o+n: whole + rights
-                            A.beg_cnt[s0 + b] = c;
-                        }
-                    }
-                    total += c;
-                }
-                #pragma unroll
-                for (int d = 16; d; d >>= 1) total += __shfl_xor_sync(kFull, total, d);
-                stage2 = (total == 0);
-                sent_total += total;
-                if (lane == 0) {
-                    nsub += (uint32_t)(2 * n - 1);
-                    if (stage2) A.beg_cnt[s0 + o] = kStage2Flag;
-                }
-            } else {
-                // ---------------- stage 1, EMIT ----------------
-                const uint32_t head = __ldg(A.beg_cnt + s0 + o);
-                stage2 = (head & kStage2Flag) != 0;
-                if (!stage2) {
-                    uint32_t carry = 0;     // edges already placed in bucket o+n
-                    const uint32_t bucket_n = __ldg(A.end_off + s0 + oe - 1);
-                    for (int ub = 0; ub < 2 * n; ub += 32) {
-                        const int u = ub + lane;
-                        const bool valid = (u < 2 * n) && (u != 1);
-                        int b = o, e = oe;
-                        if (u >= 2) {
-                            if (u & 1) b = o + (u >> 1); else e = o + (u >> 1);
-                        }
-                        const bool left = (u >= 2) && !(u & 1);
-                        uint32_t c = 0;
-                        if (valid) {
-                            if (left) c = __ldg(A.end_off + s0 + e) - __ldg(A.end_off + s0 + e - 1);
-                            else c = __ldg(A.beg_cnt + s0 + b);
-                        }
-                        // exclusive prefix of the shared bucket's counts over lanes
-                        uint32_t mine = (valid && !left) ? c : 0u;
-                        uint32_t incl = mine;
-                        #pragma unroll
-                        for (int d = 1; d < 32; d <<= 1) {
-                            uint32_t t = __shfl_up_sync(kFull, incl, d);
-                            if (lane >= d) incl += t;
-                        }
-                        const uint32_t chunk_total = __shfl_sync(kFull, incl, 31);
-                        uint32_t tagmask = 0;
-                        if (valid && c) tagmask = (uint32_t)dict_probe(T, sub_hash(T, v, b, e), (uint32_t)(e - b));
-                        // partner's tag mask decides the Noun+Josa special case
-                        uint32_t pm_in = tagmask;
-                        const uint32_t pmask = __shfl_xor_sync(kFull, pm_in, 1);
-                        if (valid && c) {
-                            lt_edge* out = A.edges + (left ? __ldg(A.end_off + s0 + e - 1)
-                                                           : bucket_n + carry + (incl - mine));
-                            bool special = false;
-                            if (u >= 2) {
-                                special = left ? ((tagmask >> LT_TAG_NOUN) & 1u) && ((pmask >> LT_TAG_JOSA) & 1u)
-                                               : ((pmask >> LT_TAG_NOUN) & 1u) && ((tagmask >> LT_TAG_JOSA) & 1u);
-                            }
+            for (int attempt = 0; attempt < 2; ++attempt) {
+                // ---------------- stage 1: whole eojeol + every left/right split ----------------
+                for (int u = lane; u < 2 * n; u += 32) tcnt[u] = 0;
+                __syncwarp();
+                uint32_t ncand_try = 0;
+                for (int q0 = 0; q0 < n * n; q0 += 32) {
+                    const int q = q0 + lane;
+                    if (q < n * n) {
+                        const int i = q / n, r = q - i * n;
+                        const int p = o + r;
+                        // task: i == 0 whole; r < i: left_i = [o, o+i); else right_i = [o+i, oe)
+                        const bool left = (i > 0) && (r < i);
+                        const int b = (i > 0 && !left) ? o + i : o;
+                        const int e = left ? o + i : oe;
+                        const uint32_t task = (i == 0) ? 0u : (left ? 2u * i : 2u * i + 1u);
+                        bool special = false;
+                        if (i > 0)
+                            special = ((sub_get(E, o, o + i) >> LT_TAG_NOUN) & 1u) && ((sub_get(E, o + i, oe) >> LT_TAG_JOSA) & 1u);
+                        if (p == b) {
+                            // the task's first item also reports its tag hits
                             if (special) {
-                                lt_edge ed;
-                                ed.b = (uint16_t)b; ed.e = (uint16_t)e; ed.len = (uint16_t)n;   // len = n (Q4)
-                                ed.tag0 = left ? LT_TAG_NOUN : LT_TAG_JOSA; ed.tag1 = LT_NO_TAG;
-                                ed.rule = LT_NO_RULE; ed.split = 0;
-                                ed.flags = left ? LT_EDGE_IS_L : 0; ed.reserved = 0;
-                                *out = ed;
+                                // Noun + Josa special case: both edges carry len = n (lookup.py:200-203)
+                                lt_edge rec = edge_proto(b, e, (uint32_t)n, left);
+                                rec.tag0 = left ? LT_TAG_NOUN : LT_TAG_JOSA;
+                                stage_hit(E, rec, hit_key(e, b, 0, 0, 0), task);
                             } else {
-                                uint32_t dummy = 0;
-                                full_lookup<true>(T, v, b, e, b == o, tagmask, out, dummy);
+                                const uint32_t mask = sub_get(E, b, e) & kSubTagMask;
+                                if (mask) {
+                                    lt_edge rec = edge_proto(b, e, (uint32_t)(e - b), b == o);
+                                    for (int k = 0; k < n_order; ++k) {
+                                        const uint32_t t = T.tag_order[k];
+                                        if ((mask >> t) & 1u) {
+                                            rec.tag0 = (uint8_t)t;
+                                            stage_hit(E, rec, hit_key(e, b, 0, 0, (uint32_t)k), task);
+                                        }
+                                    }
+                                }
                             }
                         }
-                        carry += chunk_total;
+                        if (!special)
+                            ncand_try += lemma_item(T, v, E, b, e, p, edge_proto(b, e, (uint32_t)(e - b), b == o), task);
                     }
                 }
-            }
-
-            // ---------------- stage 2: sub-word scan ----------------
-            if (stage2 && n >= 2) {
-                const int M = (T.max_len > 0) ? T.max_len : n;
-                // (i) which positions end a stand-alone Noun found by this scan
-                for (int el = 2 + lane; el <= n; el += 32) {
-                    bool any_noun = false;
-                    int b_lo = el - M; if (b_lo < 1) b_lo = 1;
-                    for (int bl = b_lo; bl < el; ++bl) {
-                        uint32_t m = (uint32_t)dict_probe(T, sub_hash(T, v, o + bl, o + el), (uint32_t)(el - bl));
-                        any_noun |= (m >> LT_TAG_NOUN) & 1u;
-                    }
-                    nend[o + el] = any_noun ? 1 : 0;
-                }
-                if (lane == 0) nend[o + 1] = 0;
                 __syncwarp();
-                // (ii) per end position, begins ascending
-                uint32_t total2 = 0;
-                for (int el = 2 + lane; el <= n; el += 32) {
-                    const int e = o + el;
-                    lt_edge* out = EMIT ? A.edges + __ldg(A.end_off + s0 + e - 1) : nullptr;
-                    uint32_t c = 0;
-                    int b_lo = el - M; if (b_lo < 1) b_lo = 1;
-                    for (int bl = b_lo; bl < el; ++bl) {
-                        const int b = o + bl;
-                        uint32_t m = (uint32_t)dict_probe(T, sub_hash(T, v, b, e), (uint32_t)(e - b));
-                        lt_edge proto;
-                        proto.b = (uint16_t)b; proto.e = (uint16_t)e; proto.len = (uint16_t)(e - b);
-                        proto.tag0 = 0; proto.tag1 = LT_NO_TAG; proto.rule = LT_NO_RULE; proto.split = 0;
-                        proto.flags = 0; proto.reserved = 0;
-                        // stand-alone tags in list order (lookup.py:104-105), then Josa after a Noun
-                        const int order[5] = {LT_TAG_NOUN, LT_TAG_ADVERB, LT_TAG_EXCLAMATION, LT_TAG_DETERMINER, LT_TAG_NUMBER};
-                        #pragma unroll
-                        for (int k = 0; k < 5; ++k) {
-                            if ((m >> order[k]) & 1u) {
-                                if (EMIT) { proto.tag0 = (uint8_t)order[k]; *out++ = proto; }
-                                ++c;
-                            }
-                        }
-                        if (nend[b] && ((m >> LT_TAG_JOSA) & 1u)) {
-                            if (EMIT) { proto.tag0 = LT_TAG_JOSA; *out++ = proto; }
-                            ++c;
-                        }
-                        c += (uint32_t)lemma_scan<EMIT>(T, v, b, e, proto, out, ncand);
+                // ---- a split survives only when both sides found something (lookup.py:205-209) ----
+                uint32_t nstaged = *nh;
+                bool too_many = nstaged > (uint32_t)HC;
+                uint32_t alive_here = 0;
+                if (!too_many) {
+                    for (uint32_t h = slots + lane; h < nstaged; h += 32) {
+                        const uint32_t task = htask[h];
+                        bool ok = true;
+                        if (task >= 2) ok = (tcnt[task] > 0) && (tcnt[task ^ 1u] > 0);
+                        if (!ok) hkey[h] = ~0ull;
+                        alive_here += ok ? 1u : 0u;
                     }
-                    if (!EMIT) cnt[e - 1] = c;
-                    total2 += c;
-                }
-                if (!EMIT) {
                     #pragma unroll
-                    for (int d = 16; d; d >>= 1) total2 += __shfl_xor_sync(kFull, total2, d);
-                    sent_total += total2;
-                    if (lane == 0) {
-                        // pairs (b, e), 1 <= b < e <= min(b+M, n), minus the (b, n) already examined by stage 1
-                        uint32_t pairs = 0;
-                        for (int bl = 1; bl < n; ++bl) pairs += (uint32_t)min(M, n - bl);
-                        nsub += pairs - (uint32_t)min(M, n - 1);
-                    }
+                    for (int d = 16; d; d >>= 1) alive_here += __shfl_xor_sync(kFull, alive_here, d);
                 }
+                uint32_t nsub_try = (uint32_t)(2 * n - 1);
+                if (!too_many && alive_here == 0 && n >= 2) {
+                    // ---------------- stage 2: sub-word scan, begins from 1 (lookup.py:259-277) ----------------
+                    __syncwarp();
+                    if (lane == 0) *nh = slots;          // forget the dead stage-1 hits
+                    const int M = (T.max_len > 0) ? T.max_len : n;
+                    // which positions end a stand-alone Noun found by this scan
+                    for (int el = 1 + lane; el <= n; el += 32) {
+                        bool any_noun = false;
+                        int b_lo = el - M; if (b_lo < 1) b_lo = 1;
+                        for (int bl = b_lo; bl < el; ++bl) any_noun |= ((sub_get(E, o + bl, o + el) >> LT_TAG_NOUN) & 1u) != 0;
+                        nend[o + el] = any_noun ? 1 : 0;
+                    }
+                    if (lane == 0) tcnt[0] = 0;
+                    __syncwarp();
+                    const int tri = M * (M + 1) / 2;
+                    const int items = (n - 1) * tri;
+                    for (int q0 = 0; q0 < items; q0 += 32) {
+                        const int q = q0 + lane;
+                        if (q < items) {
+                            const int bl = 1 + q / tri;
+                            int t = q - (bl - 1) * tri;
+                            int span = 1;
+                            while (t >= span) { t -= span; ++span; }       // t = split offset inside the span
+                            if (bl + span <= n) {
+                                const int b = o + bl, e = b + span, p = b + t;
+                                lt_edge rec = edge_proto(b, e, (uint32_t)span, false);
+                                if (t == 0) {
+                                    const uint32_t m = sub_get(E, b, e);
+                                    // stand-alone tags in list order (lookup.py:104-105), then Josa after a Noun
+                                    const int order[5] = {LT_TAG_NOUN, LT_TAG_ADVERB, LT_TAG_EXCLAMATION, LT_TAG_DETERMINER, LT_TAG_NUMBER};
+                                    #pragma unroll
+                                    for (int k = 0; k < 5; ++k) {
+                                        if ((m >> order[k]) & 1u) {
+                                            rec.tag0 = (uint8_t)order[k];
+                                            stage_hit(E, rec, hit_key(e, b, 0, 0, (uint32_t)k), 0u);
+                                        }
+                                    }
+                                    if (nend[b] && ((m >> LT_TAG_JOSA) & 1u)) {
+                                        rec.tag0 = LT_TAG_JOSA;
+                                        stage_hit(E, rec, hit_key(e, b, 0, 0, 5u), 0u);
+                                    }
+                                }
+                                ncand_try += lemma_item(T, v, E, b, e, p, rec, 0u);
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    nstaged = *nh;
+                    too_many = nstaged > (uint32_t)HC;
+                    alive_here = nstaged - slots;             // every stage-2 hit survives
+                    // pairs (b, e), 1 <= b < e <= min(b+M, n), minus the (b, n) already examined by stage 1
+                    uint32_t pairs = 0;
+                    for (int bl = 1; bl < n; ++bl) pairs += (uint32_t)min(M, n - bl);
+                    nsub_try += pairs - (uint32_t)min(M, n - 1);
+                }
+                if (too_many) {
+                    // the eojeol alone may fit once the staged edges of earlier eojeols are written out
+                    __syncwarp();
+                    if (lane == 0) *nh = slots;
+                    __syncwarp();
+                    if (attempt == 0 && slots > 0) { flush(); continue; }
+                    overflow = true;
+                    break;
+                }
+                ncand += ncand_try;
+                if (lane == 0) nsub += nsub_try;
+                // ---- final position of every survivor: rank of its key among the eojeol's survivors ----
                 __syncwarp();
+                for (uint32_t h = slots + lane; h < nstaged; h += 32) {
+                    const uint64_t key = hkey[h];
+                    uint32_t rank = 0xFFFFFFFFu;
+                    if (key != ~0ull) {
+                        rank = alive;
+                        for (uint32_t g = slots; g < nstaged; ++g) rank += (hkey[g] < key) ? 1u : 0u;
+                    }
+                    htask[h] = rank;
+                }
+                slots = nstaged;
+                alive += alive_here;
+                sent_total += alive_here;
+                __syncwarp();
+                break;
             }
-            __syncwarp();
         }
-
-        if (!EMIT) {
-            __syncwarp();
-            for (int p = lane; p < s1 - s0; p += 32) A.end_cnt[s0 + p] = cnt[p];
-            #pragma unroll
-            for (int d = 16; d; d >>= 1) ncand += __shfl_xor_sync(kFull, ncand, d);
-            if (lane == 0) {
-                A.sent_len[s] = L;
-                A.sent_edges[s] = (int32_t)sent_total;
-                int st = LT_SENT_OK;
-                if (bad) st = LT_SENT_BAD_SPACE;
-                else if (L > 0 && sent_total == 0) st = LT_SENT_NO_EDGES;
-                A.status[s] = st;
-                acc_L += (unsigned long long)L;
-                acc_P += (unsigned long long)nsub + 2ull * ncand;
-                acc_E += sent_total;
-            }
+        if (overflow) {
+            if (lane == 0) atomicOr(A.flags + kFlagStageOverflow, 1u);
+        } else {
+            flush();
+        }
+        __syncwarp();
+        for (int p = lane; p < s1 - s0; p += 32) {
+            const uint32_t c = pcnt[p];
+            A.pos[s0 + p] = make_uint2(c ? pstart[p] : 0u, c);
+        }
+        #pragma unroll
+        for (int d = 16; d; d >>= 1) ncand += __shfl_xor_sync(kFull, ncand, d);
+        if (lane == 0) {
+            A.sent_len[s] = L;
+            A.sent_edges[s] = (int32_t)sent_total;
+            int st = LT_SENT_OK;
+            if (bad) st = LT_SENT_BAD_SPACE;
+            else if (L > 0 && sent_total == 0) st = LT_SENT_NO_EDGES;
+            A.status[s] = st;
+            acc_L += (unsigned long long)L;
+            acc_P += (unsigned long long)nsub + 2ull * ncand;
+            acc_E += sent_total;
         }
         __syncwarp();
     }
-    if (!EMIT && lane == 0) {
+    if (lane == 0) {
         atomicAdd(A.counters + 0, acc_L);
         atomicAdd(A.counters + 1, acc_P);
         atomicAdd(A.counters + 2, acc_E);

@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -102,8 +103,9 @@ static int build_tables(const lt_tables_desc* d, lt_tables* t) {
     for (int i = 0; i < d->n_tag_order; ++i) D.tag_order[i] = d->tag_order[i];
 
     // ---- powers of the hash bases ----
-    int64_t max_str = 8;
+    int64_t max_str = 1;
     for (int64_t i = 0; i < d->n_dict; ++i) max_str = std::max(max_str, d->dict_off[i + 1] - d->dict_off[i]);
+    D.max_str = (int32_t)std::min<int64_t>(max_str, 65535);
     const int n_pows = 65536 + 64;
     std::vector<H2> pows(n_pows);
     pows[0] = H2{1, 1};
@@ -157,7 +159,7 @@ static int build_tables(const lt_tables_desc* d, lt_tables* t) {
             const uint16_t* c = d->rule_key_chars + 3 * k;
             const uint64_t key = rule_key(c[0], len > 1 ? c[1] : 0, len > 2 ? c[2] : 0, len);
             const int64_t first = d->rule_first[k], count = d->rule_first[k + 1] - first;
-            if (count < 0 || count > 0xFFFF) return fail(LT_ERR_INVALID, "rule key %lld has %lld rules", (long long)k, (long long)count);
+            if (count < 0 || count > 255) return fail(LT_ERR_INVALID, "rule key %lld has %lld rules (at most 255)", (long long)k, (long long)count);
             uint64_t s = fmix64(key) & (slots - 1);
             while (table[s].key != 0) {
                 if (table[s].key == key) return fail(LT_ERR_INVALID, "duplicate rule key %lld", (long long)k);
@@ -183,6 +185,12 @@ static int build_tables(const lt_tables_desc* d, lt_tables* t) {
             case LT_FUNC_TRIGRAM: D.func_dense[f] = (int8_t)D.n_tri++; break;
             default: return fail(LT_ERR_INVALID, "score function %d has unknown kind %d", f, d->funcs[f].kind);
         }
+    }
+
+    for (int f = 0; f < LT_MAX_FUNCS; ++f) {
+        for (int tmpl = 0; tmpl < 9; ++tmpl) D.seeds[f][tmpl] = feature_seed((uint32_t)tmpl, (uint32_t)f);
+        const int kind = f < d->n_funcs ? d->funcs[f].kind : 0;
+        D.seeds[f][9] = feature_seed(kind == LT_FUNC_WPREF ? kKindWPref : kKindMPref, (uint32_t)f);
     }
 
     // ---- feature strings ----
@@ -239,7 +247,18 @@ static int build_tables(const lt_tables_desc* d, lt_tables* t) {
         H2 h0, h1, h2;
         if (!str_hash(s[0], &h0) || !str_hash(s[1], &h1) || !str_hash(s[2], &h2))
             return fail(LT_ERR_INVALID, "feature %lld: string id out of range", (long long)i);
-        pending.push_back(Pending{feature_key((uint32_t)tmpl, (uint32_t)f, h0, h1, h2, (uint32_t)a[0], (uint32_t)a[1]), w});
+        // Component slots are by ROLE so that the beam kernel can keep per-word hash products:
+        // slot 0 = current word k (or its morpheme), slot 1 = previous word j (or the contextual
+        // morpheme), slot 2 = word i.  The description lists them in template order.
+        H2 r0 = h0, r1{0, 0}, r2{0, 0};
+        switch (tmpl) {
+            case 0: r0 = h1; r1 = h0; break;                 // (wj, wk, tk)
+            case 1: r0 = H2{0, 0}; r1 = h0; break;           // (wj, tk)
+            case 7: r0 = h2; r1 = h1; r2 = h0; break;        // (wi, wj, wk)
+            case 8: r0 = h1; r1 = h0; break;                 // (m?, mk)
+            default: break;                                  // 2, 4, 5: (wk) in slot 0
+        }
+        pending.push_back(Pending{feature_key((uint32_t)tmpl, (uint32_t)f, r0, r1, r2, (uint32_t)a[0], (uint32_t)a[1]), w});
     }
     for (int64_t i = 0; i < d->n_pref; ++i) {
         const int f = d->pref_func[i];
@@ -256,8 +275,10 @@ static int build_tables(const lt_tables_desc* d, lt_tables* t) {
         const uint64_t slots = next_pow2(n * (n < (1u << 22) ? 4 : 2));
         std::vector<FeatSlot> table(slots, FeatSlot{0, 0.0});
         std::vector<uint64_t> slot_k1(slots, 0);
+        uint32_t bits = 0;
+        while ((1ull << bits) < slots) ++bits;
         for (const Pending& p : pending) {
-            uint64_t s = p.key.k1 & (slots - 1);
+            uint64_t s = feature_slot(p.key.k1, bits);
             while (table[s].fp != 0) {
                 if (table[s].fp == p.key.k2 && slot_k1[s] == p.key.k1)
                     return fail(LT_ERR_COLLISION, "two feature keys share the 128-bit hash (or a key was given twice)");
@@ -268,6 +289,7 @@ static int build_tables(const lt_tables_desc* d, lt_tables* t) {
             slot_k1[s] = p.key.k1;
         }
         D.feat_mask = slots - 1;
+        D.feat_bits = bits;
         if (int rc = upload(t, table, &D.feat)) return rc;
     }
     if (int rc = upload(t, dense, &D.dense)) return rc;
@@ -301,25 +323,32 @@ struct DevBuf {
     size_t cap = 0;
 };
 
+// control words on the device: work-queue cursors, edge cursor, overflow flags
+enum { kCtlLatticeQueue = 0, kCtlBeamQueue = 1, kCtlCursor = 2, kCtlFlags = 4, kCtlWords = 8 };
+
 struct lt_batch {
     lt_tables* tables = nullptr;
     cudaStream_t own_stream = nullptr;
     cudaStream_t last_stream = nullptr;
     // inputs (host entry point) and per-unit / per-sentence arrays
-    DevBuf text, sent_off, end_cnt, beg_cnt, end_off, scan_tmp;
+    DevBuf text, sent_off, pos, scan_tmp;
     DevBuf sent_len, sent_edges, status, path_len, path_off, scores;
-    DevBuf edges, trail, path_tmp, path_out, counters, queue;
+    DevBuf edges, trail, path_tmp, path_out, counters, ctl;
     const uint16_t* d_text = nullptr;
     const int32_t* d_sent_off = nullptr;
     int32_t n_sent = 0;
     int64_t n_units = 0;
+    int32_t max_sent_units = 0;
     int32_t lcap = 0;
-    int64_t n_edges = 0;
     int32_t beam = 0;
-    bool have_lattice = false, have_paths = false;
+    int32_t hcap = 128;            // lattice staging capacity per warp (grows on overflow, sticky)
+    uint32_t edge_cap = 0;         // edge buffer capacity (grows on overflow, sticky)
+    bool edge_cap_fixed = false;   // LT_EDGE_CAP given: start there instead of the size guess (tests)
+    int64_t n_edges = 0;
+    bool have_lattice = false, have_paths = false, resolved = false;
     cudaEvent_t ev[10]{};
     bool timed = false;
-    lt_timings timings{};
+    int reruns = 0;
 };
 
 static int ensure(DevBuf& b, size_t bytes) {
@@ -330,6 +359,7 @@ static int ensure(DevBuf& b, size_t bytes) {
     size_t want = bytes + bytes / 4 + 256;
     cudaError_t e = cudaMalloc(&b.p, want);
     if (e != cudaSuccess) {
+        cudaGetLastError();
         e = cudaMalloc(&b.p, bytes);
         want = bytes;
     }
@@ -345,6 +375,9 @@ extern "C" int lt_batch_create(lt_tables* tables, lt_batch** out) {
     b->tables = tables;
     CU(cudaStreamCreateWithFlags(&b->own_stream, cudaStreamNonBlocking));
     for (auto& e : b->ev) CU(cudaEventCreate(&e));
+    // debugging / test knobs: tiny initial capacities exercise the grow-and-rerun path
+    if (const char* env = getenv("LT_HIT_CAP")) b->hcap = std::max(8, atoi(env));
+    if (const char* env = getenv("LT_EDGE_CAP")) { b->edge_cap = (uint32_t)std::max(16, atoi(env)); b->edge_cap_fixed = true; }
     *out = b;
     return LT_OK;
 }
@@ -352,9 +385,9 @@ extern "C" int lt_batch_create(lt_tables* tables, lt_batch** out) {
 extern "C" void lt_batch_destroy(lt_batch* b) {
     if (!b) return;
     cudaSetDevice(b->tables->device);
-    DevBuf* bufs[] = {&b->text, &b->sent_off, &b->end_cnt, &b->beg_cnt, &b->end_off, &b->scan_tmp, &b->sent_len,
-                      &b->sent_edges, &b->status, &b->path_len, &b->path_off, &b->scores, &b->edges, &b->trail,
-                      &b->path_tmp, &b->path_out, &b->counters, &b->queue};
+    DevBuf* bufs[] = {&b->text, &b->sent_off, &b->pos, &b->scan_tmp, &b->sent_len, &b->sent_edges, &b->status,
+                      &b->path_len, &b->path_off, &b->scores, &b->edges, &b->trail, &b->path_tmp, &b->path_out,
+                      &b->counters, &b->ctl};
     for (DevBuf* x : bufs)
         if (x->p) cudaFree(x->p);
     for (auto& e : b->ev)
@@ -376,96 +409,76 @@ static int scan_u32(lt_batch* b, const uint32_t* in, uint32_t* out, int64_t n, c
 
 static const size_t kSmemBudget = 200 * 1024;
 
-extern "C" int lt_lattice(lt_batch* b, const uint16_t* d_text, const int32_t* d_sent_off, int32_t n_sent,
-                          int64_t n_units, int32_t max_sent_units, void* stream) {
-    if (!b || n_sent < 0 || n_units < 0) return fail(LT_ERR_INVALID, "bad argument");
+// ---- launches ----------------------------------------------------------------------------------
+static int launch_lattice(lt_batch* b, cudaStream_t st) {
     lt_tables* t = b->tables;
-    CU(cudaSetDevice(t->device));
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    b->last_stream = st;
-    b->d_text = d_text;
-    b->d_sent_off = d_sent_off;
-    b->n_sent = n_sent;
-    b->n_units = n_units;
-    b->have_lattice = b->have_paths = false;
-    const int lcap = std::max(8, (max_sent_units + 7) & ~7);
-    b->lcap = lcap;
-    if (lcap > 65528) return fail(LT_ERR_INVALID, "a sentence has %d code units; at most 65528 are supported", max_sent_units);
-    const size_t warp_smem = lattice_warp_smem(lcap);
+    const int n_sent = b->n_sent;
+    const int64_t n_units = b->n_units;
+    const int lcap = b->lcap;
+    const int max_str = std::max(1, t->dev.max_str);
+    int hcap = b->hcap;
+    size_t warp_smem = lattice_warp_smem(lcap, hcap, max_str);
     int warps = (int)std::min<size_t>(kLatWarps, kSmemBudget / warp_smem);
-    if (warps < 1) return fail(LT_ERR_INVALID, "a sentence of %d code units does not fit the lattice kernel's shared memory", max_sent_units);
+    if (warps < 1)
+        return fail(LT_ERR_INVALID, "a sentence of %d code units (dictionary strings up to %d) does not fit the lattice "
+                                    "kernel's shared memory", b->max_sent_units, max_str);
 
     const size_t nu = (size_t)n_units + 1;
-    if (int rc = ensure(b->end_cnt, nu * 4)) return rc;
-    if (int rc = ensure(b->beg_cnt, nu * 4)) return rc;
-    if (int rc = ensure(b->end_off, nu * 4)) return rc;
+    if (int rc = ensure(b->pos, nu * sizeof(uint2))) return rc;
     if (int rc = ensure(b->sent_len, (size_t)std::max(1, n_sent) * 4)) return rc;
     if (int rc = ensure(b->sent_edges, (size_t)std::max(1, n_sent) * 4)) return rc;
     if (int rc = ensure(b->status, (size_t)std::max(1, n_sent) * 4)) return rc;
     if (int rc = ensure(b->counters, 8 * sizeof(unsigned long long))) return rc;
-    if (int rc = ensure(b->queue, 4 * sizeof(unsigned int))) return rc;
+    if (int rc = ensure(b->ctl, kCtlWords * sizeof(unsigned int))) return rc;
+    if (!b->edge_cap_fixed) {
+        const uint64_t guess = (uint64_t)n_units * 3 + 4096;
+        if (b->edge_cap < guess) b->edge_cap = (uint32_t)std::min<uint64_t>(guess, 0xFFFFFFF0ull);
+    }
+    if (int rc = ensure(b->edges, (size_t)b->edge_cap * sizeof(lt_edge))) return rc;
 
     CU(cudaMemsetAsync(b->counters.p, 0, 8 * sizeof(unsigned long long), st));
-    CU(cudaMemsetAsync(b->queue.p, 0, 4 * sizeof(unsigned int), st));
-    CU(cudaMemsetAsync(b->beg_cnt.p, 0, nu * 4, st));
-    CU(cudaMemsetAsync(static_cast<uint32_t*>(b->end_cnt.p) + n_units, 0, 4, st));
+    CU(cudaMemsetAsync(b->ctl.p, 0, kCtlWords * sizeof(unsigned int), st));
 
     LatticeArgs A{};
-    A.text = d_text;
-    A.sent_off = d_sent_off;
+    A.text = b->d_text;
+    A.sent_off = b->d_sent_off;
     A.n_sent = n_sent;
     A.lcap = lcap;
-    A.end_cnt = static_cast<uint32_t*>(b->end_cnt.p);
-    A.beg_cnt = static_cast<uint32_t*>(b->beg_cnt.p);
-    A.end_off = static_cast<const uint32_t*>(b->end_off.p);
-    A.edges = nullptr;
+    A.hcap = hcap;
+    A.max_str = max_str;
+    A.pos = static_cast<uint2*>(b->pos.p);
+    A.edges = static_cast<lt_edge*>(b->edges.p);
+    A.edge_cap = b->edge_cap;
+    unsigned int* ctl = static_cast<unsigned int*>(b->ctl.p);
+    A.cursor = ctl + kCtlCursor;
+    A.flags = ctl + kCtlFlags;
     A.sent_len = static_cast<int32_t*>(b->sent_len.p);
     A.sent_edges = static_cast<int32_t*>(b->sent_edges.p);
     A.status = static_cast<int32_t*>(b->status.p);
     A.counters = static_cast<unsigned long long*>(b->counters.p);
-    A.queue = static_cast<unsigned int*>(b->queue.p) + 0;
+    A.queue = ctl + kCtlLatticeQueue;
 
     const size_t smem = warp_smem * warps;
-    CU(cudaFuncSetAttribute(lattice_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CU(cudaFuncSetAttribute(lattice_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU(cudaFuncSetAttribute(lattice_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lattice_kernel<false>, warps * 32, smem));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lattice_kernel, warps * 32, smem));
     per_sm = std::max(1, per_sm);
     const int64_t want_blocks = ((int64_t)n_sent + warps - 1) / warps;
     const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(want_blocks, (int64_t)t->sm_count * per_sm));
 
     if (b->timed) CU(cudaEventRecord(b->ev[0], st));
-    if (n_sent > 0) lattice_kernel<false><<<grid, warps * 32, smem, st>>>(t->dev, A);
+    if (n_sent > 0) lattice_kernel<<<grid, warps * 32, smem, st>>>(t->dev, A);
     CU(cudaGetLastError());
     if (b->timed) CU(cudaEventRecord(b->ev[1], st));
-    if (int rc = scan_u32(b, A.end_cnt, static_cast<uint32_t*>(b->end_off.p), (int64_t)nu, st)) return rc;
-    if (b->timed) CU(cudaEventRecord(b->ev[2], st));
-
-    // total edge count decides the size of the edge array
-    uint32_t total = 0;
-    CU(cudaMemcpyAsync(&total, static_cast<uint32_t*>(b->end_off.p) + n_units, 4, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    b->n_edges = total;
-    if (int rc = ensure(b->edges, std::max<size_t>(1, total) * sizeof(lt_edge))) return rc;
-
-    A.edges = static_cast<lt_edge*>(b->edges.p);
-    A.queue = static_cast<unsigned int*>(b->queue.p) + 1;
-    if (b->timed) CU(cudaEventRecord(b->ev[3], st));
-    if (n_sent > 0 && total > 0) lattice_kernel<true><<<grid, warps * 32, smem, st>>>(t->dev, A);
-    CU(cudaGetLastError());
-    if (b->timed) CU(cudaEventRecord(b->ev[4], st));
     b->have_lattice = true;
+    b->have_paths = false;
+    b->resolved = false;
     return LT_OK;
 }
 
-extern "C" int lt_beam(lt_batch* b, int32_t beam_size, void* stream) {
-    if (!b || !b->have_lattice) return fail(LT_ERR_INVALID, "lt_beam needs a lattice: call lt_lattice first");
-    if (beam_size < 1 || beam_size > LT_MAX_BEAM) return fail(LT_ERR_INVALID, "beam_size must be in 1..%d", LT_MAX_BEAM);
+static int launch_beam(lt_batch* b, cudaStream_t st) {
     lt_tables* t = b->tables;
-    CU(cudaSetDevice(t->device));
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    b->last_stream = st;
-    b->beam = beam_size;
+    const int beam_size = b->beam;
     const int n_sent = b->n_sent;
     const size_t nu = (size_t)b->n_units + 1;
 
@@ -477,7 +490,7 @@ extern "C" int lt_beam(lt_batch* b, int32_t beam_size, void* stream) {
     if (int rc = ensure(b->scores, (size_t)std::max(1, n_sent) * 8)) return rc;
 
     const size_t dense_bytes = ((size_t)t->dev.n_tri * dense_block_bytes(t->dev.n_tags) + 15) & ~(size_t)15;
-    const size_t warp_smem = beam_warp_smem(b->lcap, beam_size);
+    const size_t warp_smem = beam_warp_smem(b->lcap, beam_size, t->dev.n_funcs);
     if (dense_bytes + warp_smem > kSmemBudget)
         return fail(LT_ERR_INVALID, "sentence length %d with beam %d does not fit the beam kernel's shared memory", b->lcap, beam_size);
     int warps = (int)std::min<size_t>(8, (kSmemBudget - dense_bytes) / warp_smem);
@@ -485,6 +498,7 @@ extern "C" int lt_beam(lt_batch* b, int32_t beam_size, void* stream) {
     while (warps > 2 && (dense_bytes + warp_smem * warps) > 48 * 1024) warps >>= 1;
     const size_t smem = dense_bytes + warp_smem * warps;
 
+    unsigned int* ctl = static_cast<unsigned int*>(b->ctl.p);
     BeamArgs A{};
     A.text = b->d_text;
     A.sent_off = b->d_sent_off;
@@ -492,28 +506,30 @@ extern "C" int lt_beam(lt_batch* b, int32_t beam_size, void* stream) {
     A.lcap = b->lcap;
     A.beam = beam_size;
     A.warps = warps;
-    A.end_off = static_cast<const uint32_t*>(b->end_off.p);
+    A.pos = static_cast<const uint2*>(b->pos.p);
     A.edges = static_cast<const lt_edge*>(b->edges.p);
     A.status = static_cast<const int32_t*>(b->status.p);
+    A.flags = ctl + kCtlFlags;
     A.trail = static_cast<uint64_t*>(b->trail.p);
     A.path_tmp = static_cast<lt_edge*>(b->path_tmp.p);
     A.path_len = static_cast<int32_t*>(b->path_len.p);
     A.scores = static_cast<double*>(b->scores.p);
     A.counters = static_cast<unsigned long long*>(b->counters.p);
-    A.queue = static_cast<unsigned int*>(b->queue.p) + 2;
+    A.queue = ctl + kCtlBeamQueue;
 
-    CU(cudaFuncSetAttribute(beam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    auto kernel = (beam_size <= 32) ? beam_kernel<1> : beam_kernel<2>;
+    CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, beam_kernel, warps * 32, smem));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, warps * 32, smem));
     per_sm = std::max(1, per_sm);
     const int64_t want_blocks = ((int64_t)n_sent + warps - 1) / warps;
     const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(want_blocks, (int64_t)t->sm_count * per_sm));
 
-    CU(cudaMemsetAsync(static_cast<unsigned int*>(b->queue.p) + 2, 0, sizeof(unsigned int), st));
+    CU(cudaMemsetAsync(ctl + kCtlBeamQueue, 0, sizeof(unsigned int), st));
     CU(cudaMemsetAsync(static_cast<unsigned long long*>(b->counters.p) + 3, 0, 4 * sizeof(unsigned long long), st));
-    CU(cudaMemsetAsync(static_cast<int32_t*>(b->path_len.p) + n_sent, 0, 4, st));
+    CU(cudaMemsetAsync(b->path_len.p, 0, (size_t)(n_sent + 1) * 4, st));
     if (b->timed) CU(cudaEventRecord(b->ev[5], st));
-    if (n_sent > 0) beam_kernel<<<grid, warps * 32, smem, st>>>(t->dev, A);
+    if (n_sent > 0) kernel<<<grid, warps * 32, smem, st>>>(t->dev, A);
     CU(cudaGetLastError());
     if (b->timed) CU(cudaEventRecord(b->ev[6], st));
     if (int rc = scan_u32(b, reinterpret_cast<const uint32_t*>(b->path_len.p), static_cast<uint32_t*>(b->path_off.p),
@@ -528,11 +544,79 @@ extern "C" int lt_beam(lt_batch* b, int32_t beam_size, void* stream) {
     }
     if (b->timed) CU(cudaEventRecord(b->ev[7], st));
     b->have_paths = true;
+    b->resolved = false;
     return LT_OK;
+}
+
+// Wait for the batch and, if the lattice outgrew a buffer (edge array or per-warp staging), enlarge
+// it and run the stages again — still on the device; capacities are sticky for later batches.
+static int resolve(lt_batch* b) {
+    if (!b->have_lattice || b->resolved) return LT_OK;
+    cudaStream_t st = b->last_stream;
+    for (int round = 0; round < 12; ++round) {
+        unsigned int ctl[kCtlWords];
+        CU(cudaMemcpyAsync(ctl, b->ctl.p, sizeof ctl, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        const bool edge_over = ctl[kCtlFlags + kFlagEdgeOverflow] != 0;
+        const bool stage_over = ctl[kCtlFlags + kFlagStageOverflow] != 0;
+        if (!edge_over && !stage_over) {
+            b->n_edges = ctl[kCtlCursor];
+            b->resolved = true;
+            return LT_OK;
+        }
+        if (edge_over) {
+            const uint64_t need = (uint64_t)ctl[kCtlCursor] + ctl[kCtlCursor] / 4 + 4096;
+            if (need > 0xFFFFFFF0ull) return fail(LT_ERR_CAPACITY, "the batch produces more than 2^32 lattice edges; split it");
+            b->edge_cap = (uint32_t)need;
+        }
+        if (stage_over) {
+            const int max_str = std::max(1, b->tables->dev.max_str);
+            const int next = b->hcap * 2;
+            if (lattice_warp_smem(b->lcap, next, max_str) > kSmemBudget)
+                return fail(LT_ERR_CAPACITY, "one eojeol yields more than %d lattice candidates; the staging buffer cannot grow further", b->hcap);
+            b->hcap = next;
+        }
+        ++b->reruns;
+        const bool want_paths = b->have_paths;
+        if (int rc = launch_lattice(b, st)) return rc;
+        if (want_paths)
+            if (int rc = launch_beam(b, st)) return rc;
+    }
+    return fail(LT_ERR_CAPACITY, "lattice buffers did not converge");
+}
+
+extern "C" int lt_lattice(lt_batch* b, const uint16_t* d_text, const int32_t* d_sent_off, int32_t n_sent,
+                          int64_t n_units, int32_t max_sent_units, void* stream) {
+    if (!b || n_sent < 0 || n_units < 0) return fail(LT_ERR_INVALID, "bad argument");
+    CU(cudaSetDevice(b->tables->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    b->last_stream = st;
+    b->d_text = d_text;
+    b->d_sent_off = d_sent_off;
+    b->n_sent = n_sent;
+    b->n_units = n_units;
+    b->max_sent_units = max_sent_units;
+    b->have_lattice = b->have_paths = false;
+    b->beam = 0;
+    b->lcap = std::max(8, (max_sent_units + 7) & ~7);
+    if (b->lcap > 4088) return fail(LT_ERR_INVALID, "a sentence has %d code units; at most 4088 are supported", max_sent_units);
+    return launch_lattice(b, st);
+}
+
+extern "C" int lt_beam(lt_batch* b, int32_t beam_size, void* stream) {
+    if (!b || !b->have_lattice) return fail(LT_ERR_INVALID, "lt_beam needs a lattice: call lt_lattice first");
+    if (beam_size < 1 || beam_size > LT_MAX_BEAM) return fail(LT_ERR_INVALID, "beam_size must be in 1..%d", LT_MAX_BEAM);
+    CU(cudaSetDevice(b->tables->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    b->last_stream = st;
+    b->beam = beam_size;
+    return launch_beam(b, st);
 }
 
 extern "C" int lt_lattice_size(lt_batch* b, int64_t* n_edges) {
     if (!b || !b->have_lattice || !n_edges) return fail(LT_ERR_INVALID, "no lattice");
+    CU(cudaSetDevice(b->tables->device));
+    if (int rc = resolve(b)) return rc;
     *n_edges = b->n_edges;
     return LT_OK;
 }
@@ -540,20 +624,29 @@ extern "C" int lt_lattice_size(lt_batch* b, int64_t* n_edges) {
 extern "C" int lt_lattice_fetch(lt_batch* b, lt_edge* edges, int64_t edge_cap, int64_t* end_off) {
     if (!b || !b->have_lattice) return fail(LT_ERR_INVALID, "no lattice");
     CU(cudaSetDevice(b->tables->device));
+    if (int rc = resolve(b)) return rc;
     if (edge_cap < b->n_edges) return fail(LT_ERR_CAPACITY, "edge buffer holds %lld, need %lld", (long long)edge_cap, (long long)b->n_edges);
-    CU(cudaStreamSynchronize(b->last_stream));
-    if (b->n_edges) CU(cudaMemcpy(edges, b->edges.p, (size_t)b->n_edges * sizeof(lt_edge), cudaMemcpyDeviceToHost));
-    if (end_off) {
-        std::vector<uint32_t> tmp((size_t)b->n_units + 1);
-        CU(cudaMemcpy(tmp.data(), b->end_off.p, tmp.size() * 4, cudaMemcpyDeviceToHost));
-        for (size_t i = 0; i < tmp.size(); ++i) end_off[i] = tmp[i];
+    // the device keeps each sentence's edges wherever its reservation landed; hand them out in
+    // sentence order (CSR by end position)
+    std::vector<lt_edge> raw((size_t)b->n_edges);
+    std::vector<uint2> pos((size_t)b->n_units + 1);
+    if (b->n_edges) CU(cudaMemcpy(raw.data(), b->edges.p, raw.size() * sizeof(lt_edge), cudaMemcpyDeviceToHost));
+    if (b->n_units) CU(cudaMemcpy(pos.data(), b->pos.p, (size_t)b->n_units * sizeof(uint2), cudaMemcpyDeviceToHost));
+    int64_t out = 0;
+    for (int64_t i = 0; i < b->n_units; ++i) {
+        if (end_off) end_off[i] = out;
+        const uint2 pc = pos[i];
+        if ((int64_t)pc.x + pc.y > b->n_edges) return fail(LT_ERR_INVALID, "corrupt lattice index");
+        for (uint32_t k = 0; k < pc.y; ++k) edges[out++] = raw[pc.x + k];
     }
+    if (end_off) end_off[b->n_units] = out;
     return LT_OK;
 }
 
 extern "C" int lt_paths_size(lt_batch* b, int64_t* n_words) {
     if (!b || !b->have_paths || !n_words) return fail(LT_ERR_INVALID, "no paths");
     CU(cudaSetDevice(b->tables->device));
+    if (int rc = resolve(b)) return rc;
     uint32_t total = 0;
     CU(cudaMemcpyAsync(&total, static_cast<uint32_t*>(b->path_off.p) + b->n_sent, 4, cudaMemcpyDeviceToHost, b->last_stream));
     CU(cudaStreamSynchronize(b->last_stream));
@@ -568,25 +661,26 @@ static int fetch_paths(lt_batch* b, int32_t* path_off, lt_edge* path_edges, int6
         if (path_off) path_off[0] = 0;
         return LT_OK;
     }
-    CU(cudaMemcpyAsync(path_off, b->path_off.p, (size_t)(n + 1) * 4, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(scores, b->scores.p, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(status, b->status.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
-    // every path has at most one word per syllable, so n_units records always suffice
-    const int64_t words_max = std::min<int64_t>(b->n_units, path_cap);
-    if (path_cap >= b->n_units) {
-        // one-shot copy without waiting for the word count: copy what can exist
+    // one round trip: control words (overflow flags) travel with the small per-sentence arrays
+    unsigned int ctl[kCtlWords];
+    for (int round = 0; round < 12; ++round) {
+        CU(cudaMemcpyAsync(ctl, b->ctl.p, sizeof ctl, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(path_off, b->path_off.p, (size_t)(n + 1) * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(scores, b->scores.p, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(status, b->status.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
-        const int64_t total = path_off[n];
-        if (total) CU(cudaMemcpyAsync(path_edges, b->path_out.p, (size_t)total * sizeof(lt_edge), cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
-    } else {
-        CU(cudaStreamSynchronize(st));
-        const int64_t total = path_off[n];
-        if (total > path_cap) return fail(LT_ERR_CAPACITY, "path buffer holds %lld records, need %lld", (long long)path_cap, (long long)total);
-        if (total) CU(cudaMemcpyAsync(path_edges, b->path_out.p, (size_t)total * sizeof(lt_edge), cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
+        if (ctl[kCtlFlags + kFlagEdgeOverflow] == 0 && ctl[kCtlFlags + kFlagStageOverflow] == 0) {
+            b->n_edges = ctl[kCtlCursor];
+            b->resolved = true;
+            break;
+        }
+        b->resolved = false;
+        if (int rc = resolve(b)) return rc;      // grows the buffers and reruns both stages
     }
-    (void)words_max;
+    const int64_t total = path_off[n];
+    if (total > path_cap) return fail(LT_ERR_CAPACITY, "path buffer holds %lld records, need %lld", (long long)path_cap, (long long)total);
+    if (total) CU(cudaMemcpyAsync(path_edges, b->path_out.p, (size_t)total * sizeof(lt_edge), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
     return LT_OK;
 }
 
@@ -632,8 +726,8 @@ extern "C" int lt_batch_counters(lt_batch* b, lt_counters* out) {
     if (!b || !out) return fail(LT_ERR_INVALID, "null argument");
     CU(cudaSetDevice(b->tables->device));
     unsigned long long c[8] = {0};
-    if (b->counters.p) {
-        CU(cudaStreamSynchronize(b->last_stream));
+    if (b->counters.p && b->have_lattice) {
+        if (int rc = resolve(b)) return rc;
         CU(cudaMemcpy(c, b->counters.p, sizeof c, cudaMemcpyDeviceToHost));
     }
     out->sentences = (uint64_t)b->n_sent;
@@ -651,15 +745,13 @@ extern "C" int lt_batch_timings(lt_batch* b, lt_timings* out) {
         return LT_OK;
     }
     if (!b->have_paths) return LT_OK;
-    CU(cudaStreamSynchronize(b->last_stream));
+    if (int rc = resolve(b)) return rc;
     auto ms = [&](int a, int c, float* dst) {
         float v = 0.f;
         if (cudaEventElapsedTime(&v, b->ev[a], b->ev[c]) == cudaSuccess) *dst = v;
         else cudaGetLastError();
     };
-    ms(0, 1, &out->ms_lattice_count);
-    ms(1, 2, &out->ms_scan);
-    ms(3, 4, &out->ms_lattice_emit);
+    ms(0, 1, &out->ms_lattice);
     ms(5, 6, &out->ms_beam);
     ms(6, 7, &out->ms_pack);
     ms(8, 0, &out->ms_h2d);

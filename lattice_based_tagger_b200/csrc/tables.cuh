@@ -69,6 +69,8 @@ struct DevTables {
     const RuleRec* rrec;
     const FeatSlot* feat;
     uint64_t feat_mask;
+    uint32_t feat_bits;           // log2(slots)
+    uint32_t reserved2;
     const unsigned char* dense;   // n_tri blocks of dense_block_bytes(n_tags)
     const H2* pows;
     int32_t n_pows;
@@ -78,11 +80,12 @@ struct DevTables {
     int32_t n_funcs;
     int32_t n_tri;                // number of LT_FUNC_TRIGRAM scorers
     int32_t has_rules;
-    int32_t reserved;
+    int32_t max_str;              // longest dictionary string (syllables)
     uint8_t tag_order[LT_MAX_TAGS];
     lt_func funcs[LT_MAX_FUNCS];
     int8_t  func_dense[LT_MAX_FUNCS];   // dense block index of a trigram scorer, -1 otherwise
     H2 bos;                        // hash of the literal 'BOS' (beam.py:21)
+    H2 seeds[LT_MAX_FUNCS][10];    // feature_seed(template 0..8, f); [9] = the scorer's preference kind
 };
 
 #if defined(__CUDACC__)
@@ -132,10 +135,10 @@ __device__ __forceinline__ RuleRec rule_load(const DevTables& T, uint32_t idx) {
 
 // feature probe, split in two so that callers can put several first-slot loads in flight
 __device__ __forceinline__ uint4 feat_first(const DevTables& T, FKey k) {
-    return ldg16(T.feat + (k.k1 & T.feat_mask));
+    return ldg16(T.feat + feature_slot(k.k1, T.feat_bits));
 }
 __device__ __forceinline__ bool feat_resolve(const DevTables& T, FKey k, uint4 s, double& w) {
-    uint64_t i = k.k1 & T.feat_mask;
+    uint64_t i = feature_slot(k.k1, T.feat_bits);
     while (true) {
         uint64_t sfp = (uint64_t)s.x | ((uint64_t)s.y << 32);
         if (sfp == k.k2) {

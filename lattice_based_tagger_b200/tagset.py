@@ -30,8 +30,8 @@ TAG_IDS = {tag: idx for idx, tag in enumerate(BUILTIN_TAGS)}
 #: tags that take part in the contextual feature (template 8, `features/feature.py:88`)
 CONTEXTUAL_TAGS = (Noun, Adverb, Adjective, Verb)
 
-#: upper bound on distinct tags a compiled table can hold (tag masks are 32-bit)
-MAX_TAGS = 32
+#: upper bound on distinct tags a compiled table can hold (29-bit tag sets next to 3 lemma bits)
+MAX_TAGS = 29
 
 __all__ = ['Noun', 'Pronoun', 'Number', 'Josa', 'Adjective', 'Verb', 'Eomi', 'Adverb',
            'Determiner', 'Exclamation', 'BOS', 'EOS', 'Unk']

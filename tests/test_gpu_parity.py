@@ -91,3 +91,27 @@ def test_demo_known_answer():
     assert [(w.word, w.tag0, w.len) for w in best.sequences[1:-1]] == [
         ('너무너무너무', 'Noun', 7), ('는', 'Josa', 7), ('아이오아이', 'Noun', 6), ('의', 'Josa', 6),
         ('노래', 'Noun', 2), ('입니다', 'Adjective', 3)]
+
+
+def test_buffers_grow_and_rerun(monkeypatch):
+    """Tiny initial staging / edge capacities force the overflow flags, the host enlarges the
+    buffers and reruns on the device; results must not change."""
+    case = _cases.random_case(4242, n_sent=40, features=True, max_sent_len=60)
+    _cases.add_features(case, _cases.observed_features(case, lo, seed=1), 1)
+    dictionary, funcs = _cases.build_objects(case, pkg)
+    sents = [s for s in case['sentences']]
+    oracle = lo.OracleTagger(dictionary, funcs)
+    monkeypatch.setenv('LT_HIT_CAP', '8')
+    monkeypatch.setenv('LT_EDGE_CAP', '16')
+    tagger = pkg.Tagger(dictionary, score_funcs=funcs)
+    for sent, (words, bindex) in zip(sents, tagger.lattice_batch(sents)):
+        assert [tuple(w) for w in words[1:-1]] == _lattice_key(oracle.lattice(sent)), sent
+    got = tagger.tag_batch(sents, beam_size=5, errors='none')
+    for sent, seq in zip(sents, got):
+        try:
+            want = oracle.tag(sent, 5)
+        except IndexError:
+            assert seq is None
+            continue
+        assert [tuple(w) for w in seq.sequences] == want.words
+        assert seq.score == want.score

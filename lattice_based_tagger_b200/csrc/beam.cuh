@@ -238,8 +238,12 @@ __device__ __forceinline__ double unsortable(uint64_t key) {
     return __longlong_as_double((long long)bits);
 }
 
+#ifndef LT_BEAM_MINB
+#define LT_BEAM_MINB 4
+#endif
+constexpr int kBeamWarps = 4;                 // warps per CTA of the beam kernel
 template <int KR>   // KR = ceil(beam / 32): kept entries per lane
-__global__ void __launch_bounds__(256) beam_kernel(const __grid_constant__ DevTables T, const __grid_constant__ BeamArgs A) {
+__global__ void __launch_bounds__(kBeamWarps * 32, LT_BEAM_MINB) beam_kernel(const __grid_constant__ DevTables T, const __grid_constant__ BeamArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;

@@ -50,11 +50,14 @@ LT_HD H2 h2_sub(H2 pre_b, H2 pre_e, H2 pow_len) {
 }
 
 // ---- dictionary key: (string, length) -------------------------------------------------------
+// slot: multiply-shift of hash a (top bits of a product depend on every input bit);
+// fingerprint: hash b combined with the length (compared in full, so it needs no mixing).
 LT_HD uint64_t dict_slot_hash(H2 h, uint32_t len) {
-    return fmix64(h.a + (uint64_t)len * 0xA24BAED4963EE407ull);
+    return (h.a + (uint64_t)len * 0xA24BAED4963EE407ull) * 0x9E3779B97F4A7C15ull;
 }
+LT_HD uint64_t dict_slot(H2 h, uint32_t len, uint32_t bits) { return dict_slot_hash(h, len) >> (64 - bits); }
 LT_HD uint64_t dict_fp(H2 h, uint32_t len) {
-    uint64_t f = fmix64(h.b ^ ((uint64_t)len * 0x9FB21C651E98DF25ull));
+    uint64_t f = h.b ^ ((uint64_t)len * 0x9FB21C651E98DF25ull);
     return f ? f : 1;
 }
 

@@ -93,7 +93,7 @@ __device__ __forceinline__ bool is_py_space(uint32_t c) {
 }
 
 // Prefix hashes of the staged syllables by warp scan: H[0] = 0, H[i+1] = H[i] * B + (c_i + 1).
-__device__ __forceinline__ void prefix_hashes(const uint16_t* ch, int L, int lane, uint64_t* ha, uint64_t* hb) {
+__device__ __noinline__ void prefix_hashes(const uint16_t* ch, int L, int lane, uint64_t* ha, uint64_t* hb) {
     H2 carry{0, 0};
     if (lane == 0) {
         ha[0] = 0;
@@ -206,7 +206,16 @@ __device__ __forceinline__ uint64_t hit_key(int e, int b, uint32_t cls, uint32_t
            (uint64_t)(k & 0x7FFFFu);
 }
 
-__device__ __forceinline__ void stage_hit(const Enum& E, const lt_edge& rec, uint64_t key, uint32_t task) {
+#ifndef LT_STAGE_ATTR
+#define LT_STAGE_ATTR __forceinline__
+#endif
+#ifndef LT_ITEM_ATTR
+#define LT_ITEM_ATTR __forceinline__
+#endif
+#ifndef LT_FLUSH_ATTR
+#define LT_FLUSH_ATTR __noinline__
+#endif
+__device__ LT_STAGE_ATTR void stage_hit(const Enum& E, const lt_edge& rec, uint64_t key, uint32_t task) {
     const uint32_t slot = atomicAdd(E.nh, 1u);
     if (slot < (uint32_t)E.hcap) {
         E.hrec[slot] = rec;
@@ -259,6 +268,8 @@ __device__ __noinline__ void apply_rules(const DevTables& T, const SentView& v, 
     const H2 pw_suf = pow_at(T, suf_len);
     for (uint32_t r = 0; r < count; ++r) {
         const RuleRec rec = rule_load(T, ref.x + r);
+        // no dictionary string is longer than max_str: most candidates die here, before any hashing
+        if (rec.eomi_len + suf_len > (uint32_t)E.max_str || (uint32_t)(p - b) + rec.stem_len > (uint32_t)E.max_str) continue;
         const H2 stem = h2_concat(pre, rec.stem, pow_at(T, rec.stem_len));
         const H2 eomi = h2_concat(rec.eomi, suf, pw_suf);
         proto.rule = ref.x + r;
@@ -269,7 +280,7 @@ __device__ __noinline__ void apply_rules(const DevTables& T, const SentView& v, 
 
 // Lemma candidates of the word [b, e) at split position p, in get_lemma_candidates order
 // (lemmatizer.py:90-112).  Returns the number of candidates the reference generates there.
-__device__ __forceinline__ uint32_t lemma_item(const DevTables& T, const SentView& v, const Enum& E, int b, int e, int p,
+__device__ LT_ITEM_ATTR uint32_t lemma_item(const DevTables& T, const SentView& v, const Enum& E, int b, int e, int p,
                                                lt_edge proto, uint32_t task) {
     uint32_t ncand = 0;
     proto.tag1 = LT_TAG_EOMI;
@@ -337,9 +348,37 @@ __device__ __forceinline__ lt_edge edge_proto(int b, int e, uint32_t len, bool i
     return p;
 }
 
+// Write the staged survivors to HBM at (reservation + rank); CSR bookkeeping in shared memory.
+__device__ LT_FLUSH_ATTR void flush_staged(const LatticeArgs& A, int lane, uint32_t slots, uint32_t alive,
+                                          const uint32_t* htask, const lt_edge* hrec, uint32_t* pcnt, uint32_t* pstart,
+                                          uint32_t* nh) {
+    if (alive > 0) {
+        uint32_t gbase = 0;
+        if (lane == 0) gbase = atomicAdd(A.cursor, alive);
+        gbase = __shfl_sync(kFull, gbase, 0);
+        const bool fits = (gbase + alive <= A.edge_cap) && (gbase + alive >= gbase);
+        if (!fits && lane == 0) atomicOr(A.flags + kFlagEdgeOverflow, 1u);
+        #pragma unroll 1
+        for (uint32_t i = lane; i < slots; i += 32) {
+            const uint32_t rank = htask[i];
+            if (rank == 0xFFFFFFFFu) continue;
+            const lt_edge rec = hrec[i];
+            if (fits) A.edges[gbase + rank] = rec;
+            atomicAdd(&pcnt[rec.e - 1], 1u);
+            atomicMin(&pstart[rec.e - 1], gbase + rank);
+        }
+    }
+    __syncwarp();
+    if (lane == 0) *nh = 0;
+    __syncwarp();
+}
+
 // ---- the kernel -----------------------------------------------------------------------------------
 
-__global__ void __launch_bounds__(kLatWarps * 32) lattice_kernel(const __grid_constant__ DevTables T,
+#ifndef LT_LAT_MINB
+#define LT_LAT_MINB 4
+#endif
+__global__ void __launch_bounds__(kLatWarps * 32, LT_LAT_MINB) lattice_kernel(const __grid_constant__ DevTables T,
                                                                 const __grid_constant__ LatticeArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
@@ -395,6 +434,7 @@ __global__ void __launch_bounds__(kLatWarps * 32) lattice_kernel(const __grid_co
             }
             sub[q] = payload;
         }
+        #pragma unroll 1
         for (int p = lane; p < s1 - s0; p += 32) { pstart[p] = 0xFFFFFFFFu; pcnt[p] = 0; }
         if (lane == 0) *nh = 0;
         __syncwarp();
@@ -406,28 +446,10 @@ __global__ void __launch_bounds__(kLatWarps * 32) lattice_kernel(const __grid_co
         uint32_t sent_total = 0;
         bool overflow = false;
 
-        // write the staged survivors to HBM at (reservation + rank); CSR bookkeeping in shared memory
         auto flush = [&]() {
-            if (alive > 0) {
-                uint32_t gbase = 0;
-                if (lane == 0) gbase = atomicAdd(A.cursor, alive);
-                gbase = __shfl_sync(kFull, gbase, 0);
-                const bool fits = (gbase + alive <= A.edge_cap) && (gbase + alive >= gbase);
-                if (!fits && lane == 0) atomicOr(A.flags + kFlagEdgeOverflow, 1u);
-                for (uint32_t i = lane; i < slots; i += 32) {
-                    const uint32_t rank = htask[i];
-                    if (rank == 0xFFFFFFFFu) continue;
-                    const lt_edge rec = hrec[i];
-                    if (fits) A.edges[gbase + rank] = rec;
-                    atomicAdd(&pcnt[rec.e - 1], 1u);
-                    atomicMin(&pstart[rec.e - 1], gbase + rank);
-                }
-            }
-            __syncwarp();
+            flush_staged(A, lane, slots, alive, htask, hrec, pcnt, pstart, nh);
             slots = 0;
             alive = 0;
-            if (lane == 0) *nh = 0;
-            __syncwarp();
         };
 
         for (int w = 0; w < n_eoj && !overflow; ++w) {
@@ -436,6 +458,7 @@ __global__ void __launch_bounds__(kLatWarps * 32) lattice_kernel(const __grid_co
             const int oe = o + n;
             for (int attempt = 0; attempt < 2; ++attempt) {
                 // ---------------- stage 1: whole eojeol + every left/right split ----------------
+                #pragma unroll 1
                 for (int u = lane; u < 2 * n; u += 32) tcnt[u] = 0;
                 __syncwarp();
                 uint32_t ncand_try = 0;
@@ -463,6 +486,7 @@ __global__ void __launch_bounds__(kLatWarps * 32) lattice_kernel(const __grid_co
                                 const uint32_t mask = sub_get(E, b, e) & kSubTagMask;
                                 if (mask) {
                                     lt_edge rec = edge_proto(b, e, (uint32_t)(e - b), b == o);
+                                    #pragma unroll 1
                                     for (int k = 0; k < n_order; ++k) {
                                         const uint32_t t = T.tag_order[k];
                                         if ((mask >> t) & 1u) {
@@ -500,9 +524,11 @@ __global__ void __launch_bounds__(kLatWarps * 32) lattice_kernel(const __grid_co
                     if (lane == 0) *nh = slots;          // forget the dead stage-1 hits
                     const int M = (T.max_len > 0) ? T.max_len : n;
                     // which positions end a stand-alone Noun found by this scan
+                    #pragma unroll 1
                     for (int el = 1 + lane; el <= n; el += 32) {
                         bool any_noun = false;
                         int b_lo = el - M; if (b_lo < 1) b_lo = 1;
+                        #pragma unroll 1
                         for (int bl = b_lo; bl < el; ++bl) any_noun |= ((sub_get(E, o + bl, o + el) >> LT_TAG_NOUN) & 1u) != 0;
                         nend[o + el] = any_noun ? 1 : 0;
                     }
@@ -523,11 +549,13 @@ __global__ void __launch_bounds__(kLatWarps * 32) lattice_kernel(const __grid_co
                                 if (t == 0) {
                                     const uint32_t m = sub_get(E, b, e);
                                     // stand-alone tags in list order (lookup.py:104-105), then Josa after a Noun
-                                    const int order[5] = {LT_TAG_NOUN, LT_TAG_ADVERB, LT_TAG_EXCLAMATION, LT_TAG_DETERMINER, LT_TAG_NUMBER};
-                                    #pragma unroll
+                                    constexpr uint32_t order = LT_TAG_NOUN | (LT_TAG_ADVERB << 4) | (LT_TAG_EXCLAMATION << 8) |
+                                                               (LT_TAG_DETERMINER << 12) | (LT_TAG_NUMBER << 16);
+                                    #pragma unroll 1
                                     for (int k = 0; k < 5; ++k) {
-                                        if ((m >> order[k]) & 1u) {
-                                            rec.tag0 = (uint8_t)order[k];
+                                        const uint32_t t = (order >> (4 * k)) & 0xFu;
+                                        if ((m >> t) & 1u) {
+                                            rec.tag0 = (uint8_t)t;
                                             stage_hit(E, rec, hit_key(e, b, 0, 0, (uint32_t)k), 0u);
                                         }
                                     }
@@ -545,9 +573,10 @@ __global__ void __launch_bounds__(kLatWarps * 32) lattice_kernel(const __grid_co
                     too_many = nstaged > (uint32_t)HC;
                     alive_here = nstaged - slots;             // every stage-2 hit survives
                     // pairs (b, e), 1 <= b < e <= min(b+M, n), minus the (b, n) already examined by stage 1
-                    uint32_t pairs = 0;
-                    for (int bl = 1; bl < n; ++bl) pairs += (uint32_t)min(M, n - bl);
-                    nsub_try += pairs - (uint32_t)min(M, n - 1);
+                    // sum_{bl=1}^{n-1} min(M, n - bl) in closed form
+                    const int m1 = min(M, n - 1);
+                    const uint32_t pairs = (uint32_t)(m1 * (m1 + 1) / 2 + (n - 1 - m1) * M);
+                    nsub_try += pairs - (uint32_t)m1;
                 }
                 if (too_many) {
                     // the eojeol alone may fit once the staged edges of earlier eojeols are written out
@@ -567,6 +596,7 @@ __global__ void __launch_bounds__(kLatWarps * 32) lattice_kernel(const __grid_co
                     uint32_t rank = 0xFFFFFFFFu;
                     if (key != ~0ull) {
                         rank = alive;
+                        #pragma unroll 1
                         for (uint32_t g = slots; g < nstaged; ++g) rank += (hkey[g] < key) ? 1u : 0u;
                     }
                     htask[h] = rank;
@@ -584,6 +614,7 @@ __global__ void __launch_bounds__(kLatWarps * 32) lattice_kernel(const __grid_co
             flush();
         }
         __syncwarp();
+        #pragma unroll 1
         for (int p = lane; p < s1 - s0; p += 32) {
             const uint32_t c = pcnt[p];
             A.pos[s0 + p] = make_uint2(c ? pstart[p] : 0u, c);

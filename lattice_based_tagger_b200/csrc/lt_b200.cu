@@ -118,13 +118,16 @@ static int build_tables(const lt_tables_desc* d, lt_tables* t) {
         const uint64_t slots = next_pow2((uint64_t)d->n_dict * (d->n_dict < (1 << 22) ? 4 : 2));
         std::vector<DictSlot> table(slots, DictSlot{0, 0, 0});
         std::vector<uint64_t> slot_h(slots, 0);
+        uint32_t dict_bits = 0;
+        while ((1ull << dict_bits) < slots) ++dict_bits;
+        D.dict_bits = dict_bits;
         for (int64_t i = 0; i < d->n_dict; ++i) {
             const int64_t len = d->dict_off[i + 1] - d->dict_off[i];
             if (len < 0 || len > 65535) return fail(LT_ERR_INVALID, "dictionary entry %lld has length %lld", (long long)i, (long long)len);
             const H2 h = hash_units(d->dict_chars + d->dict_off[i], len);
             const uint64_t fp = dict_fp(h, (uint32_t)len);
             const uint64_t sh = dict_slot_hash(h, (uint32_t)len);
-            uint64_t s = sh & (slots - 1);
+            uint64_t s = sh >> (64 - dict_bits);
             while (table[s].fp != 0) {
                 if (table[s].fp == fp && slot_h[s] == sh)
                     return fail(LT_ERR_COLLISION, "dictionary entries collide on the 128-bit key (entry %lld)", (long long)i);
@@ -149,6 +152,7 @@ static int build_tables(const lt_tables_desc* d, lt_tables* t) {
             recs[r].eomi = hash_units(d->rule_chars + e0, s1 - e0);
             recs[r].stem_len = (uint32_t)(e0 - s0);
             recs[r].eomi_len = (uint32_t)(s1 - e0);
+            recs[r].pad = 0;
         }
         if (int rc = upload(t, recs, &D.rrec)) return rc;
         const uint64_t slots = next_pow2((uint64_t)d->n_rule_keys * 4);
@@ -493,9 +497,7 @@ static int launch_beam(lt_batch* b, cudaStream_t st) {
     const size_t warp_smem = beam_warp_smem(b->lcap, beam_size, t->dev.n_funcs);
     if (dense_bytes + warp_smem > kSmemBudget)
         return fail(LT_ERR_INVALID, "sentence length %d with beam %d does not fit the beam kernel's shared memory", b->lcap, beam_size);
-    int warps = (int)std::min<size_t>(8, (kSmemBudget - dense_bytes) / warp_smem);
-    // keep several CTAs per SM resident when the per-warp footprint allows it
-    while (warps > 2 && (dense_bytes + warp_smem * warps) > 48 * 1024) warps >>= 1;
+    const int warps = (int)std::min<size_t>(kBeamWarps, (kSmemBudget - dense_bytes) / warp_smem);
     const size_t smem = dense_bytes + warp_smem * warps;
 
     unsigned int* ctl = static_cast<unsigned int*>(b->ctl.p);

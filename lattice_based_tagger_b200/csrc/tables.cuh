@@ -3,7 +3,7 @@
 // HBM layout (all built once by lt_tables_create, read-only afterwards):
 //   dict   open-addressing table, 16 B slots {fp, tagmask, lemma bits}; key = (string, length)
 //   rules  open-addressing table, 16 B slots {exact 1..3-syllable key, first rule, count|k3_first}
-//   rrec   one 40 B record per (stem, eomi) rule: hashes and lengths of both strings
+//   rrec   one 48 B record per (stem, eomi) rule: hashes and lengths of both strings
 //   feat   open-addressing table, 16 B slots {fp, fp64 weight}; key = feature tuple / preference
 //   dense  per trigram scorer: tag x tag matrix (template 3), length vectors (templates 4, 6)
 //          with presence masks — staged into shared memory by the beam kernel
@@ -33,11 +33,12 @@ struct RuleSlot {
 };
 static_assert(sizeof(RuleSlot) == 16, "RuleSlot");
 
-struct RuleRec {
+struct alignas(16) RuleRec {
     H2 stem, eomi;
     uint32_t stem_len, eomi_len;
+    uint64_t pad;
 };
-static_assert(sizeof(RuleRec) == 40, "RuleRec");
+static_assert(sizeof(RuleRec) == 48, "RuleRec");
 
 struct FeatSlot {
     uint64_t fp;        // 0 = empty
@@ -64,6 +65,8 @@ __host__ __device__ inline int dense_block_bytes(int nt) {
 struct DevTables {
     const DictSlot* dict;
     uint64_t dict_mask;
+    uint32_t dict_bits;           // log2(slots)
+    uint32_t reserved3;
     const RuleSlot* rules;
     uint64_t rule_mask;
     const RuleRec* rrec;
@@ -96,7 +99,7 @@ __device__ __forceinline__ uint4 ldg16(const void* p) {
 
 // dictionary probe: returns the 64-bit payload (tagmask | lemma << 32), 0 when absent
 __device__ __forceinline__ uint64_t dict_probe(const DevTables& T, H2 h, uint32_t len) {
-    uint64_t i = dict_slot_hash(h, len) & T.dict_mask;
+    uint64_t i = dict_slot(h, len, T.dict_bits);
     const uint64_t fp = dict_fp(h, len);
     while (true) {
         uint4 s = ldg16(T.dict + i);
@@ -121,15 +124,16 @@ __device__ __forceinline__ uint2 rule_probe(const DevTables& T, uint64_t key) {
 }
 
 __device__ __forceinline__ RuleRec rule_load(const DevTables& T, uint32_t idx) {
-    const uint64_t* p = reinterpret_cast<const uint64_t*>(T.rrec + idx);
+    const uint4* p = reinterpret_cast<const uint4*>(T.rrec + idx);
+    const uint4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
     RuleRec r;
-    r.stem.a = __ldg(p + 0);
-    r.stem.b = __ldg(p + 1);
-    r.eomi.a = __ldg(p + 2);
-    r.eomi.b = __ldg(p + 3);
-    uint64_t l = __ldg(p + 4);
-    r.stem_len = (uint32_t)l;
-    r.eomi_len = (uint32_t)(l >> 32);
+    r.stem.a = (uint64_t)a.x | ((uint64_t)a.y << 32);
+    r.stem.b = (uint64_t)a.z | ((uint64_t)a.w << 32);
+    r.eomi.a = (uint64_t)b.x | ((uint64_t)b.y << 32);
+    r.eomi.b = (uint64_t)b.z | ((uint64_t)b.w << 32);
+    r.stem_len = c.x;
+    r.eomi_len = c.y;
+    r.pad = 0;
     return r;
 }
 

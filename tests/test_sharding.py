@@ -1,0 +1,68 @@
+"""Multi-GPU host logic on CPU: world_size-2 gloo process group, the oracle standing in for the
+device tagger (the sharding code only sees a `tag_fn`)."""
+
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import lattice_based_tagger_b200 as pkg
+from lattice_based_tagger_b200 import sharding
+from oracle import lattice_oracle as lo
+from tests import _cases
+
+
+def test_shard_bounds_cover_and_balance():
+    rng = np.random.default_rng(0)
+    lengths = rng.integers(0, 80, size=1000)
+    for world in (1, 2, 3, 4, 8):
+        bounds = sharding.shard_bounds(lengths, world)
+        assert bounds[0] == 0 and bounds[-1] == 1000 and len(bounds) == world + 1
+        assert all(a <= b for a, b in zip(bounds, bounds[1:]))
+        work = [int((lengths[a:b] + 1).sum()) for a, b in zip(bounds, bounds[1:])]
+        assert max(work) - min(work) <= 2 * 81
+    assert sharding.shard_bounds([], 4) == [0, 0, 0, 0, 0]
+    assert sharding.shard_bounds([5, 5], 4)[-1] == 2
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, seed, out_dir):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    case = _cases.random_case(seed, n_sent=30, features=False)
+    dictionary, funcs = _cases.build_objects(case, pkg)
+    oracle = lo.OracleTagger(dictionary, funcs)
+
+    def tag_fn(sents):
+        out = []
+        for s in sents:
+            try:
+                best = oracle.tag(s, 5)
+                out.append((best.words, best.score))
+            except IndexError:
+                out.append(None)
+        return out
+
+    merged = sharding.tag_sharded(tag_fn, case['sentences'], rank, world)
+    whole = tag_fn(case['sentences'])
+    ok = merged == whole
+    with open(os.path.join(out_dir, 'rank%d' % rank), 'w') as f:
+        f.write('ok' if ok else 'mismatch')
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_ranks_gather_in_order(tmp_path):
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), 77, str(tmp_path)), nprocs=world, join=True)
+    for rank in range(world):
+        assert (tmp_path / ('rank%d' % rank)).read_text() == 'ok'

@@ -242,11 +242,89 @@ __device__ __forceinline__ double unsortable(uint64_t key) {
 #define LT_BEAM_MINB 4
 #endif
 constexpr int kBeamWarps = 4;                 // warps per CTA of the beam kernel
-template <int KR>   // KR = ceil(beam / 32): kept entries per lane
+
+// Prefix hashes by a scan over a GROUP of G lanes: H[0] = 0, H[i+1] = H[i] * B + (c_i + 1).
+template <int G>
+__device__ __forceinline__ void prefix_hashes_group(const uint16_t* ch, int L, int Lmax, int gl, unsigned gmask,
+                                                    uint64_t* ha, uint64_t* hb) {
+    H2 carry{0, 0};
+    if (gl == 0) {
+        ha[0] = 0;
+        hb[0] = 0;
+    }
+    constexpr uint64_t A1 = kBaseA, A2 = A1 * A1, A4 = A2 * A2, A8 = A4 * A4, A16 = A8 * A8;
+    constexpr uint64_t B1 = kBaseB, B2 = B1 * B1, B4 = B2 * B2, B8 = B4 * B4, B16 = B8 * B8;
+    for (int base = 0; base < Lmax; base += G) {
+        const int i = base + gl;
+        const uint64_t v = (i < L) ? (uint64_t)ch[i] + 1u : 0u;
+        uint64_t sa = v, sb = v, ta, tb;
+        ta = __shfl_up_sync(0xFFFFFFFFu, sa, 1, G);  tb = __shfl_up_sync(0xFFFFFFFFu, sb, 1, G);
+        if (gl >= 1)  { sa += ta * A1;  sb += tb * B1; }
+        ta = __shfl_up_sync(0xFFFFFFFFu, sa, 2, G);  tb = __shfl_up_sync(0xFFFFFFFFu, sb, 2, G);
+        if (gl >= 2)  { sa += ta * A2;  sb += tb * B2; }
+        ta = __shfl_up_sync(0xFFFFFFFFu, sa, 4, G);  tb = __shfl_up_sync(0xFFFFFFFFu, sb, 4, G);
+        if (gl >= 4)  { sa += ta * A4;  sb += tb * B4; }
+        ta = __shfl_up_sync(0xFFFFFFFFu, sa, 8, G);  tb = __shfl_up_sync(0xFFFFFFFFu, sb, 8, G);
+        if (gl >= 8)  { sa += ta * A8;  sb += tb * B8; }
+        if (G == 32) {
+            ta = __shfl_up_sync(0xFFFFFFFFu, sa, 16, G); tb = __shfl_up_sync(0xFFFFFFFFu, sb, 16, G);
+            if (gl >= 16) { sa += ta * A16; sb += tb * B16; }
+        }
+        uint64_t pa = 1, pb = 1;   // B^(gl+1)
+        {
+            uint64_t xa = A1, xb = B1;
+            const int k = gl + 1;
+            #pragma unroll
+            for (int bit = 0; bit < 6; ++bit) {
+                if (k & (1 << bit)) { pa *= xa; pb *= xb; }
+                xa *= xa; xb *= xb;
+            }
+        }
+        const uint64_t outa = carry.a * pa + sa, outb = carry.b * pb + sb;
+        if (i < L) {
+            ha[i + 1] = outa;
+            hb[i + 1] = outb;
+        }
+        carry.a = __shfl_sync(0xFFFFFFFFu, outa, G - 1, G);
+        carry.b = __shfl_sync(0xFFFFFFFFu, outb, G - 1, G);
+    }
+    __syncwarp();
+}
+
+// Maximum of a group-uniform value over the groups of a warp, so that both groups run the same
+// number of loop iterations and stay converged (lock-step) — otherwise two half-warp groups would
+// simply serialise.
+template <int G>
+__device__ __forceinline__ uint32_t warp_max(uint32_t x) {
+    if (G == 32) return x;
+    const uint32_t y = __shfl_xor_sync(0xFFFFFFFFu, x, 16);
+    return x > y ? x : y;
+}
+
+// Collectives always name the full warp: a *_sync with a half-warp mask makes the hardware treat
+// the two halves as separate convergence groups, which then run one after the other.
+template <int G>
+__device__ __forceinline__ uint32_t group_max(uint32_t x, int lane) {
+    if (G == 32) return __reduce_max_sync(0xFFFFFFFFu, x);
+    const bool hi_half = lane >= 16;
+    const uint32_t m0 = __reduce_max_sync(0xFFFFFFFFu, hi_half ? 0u : x);
+    const uint32_t m1 = __reduce_max_sync(0xFFFFFFFFu, hi_half ? x : 0u);
+    return hi_half ? m1 : m0;
+}
+// ballot restricted to the caller's group, bits at absolute lane positions
+#define LT_GBALLOT(pred) (__ballot_sync(0xFFFFFFFFu, (pred)) & gmask)
+
+// KR = ceil(beam / G) kept entries per lane; G = lanes per sentence (32: one sentence per warp,
+// 16: two sentences per warp — small beams generate about 16 candidates per position, so half a
+// warp per sentence doubles the useful lanes of every phase).
+template <int KR, int G>
 __global__ void __launch_bounds__(kBeamWarps * 32, LT_BEAM_MINB) beam_kernel(const __grid_constant__ DevTables T, const __grid_constant__ BeamArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
+    const int gl = lane & (G - 1);                       // lane within the sentence's group
+    const int gshift = lane & ~(G - 1);                  // first lane of the group
+    const unsigned gmask = (G == 32) ? 0xFFFFFFFFu : (((1u << G) - 1u) << gshift);
+    const int group = (threadIdx.x >> 5) * (32 / G) + (lane / G);
     const int K = A.beam;
     const int NT = T.n_tags;
 
@@ -259,7 +337,7 @@ __global__ void __launch_bounds__(kBeamWarps * 32, LT_BEAM_MINB) beam_kernel(con
     if (A.flags[kFlagEdgeOverflow] | A.flags[kFlagStageOverflow]) return;   // lattice incomplete: the host grows the buffer and reruns
 
     const size_t units = (size_t)A.lcap + 8;
-    unsigned char* wbase = smem_raw + dense_bytes + (size_t)warp * beam_warp_smem(A.lcap, K, T.n_funcs);
+    unsigned char* wbase = smem_raw + dense_bytes + (size_t)group * beam_warp_smem(A.lcap, K, T.n_funcs);
     uint64_t* ha = reinterpret_cast<uint64_t*>(wbase);
     uint64_t* hb = ha + units;
     uint2* spos = reinterpret_cast<uint2*>(hb + units);
@@ -291,40 +369,39 @@ __global__ void __launch_bounds__(kBeamWarps * 32, LT_BEAM_MINB) beam_kernel(con
     const int nf = T.n_funcs;
 
     while (true) {
+        // the warp takes one sentence per group; a group without a (taggable) sentence idles with L = 0
         unsigned int s = 0;
-        if (lane == 0) s = atomicAdd(A.queue, 1u);
+        if (lane == 0) s = atomicAdd(A.queue, (unsigned)(32 / G));
         s = __shfl_sync(kFull, s, 0);
         if (s >= (unsigned)A.n_sent) break;
-        const int s0 = __ldg(A.sent_off + s), s1 = __ldg(A.sent_off + s + 1);
-        const int st = __ldg(A.status + s);
-        if (st != LT_SENT_OK) {
-            if (lane == 0) { A.path_len[s] = 0; A.scores[s] = 0.0; }
-            continue;
-        }
+        s += (unsigned)(lane / G);
+        const bool have = s < (unsigned)A.n_sent;
+        const int s0 = have ? __ldg(A.sent_off + s) : 0, s1 = have ? __ldg(A.sent_off + s + 1) : 0;
+        const int st = have ? __ldg(A.status + s) : LT_SENT_BAD_SPACE;
         // ---- stage syllables, prefix hashes and the sentence's CSR row ----
         int L = 0;
-        for (int base = s0; base < s1; base += 32) {
-            int idx = base + lane;
-            bool valid = idx < s1;
-            uint32_t c = valid ? (uint32_t)__ldg(A.text + idx) : 0x20u;
-            bool keep = valid && (c != 0x20u);
-            unsigned km = __ballot_sync(kFull, keep);
-            int pos = L + __popc(km & ((1u << lane) - 1u));
+        const int raw_len = (st == LT_SENT_OK) ? (s1 - s0) : 0;
+        const int raw_max = (int)warp_max<G>((uint32_t)raw_len);
+        for (int base = 0; base < raw_max; base += G) {
+            const int idx = s0 + base + gl;
+            const bool valid = base + gl < raw_len;
+            const uint32_t c = valid ? (uint32_t)__ldg(A.text + idx) : 0x20u;
+            const bool keep = valid && (c != 0x20u);
+            const unsigned km = LT_GBALLOT(keep) >> gshift;
+            const int pos = L + __popc(km & ((1u << gl) - 1u));
             if (keep) ch[pos] = (uint16_t)c;
             L += __popc(km);
         }
         __syncwarp();
-        for (int i = lane; i < L; i += 32) spos[i] = __ldg(A.pos + s0 + i);
-        prefix_hashes(ch, L, lane, ha, hb);
+        for (int i = gl; i < L; i += G) spos[i] = __ldg(A.pos + s0 + i);
+        const int Lmax = (int)warp_max<G>((uint32_t)L);
+        prefix_hashes_group<G>(ch, L, Lmax, gl, gmask, ha, hb);
         SentView v{ch, ha, hb, nullptr};
 
-        if (L == 0) {
-            if (lane == 0) { A.path_len[s] = 0; A.scores[s] = 0.0; }
-            continue;
-        }
+        if (L == 0 && have && gl == 0) { A.path_len[s] = 0; A.scores[s] = 0.0; }
 
         // beam[0] = [BOS] (beam.py:21-23)
-        if (lane == 0) {
+        if (gl == 0) {
             e_score[0] = 0.0;
             e_p1[0] = h2_mul(T.bos, kM1a, kM1b);
             e_j2[0] = h2_mul(T.bos, kM2a, kM2b);
@@ -335,47 +412,49 @@ __global__ void __launch_bounds__(kBeamWarps * 32, LT_BEAM_MINB) beam_kernel(con
         }
         __syncwarp();
 
-        for (int e = 1; e <= L; ++e) {
+        for (int e = 1; e <= Lmax; ++e) {
+            const bool on = e <= L;                     // this group's sentence still has positions
             const int slot_e = e % kRing;
-            const uint2 bucket = spos[e - 1];
+            const uint2 bucket = on ? spos[e - 1] : make_uint2(0u, 0u);
             const uint32_t es = bucket.x, ne = bucket.y;
             const int jmax = (e < LT_WINDOW) ? e : LT_WINDOW;
+            const uint32_t ne_max = warp_max<G>(ne);
 
             // ---- 1. edges per span (bucket sorted by begin ascending = span descending) ----
             uint32_t my_cnt = 0;            // lane j (1..8) counts span j
             uint4 raw0 = make_uint4(0, 0, 0, 0);
-            for (uint32_t base = 0; base < ne; base += 32) {
-                uint32_t idx = base + lane;
+            for (uint32_t base = 0; base < ne_max; base += G) {
+                const uint32_t idx = base + gl;
                 int span = 0;
                 if (idx < ne) {
-                    uint4 raw = ldg16(A.edges + es + idx);
+                    const uint4 raw = ldg16(A.edges + es + idx);
                     if (base == 0) raw0 = raw;
                     span = (int)(raw.x >> 16) - (int)(raw.x & 0xFFFFu);
                 }
                 #pragma unroll
                 for (int j = 1; j <= LT_WINDOW; ++j) {
-                    uint32_t c = __popc(__ballot_sync(kFull, span == j));
-                    if (lane == j) my_cnt += c;
+                    const uint32_t c = __popc(LT_GBALLOT(span == j));
+                    if (gl == j) my_cnt += c;
                 }
             }
-            // lane j: group start = ne - sum_{j' <= j} cnt[j'] ... spans descend along the bucket
+            // lane j: group start = ne - sum_{j' <= j} cnt[j']: spans descend along the bucket
             {
-                uint32_t c = (lane >= 1 && lane <= LT_WINDOW) ? my_cnt : 0u;
+                const uint32_t c = (gl >= 1 && gl <= LT_WINDOW) ? my_cnt : 0u;
                 uint32_t incl = c;      // inclusive prefix over lanes 1..j
                 #pragma unroll
                 for (int d = 1; d < 16; d <<= 1) {
-                    uint32_t t = __shfl_up_sync(kFull, incl, d);
-                    if (lane >= d) incl += t;
+                    const uint32_t t = __shfl_up_sync(kFull, incl, d, G);
+                    if (gl >= d) incl += t;
                 }
-                if (lane >= 1 && lane <= LT_WINDOW) {
-                    s_cnt[lane] = c;
-                    s_gstart[lane] = ne - incl;                 // bucket-local index of the group's first edge
-                    uint32_t np = (lane <= jmax) ? s_nbeam[(e - lane) % kRing] : 0u;
-                    s_ncand[lane] = np * (c ? c : 1u);
+                if (gl >= 1 && gl <= LT_WINDOW) {
+                    s_cnt[gl] = c;
+                    s_gstart[gl] = ne - incl;                 // bucket-local index of the group's first edge
+                    const uint32_t np = (on && gl <= jmax) ? s_nbeam[(e - gl) % kRing] : 0u;
+                    s_ncand[gl] = np * (c ? c : 1u);
                 }
             }
             __syncwarp();
-            const uint32_t in_window = ne - s_gstart[LT_WINDOW] ;   // = sum of cnt[1..8]
+            const uint32_t in_window = ne - s_gstart[LT_WINDOW];    // = sum of cnt[1..8]
             const uint32_t first_in = ne - in_window;               // bucket-local index of the first window edge
             uint32_t N = 0;
             #pragma unroll
@@ -384,26 +463,27 @@ __global__ void __launch_bounds__(kBeamWarps * 32, LT_BEAM_MINB) beam_kernel(con
             // ---- 2. edge prep into the cache: window edges, then the unknown word of every empty span ----
             {
                 const uint32_t n_cached = in_window < (uint32_t)kECache ? in_window : (uint32_t)kECache;
-                for (uint32_t base = 0; base < n_cached + LT_WINDOW; base += 32) {
-                    const uint32_t ci = base + lane;
+                const uint32_t prep_max = warp_max<G>(n_cached + LT_WINDOW);
+                for (uint32_t base = 0; base < prep_max; base += G) {
+                    const uint32_t ci = base + gl;
                     bool active = false;
                     EdgeView k;
                     uint32_t slot = 0, eref = kTrailUnk;
-                    // the first 32 bucket entries are still in the registers of lane (bucket index)
+                    // the first G bucket entries are still in the registers of lane (bucket index)
                     const uint32_t bidx = first_in + ci;
                     uint4 r0;
-                    r0.x = __shfl_sync(kFull, raw0.x, bidx & 31);
-                    r0.y = __shfl_sync(kFull, raw0.y, bidx & 31);
-                    r0.z = __shfl_sync(kFull, raw0.z, bidx & 31);
-                    r0.w = __shfl_sync(kFull, raw0.w, bidx & 31);
+                    r0.x = __shfl_sync(kFull, raw0.x, bidx & (G - 1), G);
+                    r0.y = __shfl_sync(kFull, raw0.y, bidx & (G - 1), G);
+                    r0.z = __shfl_sync(kFull, raw0.z, bidx & (G - 1), G);
+                    r0.w = __shfl_sync(kFull, raw0.w, bidx & (G - 1), G);
                     if (ci < n_cached) {
-                        unpack_edge((bidx < 32) ? r0 : ldg16(A.edges + es + bidx), k);
+                        unpack_edge((bidx < (uint32_t)G) ? r0 : ldg16(A.edges + es + bidx), k);
                         slot = ci;
                         eref = es + bidx;
                         active = true;
                     } else {
                         const int j = (int)(ci - n_cached) + 1;
-                        if (j <= jmax && s_cnt[j] == 0) {
+                        if (on && j <= jmax && s_cnt[j] == 0) {
                             unknown_edge(e - j, e, k);
                             slot = (uint32_t)(kECache + j - 1);
                             active = true;
@@ -436,8 +516,9 @@ __global__ void __launch_bounds__(kBeamWarps * 32, LT_BEAM_MINB) beam_kernel(con
             #pragma unroll
             for (int r = 0; r < KR; ++r) { keep_key[r] = 0; keep_pay[r] = 0; }
 
-            for (uint32_t c0 = 0; c0 < N; c0 += 32) {
-                uint32_t c = c0 + lane;
+            const uint32_t N_max = warp_max<G>(N);
+            for (uint32_t c0 = 0; c0 < N_max; c0 += G) {
+                const uint32_t c = c0 + gl;
                 bool valid = c < N;
                 int j = 0;
                 uint32_t rem = c;
@@ -462,7 +543,7 @@ __global__ void __launch_bounds__(kBeamWarps * 32, LT_BEAM_MINB) beam_kernel(con
                     const uint32_t tj = pmeta & kMetaTagMask;
                     // cache slot of the edge
                     const uint32_t widx = s_gstart[j] - first_in + eidx;     // index among window edges
-                    uint32_t slot = unk_edge ? (uint32_t)(kECache + j - 1) : widx;
+                    const uint32_t slot = unk_edge ? (uint32_t)(kECache + j - 1) : widx;
                     H2 e0, g0;
                     uint32_t emeta, epresent = 0;
                     const bool uncached = !unk_edge && widx >= (uint32_t)kECache;
@@ -548,7 +629,7 @@ __global__ void __launch_bounds__(kBeamWarps * 32, LT_BEAM_MINB) beam_kernel(con
                         acc_T += 1;
                     }
                 }
-                // ---- top-K of (kept so far) U (this chunk): K rounds of warp arg-max ----
+                // ---- top-K of (kept so far) U (this chunk): K rounds of group arg-max ----
                 // Priority on equal keys: kept entries (earlier candidates) by rank, then chunk lanes in order.
                 uint64_t new_key[KR];
                 uint32_t new_pay[KR];
@@ -558,7 +639,12 @@ __global__ void __launch_bounds__(kBeamWarps * 32, LT_BEAM_MINB) beam_kernel(con
                 #pragma unroll
                 for (int r = 0; r < KR; ++r) pool_key[r] = keep_key[r];
                 pool_key[KR] = ckey;
-                for (int round = 0; round < K; ++round) {
+                // rounds needed: min(K, pool size), the same for both groups of the warp
+                uint32_t pool_n = __popc(LT_GBALLOT(ckey != 0));
+                #pragma unroll
+                for (int r = 0; r < KR; ++r) pool_n += __popc(LT_GBALLOT(keep_key[r] != 0));
+                const int rounds = (int)warp_max<G>(pool_n < (uint32_t)K ? pool_n : (uint32_t)K);
+                for (int round = 0; round < rounds; ++round) {
                     // lane-local best: lower pool index wins ties
                     uint64_t best = pool_key[0];
                     int cls = 0;
@@ -566,31 +652,31 @@ __global__ void __launch_bounds__(kBeamWarps * 32, LT_BEAM_MINB) beam_kernel(con
                     for (int r = 1; r <= KR; ++r)
                         if (pool_key[r] > best) { best = pool_key[r]; cls = r; }
                     const uint32_t hi = (uint32_t)(best >> 32), lo = (uint32_t)best;
-                    const uint32_t mhi = __reduce_max_sync(kFull, hi);
-                    if (mhi == 0) break;                                    // pool exhausted
-                    const bool c1 = (hi == mhi);
-                    const uint32_t mlo = __reduce_max_sync(kFull, c1 ? lo : 0u);
+                    const uint32_t mhi = group_max<G>(hi, lane);
+                    const bool c1 = (hi == mhi) && (mhi != 0);              // mhi == 0: this group's pool is exhausted
+                    const uint32_t mlo = group_max<G>(c1 ? lo : 0u, lane);
                     const bool c2 = c1 && (lo == mlo);
                     int win_cls = 0;
                     unsigned wm = 0;
                     #pragma unroll
                     for (int r = 0; r <= KR; ++r) {
-                        unsigned m = __ballot_sync(kFull, c2 && cls == r);
+                        const unsigned m = LT_GBALLOT(c2 && cls == r);
                         if (wm == 0 && m != 0) { wm = m; win_cls = r; }
                     }
-                    const int src = __ffs(wm) - 1;
+                    const bool sel = wm != 0;                               // false: this group's pool is exhausted
+                    const int src = sel ? __ffs(wm) - 1 : lane;             // absolute lane of the winner
                     uint32_t pay_mine = cpay;
                     #pragma unroll
                     for (int r = 0; r < KR; ++r)
                         if (win_cls == r) pay_mine = keep_pay[r];
-                    const uint32_t wpay = __shfl_sync(kFull, pay_mine, src);
+                    const uint32_t wpay = __shfl_sync(kFull, pay_mine, src, G);
                     const uint64_t wkey = ((uint64_t)mhi << 32) | mlo;
-                    if (lane == (round & 31)) {
+                    if (sel && gl == (round % G)) {
                         #pragma unroll
                         for (int r = 0; r < KR; ++r)
-                            if ((round >> 5) == r) { new_key[r] = wkey; new_pay[r] = wpay; }
+                            if ((round / G) == r) { new_key[r] = wkey; new_pay[r] = wpay; }
                     }
-                    if (lane == src) {
+                    if (sel && lane == src) {
                         #pragma unroll
                         for (int r = 0; r <= KR; ++r)
                             if (win_cls == r) pool_key[r] = 0;
@@ -604,10 +690,10 @@ __global__ void __launch_bounds__(kBeamWarps * 32, LT_BEAM_MINB) beam_kernel(con
             int nl = 0;
             #pragma unroll
             for (int r = 0; r < KR; ++r) {
-                const unsigned m = __ballot_sync(kFull, keep_key[r] != 0);
+                const unsigned m = LT_GBALLOT(keep_key[r] != 0);
                 nl += __popc(m);
                 if (keep_key[r] != 0) {
-                    const int rank = r * 32 + lane;
+                    const int rank = r * G + gl;
                     const uint32_t kp = keep_pay[r];
                     const int j = (int)((kp >> 27) & 0xFu);
                     const uint32_t prank = (kp >> 20) & 0x7Fu;
@@ -633,19 +719,19 @@ __global__ void __launch_bounds__(kBeamWarps * 32, LT_BEAM_MINB) beam_kernel(con
                     e_pp[dst] = h2_add(wk1, e_j2[pslot]);
                     e_j2[dst] = h2_mul(k.wk, kM2a, kM2b);
                     e_c1[dst] = k_ctx ? h2_mul(k.mk, kM1a, kM1b) : (j_ctx ? e_c1[pslot] : H2{0, 0});
-                    uint32_t ul = k.len < 8u ? k.len : 8u;
+                    const uint32_t ul = k.len < 8u ? k.len : 8u;
                     e_meta[dst] = k.tag0 | kMetaHasI | ((k_ctx || j_ctx) ? kMetaHasCtx : 0u) | (ul << kMetaUnkLenShift);
                     A.trail[(size_t)(s0 + e - 1) * K + rank] =
                         (uint64_t)eref | ((uint64_t)j << 32) | ((uint64_t)prank << 40);
                 }
             }
-            if (lane == 0) s_nbeam[slot_e] = (uint32_t)nl;
-            acc_B += (lane == 0) ? (unsigned long long)nl : 0ull;
+            if (gl == 0) s_nbeam[slot_e] = (uint32_t)nl;
+            acc_B += (gl == 0) ? (unsigned long long)nl : 0ull;
             __syncwarp();
         }
 
         // ---- best path: matures[0] (tagger.py:78) ----
-        if (lane == 0) {
+        if (gl == 0 && L > 0) {
             A.scores[s] = e_score[(L % kRing) * K + 0];
             int e = L, r = 0, W = 0;
             while (e > 0) {
@@ -675,6 +761,8 @@ __global__ void __launch_bounds__(kBeamWarps * 32, LT_BEAM_MINB) beam_kernel(con
     for (int d = 16; d; d >>= 1) {
         acc_T += __shfl_xor_sync(kFull, acc_T, d);
         acc_F += __shfl_xor_sync(kFull, acc_F, d);
+        acc_B += __shfl_xor_sync(kFull, acc_B, d);
+        acc_W += __shfl_xor_sync(kFull, acc_W, d);
     }
     if (lane == 0) {
         atomicAdd(A.counters + 3, acc_T);

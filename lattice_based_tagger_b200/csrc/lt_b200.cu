@@ -346,6 +346,8 @@ struct lt_batch {
     int32_t lcap = 0;
     int32_t beam = 0;
     int32_t hcap = 128;            // lattice staging capacity per warp (grows on overflow, sticky)
+    int32_t half_warp_max_beam = 0;   // beams up to this size run two sentences per warp (LT_HALF_WARP_MAX_BEAM;
+                                      // measured slower than one sentence per warp at C2, so off by default)
     uint32_t edge_cap = 0;         // edge buffer capacity (grows on overflow, sticky)
     bool edge_cap_fixed = false;   // LT_EDGE_CAP given: start there instead of the size guess (tests)
     int64_t n_edges = 0;
@@ -381,6 +383,7 @@ extern "C" int lt_batch_create(lt_tables* tables, lt_batch** out) {
     for (auto& e : b->ev) CU(cudaEventCreate(&e));
     // debugging / test knobs: tiny initial capacities exercise the grow-and-rerun path
     if (const char* env = getenv("LT_HIT_CAP")) b->hcap = std::max(8, atoi(env));
+    if (const char* env = getenv("LT_HALF_WARP_MAX_BEAM")) b->half_warp_max_beam = atoi(env);
     if (const char* env = getenv("LT_EDGE_CAP")) { b->edge_cap = (uint32_t)std::max(16, atoi(env)); b->edge_cap_fixed = true; }
     *out = b;
     return LT_OK;
@@ -494,11 +497,15 @@ static int launch_beam(lt_batch* b, cudaStream_t st) {
     if (int rc = ensure(b->scores, (size_t)std::max(1, n_sent) * 8)) return rc;
 
     const size_t dense_bytes = ((size_t)t->dev.n_tri * dense_block_bytes(t->dev.n_tags) + 15) & ~(size_t)15;
-    const size_t warp_smem = beam_warp_smem(b->lcap, beam_size, t->dev.n_funcs);
-    if (dense_bytes + warp_smem > kSmemBudget)
+    const size_t group_smem = beam_warp_smem(b->lcap, beam_size, t->dev.n_funcs);
+    // small beams produce ~16 candidates per position: two sentences per warp (groups of 16 lanes)
+    int half = (beam_size <= b->half_warp_max_beam) ? 1 : 0;
+    if (half && dense_bytes + 2 * group_smem > kSmemBudget) half = 0;
+    const int per_warp = half ? 2 : 1;
+    if (dense_bytes + group_smem * per_warp > kSmemBudget)
         return fail(LT_ERR_INVALID, "sentence length %d with beam %d does not fit the beam kernel's shared memory", b->lcap, beam_size);
-    const int warps = (int)std::min<size_t>(kBeamWarps, (kSmemBudget - dense_bytes) / warp_smem);
-    const size_t smem = dense_bytes + warp_smem * warps;
+    const int warps = (int)std::min<size_t>(kBeamWarps, (kSmemBudget - dense_bytes) / (group_smem * per_warp));
+    const size_t smem = dense_bytes + group_smem * per_warp * warps;
 
     unsigned int* ctl = static_cast<unsigned int*>(b->ctl.p);
     BeamArgs A{};
@@ -519,12 +526,13 @@ static int launch_beam(lt_batch* b, cudaStream_t st) {
     A.counters = static_cast<unsigned long long*>(b->counters.p);
     A.queue = ctl + kCtlBeamQueue;
 
-    auto kernel = (beam_size <= 32) ? beam_kernel<1> : beam_kernel<2>;
+    auto kernel = half ? beam_kernel<1, 16> : ((beam_size <= 32) ? beam_kernel<1, 32> : beam_kernel<2, 32>);
     CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, warps * 32, smem));
     per_sm = std::max(1, per_sm);
-    const int64_t want_blocks = ((int64_t)n_sent + warps - 1) / warps;
+    const int64_t per_block = (int64_t)warps * per_warp;
+    const int64_t want_blocks = ((int64_t)n_sent + per_block - 1) / per_block;
     const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(want_blocks, (int64_t)t->sm_count * per_sm));
 
     CU(cudaMemsetAsync(ctl + kCtlBeamQueue, 0, sizeof(unsigned int), st));

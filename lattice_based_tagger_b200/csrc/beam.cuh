@@ -32,6 +32,7 @@ namespace lt {
 constexpr int kRing = LT_WINDOW + 1;
 constexpr int kECache = 24;                   // cached window edges per position (+ 8 unknown spans)
 constexpr int kECacheAll = kECache + LT_WINDOW;
+constexpr int kRoundsMaxBeam = 6;             // beams above this use the sorting-network top-K (one sentence per warp)
 constexpr uint32_t kCtxMask = (1u << LT_TAG_NOUN) | (1u << LT_TAG_ADVERB) | (1u << LT_TAG_ADJECTIVE) | (1u << LT_TAG_VERB);
 
 // entry meta bits
@@ -317,7 +318,7 @@ __device__ __forceinline__ uint32_t group_max(uint32_t x, int lane) {
 // KR = ceil(beam / G) kept entries per lane; G = lanes per sentence (32: one sentence per warp,
 // 16: two sentences per warp — small beams generate about 16 candidates per position, so half a
 // warp per sentence doubles the useful lanes of every phase).
-template <int KR, int G>
+template <int KR, int G, bool SORTNET>   // SORTNET: sorting-network top-K (G == 32, KR == 1), else arg-max rounds
 __global__ void __launch_bounds__(kBeamWarps * 32, LT_BEAM_MINB) beam_kernel(const __grid_constant__ DevTables T, const __grid_constant__ BeamArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
@@ -625,10 +626,51 @@ __global__ void __launch_bounds__(kBeamWarps * 32, LT_BEAM_MINB) beam_kernel(con
                         double newscore = __dadd_rn(pscore, inc);        // Sequence.add, beam.py:115
                         newscore = __dadd_rn(newscore, 0.0);             // -0.0 sorts as 0.0
                         ckey = sortable(newscore);
-                        cpay = (unk_edge ? 0x80000000u : 0u) | ((uint32_t)j << 27) | (prank << 20) | (s_gstart[j] + eidx);
+                        // payload doubles as the generation ordinal: begin ascending (= span descending), parent
+                        // rank ascending, edge order ascending (beam.py:30-48)
+                        cpay = ((uint32_t)(LT_WINDOW - j) << 27) | (prank << 20) | (unk_edge ? 0u : s_gstart[j] + eidx);
                         acc_T += 1;
                     }
                 }
+                if constexpr (SORTNET) {
+                    // ---- top-K by sorting network: sort the chunk (best first), then merge with the kept list ----
+                    // order: larger key first; equal keys: smaller payload (= earlier candidate) first
+                    uint64_t bk = ckey;
+                    uint32_t bp = cpay;
+                    #pragma unroll
+                    for (int size = 2; size <= 32; size <<= 1) {
+                        #pragma unroll
+                        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                            const uint64_t ok = __shfl_xor_sync(kFull, bk, stride);
+                            const uint32_t op = __shfl_xor_sync(kFull, bp, stride);
+                            const bool mine_first = (bk > ok) || (bk == ok && bp < op);
+                            const bool lower = (lane & stride) == 0;
+                            const bool descending = (lane & size) == 0;      // this block sorts best-first
+                            const bool keep_mine = (lower == descending) ? mine_first : !mine_first;
+                            if (!keep_mine) { bk = ok; bp = op; }
+                        }
+                    }
+                    if (c0 == 0) {
+                        keep_key[0] = bk;
+                        keep_pay[0] = bp;
+                    } else {
+                        // kept list is best-first in lanes 0..31; against the reversed chunk the lane-wise
+                        // winners form a bitonic sequence holding the 32 best of the union
+                        const uint64_t rk = __shfl_sync(kFull, bk, 31 - lane);
+                        const uint32_t rp = __shfl_sync(kFull, bp, 31 - lane);
+                        // kept entries are earlier candidates: they win ties
+                        if (rk > keep_key[0]) { keep_key[0] = rk; keep_pay[0] = rp; }
+                        #pragma unroll
+                        for (int stride = 16; stride > 0; stride >>= 1) {
+                            const uint64_t ok = __shfl_xor_sync(kFull, keep_key[0], stride);
+                            const uint32_t op = __shfl_xor_sync(kFull, keep_pay[0], stride);
+                            const bool mine_first = (keep_key[0] > ok) || (keep_key[0] == ok && keep_pay[0] < op);
+                            const bool lower = (lane & stride) == 0;
+                            if (lower != mine_first) { keep_key[0] = ok; keep_pay[0] = op; }
+                        }
+                    }
+                    if (lane >= K) { keep_key[0] = 0; keep_pay[0] = 0; }
+                } else {
                 // ---- top-K of (kept so far) U (this chunk): K rounds of group arg-max ----
                 // Priority on equal keys: kept entries (earlier candidates) by rank, then chunk lanes in order.
                 uint64_t new_key[KR];
@@ -684,6 +726,7 @@ __global__ void __launch_bounds__(kBeamWarps * 32, LT_BEAM_MINB) beam_kernel(con
                 }
                 #pragma unroll
                 for (int r = 0; r < KR; ++r) { keep_key[r] = new_key[r]; keep_pay[r] = new_pay[r]; }
+                }
             }
 
             // ---- 5. survivors -> ring entries + trail ----
@@ -695,9 +738,9 @@ __global__ void __launch_bounds__(kBeamWarps * 32, LT_BEAM_MINB) beam_kernel(con
                 if (keep_key[r] != 0) {
                     const int rank = r * G + gl;
                     const uint32_t kp = keep_pay[r];
-                    const int j = (int)((kp >> 27) & 0xFu);
+                    const int j = LT_WINDOW - (int)((kp >> 27) & 0xFu);
                     const uint32_t prank = (kp >> 20) & 0x7Fu;
-                    const bool unk_edge = (kp >> 31) != 0;
+                    const bool unk_edge = (s_cnt[j] == 0);
                     const int pslot = ((e - j) % kRing) * K + (int)prank;
                     EdgeView k;
                     uint32_t eref = kTrailUnk;

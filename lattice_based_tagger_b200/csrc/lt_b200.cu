@@ -526,7 +526,9 @@ static int launch_beam(lt_batch* b, cudaStream_t st) {
     A.counters = static_cast<unsigned long long*>(b->counters.p);
     A.queue = ctl + kCtlBeamQueue;
 
-    auto kernel = half ? beam_kernel<1, 16> : ((beam_size <= 32) ? beam_kernel<1, 32> : beam_kernel<2, 32>);
+    auto kernel = half ? beam_kernel<1, 16, false>
+                       : (beam_size <= kRoundsMaxBeam ? beam_kernel<1, 32, false>
+                          : (beam_size <= 32 ? beam_kernel<1, 32, true> : beam_kernel<2, 32, false>));
     CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, warps * 32, smem));

@@ -461,6 +461,11 @@ def cpu_baseline(args, cfg, sents, feature_dic, coef, beam, h_poff, h_edges, h_s
     sample = sents[:n_sample]
     dt, results, totals = arm.run(sample)
     arm.close()
+    # one process = one core (the reference itself is single-threaded)
+    solo = CpuArm(args.config, list(feature_dic.keys()), coef, beam, cores=1)
+    n_solo = int(max(32, min(len(sents), rate / arm.cores * 4.0)))
+    solo_dt, _, _ = solo.run(sents[:n_solo])
+    solo.close()
     # parity of the timed CPU sample against the GPU's last end-to-end step
     poff = h_poff.numpy()[:4 * (n + 1)].view(np.int32)
     edges = h_edges.numpy()[:16 * int(poff[n])].view(_native.EDGE_DTYPE)
@@ -480,7 +485,8 @@ def cpu_baseline(args, cfg, sents, feature_dic, coef, beam, h_poff, h_edges, h_s
     return {'cpu_baseline': {'value': len(sample) / dt, 'unit': UNIT, 'cores': arm.cores, 'kind': 'port',
                              'sample': '%d of %d sentences, multiprocessing.Pool(%d) over the pure-Python oracle '
                                        'port of Tagger.tag' % (len(sample), len(sents), arm.cores),
-                             'transitions_per_sec': totals.get('T', 0) / dt},
+                             'transitions_per_sec': totals.get('T', 0) / dt,
+                             'single_core': {'value': n_solo / solo_dt, 'unit': UNIT, 'sample': '%d sentences, 1 process' % n_solo}},
             'parity': {'checked': len(sample), 'mismatches': mismatches,
                        'what': 'segmentation, tags, lemmas and fp64 score bit-exact vs the CPU sample'}}
 

@@ -115,3 +115,24 @@ def test_buffers_grow_and_rerun(monkeypatch):
             continue
         assert [tuple(w) for w in seq.sequences] == want.words
         assert seq.score == want.score
+
+
+def test_trained_weight_format_end_to_end():
+    """Tagged corpus -> scan_features -> trainer weight format -> load_params -> GPU tagger, against
+    the oracle fed with the same objects."""
+    from lattice_based_tagger_b200.features import scan_features
+    from lattice_based_tagger_b200.trainer import load_params
+    pairs = [('너무너무너무 는  아이오아이 의  노래  입니다',
+              '너무너무너무/Noun 는/Josa  아이오아이/Noun 의/Josa  노래/Noun  이/Adjective+ㅂ니다/Eomi'),
+             ('아이오아이 는  공연 을  했다', '아이오아이/Noun 는/Josa  공연/Noun 을/Josa  하/Verb+았다/Eomi')]
+    idx_to_feature, _, counts = scan_features(pairs, pkg.features.SimpleTrigramEncoder(),
+                                              predefined_features={(6, n): 1 for n in range(1, 9)})
+    params = {'idx_to_feature': idx_to_feature, 'coefficient': [0.1 * c for c in counts]}
+    funcs = pkg.beam.BeamScoreFunctions(pkg.beam.RegularizationScore(), load_params(params))
+    dictionary = pkg.dictionary.DemoMorphemeDictionary()
+    tagger = pkg.Tagger(dictionary, score_funcs=funcs)
+    oracle = lo.OracleTagger(dictionary, funcs)
+    for sent in ('너무너무너무는 아이오아이의 노래 입니다', '아이오아이는 공연을 했다', '노래를 했다 우와'):
+        got, want = tagger.tag(sent), oracle.tag(sent, 5)
+        assert [tuple(w) for w in got.sequences] == want.words
+        assert got.score == want.score

@@ -196,11 +196,11 @@ __device__ __noinline__ uint32_t edge_score(const DevTables& T, const unsigned c
         if (k.len == 1 && tk == LT_TAG_NOUN) a = __dadd_rn(a, fn.p[2]);
     } else if (fn.kind == LT_FUNC_MPREF) {
         // score_funcs.py:84-88
-        FKey k0 = feature_key_sum(T.seeds[f][9], feature_head(tk, 0), g0);
-        uint4 s0 = feat_first(T, k0);
+        FKey k0 = feature_key_sum32(T.seeds[f][9], feature_head32(tk, 0), g0);
+        FeatProbe s0 = feat_first(T, k0);
         if (k.tag1 != LT_NO_TAG) {
-            FKey k1 = feature_key_sum(T.seeds[f][9], feature_head(k.tag1, 0), h2_mul(k.m1, kM0a, kM0b));
-            uint4 s1 = feat_first(T, k1);
+            FKey k1 = feature_key_sum32(T.seeds[f][9], feature_head32(k.tag1, 0), h2_mul(k.m1, kM0a, kM0b));
+            FeatProbe s1 = feat_first(T, k1);
             feat_resolve(T, k1, s1, b2);
         }
         feat_resolve(T, k0, s0, a);
@@ -208,17 +208,17 @@ __device__ __noinline__ uint32_t edge_score(const DevTables& T, const unsigned c
         b2 = 0.0;
     } else if (fn.kind == LT_FUNC_WPREF) {
         // score_funcs.py:99-100
-        FKey k0 = feature_key_sum(T.seeds[f][9], feature_head(tk, 0), e0);
-        uint4 s0 = feat_first(T, k0);
+        FKey k0 = feature_key_sum32(T.seeds[f][9], feature_head32(tk, 0), e0);
+        FeatProbe s0 = feat_first(T, k0);
         feat_resolve(T, k0, s0, a);
     } else {
         // templates 4 (wk.len) and 5 (wk.word, wk.tag0, wk.is_l), features/feature.py:100,104
         const DenseView D = dense_view(dense_smem + (size_t)T.func_dense[f] * dense_block_bytes(T.n_tags), T.n_tags);
-        FKey q5 = feature_key_sum(T.seeds[f][5], feature_head(tk, (k.flags & LT_EDGE_IS_L) ? 1u : 0u), e0);
-        uint4 s5 = feat_first(T, q5);
+        FKey q5 = feature_key_sum32(T.seeds[f][5], feature_head32(tk, (k.flags & LT_EDGE_IS_L) ? 1u : 0u), e0);
+        FeatProbe s5 = feat_first(T, q5);
         if (k.len >= (uint32_t)kT4Dense) {
             FKey q4 = feature_key_sum(T.seeds[f][4], feature_head(k.len, 0), H2{0, 0});
-            uint4 s4 = feat_first(T, q4);
+            FeatProbe s4 = feat_first(T, q4);
             if (feat_resolve(T, q4, s4, a)) present |= 1u;
         } else if ((D.m4[k.len >> 5] >> (k.len & 31)) & 1u) {
             a = D.t4[k.len];
@@ -227,6 +227,27 @@ __device__ __noinline__ uint32_t edge_score(const DevTables& T, const unsigned c
         if (feat_resolve(T, q5, s5, b2)) present |= 2u;
     }
     return present;
+}
+
+// numpy's association from eight surviving weights on: rare, so the nine weights are
+// simply gathered again and summed by numpy_order_sum9.
+__device__ __noinline__ double trigram_sum_tree(const DevTables& T, const DenseView& D, int NT, int f, FKey q0, FKey q1,
+                                                FKey q2, FKey q7, FKey q8, uint32_t tj, uint32_t tk, uint32_t epresent,
+                                                double val4, double val5, bool j_unk, uint32_t ul, bool has_i, bool ctx8) {
+    double w[9];
+    uint32_t present = 0;
+    #pragma unroll
+    for (int i = 0; i < 9; ++i) w[i] = 0.0;
+    if (feat_resolve(T, q0, feat_first(T, q0), w[0])) present |= 1u << 0;
+    if (feat_resolve(T, q1, feat_first(T, q1), w[1])) present |= 1u << 1;
+    if (feat_resolve(T, q2, feat_first(T, q2), w[2])) present |= 1u << 2;
+    if ((D.m3[tj] >> tk) & 1u) { w[3] = D.t3[tj * NT + tk]; present |= 1u << 3; }
+    if ((epresent >> (2 * f)) & 1u) { w[4] = val4; present |= 1u << 4; }
+    if ((epresent >> (2 * f + 1)) & 1u) { w[5] = val5; present |= 1u << 5; }
+    if (j_unk && ((D.m6[0] >> ul) & 1u)) { w[6] = D.t6[ul]; present |= 1u << 6; }
+    if (has_i && feat_resolve(T, q7, feat_first(T, q7), w[7])) present |= 1u << 7;
+    if (ctx8 && feat_resolve(T, q8, feat_first(T, q8), w[8])) present |= 1u << 8;
+    return numpy_order_sum9(w, present);
 }
 
 // order-preserving integer image of an fp64 score (larger score -> larger key); 0 is "no candidate"
@@ -538,7 +559,7 @@ __global__ void __launch_bounds__(kBeamWarps * 32, LT_BEAM_MINB) beam_kernel(con
                     const uint32_t cj = s_cnt[j];
                     const bool unk_edge = (cj == 0);
                     const uint32_t nedge = unk_edge ? 1u : cj;
-                    const uint32_t prank = rem / nedge, eidx = rem - prank * nedge;
+                    const uint32_t prank = (nedge == 1u) ? rem : rem / nedge, eidx = rem - prank * nedge;
                     const int pslot = ((e - j) % kRing) * K + (int)prank;
                     const uint32_t pmeta = e_meta[pslot];
                     const uint32_t tj = pmeta & kMetaTagMask;
@@ -586,40 +607,38 @@ __global__ void __launch_bounds__(kBeamWarps * 32, LT_BEAM_MINB) beam_kernel(con
                                 // SimpleTrigramFeatureScore.score (score_funcs.py:137-144)
                                 const DenseView D = dense_view(dense_smem + (size_t)T.func_dense[f] * dense_block_bytes(NT), NT);
                                 acc_F += 6u + (j_unk ? 1u : 0u) + (has_i ? 1u : 0u) + (ctx8 ? 1u : 0u);
-                                const H2 sum0 = h2_add(e0, p1);
-                                FKey q0 = feature_key_sum(T.seeds[f][0], feature_head(tk, 0), sum0);
-                                FKey q1 = feature_key_sum(T.seeds[f][1], feature_head(tk, 0), p1);
-                                FKey q2 = feature_key_sum(T.seeds[f][2], feature_head(tj, tk), e0);
-                                uint4 s0 = feat_first(T, q0);
-                                uint4 s1 = feat_first(T, q1);
-                                uint4 s2 = feat_first(T, q2);
-                                FKey q7, q8;
-                                uint4 s7 = make_uint4(0, 0, 0, 0), s8 = make_uint4(0, 0, 0, 0);
-                                if (has_i) {
-                                    q7 = feature_key_sum(T.seeds[f][7], 0, h2_add(e0, e_pp[pslot]));
-                                    s7 = feat_first(T, q7);
-                                }
-                                if (ctx8) {
-                                    q8 = feature_key_sum(T.seeds[f][8], 0, h2_add(g0, e_c1[pslot]));
-                                    s8 = feat_first(T, q8);
-                                }
-                                double w[9];
-                                uint32_t present = 0;
-                                #pragma unroll
-                                for (int i = 0; i < 9; ++i) w[i] = 0.0;
-                                if (feat_resolve(T, q0, s0, w[0])) present |= 1u << 0;
-                                if (feat_resolve(T, q1, s1, w[1])) present |= 1u << 1;
-                                if (feat_resolve(T, q2, s2, w[2])) present |= 1u << 2;
-                                if ((D.m3[tj] >> tk) & 1u) { w[3] = D.t3[tj * NT + tk]; present |= 1u << 3; }
-                                if ((epresent >> (2 * f)) & 1u) { w[4] = val; present |= 1u << 4; }
-                                if ((epresent >> (2 * f + 1)) & 1u) { w[5] = val5; present |= 1u << 5; }
-                                if (j_unk) {
-                                    const uint32_t ul = (pmeta >> kMetaUnkLenShift) & 0xFu;
-                                    if ((D.m6[0] >> ul) & 1u) { w[6] = D.t6[ul]; present |= 1u << 6; }
-                                }
-                                if (has_i && feat_resolve(T, q7, s7, w[7])) present |= 1u << 7;
-                                if (ctx8 && feat_resolve(T, q8, s8, w[8])) present |= 1u << 8;
-                                val = present ? numpy_order_sum9(w, present) : 0.0;
+                                const H2 pp = has_i ? e_pp[pslot] : H2{0, 0};
+                                const H2 c1v = ctx8 ? e_c1[pslot] : H2{0, 0};
+                                const uint32_t hk = feature_head32(tk, 0);
+                                const FKey q0 = feature_key_sum32(T.seeds[f][0], hk, h2_add(e0, p1));
+                                const FKey q1 = feature_key_sum32(T.seeds[f][1], hk, p1);
+                                const FKey q2 = feature_key_sum32(T.seeds[f][2], feature_head32(tj, tk), e0);
+                                const FKey q7 = feature_key_sum32(T.seeds[f][7], 0u, h2_add(e0, pp));
+                                const FKey q8 = feature_key_sum32(T.seeds[f][8], 0u, h2_add(g0, c1v));
+                                // all first-slot loads in flight before any is consumed
+                                const FeatProbe s0 = feat_first(T, q0);
+                                const FeatProbe s1 = feat_first(T, q1);
+                                const FeatProbe s2 = feat_first(T, q2);
+                                FeatProbe s7, s8;
+                                if (has_i) s7 = feat_first(T, q7);
+                                if (ctx8) s8 = feat_first(T, q8);
+                                // running left-to-right sum = numpy's order while fewer than 8 weights survive
+                                double acc = 0.0, w;
+                                int n = 0;
+                                if (feat_resolve(T, q0, s0, w)) { acc = __dadd_rn(acc, w); ++n; }
+                                if (feat_resolve(T, q1, s1, w)) { acc = __dadd_rn(acc, w); ++n; }
+                                if (feat_resolve(T, q2, s2, w)) { acc = __dadd_rn(acc, w); ++n; }
+                                if ((D.m3[tj] >> tk) & 1u) { acc = __dadd_rn(acc, D.t3[tj * NT + tk]); ++n; }
+                                if ((epresent >> (2 * f)) & 1u) { acc = __dadd_rn(acc, val); ++n; }
+                                if ((epresent >> (2 * f + 1)) & 1u) { acc = __dadd_rn(acc, val5); ++n; }
+                                const uint32_t ul = (pmeta >> kMetaUnkLenShift) & 0xFu;
+                                if (j_unk && ((D.m6[0] >> ul) & 1u)) { acc = __dadd_rn(acc, D.t6[ul]); ++n; }
+                                if (has_i && feat_resolve(T, q7, s7, w)) { acc = __dadd_rn(acc, w); ++n; }
+                                if (ctx8 && feat_resolve(T, q8, s8, w)) { acc = __dadd_rn(acc, w); ++n; }
+                                if (n >= 8)   // numpy switches to an 8-lane tree: redo the gather and add in that order (rare)
+                                    acc = trigram_sum_tree(T, D, NT, f, q0, q1, q2, q7, q8, tj, tk, epresent, val, val5, j_unk, ul,
+                                                           has_i, ctx8);
+                                val = n ? acc : 0.0;
                             }
                             inc = __dadd_rn(inc, val);          // score += f(...), score_funcs.py:51-53
                         }

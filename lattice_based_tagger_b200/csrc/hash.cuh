@@ -106,6 +106,16 @@ LT_HD FKey feature_key_sum(H2 seed, uint64_t head, H2 sum) {
     return k;
 }
 
+// same key for a head that fits 32 bits (tag ids, flags): a 32 x 64 multiply is cheaper on the device
+LT_HD FKey feature_key_sum32(H2 seed, uint32_t head, H2 sum) {
+    FKey k;
+    k.k1 = seed.a + (uint64_t)head * kTa + sum.a;
+    k.k2 = seed.b + (uint64_t)head * kTb + sum.b;
+    if (k.k2 == 0) k.k2 = 1;
+    return k;
+}
+LT_HD uint32_t feature_head32(uint32_t a0, uint32_t a1) { return (a0 << 24) | a1; }   // a0 < 256, a1 < 2^24
+
 LT_HD FKey feature_key(uint32_t kind, uint32_t func, H2 s0, H2 s1, H2 s2, uint32_t a0, uint32_t a1) {
     H2 sum{s0.a * kM0a + s1.a * kM1a + s2.a * kM2a, s0.b * kM0b + s1.b * kM1b + s2.b * kM2b};
     return feature_key_sum(feature_seed(kind, func), feature_head(a0, a1), sum);

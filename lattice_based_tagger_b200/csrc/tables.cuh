@@ -138,11 +138,19 @@ __device__ __forceinline__ RuleRec rule_load(const DevTables& T, uint32_t idx) {
 }
 
 // feature probe, split in two so that callers can put several first-slot loads in flight
-__device__ __forceinline__ uint4 feat_first(const DevTables& T, FKey k) {
-    return ldg16(T.feat + feature_slot(k.k1, T.feat_bits));
+struct FeatProbe {
+    uint4 s;        // first slot
+    uint32_t i;     // its index
+};
+__device__ __forceinline__ FeatProbe feat_first(const DevTables& T, FKey k) {
+    FeatProbe p;
+    p.i = (uint32_t)feature_slot(k.k1, T.feat_bits);
+    p.s = ldg16(T.feat + p.i);
+    return p;
 }
-__device__ __forceinline__ bool feat_resolve(const DevTables& T, FKey k, uint4 s, double& w) {
-    uint64_t i = feature_slot(k.k1, T.feat_bits);
+__device__ __forceinline__ bool feat_resolve(const DevTables& T, FKey k, FeatProbe p, double& w) {
+    uint32_t i = p.i;
+    uint4 s = p.s;
     while (true) {
         uint64_t sfp = (uint64_t)s.x | ((uint64_t)s.y << 32);
         if (sfp == k.k2) {
@@ -150,7 +158,7 @@ __device__ __forceinline__ bool feat_resolve(const DevTables& T, FKey k, uint4 s
             return true;
         }
         if (sfp == 0) return false;
-        i = (i + 1) & T.feat_mask;
+        i = (i + 1) & (uint32_t)T.feat_mask;
         s = ldg16(T.feat + i);
     }
 }

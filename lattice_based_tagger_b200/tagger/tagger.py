@@ -190,8 +190,8 @@ class Tagger:
         n = len(sents)
         n_units = int(offsets[-1])
         dev = torch.device('cuda', self.device)
-        d_text = torch.from_numpy(text.view(np.int16)).to(dev)
-        d_off = torch.from_numpy(offsets).to(dev)
+        d_text = torch.from_numpy(text.view(np.int16).copy()).to(dev)
+        d_off = torch.from_numpy(offsets.copy()).to(dev)
         max_units = int(np.diff(offsets).max()) if n else 0
         stream = torch.cuda.current_stream(dev)
         _native.check(self._lib.lt_lattice(self._batch, ctypes.c_void_p(d_text.data_ptr()),

@@ -63,8 +63,18 @@ def main():
     top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
     blk = sass_rows(report, kernel)
     ix = {h: i for i, h in enumerate(blk['hdr'])}
-    mangled = re.sub(r'[^A-Za-z0-9_]', '', kernel.split('<')[0].split('::')[-1])
-    info = line_info(lib, mangled if '<' not in kernel else mangled)
+    # section name of exactly this instantiation: beam_kernel<(int)1, (int)32, (bool)0> -> beam_kernelILi1ELi32ELb0EE
+    full = blk['name']
+    base_name = re.search(r'(\w+)\s*(<|\()', re.sub(r'^void\s+', '', full).replace('lt::', '')).group(1)
+    mangled = base_name
+    m = re.search(r'<([^>]*)>', full)
+    if m:
+        parts = []
+        for arg in m.group(1).split(','):
+            t, v = re.match(r'\s*\((\w+)\)(-?\d+)', arg).groups()
+            parts.append({'int': 'Li', 'bool': 'Lb', 'unsigned int': 'Lj'}.get(t, 'Li') + v + 'E')
+        mangled = base_name + 'I' + ''.join(parts) + 'E'
+    info = line_info(lib, mangled)
     base = int(blk['rows'][0][ix['Address']], 16) if blk['rows'][0][ix['Address']].startswith('0x') else int(blk['rows'][0][ix['Address']])
     by_line = collections.defaultdict(lambda: [0.0, 0.0])
     tot_i = tot_s = 0.0

@@ -136,3 +136,70 @@ def test_trained_weight_format_end_to_end():
         got, want = tagger.tag(sent), oracle.tag(sent, 5)
         assert [tuple(w) for w in got.sequences] == want.words
         assert got.score == want.score
+
+
+def test_edge_cases_against_oracle():
+    """Inputs the reference treats specially: blank sentences, repeated / leading / trailing spaces,
+    a dictionary entry longer than the beam window, a dictionary without stand-alone tags
+    (MorphemeLookup.max_len = 0 -> the sub-word scan is unbounded, lookup.py:229-230), single
+    syllables, and a long sentence."""
+    tag_to_morphs = {
+        'Josa': {'는', '을', '가'}, 'Noun': {'가나다라마바사아자차', '가', '나다', '라마'},
+        'Eomi': {'다', 'ㄴ다', '았다'}, 'Verb': {'하', '가'}, 'Adjective': {'나'},
+    }
+    rules = {'한': (('하', 'ㄴ'),), '갔': (('가', '았'),), '했다': (('하', '았다'),)}
+    dictionary = pkg.dictionary.MorphemeDictionary(tag_to_morphs, rules)
+    funcs = pkg.beam.BeamScoreFunctions(pkg.beam.RegularizationScore(-0.3, 0.4, -0.1))
+    sents = ['', ' ', '   ', '가', ' 가 ', '가  나다', '가나다라마바사아자차', '가나다라마바사아자차는 갔다', '한다 했다 갔다',
+             '나다라마가는' * 40, '가 ' * 100, 'x가나다라마y']
+    tagger = pkg.Tagger(dictionary, score_funcs=funcs)
+    oracle = lo.OracleTagger(dictionary, funcs)
+    for k in (1, 5, 40):
+        got = tagger.tag_batch(sents, beam_size=k, errors='none')
+        for sent, seq in zip(sents, got):
+            try:
+                want = oracle.tag(sent, k)
+            except IndexError:
+                assert seq is None, repr(sent)
+                continue
+            assert [tuple(w) for w in seq.sequences] == want.words, (repr(sent), k)
+            assert seq.score == want.score
+    # no stand-alone tag, no predicate tag: max_len = 0
+    only = pkg.dictionary.MorphemeDictionary({'Josa': {'는', '가'}, 'Eomi': {'다'}, 'Pronoun': {'나', '너는'}}, {})
+    tagger2 = pkg.Tagger(only, score_funcs=funcs)
+    oracle2 = lo.OracleTagger(only, funcs)
+    assert tagger2.eojeol_lookup.max_len == 0
+    for sent in ['나는 너는', '가나는다', '너는나']:
+        words, _ = tagger2.lattice_batch([sent])[0]
+        assert [tuple(w) for w in words[1:-1]] == _lattice_key(oracle2.lattice(sent))
+        try:
+            want = oracle2.tag(sent)
+        except IndexError:
+            with pytest.raises(IndexError):
+                tagger2.tag(sent)
+            continue
+        assert [tuple(w) for w in tagger2.tag(sent).sequences] == want.words
+
+
+def test_rejected_inputs():
+    dictionary = pkg.dictionary.DemoMorphemeDictionary()
+    funcs = pkg.beam.BeamScoreFunctions(pkg.beam.RegularizationScore())
+    tagger = pkg.Tagger(dictionary, score_funcs=funcs)
+    with pytest.raises(ValueError):
+        tagger.tag('노래 \U0001F600')                       # outside the BMP
+    with pytest.raises(ValueError):
+        tagger.tag_batch(['노래'], beam_size=65)
+    with pytest.raises(TypeError):
+        pkg.Tagger(dictionary, score_funcs=None).tag('노래')
+    import numpy as np
+    enc = pkg.features.SimpleTrigramEncoder({(4, 1): 0})
+    with pytest.raises(ValueError):
+        pkg.Tagger(dictionary, score_funcs=pkg.beam.BeamScoreFunctions(
+            pkg.beam.SimpleTrigramFeatureScore(enc, np.zeros(1, dtype=np.float32))))
+
+    class Custom(pkg.beam.BeamScoreFunction):
+        pass
+    with pytest.raises(ValueError):
+        pkg.Tagger(dictionary, score_funcs=pkg.beam.BeamScoreFunctions(Custom()))
+    with pytest.raises(ValueError):
+        pkg.Tagger(object(), score_funcs=funcs)              # not a morpheme dictionary

@@ -58,6 +58,7 @@ struct BeamArgs {
     double* scores;             // [n_sent]
     unsigned long long* counters;   // [3]=T [4]=F [5]=Bk [6]=W
     unsigned int* queue;
+    const uint32_t* order;      // queue position -> sentence index (longest first), or nullptr
 };
 
 // per-edge cache entry (shared memory, struct of arrays)
@@ -398,6 +399,7 @@ __global__ void __launch_bounds__(kBeamWarps * 32, LT_BEAM_MINB) beam_kernel(con
         if (s >= (unsigned)A.n_sent) break;
         s += (unsigned)(lane / G);
         const bool have = s < (unsigned)A.n_sent;
+        if (have && A.order) s = __ldg(A.order + s);
         const int s0 = have ? __ldg(A.sent_off + s) : 0, s1 = have ? __ldg(A.sent_off + s + 1) : 0;
         const int st = have ? __ldg(A.status + s) : LT_SENT_BAD_SPACE;
         // ---- stage syllables, prefix hashes and the sentence's CSR row ----

@@ -56,6 +56,7 @@ struct LatticeArgs {
     int32_t* status;            // [n_sent]
     unsigned long long* counters;   // [0]=L [1]=P [2]=E
     unsigned int* queue;        // work-queue cursor
+    const uint32_t* order;      // queue position -> sentence index (longest first), or nullptr
 };
 
 __host__ __device__ inline size_t lattice_warp_smem(int lcap, int hcap, int max_str) {
@@ -410,6 +411,7 @@ __global__ void __launch_bounds__(kLatWarps * 32, LT_LAT_MINB) lattice_kernel(co
         if (lane == 0) s = atomicAdd(A.queue, 1u);
         s = __shfl_sync(kFull, s, 0);
         if (s >= (unsigned)A.n_sent) break;
+        if (A.order) s = __ldg(A.order + s);
         const int s0 = __ldg(A.sent_off + s), s1 = __ldg(A.sent_off + s + 1);
         int n_eoj;
         bool bad;

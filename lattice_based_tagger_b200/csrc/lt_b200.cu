@@ -337,7 +337,7 @@ struct lt_batch {
     // inputs (host entry point) and per-unit / per-sentence arrays
     DevBuf text, sent_off, pos, scan_tmp;
     DevBuf sent_len, sent_edges, status, path_len, path_off, scores;
-    DevBuf edges, trail, path_tmp, path_out, counters, ctl;
+    DevBuf edges, trail, path_tmp, path_out, counters, ctl, order;
     const uint16_t* d_text = nullptr;
     const int32_t* d_sent_off = nullptr;
     int32_t n_sent = 0;
@@ -346,6 +346,7 @@ struct lt_batch {
     int32_t lcap = 0;
     int32_t beam = 0;
     int32_t hcap = 128;            // lattice staging capacity per warp (grows on overflow, sticky)
+    bool sort_by_length = true;    // persistent warps pull the longest sentences first (LT_SORT_BY_LENGTH=0 disables)
     int32_t half_warp_max_beam = 0;   // beams up to this size run two sentences per warp (LT_HALF_WARP_MAX_BEAM;
                                       // measured slower than one sentence per warp at C2, so off by default)
     uint32_t edge_cap = 0;         // edge buffer capacity (grows on overflow, sticky)
@@ -383,6 +384,7 @@ extern "C" int lt_batch_create(lt_tables* tables, lt_batch** out) {
     for (auto& e : b->ev) CU(cudaEventCreate(&e));
     // debugging / test knobs: tiny initial capacities exercise the grow-and-rerun path
     if (const char* env = getenv("LT_HIT_CAP")) b->hcap = std::max(8, atoi(env));
+    if (const char* env = getenv("LT_SORT_BY_LENGTH")) b->sort_by_length = atoi(env) != 0;
     if (const char* env = getenv("LT_HALF_WARP_MAX_BEAM")) b->half_warp_max_beam = atoi(env);
     if (const char* env = getenv("LT_EDGE_CAP")) { b->edge_cap = (uint32_t)std::max(16, atoi(env)); b->edge_cap_fixed = true; }
     *out = b;
@@ -394,7 +396,7 @@ extern "C" void lt_batch_destroy(lt_batch* b) {
     cudaSetDevice(b->tables->device);
     DevBuf* bufs[] = {&b->text, &b->sent_off, &b->pos, &b->scan_tmp, &b->sent_len, &b->sent_edges, &b->status,
                       &b->path_len, &b->path_off, &b->scores, &b->edges, &b->trail, &b->path_tmp, &b->path_out,
-                      &b->counters, &b->ctl};
+                      &b->counters, &b->ctl, &b->order};
     for (DevBuf* x : bufs)
         if (x->p) cudaFree(x->p);
     for (auto& e : b->ev)
@@ -464,6 +466,13 @@ static int launch_lattice(lt_batch* b, cudaStream_t st) {
     A.status = static_cast<int32_t*>(b->status.p);
     A.counters = static_cast<unsigned long long*>(b->counters.p);
     A.queue = ctl + kCtlLatticeQueue;
+    A.order = nullptr;
+    if (b->sort_by_length && n_sent > 1) {
+        if (int rc = ensure(b->order, (size_t)n_sent * 4)) return rc;
+        length_order<<<1, 1024, 0, st>>>(b->d_sent_off, n_sent, static_cast<uint32_t*>(b->order.p));
+        CU(cudaGetLastError());
+        A.order = static_cast<const uint32_t*>(b->order.p);
+    }
 
     const size_t smem = warp_smem * warps;
     CU(cudaFuncSetAttribute(lattice_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -525,6 +534,7 @@ static int launch_beam(lt_batch* b, cudaStream_t st) {
     A.scores = static_cast<double*>(b->scores.p);
     A.counters = static_cast<unsigned long long*>(b->counters.p);
     A.queue = ctl + kCtlBeamQueue;
+    A.order = (b->sort_by_length && n_sent > 1) ? static_cast<const uint32_t*>(b->order.p) : nullptr;
 
     auto kernel = half ? beam_kernel<1, 16, false>
                        : (beam_size <= kRoundsMaxBeam ? beam_kernel<1, 32, false>

@@ -88,6 +88,43 @@ __global__ void __launch_bounds__(kScanThreads) scan_apply(const uint32_t* __res
     }
 }
 
+// Work order: sentence indices sorted by raw length, longest first, so that the persistent warps of
+// the lattice / beam kernels pull the expensive sentences early and the launch tail stays short.
+// One CTA: histogram of lengths (clamped), descending scan, scatter.  The order inside a length
+// bucket is arbitrary (atomics); results do not depend on it.
+constexpr int kOrderBins = 1024;
+__global__ void __launch_bounds__(1024) length_order(const int32_t* __restrict__ sent_off, int32_t n_sent,
+                                                     uint32_t* __restrict__ order) {
+    __shared__ uint32_t bins[kOrderBins];
+    for (int i = threadIdx.x; i < kOrderBins; i += blockDim.x) bins[i] = 0;
+    __syncthreads();
+    for (int s = threadIdx.x; s < n_sent; s += blockDim.x) {
+        int len = sent_off[s + 1] - sent_off[s];
+        len = len < 0 ? 0 : (len >= kOrderBins ? kOrderBins - 1 : len);
+        atomicAdd(&bins[kOrderBins - 1 - len], 1u);          // bin 0 = longest
+    }
+    __syncthreads();
+    // exclusive scan of 1024 bins by 1024 threads (Hillis-Steele in shared memory)
+    __shared__ uint32_t tmp[kOrderBins];
+    const int t = threadIdx.x;
+    uint32_t v = (t < kOrderBins) ? bins[t] : 0u;
+    tmp[t] = v;
+    __syncthreads();
+    for (int d = 1; d < kOrderBins; d <<= 1) {
+        uint32_t add = (t >= d) ? tmp[t - d] : 0u;
+        __syncthreads();
+        tmp[t] += add;
+        __syncthreads();
+    }
+    bins[t] = tmp[t] - v;           // start of every bin
+    __syncthreads();
+    for (int s = threadIdx.x; s < n_sent; s += blockDim.x) {
+        int len = sent_off[s + 1] - sent_off[s];
+        len = len < 0 ? 0 : (len >= kOrderBins ? kOrderBins - 1 : len);
+        order[atomicAdd(&bins[kOrderBins - 1 - len], 1u)] = (uint32_t)s;
+    }
+}
+
 // best paths: reversed per-sentence scratch -> contiguous forward order
 __global__ void pack_paths(const lt_edge* __restrict__ tmp, const int32_t* __restrict__ sent_off,
                            const uint32_t* __restrict__ path_off, int32_t n_sent, lt_edge* __restrict__ out) {

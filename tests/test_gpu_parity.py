@@ -77,6 +77,9 @@ def test_error_behaviour():
         tagger.tag('가나다라')                      # no dictionary hit at all
     empty = tagger.tag('')
     assert [w.word for w in empty.sequences] == ['BOS', 'EOS'] and empty.score == 0
+    assert tagger.tag_batch([]) == []
+    assert [len(s.sequences) for s in tagger.tag_batch(['', ' ', ''])] == [2, 2, 2]
+    assert tagger.lattice_batch([]) == []
     with pytest.raises(ValueError):
         tagger.tag('노래\t입니다')
     with pytest.raises(ValueError):

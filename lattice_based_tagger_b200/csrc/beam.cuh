@@ -763,28 +763,45 @@ __global__ void __launch_bounds__(kBeamWarps * 32, LT_BEAM_MINB) beam_kernel(con
                     const uint32_t prank = (kp >> 20) & 0x7Fu;
                     const bool unk_edge = (s_cnt[j] == 0);
                     const int pslot = ((e - j) % kRing) * K + (int)prank;
-                    EdgeView k;
-                    uint32_t eref = kTrailUnk;
-                    if (unk_edge) {
-                        unknown_edge(e - j, e, k);
+                    // the survivor's edge was prepared for this position: its word / morph products with M0
+                    // are in the cache, and x * M0 -> x * M1 is one multiplication by M1 / M0
+                    const uint32_t widx = (kp & 0xFFFFFu) - first_in;
+                    const bool cached = unk_edge || widx < (uint32_t)kECache;
+                    H2 wk1, wk2, mk1;
+                    uint32_t tag0, len, eref = kTrailUnk;
+                    if (cached) {
+                        const uint32_t cslot = unk_edge ? (uint32_t)(kECache + j - 1) : widx;
+                        const H2 e0 = C.e0[cslot], g0 = C.g0[cslot];
+                        const uint32_t em = C.meta[cslot];
+                        tag0 = em & 0xFFu;
+                        len = (em >> 8) & 0xFFFFu;
+                        eref = C.eref[cslot];
+                        wk1 = h2_mul(e0, kM1over0a, kM1over0b);
+                        wk2 = h2_mul(e0, kM2over0a, kM2over0b);
+                        mk1 = h2_mul(g0, kM1over0a, kM1over0b);
                     } else {
+                        EdgeView k;
                         eref = es + (kp & 0xFFFFFu);
                         unpack_edge(ldg16(A.edges + eref), k);
+                        edge_hashes(T, v, k, false);
+                        tag0 = k.tag0;
+                        len = k.len;
+                        wk1 = h2_mul(k.wk, kM1a, kM1b);
+                        wk2 = h2_mul(k.wk, kM2a, kM2b);
+                        mk1 = h2_mul(k.mk, kM1a, kM1b);
                     }
-                    edge_hashes(T, v, k, false);
                     const uint32_t pmeta = e_meta[pslot];
                     const uint32_t tj = pmeta & kMetaTagMask;
-                    const bool k_ctx = (k.tag0 < 32) && ((kCtxMask >> k.tag0) & 1u);
+                    const bool k_ctx = (tag0 < 32) && ((kCtxMask >> tag0) & 1u);
                     const bool j_ctx = (tj < 32) && ((kCtxMask >> tj) & 1u);
                     const int dst = slot_e * K + rank;
-                    const H2 wk1 = h2_mul(k.wk, kM1a, kM1b);
                     e_score[dst] = unsortable(keep_key[r]);
                     e_p1[dst] = wk1;
                     e_pp[dst] = h2_add(wk1, e_j2[pslot]);
-                    e_j2[dst] = h2_mul(k.wk, kM2a, kM2b);
-                    e_c1[dst] = k_ctx ? h2_mul(k.mk, kM1a, kM1b) : (j_ctx ? e_c1[pslot] : H2{0, 0});
-                    const uint32_t ul = k.len < 8u ? k.len : 8u;
-                    e_meta[dst] = k.tag0 | kMetaHasI | ((k_ctx || j_ctx) ? kMetaHasCtx : 0u) | (ul << kMetaUnkLenShift);
+                    e_j2[dst] = wk2;
+                    e_c1[dst] = k_ctx ? mk1 : (j_ctx ? e_c1[pslot] : H2{0, 0});
+                    const uint32_t ul = len < 8u ? len : 8u;
+                    e_meta[dst] = tag0 | kMetaHasI | ((k_ctx || j_ctx) ? kMetaHasCtx : 0u) | (ul << kMetaUnkLenShift);
                     A.trail[(size_t)(s0 + e - 1) * K + rank] =
                         (uint64_t)eref | ((uint64_t)j << 32) | ((uint64_t)prank << 40);
                 }

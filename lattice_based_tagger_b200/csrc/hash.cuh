@@ -87,6 +87,17 @@ constexpr uint64_t kTa = 0x8CB92BA72F3D8DD7ull, kTb = 0xA0761D6478BD642Full;
 constexpr uint64_t kSlotMul = 0x9E3779B97F4A7C15ull;
 
 LT_HD H2 h2_mul(H2 h, uint64_t ma, uint64_t mb) { return H2{h.a * ma, h.b * mb}; }
+
+// inverse of an odd number modulo 2^64 (Newton iteration): the slot multipliers are odd, so a product
+// h * M0 can be turned into h * M1 by one multiplication with M1 / M0
+constexpr uint64_t inv64(uint64_t a) {
+    uint64_t x = a;                     // correct to 3 bits
+    for (int i = 0; i < 6; ++i) x *= 2 - a * x;
+    return x;
+}
+constexpr uint64_t kM1over0a = kM1a * inv64(kM0a), kM1over0b = kM1b * inv64(kM0b);
+constexpr uint64_t kM2over0a = kM2a * inv64(kM0a), kM2over0b = kM2b * inv64(kM0b);
+static_assert(kM0a * inv64(kM0a) == 1 && kM0b * inv64(kM0b) == 1, "inv64");
 LT_HD H2 h2_add(H2 x, H2 y) { return H2{x.a + y.a, x.b + y.b}; }
 
 LT_HD H2 feature_seed(uint32_t kind, uint32_t func) {

@@ -30,9 +30,11 @@
 namespace lt {
 
 constexpr int kRing = LT_WINDOW + 1;
-constexpr int kECache = 24;                   // cached window edges per position (+ 8 unknown spans)
-constexpr int kECacheAll = kECache + LT_WINDOW;
-constexpr int kRoundsMaxBeam = 6;             // beams above this use the sorting-network top-K (one sentence per warp)
+constexpr int kEdgeRing = 64;                 // prepared dictionary edges: ring over the global edge index
+constexpr int kBucketCached = 32;             // bucket-local edge indices below this are served from the ring
+constexpr int kUnkBlock = 4;                  // end positions whose unknown words are prepared together
+constexpr int kCacheSlots = kEdgeRing + kUnkBlock * LT_WINDOW;
+constexpr int kRankMaxBeam = 16;              // beams up to this size select by rank counting, larger ones by sorting network
 constexpr uint32_t kCtxMask = (1u << LT_TAG_NOUN) | (1u << LT_TAG_ADVERB) | (1u << LT_TAG_ADJECTIVE) | (1u << LT_TAG_VERB);
 
 // entry meta bits
@@ -61,30 +63,35 @@ struct BeamArgs {
     const uint32_t* order;      // queue position -> sentence index (longest first), or nullptr
 };
 
-// per-edge cache entry (shared memory, struct of arrays)
+// Prepared edges (shared memory, struct of arrays).  Slots [0, kEdgeRing): dictionary edges at
+// (global edge index % kEdgeRing); slots kEdgeRing + ((e - 1) % kUnkBlock) * 8 + (span - 1): the
+// unknown word of (end position e, span).
 struct EdgeCache {
     H2* e0;            // word hash   * M0
     H2* g0;            // morph0 hash * M0
-    double* kval;      // kRingVals doubles per edge: score-program values that depend on the edge only
+    double* kval;      // 2 doubles per scorer: score-program values that depend on the edge only
     uint32_t* meta;    // tag0 | len << 8 (16 bits) | flags << 24
-    uint32_t* eref;    // global edge index (kTrailUnk for unknown words)
-    uint32_t* present; // bit f*2: template 4 present, bit f*2+1: template 5 present (per scorer f)
+    uint32_t* present; // bit f*2: template 4 present, bit f*2+1: template 5 present (scorer f); bits 24..31: min(255, e - b)
 };
 
 // doubles per edge in kval (stride 2 * n_funcs): for scorer f: [2f] = REG / MPREF / WPREF value or
 // template-4 weight, [2f+1] = template-5 weight
 
 __host__ __device__ inline size_t beam_warp_smem(int lcap, int beam, int n_funcs) {
-    size_t units = (size_t)lcap + 8;
+    const size_t units = (size_t)lcap + 8;
+    const size_t nf = (size_t)(n_funcs > 0 ? n_funcs : 1);
     size_t bytes = units * 8 * 2;                          // ha, hb
     bytes += units * 8;                                    // pos (uint2)
     bytes += (size_t)kRing * beam * (8 + 64);              // score, p1, pp, j2, c1
-    bytes += (size_t)kECacheAll * (16 + 16 + 16 * (n_funcs > 0 ? n_funcs : 1));   // e0, g0, kval
+    bytes += (size_t)kCacheSlots * (16 + 16 + 16 * nf);    // e0, g0, kval
+    bytes += 32 * 8;                                       // selected keys by rank
     bytes += units * 2;                                    // chars
     bytes = (bytes + 7) & ~(size_t)7;
     bytes += (size_t)kRing * beam * 4;                     // meta
-    bytes += (size_t)kECacheAll * 12;                      // cache meta, eref, present
-    bytes += 64 * 4;                                       // per-span tables + ring sizes
+    bytes += (size_t)kCacheSlots * 8;                      // cache meta, present
+    bytes += 6 * 16 * 4;                                   // per-span tables + ring sizes
+    bytes += 2 * 64 * 4 + 32 * 4;                          // selection pool (high / low words), selected payloads
+    bytes += (size_t)kRing * beam;                         // ranks of the entries that do not end in an unknown word
     return (bytes + 15) & ~(size_t)15;
 }
 
@@ -264,39 +271,38 @@ __device__ __forceinline__ double unsortable(uint64_t key) {
 #ifndef LT_BEAM_MINB
 #define LT_BEAM_MINB 4
 #endif
+#ifndef LT_PROBE_SPLIT
+#define LT_PROBE_SPLIT 1       // 1: the loads of templates 7 and 8 are issued after templates 0..2 are consumed
+#endif
 constexpr int kBeamWarps = 4;                 // warps per CTA of the beam kernel
 
-// Prefix hashes by a scan over a GROUP of G lanes: H[0] = 0, H[i+1] = H[i] * B + (c_i + 1).
-template <int G>
-__device__ __forceinline__ void prefix_hashes_group(const uint16_t* ch, int L, int Lmax, int gl, unsigned gmask,
-                                                    uint64_t* ha, uint64_t* hb) {
+// Prefix hashes of the staged syllables by warp scan: H[0] = 0, H[i+1] = H[i] * B + (c_i + 1).
+__device__ __forceinline__ void beam_prefix_hashes(const uint16_t* ch, int L, int lane, uint64_t* ha, uint64_t* hb) {
     H2 carry{0, 0};
-    if (gl == 0) {
+    if (lane == 0) {
         ha[0] = 0;
         hb[0] = 0;
     }
     constexpr uint64_t A1 = kBaseA, A2 = A1 * A1, A4 = A2 * A2, A8 = A4 * A4, A16 = A8 * A8;
     constexpr uint64_t B1 = kBaseB, B2 = B1 * B1, B4 = B2 * B2, B8 = B4 * B4, B16 = B8 * B8;
-    for (int base = 0; base < Lmax; base += G) {
-        const int i = base + gl;
+    for (int base = 0; base < L; base += 32) {
+        const int i = base + lane;
         const uint64_t v = (i < L) ? (uint64_t)ch[i] + 1u : 0u;
         uint64_t sa = v, sb = v, ta, tb;
-        ta = __shfl_up_sync(0xFFFFFFFFu, sa, 1, G);  tb = __shfl_up_sync(0xFFFFFFFFu, sb, 1, G);
-        if (gl >= 1)  { sa += ta * A1;  sb += tb * B1; }
-        ta = __shfl_up_sync(0xFFFFFFFFu, sa, 2, G);  tb = __shfl_up_sync(0xFFFFFFFFu, sb, 2, G);
-        if (gl >= 2)  { sa += ta * A2;  sb += tb * B2; }
-        ta = __shfl_up_sync(0xFFFFFFFFu, sa, 4, G);  tb = __shfl_up_sync(0xFFFFFFFFu, sb, 4, G);
-        if (gl >= 4)  { sa += ta * A4;  sb += tb * B4; }
-        ta = __shfl_up_sync(0xFFFFFFFFu, sa, 8, G);  tb = __shfl_up_sync(0xFFFFFFFFu, sb, 8, G);
-        if (gl >= 8)  { sa += ta * A8;  sb += tb * B8; }
-        if (G == 32) {
-            ta = __shfl_up_sync(0xFFFFFFFFu, sa, 16, G); tb = __shfl_up_sync(0xFFFFFFFFu, sb, 16, G);
-            if (gl >= 16) { sa += ta * A16; sb += tb * B16; }
-        }
-        uint64_t pa = 1, pb = 1;   // B^(gl+1)
+        ta = __shfl_up_sync(kFull, sa, 1);  tb = __shfl_up_sync(kFull, sb, 1);
+        if (lane >= 1)  { sa += ta * A1;  sb += tb * B1; }
+        ta = __shfl_up_sync(kFull, sa, 2);  tb = __shfl_up_sync(kFull, sb, 2);
+        if (lane >= 2)  { sa += ta * A2;  sb += tb * B2; }
+        ta = __shfl_up_sync(kFull, sa, 4);  tb = __shfl_up_sync(kFull, sb, 4);
+        if (lane >= 4)  { sa += ta * A4;  sb += tb * B4; }
+        ta = __shfl_up_sync(kFull, sa, 8);  tb = __shfl_up_sync(kFull, sb, 8);
+        if (lane >= 8)  { sa += ta * A8;  sb += tb * B8; }
+        ta = __shfl_up_sync(kFull, sa, 16); tb = __shfl_up_sync(kFull, sb, 16);
+        if (lane >= 16) { sa += ta * A16; sb += tb * B16; }
+        uint64_t pa = 1, pb = 1;   // B^(lane+1)
         {
             uint64_t xa = A1, xb = B1;
-            const int k = gl + 1;
+            const int k = lane + 1;
             #pragma unroll
             for (int bit = 0; bit < 6; ++bit) {
                 if (k & (1 << bit)) { pa *= xa; pb *= xb; }
@@ -308,46 +314,43 @@ __device__ __forceinline__ void prefix_hashes_group(const uint16_t* ch, int L, i
             ha[i + 1] = outa;
             hb[i + 1] = outb;
         }
-        carry.a = __shfl_sync(0xFFFFFFFFu, outa, G - 1, G);
-        carry.b = __shfl_sync(0xFFFFFFFFu, outb, G - 1, G);
+        carry.a = __shfl_sync(kFull, outa, 31);
+        carry.b = __shfl_sync(kFull, outb, 31);
     }
     __syncwarp();
 }
 
-// Maximum of a group-uniform value over the groups of a warp, so that both groups run the same
-// number of loop iterations and stay converged (lock-step) — otherwise two half-warp groups would
-// simply serialise.
-template <int G>
-__device__ __forceinline__ uint32_t warp_max(uint32_t x) {
-    if (G == 32) return x;
-    const uint32_t y = __shfl_xor_sync(0xFFFFFFFFu, x, 16);
-    return x > y ? x : y;
+// Edge prep: hash products and the edge-only part of the score program into cache slot `slot`.
+__device__ __forceinline__ void prep_edge(const DevTables& T, const SentView& v, const unsigned char* dense_smem,
+                                          EdgeView& k, bool need_m1, int nf, int kvs, const EdgeCache& C, uint32_t slot) {
+    edge_hashes(T, v, k, need_m1);
+    const H2 e0 = h2_mul(k.wk, kM0a, kM0b), g0 = h2_mul(k.mk, kM0a, kM0b);
+    uint32_t present = 0;
+    #pragma unroll 1
+    for (int f = 0; f < nf; ++f) {
+        double a, b2;
+        present |= edge_score(T, dense_smem, k, e0, g0, f, a, b2) << (2 * f);
+        C.kval[slot * kvs + 2 * f] = a;
+        C.kval[slot * kvs + 2 * f + 1] = b2;
+    }
+    C.e0[slot] = e0;
+    C.g0[slot] = g0;
+    C.meta[slot] = k.tag0 | (k.len << 8) | (k.flags << 24);
+    const uint32_t span = (uint32_t)(k.e - k.b);
+    C.present[slot] = present | ((span < 255u ? span : 255u) << 24);
 }
 
-// Collectives always name the full warp: a *_sync with a half-warp mask makes the hardware treat
-// the two halves as separate convergence groups, which then run one after the other.
-template <int G>
-__device__ __forceinline__ uint32_t group_max(uint32_t x, int lane) {
-    if (G == 32) return __reduce_max_sync(0xFFFFFFFFu, x);
-    const bool hi_half = lane >= 16;
-    const uint32_t m0 = __reduce_max_sync(0xFFFFFFFFu, hi_half ? 0u : x);
-    const uint32_t m1 = __reduce_max_sync(0xFFFFFFFFu, hi_half ? x : 0u);
-    return hi_half ? m1 : m0;
-}
-// ballot restricted to the caller's group, bits at absolute lane positions
-#define LT_GBALLOT(pred) (__ballot_sync(0xFFFFFFFFu, (pred)) & gmask)
-
-// KR = ceil(beam / G) kept entries per lane; G = lanes per sentence (32: one sentence per warp,
-// 16: two sentences per warp — small beams generate about 16 candidates per position, so half a
-// warp per sentence doubles the useful lanes of every phase).
-template <int KR, int G, bool SORTNET>   // SORTNET: sorting-network top-K (G == 32, KR == 1), else arg-max rounds
+// MODE selects the top-K of a position's candidates:
+//   2  rank by counting (beam <= kRankMaxBeam): every candidate counts the pool entries that beat it
+//   1  32-lane bitonic sorting network per chunk + bitonic merge with the kept list (beam <= 32)
+//   0  rounds of warp arg-max with two kept entries per lane (beam 33..64)
+template <int MODE>
 __global__ void __launch_bounds__(kBeamWarps * 32, LT_BEAM_MINB) beam_kernel(const __grid_constant__ DevTables T, const __grid_constant__ BeamArgs A) {
+    constexpr int KR = (MODE == 0) ? 2 : 1;      // kept entries per lane
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
-    const int gl = lane & (G - 1);                       // lane within the sentence's group
-    const int gshift = lane & ~(G - 1);                  // first lane of the group
-    const unsigned gmask = (G == 32) ? 0xFFFFFFFFu : (((1u << G) - 1u) << gshift);
-    const int group = (threadIdx.x >> 5) * (32 / G) + (lane / G);
+    const int warp = threadIdx.x >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
     const int K = A.beam;
     const int NT = T.n_tags;
 
@@ -360,7 +363,7 @@ __global__ void __launch_bounds__(kBeamWarps * 32, LT_BEAM_MINB) beam_kernel(con
     if (A.flags[kFlagEdgeOverflow] | A.flags[kFlagStageOverflow]) return;   // lattice incomplete: the host grows the buffer and reruns
 
     const size_t units = (size_t)A.lcap + 8;
-    unsigned char* wbase = smem_raw + dense_bytes + (size_t)group * beam_warp_smem(A.lcap, K, T.n_funcs);
+    unsigned char* wbase = smem_raw + dense_bytes + (size_t)warp * beam_warp_smem(A.lcap, K, T.n_funcs);
     uint64_t* ha = reinterpret_cast<uint64_t*>(wbase);
     uint64_t* hb = ha + units;
     uint2* spos = reinterpret_cast<uint2*>(hb + units);
@@ -371,61 +374,61 @@ __global__ void __launch_bounds__(kBeamWarps * 32, LT_BEAM_MINB) beam_kernel(con
     H2* e_c1 = e_j2 + kRing * K;                                // contextual morph * M1
     EdgeCache C;
     C.e0 = e_c1 + kRing * K;
-    C.g0 = C.e0 + kECacheAll;
-    C.kval = reinterpret_cast<double*>(C.g0 + kECacheAll);
+    C.g0 = C.e0 + kCacheSlots;
+    C.kval = reinterpret_cast<double*>(C.g0 + kCacheSlots);
     const int kvs = 2 * (T.n_funcs > 0 ? T.n_funcs : 1);   // kval stride
-    uint16_t* ch = reinterpret_cast<uint16_t*>(C.kval + (size_t)kECacheAll * kvs);
+    uint64_t* s_newkey = reinterpret_cast<uint64_t*>(C.kval + (size_t)kCacheSlots * kvs);   // [32] selected keys by rank
+    uint16_t* ch = reinterpret_cast<uint16_t*>(s_newkey + 32);
     uintptr_t after = (reinterpret_cast<uintptr_t>(ch + units) + 7) & ~(uintptr_t)7;
     uint32_t* e_meta = reinterpret_cast<uint32_t*>(after);
     C.meta = e_meta + kRing * K;
-    C.eref = C.meta + kECacheAll;
-    C.present = C.eref + kECacheAll;
-    uint32_t* s_cnt = C.present + kECacheAll;       // [9] edges per span
-    uint32_t* s_gstart = s_cnt + 16;                // [9] first bucket-local index of the span's group
+    C.present = C.meta + kCacheSlots;
+    uint32_t* s_cnt = C.present + kCacheSlots;      // [9] edges per span
+    uint32_t* s_gstart = s_cnt + 16;                // [9] bucket-local index of the span's first edge
     uint32_t* s_ncand = s_gstart + 16;              // [9] candidates of the span
     uint32_t* s_nbeam = s_ncand + 16;               // [kRing] entries per ring slot
+    uint32_t* s_nnon = s_nbeam + 16;                // [kRing] entries per ring slot that do not end in an unknown word
+    uint32_t* p_hi = s_nnon + 32;                   // [64] selection pool, high words: kept entries, then the chunk's lanes
+    uint32_t* p_lo = p_hi + 64;                     // [64] low words
+    uint32_t* s_newpay = p_lo + 64;                 // [32] selected payloads by rank
+    uint8_t* s_nonunk = reinterpret_cast<uint8_t*>(s_newpay + 32);   // [kRing * K] ranks of the non-unknown entries, ascending
 
-    unsigned long long acc_T = 0, acc_F = 0, acc_B = 0, acc_W = 0;
+    uint32_t acc_T = 0, acc_F = 0, acc_B = 0, acc_W = 0;     // per lane and launch: far below 2^32
 
     bool need_m1 = false;
     for (int f = 0; f < T.n_funcs; ++f) need_m1 |= (T.funcs[f].kind == LT_FUNC_MPREF);
     const int nf = T.n_funcs;
 
     while (true) {
-        // the warp takes one sentence per group; a group without a (taggable) sentence idles with L = 0
         unsigned int s = 0;
-        if (lane == 0) s = atomicAdd(A.queue, (unsigned)(32 / G));
+        if (lane == 0) s = atomicAdd(A.queue, 1u);
         s = __shfl_sync(kFull, s, 0);
         if (s >= (unsigned)A.n_sent) break;
-        s += (unsigned)(lane / G);
-        const bool have = s < (unsigned)A.n_sent;
-        if (have && A.order) s = __ldg(A.order + s);
-        const int s0 = have ? __ldg(A.sent_off + s) : 0, s1 = have ? __ldg(A.sent_off + s + 1) : 0;
-        const int st = have ? __ldg(A.status + s) : LT_SENT_BAD_SPACE;
+        if (A.order) s = __ldg(A.order + s);
+        const int s0 = __ldg(A.sent_off + s), s1 = __ldg(A.sent_off + s + 1);
+        const int st = __ldg(A.status + s);
         // ---- stage syllables, prefix hashes and the sentence's CSR row ----
         int L = 0;
         const int raw_len = (st == LT_SENT_OK) ? (s1 - s0) : 0;
-        const int raw_max = (int)warp_max<G>((uint32_t)raw_len);
-        for (int base = 0; base < raw_max; base += G) {
-            const int idx = s0 + base + gl;
-            const bool valid = base + gl < raw_len;
+        for (int base = 0; base < raw_len; base += 32) {
+            const int idx = s0 + base + lane;
+            const bool valid = base + lane < raw_len;
             const uint32_t c = valid ? (uint32_t)__ldg(A.text + idx) : 0x20u;
             const bool keep = valid && (c != 0x20u);
-            const unsigned km = LT_GBALLOT(keep) >> gshift;
-            const int pos = L + __popc(km & ((1u << gl) - 1u));
+            const unsigned km = __ballot_sync(kFull, keep);
+            const int pos = L + __popc(km & lt_mask);
             if (keep) ch[pos] = (uint16_t)c;
             L += __popc(km);
         }
         __syncwarp();
-        for (int i = gl; i < L; i += G) spos[i] = __ldg(A.pos + s0 + i);
-        const int Lmax = (int)warp_max<G>((uint32_t)L);
-        prefix_hashes_group<G>(ch, L, Lmax, gl, gmask, ha, hb);
+        for (int i = lane; i < L; i += 32) spos[i] = __ldg(A.pos + s0 + i);
+        beam_prefix_hashes(ch, L, lane, ha, hb);
         SentView v{ch, ha, hb, nullptr};
 
-        if (L == 0 && have && gl == 0) { A.path_len[s] = 0; A.scores[s] = 0.0; }
+        if (L == 0 && lane == 0) { A.path_len[s] = 0; A.scores[s] = 0.0; }
 
         // beam[0] = [BOS] (beam.py:21-23)
-        if (gl == 0) {
+        if (lane == 0) {
             e_score[0] = 0.0;
             e_p1[0] = h2_mul(T.bos, kM1a, kM1b);
             e_j2[0] = h2_mul(T.bos, kM2a, kM2b);
@@ -433,104 +436,102 @@ __global__ void __launch_bounds__(kBeamWarps * 32, LT_BEAM_MINB) beam_kernel(con
             e_c1[0] = H2{0, 0};
             e_meta[0] = (uint32_t)LT_TAG_BOS;
             s_nbeam[0] = 1;
+            s_nnon[0] = 1;
+            s_nonunk[0] = 0;
         }
         __syncwarp();
 
-        for (int e = 1; e <= Lmax; ++e) {
-            const bool on = e <= L;                     // this group's sentence still has positions
+        uint32_t ring_lo = 0, ring_hi = 0;      // global edge indices [ring_lo, ring_hi) are prepared
+
+        for (int e = 1; e <= L; ++e) {
             const int slot_e = e % kRing;
-            const uint2 bucket = on ? spos[e - 1] : make_uint2(0u, 0u);
+            const uint2 bucket = spos[e - 1];
             const uint32_t es = bucket.x, ne = bucket.y;
             const int jmax = (e < LT_WINDOW) ? e : LT_WINDOW;
-            const uint32_t ne_max = warp_max<G>(ne);
 
-            // ---- 1. edges per span (bucket sorted by begin ascending = span descending) ----
-            uint32_t my_cnt = 0;            // lane j (1..8) counts span j
-            uint4 raw0 = make_uint4(0, 0, 0, 0);
-            for (uint32_t base = 0; base < ne_max; base += G) {
-                const uint32_t idx = base + gl;
-                int span = 0;
-                if (idx < ne) {
-                    const uint4 raw = ldg16(A.edges + es + idx);
-                    if (base == 0) raw0 = raw;
-                    span = (int)(raw.x >> 16) - (int)(raw.x & 0xFFFFu);
-                }
-                #pragma unroll
-                for (int j = 1; j <= LT_WINDOW; ++j) {
-                    const uint32_t c = __popc(LT_GBALLOT(span == j));
-                    if (gl == j) my_cnt += c;
+            // ---- 1. EDGE PREP of dictionary edges, 32 consecutive edges at a time ----
+            // Buckets of consecutive end positions are adjacent in HBM (one reservation per sentence, edges
+            // ranked by end), so one pass normally prepares the edges of many positions ahead.
+            if (ne > 0) {
+                const uint32_t need_hi = es + (ne < (uint32_t)kBucketCached ? ne : (uint32_t)kBucketCached);
+                if (es < ring_lo || es > ring_hi || need_hi > ring_hi) {
+                    uint32_t start = ring_hi;
+                    if (es < ring_lo || es > ring_hi) { start = es; ring_lo = es; }
+                    // how far beyond this bucket the sentence's edges continue without a gap
+                    const int p = e + lane;                       // 0-based index of end position e + 1 + lane
+                    const uint2 nb = (p < L) ? spos[p] : make_uint2(0u, 0u);
+                    uint32_t incl = nb.y;
+                    #pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const uint32_t t = __shfl_up_sync(kFull, incl, d);
+                        if (lane >= d) incl += t;
+                    }
+                    const bool gap = (p >= L) || (nb.y != 0 && nb.x != es + ne + (incl - nb.y));
+                    const unsigned gaps = __ballot_sync(kFull, gap);
+                    const int run = gaps ? __ffs(gaps) - 1 : 32;     // positions ahead that continue the range
+                    const uint32_t ahead = run ? __shfl_sync(kFull, incl, run - 1) : 0u;
+                    const uint32_t avail = es + ne + ahead - start;
+                    const uint32_t n = avail < 32u ? avail : 32u;
+                    if ((uint32_t)lane < n) {
+                        const uint32_t gi = start + lane;
+                        EdgeView k;
+                        unpack_edge(ldg16(A.edges + gi), k);
+                        prep_edge(T, v, dense_smem, k, need_m1, nf, kvs, C, gi & (kEdgeRing - 1));
+                    }
+                    ring_hi = start + n;
+                    if (ring_hi - ring_lo > (uint32_t)kEdgeRing) ring_lo = ring_hi - kEdgeRing;
+                    __syncwarp();
                 }
             }
-            // lane j: group start = ne - sum_{j' <= j} cnt[j']: spans descend along the bucket
-            {
-                const uint32_t c = (gl >= 1 && gl <= LT_WINDOW) ? my_cnt : 0u;
-                uint32_t incl = c;      // inclusive prefix over lanes 1..j
-                #pragma unroll
-                for (int d = 1; d < 16; d <<= 1) {
-                    const uint32_t t = __shfl_up_sync(kFull, incl, d, G);
-                    if (gl >= d) incl += t;
-                }
-                if (gl >= 1 && gl <= LT_WINDOW) {
-                    s_cnt[gl] = c;
-                    s_gstart[gl] = ne - incl;                 // bucket-local index of the group's first edge
-                    const uint32_t np = (on && gl <= jmax) ? s_nbeam[(e - gl) % kRing] : 0u;
-                    s_ncand[gl] = np * (c ? c : 1u);
-                }
-            }
-            __syncwarp();
-            const uint32_t in_window = ne - s_gstart[LT_WINDOW];    // = sum of cnt[1..8]
-            const uint32_t first_in = ne - in_window;               // bucket-local index of the first window edge
-            uint32_t N = 0;
-            #pragma unroll
-            for (int j = 1; j <= LT_WINDOW; ++j) N += s_ncand[j];
-
-            // ---- 2. edge prep into the cache: window edges, then the unknown word of every empty span ----
-            {
-                const uint32_t n_cached = in_window < (uint32_t)kECache ? in_window : (uint32_t)kECache;
-                const uint32_t prep_max = warp_max<G>(n_cached + LT_WINDOW);
-                for (uint32_t base = 0; base < prep_max; base += G) {
-                    const uint32_t ci = base + gl;
-                    bool active = false;
+            // ---- the unknown words of kUnkBlock end positions at a time, lanes = (position, span) ----
+            if (((e - 1) & (kUnkBlock - 1)) == 0) {
+                const int pe = e + (lane >> 3);
+                const int j = (lane & 7) + 1;
+                if (pe <= L && j <= pe) {
                     EdgeView k;
-                    uint32_t slot = 0, eref = kTrailUnk;
-                    // the first G bucket entries are still in the registers of lane (bucket index)
-                    const uint32_t bidx = first_in + ci;
-                    uint4 r0;
-                    r0.x = __shfl_sync(kFull, raw0.x, bidx & (G - 1), G);
-                    r0.y = __shfl_sync(kFull, raw0.y, bidx & (G - 1), G);
-                    r0.z = __shfl_sync(kFull, raw0.z, bidx & (G - 1), G);
-                    r0.w = __shfl_sync(kFull, raw0.w, bidx & (G - 1), G);
-                    if (ci < n_cached) {
-                        unpack_edge((bidx < (uint32_t)G) ? r0 : ldg16(A.edges + es + bidx), k);
-                        slot = ci;
-                        eref = es + bidx;
-                        active = true;
+                    unknown_edge(pe - j, pe, k);
+                    prep_edge(T, v, dense_smem, k, need_m1, nf, kvs, C, (uint32_t)(kEdgeRing + lane));
+                }
+                __syncwarp();
+            }
+            const uint32_t unk_base = (uint32_t)(kEdgeRing + (((e - 1) & (kUnkBlock - 1)) << 3) - 1);   // + span
+
+            // ---- 2. edges per span (bucket sorted by begin ascending = span descending) ----
+            if (lane >= 1 && lane <= LT_WINDOW) s_cnt[lane] = 0;
+            __syncwarp();
+            for (uint32_t base = 0; base < ne; base += 32) {
+                const uint32_t idx = base + lane;
+                const unsigned act = __ballot_sync(kFull, idx < ne);
+                if (idx < ne) {
+                    uint32_t span;
+                    if (idx < (uint32_t)kBucketCached) {
+                        span = C.present[(es + idx) & (kEdgeRing - 1)] >> 24;
                     } else {
-                        const int j = (int)(ci - n_cached) + 1;
-                        if (on && j <= jmax && s_cnt[j] == 0) {
-                            unknown_edge(e - j, e, k);
-                            slot = (uint32_t)(kECache + j - 1);
-                            active = true;
-                        }
+                        const uint32_t x = __ldg(reinterpret_cast<const uint32_t*>(A.edges + es + idx));
+                        span = (x >> 16) - (x & 0xFFFFu);
                     }
-                    if (active) {
-                        edge_hashes(T, v, k, need_m1);
-                        const H2 e0 = h2_mul(k.wk, kM0a, kM0b), g0 = h2_mul(k.mk, kM0a, kM0b);
-                        uint32_t present = 0;
-                        #pragma unroll 1
-                        for (int f = 0; f < nf; ++f) {
-                            double a, b2;
-                            present |= edge_score(T, dense_smem, k, e0, g0, f, a, b2) << (2 * f);
-                            C.kval[slot * kvs + 2 * f] = a;
-                            C.kval[slot * kvs + 2 * f + 1] = b2;
-                        }
-                        C.e0[slot] = e0;
-                        C.g0[slot] = g0;
-                        C.meta[slot] = k.tag0 | (k.len << 8) | (k.flags << 24);
-                        C.eref[slot] = eref;
-                        C.present[slot] = present;
+                    const unsigned same = __match_any_sync(act, span);
+                    if (span <= (uint32_t)LT_WINDOW && (same & lt_mask) == 0) {
+                        // first lane of the span's group in this chunk (a group may continue from the previous chunk)
+                        const uint32_t old = s_cnt[span];
+                        if (old == 0) s_gstart[span] = idx;
+                        s_cnt[span] = old + __popc(same);
                     }
                 }
+                __syncwarp();
+            }
+            uint32_t N;
+            {
+                uint32_t nc = 0;
+                if (lane >= 1 && lane <= jmax) {
+                    const uint32_t c = s_cnt[lane];
+                    const int ps = (e - lane) % kRing;
+                    // an unknown word may follow an unknown word only from the window's first begin (beam.py:44-45):
+                    // elsewhere only the parents that do not end in an unknown word generate a candidate
+                    nc = c ? s_nbeam[ps] * c : ((lane < jmax) ? s_nnon[ps] : s_nbeam[ps]);
+                }
+                if (lane >= 1 && lane <= LT_WINDOW) s_ncand[lane] = nc;
+                N = __reduce_add_sync(kFull, nc);
             }
             __syncwarp();
 
@@ -539,10 +540,10 @@ __global__ void __launch_bounds__(kBeamWarps * 32, LT_BEAM_MINB) beam_kernel(con
             uint32_t keep_pay[KR];
             #pragma unroll
             for (int r = 0; r < KR; ++r) { keep_key[r] = 0; keep_pay[r] = 0; }
+            uint32_t nk = 0;      // kept entries so far (MODE 2)
 
-            const uint32_t N_max = warp_max<G>(N);
-            for (uint32_t c0 = 0; c0 < N_max; c0 += G) {
-                const uint32_t c = c0 + gl;
+            for (uint32_t c0 = 0; c0 < N; c0 += 32) {
+                const uint32_t c = c0 + lane;
                 bool valid = c < N;
                 int j = 0;
                 uint32_t rem = c;
@@ -560,21 +561,26 @@ __global__ void __launch_bounds__(kBeamWarps * 32, LT_BEAM_MINB) beam_kernel(con
                 if (valid) {
                     const uint32_t cj = s_cnt[j];
                     const bool unk_edge = (cj == 0);
-                    const uint32_t nedge = unk_edge ? 1u : cj;
-                    const uint32_t prank = (nedge == 1u) ? rem : rem / nedge, eidx = rem - prank * nedge;
-                    const int pslot = ((e - j) % kRing) * K + (int)prank;
+                    const int pbase = ((e - j) % kRing) * K;
+                    uint32_t prank, eidx = 0;
+                    if (unk_edge) {
+                        prank = (j < jmax) ? (uint32_t)s_nonunk[pbase + rem] : rem;
+                    } else {
+                        prank = (cj == 1u) ? rem : rem / cj;
+                        eidx = rem - prank * cj;
+                    }
+                    const int pslot = pbase + (int)prank;
                     const uint32_t pmeta = e_meta[pslot];
                     const uint32_t tj = pmeta & kMetaTagMask;
-                    // cache slot of the edge
-                    const uint32_t widx = s_gstart[j] - first_in + eidx;     // index among window edges
-                    const uint32_t slot = unk_edge ? (uint32_t)(kECache + j - 1) : widx;
+                    const uint32_t bidx = unk_edge ? 0u : s_gstart[j] + eidx;      // bucket-local edge index
+                    const uint32_t slot = unk_edge ? unk_base + (uint32_t)j : ((es + bidx) & (kEdgeRing - 1));
                     H2 e0, g0;
                     uint32_t emeta, epresent = 0;
-                    const bool uncached = !unk_edge && widx >= (uint32_t)kECache;
+                    const bool uncached = !unk_edge && bidx >= (uint32_t)kBucketCached;
                     EdgeView kfly;
                     if (uncached) {
-                        // bucket larger than the cache: prepare this edge on the fly
-                        unpack_edge(ldg16(A.edges + es + s_gstart[j] + eidx), kfly);
+                        // bucket larger than the cached part: prepare this edge on the fly
+                        unpack_edge(ldg16(A.edges + es + bidx), kfly);
                         edge_hashes(T, v, kfly, need_m1);
                         e0 = h2_mul(kfly.wk, kM0a, kM0b);
                         g0 = h2_mul(kfly.mk, kM0a, kM0b);
@@ -586,74 +592,137 @@ __global__ void __launch_bounds__(kBeamWarps * 32, LT_BEAM_MINB) beam_kernel(con
                         epresent = C.present[slot];
                     }
                     const uint32_t tk = emeta & 0xFFu;
-                    // two unknown words in a row are only allowed from the window's first begin (beam.py:44-45)
-                    if (tj == LT_TAG_UNK && tk == LT_TAG_UNK && j < jmax) {
-                        valid = false;
-                    } else {
-                        const double pscore = e_score[pslot];
-                        const H2 p1 = e_p1[pslot];
-                        const bool has_i = (pmeta & kMetaHasI) != 0;
-                        const bool j_unk = (tj == LT_TAG_UNK);
-                        const bool ctx8 = ((kCtxMask >> tk) & 1u) && (pmeta & kMetaHasCtx);
-                        double inc = 0.0;
-                        #pragma unroll 1
-                        for (int f = 0; f < nf; ++f) {
-                            double val, val5;
-                            if (uncached) {
-                                epresent |= edge_score(T, dense_smem, kfly, e0, g0, f, val, val5) << (2 * f);
-                            } else {
-                                val = C.kval[slot * kvs + 2 * f];
-                                val5 = C.kval[slot * kvs + 2 * f + 1];
-                            }
-                            if (T.funcs[f].kind == LT_FUNC_TRIGRAM) {
-                                // SimpleTrigramFeatureScore.score (score_funcs.py:137-144)
-                                const DenseView D = dense_view(dense_smem + (size_t)T.func_dense[f] * dense_block_bytes(NT), NT);
-                                acc_F += 6u + (j_unk ? 1u : 0u) + (has_i ? 1u : 0u) + (ctx8 ? 1u : 0u);
-                                const H2 pp = has_i ? e_pp[pslot] : H2{0, 0};
-                                const H2 c1v = ctx8 ? e_c1[pslot] : H2{0, 0};
-                                const uint32_t hk = feature_head32(tk, 0);
-                                const FKey q0 = feature_key_sum32(T.seeds[f][0], hk, h2_add(e0, p1));
-                                const FKey q1 = feature_key_sum32(T.seeds[f][1], hk, p1);
-                                const FKey q2 = feature_key_sum32(T.seeds[f][2], feature_head32(tj, tk), e0);
-                                const FKey q7 = feature_key_sum32(T.seeds[f][7], 0u, h2_add(e0, pp));
-                                const FKey q8 = feature_key_sum32(T.seeds[f][8], 0u, h2_add(g0, c1v));
-                                // all first-slot loads in flight before any is consumed
-                                const FeatProbe s0 = feat_first(T, q0);
-                                const FeatProbe s1 = feat_first(T, q1);
-                                const FeatProbe s2 = feat_first(T, q2);
-                                FeatProbe s7, s8;
-                                if (has_i) s7 = feat_first(T, q7);
-                                if (ctx8) s8 = feat_first(T, q8);
-                                // running left-to-right sum = numpy's order while fewer than 8 weights survive
-                                double acc = 0.0, w;
-                                int n = 0;
-                                if (feat_resolve(T, q0, s0, w)) { acc = __dadd_rn(acc, w); ++n; }
-                                if (feat_resolve(T, q1, s1, w)) { acc = __dadd_rn(acc, w); ++n; }
-                                if (feat_resolve(T, q2, s2, w)) { acc = __dadd_rn(acc, w); ++n; }
-                                if ((D.m3[tj] >> tk) & 1u) { acc = __dadd_rn(acc, D.t3[tj * NT + tk]); ++n; }
-                                if ((epresent >> (2 * f)) & 1u) { acc = __dadd_rn(acc, val); ++n; }
-                                if ((epresent >> (2 * f + 1)) & 1u) { acc = __dadd_rn(acc, val5); ++n; }
-                                const uint32_t ul = (pmeta >> kMetaUnkLenShift) & 0xFu;
-                                if (j_unk && ((D.m6[0] >> ul) & 1u)) { acc = __dadd_rn(acc, D.t6[ul]); ++n; }
-                                if (has_i && feat_resolve(T, q7, s7, w)) { acc = __dadd_rn(acc, w); ++n; }
-                                if (ctx8 && feat_resolve(T, q8, s8, w)) { acc = __dadd_rn(acc, w); ++n; }
-                                if (n >= 8)   // numpy switches to an 8-lane tree: redo the gather and add in that order (rare)
-                                    acc = trigram_sum_tree(T, D, NT, f, q0, q1, q2, q7, q8, tj, tk, epresent, val, val5, j_unk, ul,
-                                                           has_i, ctx8);
-                                val = n ? acc : 0.0;
-                            }
-                            inc = __dadd_rn(inc, val);          // score += f(...), score_funcs.py:51-53
+                    // (only a dictionary that files entries under the tag 'Unknown' can still meet beam.py:44-45 here)
+                    valid = !(tj == LT_TAG_UNK && tk == LT_TAG_UNK && j < jmax);
+                    const double pscore = e_score[pslot];
+                    const H2 p1 = e_p1[pslot];
+                    const bool has_i = (pmeta & kMetaHasI) != 0;
+                    const bool j_unk = (tj == LT_TAG_UNK);
+                    const bool ctx8 = ((kCtxMask >> tk) & 1u) && (pmeta & kMetaHasCtx);
+                    double inc = 0.0;
+                    #pragma unroll 1
+                    for (int f = 0; f < nf; ++f) {
+                        double val, val5;
+                        if (uncached) {
+                            epresent |= edge_score(T, dense_smem, kfly, e0, g0, f, val, val5) << (2 * f);
+                        } else {
+                            val = C.kval[slot * kvs + 2 * f];
+                            val5 = C.kval[slot * kvs + 2 * f + 1];
                         }
-                        double newscore = __dadd_rn(pscore, inc);        // Sequence.add, beam.py:115
-                        newscore = __dadd_rn(newscore, 0.0);             // -0.0 sorts as 0.0
-                        ckey = sortable(newscore);
-                        // payload doubles as the generation ordinal: begin ascending (= span descending), parent
-                        // rank ascending, edge order ascending (beam.py:30-48)
-                        cpay = ((uint32_t)(LT_WINDOW - j) << 27) | (prank << 20) | (unk_edge ? 0u : s_gstart[j] + eidx);
-                        acc_T += 1;
+                        if (T.funcs[f].kind == LT_FUNC_TRIGRAM) {
+                            // SimpleTrigramFeatureScore.score (score_funcs.py:137-144)
+                            const DenseView D = dense_view(dense_smem + (size_t)T.func_dense[f] * dense_block_bytes(NT), NT);
+                            acc_F += valid ? 6u + (j_unk ? 1u : 0u) + (has_i ? 1u : 0u) + (ctx8 ? 1u : 0u) : 0u;
+                            const H2 pp = has_i ? e_pp[pslot] : H2{0, 0};
+                            const H2 c1v = ctx8 ? e_c1[pslot] : H2{0, 0};
+                            const uint32_t hk = feature_head32(tk, 0);
+                            const FKey q0 = feature_key_sum32(T.seeds[f][0], hk, h2_add(e0, p1));
+                            const FKey q1 = feature_key_sum32(T.seeds[f][1], hk, p1);
+                            const FKey q2 = feature_key_sum32(T.seeds[f][2], feature_head32(tj, tk), e0);
+                            const FKey q7 = feature_key_sum32(T.seeds[f][7], 0u, h2_add(e0, pp));
+                            const FKey q8 = feature_key_sum32(T.seeds[f][8], 0u, h2_add(g0, c1v));
+                            // all first-slot loads in flight before any is consumed
+                            const FeatProbe s0 = feat_first(T, q0);
+                            const FeatProbe s1 = feat_first(T, q1);
+                            const FeatProbe s2 = feat_first(T, q2);
+                            FeatProbe s7, s8;
+#if !LT_PROBE_SPLIT
+                            if (has_i) s7 = feat_first(T, q7);
+                            if (ctx8) s8 = feat_first(T, q8);
+#endif
+                            // running left-to-right sum = numpy's order while fewer than 8 weights survive
+                            double acc = 0.0, w;
+                            int n = 0;
+                            if (feat_resolve(T, q0, s0, w)) { acc = __dadd_rn(acc, w); ++n; }
+                            if (feat_resolve(T, q1, s1, w)) { acc = __dadd_rn(acc, w); ++n; }
+                            if (feat_resolve(T, q2, s2, w)) { acc = __dadd_rn(acc, w); ++n; }
+#if LT_PROBE_SPLIT
+                            if (has_i) s7 = feat_first(T, q7);
+                            if (ctx8) s8 = feat_first(T, q8);
+#endif
+                            if ((D.m3[tj] >> tk) & 1u) { acc = __dadd_rn(acc, D.t3[tj * NT + tk]); ++n; }
+                            if ((epresent >> (2 * f)) & 1u) { acc = __dadd_rn(acc, val); ++n; }
+                            if ((epresent >> (2 * f + 1)) & 1u) { acc = __dadd_rn(acc, val5); ++n; }
+                            const uint32_t ul = (pmeta >> kMetaUnkLenShift) & 0xFu;
+                            if (j_unk && ((D.m6[0] >> ul) & 1u)) { acc = __dadd_rn(acc, D.t6[ul]); ++n; }
+                            if (has_i && feat_resolve(T, q7, s7, w)) { acc = __dadd_rn(acc, w); ++n; }
+                            if (ctx8 && feat_resolve(T, q8, s8, w)) { acc = __dadd_rn(acc, w); ++n; }
+                            if (n >= 8)   // numpy switches to an 8-lane tree: redo the gather and add in that order (rare)
+                                acc = trigram_sum_tree(T, D, NT, f, q0, q1, q2, q7, q8, tj, tk, epresent, val, val5, j_unk, ul,
+                                                       has_i, ctx8);
+                            val = n ? acc : 0.0;
+                        }
+                        inc = __dadd_rn(inc, val);          // score += f(...), score_funcs.py:51-53
                     }
+                    double newscore = __dadd_rn(pscore, inc);        // Sequence.add, beam.py:115
+                    newscore = __dadd_rn(newscore, 0.0);             // -0.0 sorts as 0.0
+                    ckey = valid ? sortable(newscore) : 0ull;
+                    acc_T += valid ? 1u : 0u;
+                    // payload doubles as the generation ordinal: begin ascending (= span descending), parent
+                    // rank ascending, edge order ascending (beam.py:30-48)
+                    cpay = ((uint32_t)(LT_WINDOW - j) << 27) | (prank << 20) | bidx;
                 }
-                if constexpr (SORTNET) {
+                if constexpr (MODE == 2) {
+                    // ---- top-K by rank counting: an entry's rank = number of pool entries that beat it ----
+                    // pool = kept entries (earlier candidates, they win ties) + this chunk's lanes in generation order
+                    const uint32_t nc = (N - c0 < 32u) ? (N - c0) : 32u;
+                    const uint32_t chi = (uint32_t)(ckey >> 32);
+                    const uint64_t kkey = keep_key[0];
+                    const uint32_t khi = (uint32_t)(kkey >> 32);
+                    p_hi[32 + lane] = chi;
+                    p_lo[32 + lane] = (uint32_t)ckey;
+                    if ((uint32_t)lane < nk) { p_hi[lane] = khi; p_lo[lane] = (uint32_t)kkey; }
+                    __syncwarp();
+                    // fast pass on the high words; any equal pair of high words falls back to the full keys
+                    uint32_t gt_c = 0, eq_c = 0, gt_k = 0, eq_k = 0;
+                    if (nk == 0) {
+                        #pragma unroll 4
+                        for (uint32_t l = 0; l < nc; ++l) {
+                            const uint32_t h = p_hi[32 + l];
+                            gt_c += (h > chi) ? 1u : 0u;
+                            eq_c += (h == chi) ? 1u : 0u;
+                        }
+                    } else {
+                        #pragma unroll 4
+                        for (uint32_t l = 0; l < nc; ++l) {
+                            const uint32_t h = p_hi[32 + l];
+                            gt_c += (h > chi) ? 1u : 0u;
+                            eq_c += (h == chi) ? 1u : 0u;
+                            gt_k += (h > khi) ? 1u : 0u;
+                            eq_k += (h == khi) ? 1u : 0u;
+                        }
+                        #pragma unroll 4
+                        for (uint32_t r = 0; r < nk; ++r) {
+                            const uint32_t h = p_hi[r];
+                            gt_c += (h > chi) ? 1u : 0u;
+                            eq_c += (h == chi) ? 1u : 0u;
+                        }
+                    }
+                    const bool ambiguous = (ckey != 0 && eq_c > 1u) || ((uint32_t)lane < nk && eq_k > 0u);
+                    if (__any_sync(kFull, ambiguous)) {
+                        gt_c = 0;
+                        gt_k = 0;
+                        #pragma unroll 1
+                        for (uint32_t l = 0; l < nc; ++l) {
+                            const uint64_t o = ((uint64_t)p_hi[32 + l] << 32) | p_lo[32 + l];
+                            gt_c += (o > ckey || (o == ckey && l < (uint32_t)lane)) ? 1u : 0u;
+                            gt_k += (o > kkey) ? 1u : 0u;
+                        }
+                        #pragma unroll 1
+                        for (uint32_t r = 0; r < nk; ++r) {
+                            const uint64_t o = ((uint64_t)p_hi[r] << 32) | p_lo[r];
+                            gt_c += (o >= ckey) ? 1u : 0u;
+                        }
+                    }
+                    const uint32_t nvalid = __popc(__ballot_sync(kFull, ckey != 0));
+                    if (ckey != 0 && gt_c < (uint32_t)K) { s_newkey[gt_c] = ckey; s_newpay[gt_c] = cpay; }
+                    if ((uint32_t)lane < nk && lane + gt_k < (uint32_t)K) { s_newkey[lane + gt_k] = kkey; s_newpay[lane + gt_k] = keep_pay[0]; }
+                    __syncwarp();
+                    nk = (nk + nvalid < (uint32_t)K) ? nk + nvalid : (uint32_t)K;
+                    keep_key[0] = ((uint32_t)lane < nk) ? s_newkey[lane] : 0ull;
+                    keep_pay[0] = ((uint32_t)lane < nk) ? s_newpay[lane] : 0u;
+                    __syncwarp();
+                } else if constexpr (MODE == 1) {
                     // ---- top-K by sorting network: sort the chunk (best first), then merge with the kept list ----
                     // order: larger key first; equal keys: smaller payload (= earlier candidate) first
                     uint64_t bk = ckey;
@@ -692,96 +761,93 @@ __global__ void __launch_bounds__(kBeamWarps * 32, LT_BEAM_MINB) beam_kernel(con
                     }
                     if (lane >= K) { keep_key[0] = 0; keep_pay[0] = 0; }
                 } else {
-                // ---- top-K of (kept so far) U (this chunk): K rounds of group arg-max ----
-                // Priority on equal keys: kept entries (earlier candidates) by rank, then chunk lanes in order.
-                uint64_t new_key[KR];
-                uint32_t new_pay[KR];
-                #pragma unroll
-                for (int r = 0; r < KR; ++r) { new_key[r] = 0; new_pay[r] = 0; }
-                uint64_t pool_key[KR + 1];
-                #pragma unroll
-                for (int r = 0; r < KR; ++r) pool_key[r] = keep_key[r];
-                pool_key[KR] = ckey;
-                // rounds needed: min(K, pool size), the same for both groups of the warp
-                uint32_t pool_n = __popc(LT_GBALLOT(ckey != 0));
-                #pragma unroll
-                for (int r = 0; r < KR; ++r) pool_n += __popc(LT_GBALLOT(keep_key[r] != 0));
-                const int rounds = (int)warp_max<G>(pool_n < (uint32_t)K ? pool_n : (uint32_t)K);
-                for (int round = 0; round < rounds; ++round) {
-                    // lane-local best: lower pool index wins ties
-                    uint64_t best = pool_key[0];
-                    int cls = 0;
+                    // ---- top-K of (kept so far) U (this chunk): K rounds of warp arg-max ----
+                    // Priority on equal keys: kept entries (earlier candidates) by rank, then chunk lanes in order.
+                    uint64_t new_key[KR];
+                    uint32_t new_pay[KR];
                     #pragma unroll
-                    for (int r = 1; r <= KR; ++r)
-                        if (pool_key[r] > best) { best = pool_key[r]; cls = r; }
-                    const uint32_t hi = (uint32_t)(best >> 32), lo = (uint32_t)best;
-                    const uint32_t mhi = group_max<G>(hi, lane);
-                    const bool c1 = (hi == mhi) && (mhi != 0);              // mhi == 0: this group's pool is exhausted
-                    const uint32_t mlo = group_max<G>(c1 ? lo : 0u, lane);
-                    const bool c2 = c1 && (lo == mlo);
-                    int win_cls = 0;
-                    unsigned wm = 0;
+                    for (int r = 0; r < KR; ++r) { new_key[r] = 0; new_pay[r] = 0; }
+                    uint64_t pool_key[KR + 1];
                     #pragma unroll
-                    for (int r = 0; r <= KR; ++r) {
-                        const unsigned m = LT_GBALLOT(c2 && cls == r);
-                        if (wm == 0 && m != 0) { wm = m; win_cls = r; }
-                    }
-                    const bool sel = wm != 0;                               // false: this group's pool is exhausted
-                    const int src = sel ? __ffs(wm) - 1 : lane;             // absolute lane of the winner
-                    uint32_t pay_mine = cpay;
+                    for (int r = 0; r < KR; ++r) pool_key[r] = keep_key[r];
+                    pool_key[KR] = ckey;
+                    uint32_t pool_n = __popc(__ballot_sync(kFull, ckey != 0));
                     #pragma unroll
-                    for (int r = 0; r < KR; ++r)
-                        if (win_cls == r) pay_mine = keep_pay[r];
-                    const uint32_t wpay = __shfl_sync(kFull, pay_mine, src, G);
-                    const uint64_t wkey = ((uint64_t)mhi << 32) | mlo;
-                    if (sel && gl == (round % G)) {
+                    for (int r = 0; r < KR; ++r) pool_n += __popc(__ballot_sync(kFull, keep_key[r] != 0));
+                    const int rounds = (int)(pool_n < (uint32_t)K ? pool_n : (uint32_t)K);
+                    for (int round = 0; round < rounds; ++round) {
+                        // lane-local best: lower pool index wins ties
+                        uint64_t best = pool_key[0];
+                        int cls = 0;
+                        #pragma unroll
+                        for (int r = 1; r <= KR; ++r)
+                            if (pool_key[r] > best) { best = pool_key[r]; cls = r; }
+                        const uint32_t hi = (uint32_t)(best >> 32), lo = (uint32_t)best;
+                        const uint32_t mhi = __reduce_max_sync(kFull, hi);
+                        const bool c1 = (hi == mhi);
+                        const uint32_t mlo = __reduce_max_sync(kFull, c1 ? lo : 0u);
+                        const bool c2 = c1 && (lo == mlo);
+                        int win_cls = 0;
+                        unsigned wm = 0;
+                        #pragma unroll
+                        for (int r = 0; r <= KR; ++r) {
+                            const unsigned m = __ballot_sync(kFull, c2 && cls == r);
+                            if (wm == 0 && m != 0) { wm = m; win_cls = r; }
+                        }
+                        const int src = __ffs(wm) - 1;                          // lane of the winner
+                        uint32_t pay_mine = cpay;
                         #pragma unroll
                         for (int r = 0; r < KR; ++r)
-                            if ((round / G) == r) { new_key[r] = wkey; new_pay[r] = wpay; }
+                            if (win_cls == r) pay_mine = keep_pay[r];
+                        const uint32_t wpay = __shfl_sync(kFull, pay_mine, src);
+                        const uint64_t wkey = ((uint64_t)mhi << 32) | mlo;
+                        if (lane == (round & 31)) {
+                            #pragma unroll
+                            for (int r = 0; r < KR; ++r)
+                                if ((round >> 5) == r) { new_key[r] = wkey; new_pay[r] = wpay; }
+                        }
+                        if (lane == src) {
+                            #pragma unroll
+                            for (int r = 0; r <= KR; ++r)
+                                if (win_cls == r) pool_key[r] = 0;
+                        }
                     }
-                    if (sel && lane == src) {
-                        #pragma unroll
-                        for (int r = 0; r <= KR; ++r)
-                            if (win_cls == r) pool_key[r] = 0;
-                    }
-                }
-                #pragma unroll
-                for (int r = 0; r < KR; ++r) { keep_key[r] = new_key[r]; keep_pay[r] = new_pay[r]; }
+                    #pragma unroll
+                    for (int r = 0; r < KR; ++r) { keep_key[r] = new_key[r]; keep_pay[r] = new_pay[r]; }
                 }
             }
 
             // ---- 5. survivors -> ring entries + trail ----
-            int nl = 0;
+            int nl = 0, nn = 0;
             #pragma unroll
             for (int r = 0; r < KR; ++r) {
-                const unsigned m = LT_GBALLOT(keep_key[r] != 0);
-                nl += __popc(m);
-                if (keep_key[r] != 0) {
-                    const int rank = r * G + gl;
+                const bool have = keep_key[r] != 0;
+                uint32_t tag0 = LT_TAG_UNK;
+                if (have) {
+                    const int rank = r * 32 + lane;
                     const uint32_t kp = keep_pay[r];
                     const int j = LT_WINDOW - (int)((kp >> 27) & 0xFu);
                     const uint32_t prank = (kp >> 20) & 0x7Fu;
+                    const uint32_t bidx = kp & 0xFFFFFu;
                     const bool unk_edge = (s_cnt[j] == 0);
                     const int pslot = ((e - j) % kRing) * K + (int)prank;
                     // the survivor's edge was prepared for this position: its word / morph products with M0
                     // are in the cache, and x * M0 -> x * M1 is one multiplication by M1 / M0
-                    const uint32_t widx = (kp & 0xFFFFFu) - first_in;
-                    const bool cached = unk_edge || widx < (uint32_t)kECache;
+                    const bool cached = unk_edge || bidx < (uint32_t)kBucketCached;
                     H2 wk1, wk2, mk1;
-                    uint32_t tag0, len, eref = kTrailUnk;
+                    uint32_t len, eref = kTrailUnk;
+                    if (!unk_edge) eref = es + bidx;
                     if (cached) {
-                        const uint32_t cslot = unk_edge ? (uint32_t)(kECache + j - 1) : widx;
+                        const uint32_t cslot = unk_edge ? unk_base + (uint32_t)j : (eref & (kEdgeRing - 1));
                         const H2 e0 = C.e0[cslot], g0 = C.g0[cslot];
                         const uint32_t em = C.meta[cslot];
                         tag0 = em & 0xFFu;
                         len = (em >> 8) & 0xFFFFu;
-                        eref = C.eref[cslot];
                         wk1 = h2_mul(e0, kM1over0a, kM1over0b);
                         wk2 = h2_mul(e0, kM2over0a, kM2over0b);
                         mk1 = h2_mul(g0, kM1over0a, kM1over0b);
                     } else {
                         EdgeView k;
-                        eref = es + (kp & 0xFFFFFu);
                         unpack_edge(ldg16(A.edges + eref), k);
                         edge_hashes(T, v, k, false);
                         tag0 = k.tag0;
@@ -805,14 +871,20 @@ __global__ void __launch_bounds__(kBeamWarps * 32, LT_BEAM_MINB) beam_kernel(con
                     A.trail[(size_t)(s0 + e - 1) * K + rank] =
                         (uint64_t)eref | ((uint64_t)j << 32) | ((uint64_t)prank << 40);
                 }
+                // ranks of the entries that may be followed by an unknown word, ascending
+                const unsigned m_have = __ballot_sync(kFull, have);
+                const unsigned m_non = __ballot_sync(kFull, have && tag0 != LT_TAG_UNK);
+                if (have && tag0 != LT_TAG_UNK) s_nonunk[slot_e * K + nn + __popc(m_non & lt_mask)] = (uint8_t)(r * 32 + lane);
+                nl += __popc(m_have);
+                nn += __popc(m_non);
             }
-            if (gl == 0) s_nbeam[slot_e] = (uint32_t)nl;
-            acc_B += (gl == 0) ? (unsigned long long)nl : 0ull;
+            if (lane == 0) { s_nbeam[slot_e] = (uint32_t)nl; s_nnon[slot_e] = (uint32_t)nn; }
+            acc_B += (lane == 0) ? (uint32_t)nl : 0u;
             __syncwarp();
         }
 
         // ---- best path: matures[0] (tagger.py:78) ----
-        if (gl == 0 && L > 0) {
+        if (lane == 0 && L > 0) {
             A.scores[s] = e_score[(L % kRing) * K + 0];
             int e = L, r = 0, W = 0;
             while (e > 0) {
@@ -833,23 +905,24 @@ __global__ void __launch_bounds__(kBeamWarps * 32, LT_BEAM_MINB) beam_kernel(con
                 e -= span;
             }
             A.path_len[s] = W;
-            acc_W += (unsigned long long)W;
+            acc_W += (uint32_t)W;
         }
         __syncwarp();
     }
     // counters
+    unsigned long long t64 = acc_T, f64 = acc_F, b64 = acc_B, w64 = acc_W;
     #pragma unroll
     for (int d = 16; d; d >>= 1) {
-        acc_T += __shfl_xor_sync(kFull, acc_T, d);
-        acc_F += __shfl_xor_sync(kFull, acc_F, d);
-        acc_B += __shfl_xor_sync(kFull, acc_B, d);
-        acc_W += __shfl_xor_sync(kFull, acc_W, d);
+        t64 += __shfl_xor_sync(kFull, t64, d);
+        f64 += __shfl_xor_sync(kFull, f64, d);
+        b64 += __shfl_xor_sync(kFull, b64, d);
+        w64 += __shfl_xor_sync(kFull, w64, d);
     }
     if (lane == 0) {
-        atomicAdd(A.counters + 3, acc_T);
-        atomicAdd(A.counters + 4, acc_F);
-        atomicAdd(A.counters + 5, acc_B);
-        atomicAdd(A.counters + 6, acc_W);
+        atomicAdd(A.counters + 3, t64);
+        atomicAdd(A.counters + 4, f64);
+        atomicAdd(A.counters + 5, b64);
+        atomicAdd(A.counters + 6, w64);
     }
 }
 

@@ -56,6 +56,14 @@ LT_HD uint64_t dict_slot_hash(H2 h, uint32_t len) {
     return (h.a + (uint64_t)len * 0xA24BAED4963EE407ull) * 0x9E3779B97F4A7C15ull;
 }
 LT_HD uint64_t dict_slot(H2 h, uint32_t len, uint32_t bits) { return dict_slot_hash(h, len) >> (64 - bits); }
+
+// ---- cuckoo placement --------------------------------------------------------------------------
+// The dictionary and the feature table are cuckoo tables: a key lives in one of TWO slots, both
+// derived from the same 64-bit slot hash x.  A lookup loads both slots at once and never follows a
+// chain, so a warp's probe costs one memory round trip whatever the other lanes hit.
+constexpr uint64_t kSlotMul2 = 0xC2B2AE3D27D4EB4Full;   // odd
+LT_HD uint64_t cuckoo_slot1(uint64_t x, uint32_t bits) { return x >> (64 - bits); }
+LT_HD uint64_t cuckoo_slot2(uint64_t x, uint32_t bits) { return ((x ^ (x >> 32)) * kSlotMul2) >> (64 - bits); }
 LT_HD uint64_t dict_fp(H2 h, uint32_t len) {
     uint64_t f = h.b ^ ((uint64_t)len * 0x9FB21C651E98DF25ull);
     return f ? f : 1;
@@ -132,8 +140,8 @@ LT_HD FKey feature_key(uint32_t kind, uint32_t func, H2 s0, H2 s1, H2 s2, uint32
     return feature_key_sum(feature_seed(kind, func), feature_head(a0, a1), sum);
 }
 
-// slot of a key in a table of 2^bits slots
-LT_HD uint64_t feature_slot(uint64_t k1, uint32_t bits) { return (k1 * kSlotMul) >> (64 - bits); }
+// slot hash of a key (cuckoo_slot1 / cuckoo_slot2 turn it into the key's two slots)
+LT_HD uint64_t feature_slot_hash(uint64_t k1) { return k1 * kSlotMul; }
 
 constexpr uint32_t kKindMPref = 16;
 constexpr uint32_t kKindWPref = 17;

@@ -70,6 +70,54 @@ static uint64_t next_pow2(uint64_t x) {
     return p;
 }
 
+// Cuckoo table builder (two slots per key, one entry per slot).  An item is identified by its slot
+// hash x and its fingerprint; two items equal in both are a 128-bit collision (or a repeated key).
+// Placement is the usual random walk: take a free slot of the two, else evict the occupant of the
+// slot the walk did not just come from and re-place that one; a walk that does not end doubles the table.
+struct CuckooItem {
+    uint64_t x, fp, payload;
+};
+struct CuckooSlot {
+    uint64_t fp, payload;
+};
+static int build_cuckoo(const std::vector<CuckooItem>& items, uint64_t min_slots, std::vector<CuckooSlot>* table,
+                        uint32_t* bits_out, const char* what) {
+    uint32_t bits = 4;
+    while ((1ull << bits) < min_slots) ++bits;
+    for (; bits <= 40; ++bits) {
+        const uint64_t slots = 1ull << bits;
+        std::vector<int64_t> owner(slots, -1);
+        bool placed_all = true;
+        for (int64_t idx = 0; idx < (int64_t)items.size() && placed_all; ++idx) {
+            const uint64_t a0 = cuckoo_slot1(items[idx].x, bits), b0 = cuckoo_slot2(items[idx].x, bits);
+            for (uint64_t sl : {a0, b0}) {
+                const int64_t o = owner[sl];
+                if (o >= 0 && items[o].x == items[idx].x && items[o].fp == items[idx].fp)
+                    return fail(LT_ERR_COLLISION, "two %s share the 128-bit hash (or one was given twice)", what);
+            }
+            int64_t cur = idx;
+            uint64_t from = ~0ull;
+            bool placed = false;
+            for (int kick = 0; kick < 2000; ++kick) {
+                const uint64_t a = cuckoo_slot1(items[cur].x, bits), b = cuckoo_slot2(items[cur].x, bits);
+                if (owner[a] < 0) { owner[a] = cur; placed = true; break; }
+                if (owner[b] < 0) { owner[b] = cur; placed = true; break; }
+                const uint64_t v = (a == from) ? b : a;
+                std::swap(cur, owner[v]);
+                from = v;
+            }
+            placed_all = placed;
+        }
+        if (!placed_all) continue;
+        table->assign(slots, CuckooSlot{0, 0});
+        for (uint64_t sl = 0; sl < slots; ++sl)
+            if (owner[sl] >= 0) (*table)[sl] = CuckooSlot{items[owner[sl]].fp, items[owner[sl]].payload};
+        *bits_out = bits;
+        return LT_OK;
+    }
+    return fail(LT_ERR_CAPACITY, "could not place the %s in a cuckoo table", what);
+}
+
 template <typename T>
 static int upload(lt_tables* t, const std::vector<T>& host, const T** out) {
     void* d = nullptr;
@@ -115,30 +163,23 @@ static int build_tables(const lt_tables_desc* d, lt_tables* t) {
 
     // ---- dictionary ----
     {
-        const uint64_t slots = next_pow2((uint64_t)d->n_dict * (d->n_dict < (1 << 22) ? 4 : 2));
-        std::vector<DictSlot> table(slots, DictSlot{0, 0, 0});
-        std::vector<uint64_t> slot_h(slots, 0);
-        uint32_t dict_bits = 0;
-        while ((1ull << dict_bits) < slots) ++dict_bits;
-        D.dict_bits = dict_bits;
+        std::vector<CuckooItem> items((size_t)d->n_dict);
         for (int64_t i = 0; i < d->n_dict; ++i) {
             const int64_t len = d->dict_off[i + 1] - d->dict_off[i];
             if (len < 0 || len > 65535) return fail(LT_ERR_INVALID, "dictionary entry %lld has length %lld", (long long)i, (long long)len);
             const H2 h = hash_units(d->dict_chars + d->dict_off[i], len);
-            const uint64_t fp = dict_fp(h, (uint32_t)len);
-            const uint64_t sh = dict_slot_hash(h, (uint32_t)len);
-            uint64_t s = sh >> (64 - dict_bits);
-            while (table[s].fp != 0) {
-                if (table[s].fp == fp && slot_h[s] == sh)
-                    return fail(LT_ERR_COLLISION, "dictionary entries collide on the 128-bit key (entry %lld)", (long long)i);
-                s = (s + 1) & (slots - 1);
-            }
-            table[s].fp = fp;
-            table[s].tagmask = d->dict_tagmask[i];
-            table[s].lemma = d->dict_lemma[i];
-            slot_h[s] = sh;
+            items[i] = CuckooItem{dict_slot_hash(h, (uint32_t)len), dict_fp(h, (uint32_t)len),
+                                  (uint64_t)d->dict_tagmask[i] | ((uint64_t)d->dict_lemma[i] << 32)};
         }
-        D.dict_mask = slots - 1;
+        std::vector<CuckooSlot> slots;
+        if (int rc = build_cuckoo(items, next_pow2((uint64_t)d->n_dict * (d->n_dict < (1 << 22) ? 4 : 2)), &slots, &D.dict_bits,
+                                  "dictionary entries"))
+            return rc;
+        static_assert(sizeof(CuckooSlot) == sizeof(DictSlot), "slot layout");
+        std::vector<DictSlot> table(slots.size());
+        for (size_t i = 0; i < slots.size(); ++i)
+            table[i] = DictSlot{slots[i].fp, (uint32_t)slots[i].payload, (uint32_t)(slots[i].payload >> 32)};
+        D.dict_mask = table.size() - 1;
         if (int rc = upload(t, table, &D.dict)) return rc;
     }
 
@@ -276,24 +317,21 @@ static int build_tables(const lt_tables_desc* d, lt_tables* t) {
     }
     {
         const uint64_t n = pending.size();
-        const uint64_t slots = next_pow2(n * (n < (1u << 22) ? 4 : 2));
-        std::vector<FeatSlot> table(slots, FeatSlot{0, 0.0});
-        std::vector<uint64_t> slot_k1(slots, 0);
-        uint32_t bits = 0;
-        while ((1ull << bits) < slots) ++bits;
-        for (const Pending& p : pending) {
-            uint64_t s = feature_slot(p.key.k1, bits);
-            while (table[s].fp != 0) {
-                if (table[s].fp == p.key.k2 && slot_k1[s] == p.key.k1)
-                    return fail(LT_ERR_COLLISION, "two feature keys share the 128-bit hash (or a key was given twice)");
-                s = (s + 1) & (slots - 1);
-            }
-            table[s].fp = p.key.k2;
-            table[s].w = p.w;
-            slot_k1[s] = p.key.k1;
+        std::vector<CuckooItem> items((size_t)n);
+        for (uint64_t i = 0; i < n; ++i) {
+            uint64_t wbits;
+            memcpy(&wbits, &pending[i].w, 8);
+            items[i] = CuckooItem{feature_slot_hash(pending[i].key.k1), pending[i].key.k2, wbits};
         }
-        D.feat_mask = slots - 1;
-        D.feat_bits = bits;
+        std::vector<CuckooSlot> slots;
+        if (int rc = build_cuckoo(items, next_pow2(n * (n < (1u << 22) ? 4 : 2)), &slots, &D.feat_bits, "feature keys")) return rc;
+        static_assert(sizeof(CuckooSlot) == sizeof(FeatSlot), "slot layout");
+        std::vector<FeatSlot> table(slots.size());
+        for (size_t i = 0; i < slots.size(); ++i) {
+            table[i].fp = slots[i].fp;
+            memcpy(&table[i].w, &slots[i].payload, 8);
+        }
+        D.feat_mask = table.size() - 1;
         if (int rc = upload(t, table, &D.feat)) return rc;
     }
     if (int rc = upload(t, dense, &D.dense)) return rc;
@@ -347,8 +385,6 @@ struct lt_batch {
     int32_t beam = 0;
     int32_t hcap = 128;            // lattice staging capacity per warp (grows on overflow, sticky)
     bool sort_by_length = true;    // persistent warps pull the longest sentences first (LT_SORT_BY_LENGTH=0 disables)
-    int32_t half_warp_max_beam = 0;   // beams up to this size run two sentences per warp (LT_HALF_WARP_MAX_BEAM;
-                                      // measured slower than one sentence per warp at C2, so off by default)
     uint32_t edge_cap = 0;         // edge buffer capacity (grows on overflow, sticky)
     bool edge_cap_fixed = false;   // LT_EDGE_CAP given: start there instead of the size guess (tests)
     int64_t n_edges = 0;
@@ -385,7 +421,6 @@ extern "C" int lt_batch_create(lt_tables* tables, lt_batch** out) {
     // debugging / test knobs: tiny initial capacities exercise the grow-and-rerun path
     if (const char* env = getenv("LT_HIT_CAP")) b->hcap = std::max(8, atoi(env));
     if (const char* env = getenv("LT_SORT_BY_LENGTH")) b->sort_by_length = atoi(env) != 0;
-    if (const char* env = getenv("LT_HALF_WARP_MAX_BEAM")) b->half_warp_max_beam = atoi(env);
     if (const char* env = getenv("LT_EDGE_CAP")) { b->edge_cap = (uint32_t)std::max(16, atoi(env)); b->edge_cap_fixed = true; }
     *out = b;
     return LT_OK;
@@ -507,14 +542,10 @@ static int launch_beam(lt_batch* b, cudaStream_t st) {
 
     const size_t dense_bytes = ((size_t)t->dev.n_tri * dense_block_bytes(t->dev.n_tags) + 15) & ~(size_t)15;
     const size_t group_smem = beam_warp_smem(b->lcap, beam_size, t->dev.n_funcs);
-    // small beams produce ~16 candidates per position: two sentences per warp (groups of 16 lanes)
-    int half = (beam_size <= b->half_warp_max_beam) ? 1 : 0;
-    if (half && dense_bytes + 2 * group_smem > kSmemBudget) half = 0;
-    const int per_warp = half ? 2 : 1;
-    if (dense_bytes + group_smem * per_warp > kSmemBudget)
+    if (dense_bytes + group_smem > kSmemBudget)
         return fail(LT_ERR_INVALID, "sentence length %d with beam %d does not fit the beam kernel's shared memory", b->lcap, beam_size);
-    const int warps = (int)std::min<size_t>(kBeamWarps, (kSmemBudget - dense_bytes) / (group_smem * per_warp));
-    const size_t smem = dense_bytes + group_smem * per_warp * warps;
+    const int warps = (int)std::min<size_t>(kBeamWarps, (kSmemBudget - dense_bytes) / group_smem);
+    const size_t smem = dense_bytes + group_smem * warps;
 
     unsigned int* ctl = static_cast<unsigned int*>(b->ctl.p);
     BeamArgs A{};
@@ -536,15 +567,12 @@ static int launch_beam(lt_batch* b, cudaStream_t st) {
     A.queue = ctl + kCtlBeamQueue;
     A.order = (b->sort_by_length && n_sent > 1) ? static_cast<const uint32_t*>(b->order.p) : nullptr;
 
-    auto kernel = half ? beam_kernel<1, 16, false>
-                       : (beam_size <= kRoundsMaxBeam ? beam_kernel<1, 32, false>
-                          : (beam_size <= 32 ? beam_kernel<1, 32, true> : beam_kernel<2, 32, false>));
+    auto kernel = beam_size <= kRankMaxBeam ? beam_kernel<2> : (beam_size <= 32 ? beam_kernel<1> : beam_kernel<0>);
     CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, warps * 32, smem));
     per_sm = std::max(1, per_sm);
-    const int64_t per_block = (int64_t)warps * per_warp;
-    const int64_t want_blocks = ((int64_t)n_sent + per_block - 1) / per_block;
+    const int64_t want_blocks = ((int64_t)n_sent + warps - 1) / warps;
     const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(want_blocks, (int64_t)t->sm_count * per_sm));
 
     CU(cudaMemsetAsync(ctl + kCtlBeamQueue, 0, sizeof(unsigned int), st));

@@ -1,10 +1,10 @@
 // tables.cuh — layout of the device-resident tables and the probe routines the kernels use.
 //
 // HBM layout (all built once by lt_tables_create, read-only afterwards):
-//   dict   open-addressing table, 16 B slots {fp, tagmask, lemma bits}; key = (string, length)
+//   dict   cuckoo table (two slots per key), 16 B slots {fp, tagmask, lemma bits}; key = (string, length)
 //   rules  open-addressing table, 16 B slots {exact 1..3-syllable key, first rule, count|k3_first}
 //   rrec   one 48 B record per (stem, eomi) rule: hashes and lengths of both strings
-//   feat   open-addressing table, 16 B slots {fp, fp64 weight}; key = feature tuple / preference
+//   feat   cuckoo table (two slots per key), 16 B slots {fp, fp64 weight}; key = feature tuple / preference
 //   dense  per trigram scorer: tag x tag matrix (template 3), length vectors (templates 4, 6)
 //          with presence masks — staged into shared memory by the beam kernel
 //   pows   base^n pairs for composing polynomial hashes
@@ -99,15 +99,14 @@ __device__ __forceinline__ uint4 ldg16(const void* p) {
 
 // dictionary probe: returns the 64-bit payload (tagmask | lemma << 32), 0 when absent
 __device__ __forceinline__ uint64_t dict_probe(const DevTables& T, H2 h, uint32_t len) {
-    uint64_t i = dict_slot(h, len, T.dict_bits);
+    const uint64_t x = dict_slot_hash(h, len);
     const uint64_t fp = dict_fp(h, len);
-    while (true) {
-        uint4 s = ldg16(T.dict + i);
-        uint64_t sfp = (uint64_t)s.x | ((uint64_t)s.y << 32);
-        if (sfp == fp) return (uint64_t)s.z | ((uint64_t)s.w << 32);
-        if (sfp == 0) return 0;
-        i = (i + 1) & T.dict_mask;
-    }
+    const uint4 s = ldg16(T.dict + cuckoo_slot1(x, T.dict_bits));
+    const uint4 t = ldg16(T.dict + cuckoo_slot2(x, T.dict_bits));
+    const uint32_t flo = (uint32_t)fp, fhi = (uint32_t)(fp >> 32);
+    if (s.x == flo && s.y == fhi) return (uint64_t)s.z | ((uint64_t)s.w << 32);
+    if (t.x == flo && t.y == fhi) return (uint64_t)t.z | ((uint64_t)t.w << 32);
+    return 0;
 }
 
 // rule probe: (first, count|flag) of an exact 1..3 syllable key; count = 0 when absent
@@ -137,30 +136,23 @@ __device__ __forceinline__ RuleRec rule_load(const DevTables& T, uint32_t idx) {
     return r;
 }
 
-// feature probe, split in two so that callers can put several first-slot loads in flight
+// feature probe, split in two so that callers can put the loads of several probes in flight
 struct FeatProbe {
-    uint4 s;        // first slot
-    uint32_t i;     // its index
+    uint4 s, t;     // the key's two slots
 };
 __device__ __forceinline__ FeatProbe feat_first(const DevTables& T, FKey k) {
     FeatProbe p;
-    p.i = (uint32_t)feature_slot(k.k1, T.feat_bits);
-    p.s = ldg16(T.feat + p.i);
+    const uint64_t x = feature_slot_hash(k.k1);
+    p.s = ldg16(T.feat + cuckoo_slot1(x, T.feat_bits));
+    p.t = ldg16(T.feat + cuckoo_slot2(x, T.feat_bits));
     return p;
 }
 __device__ __forceinline__ bool feat_resolve(const DevTables& T, FKey k, FeatProbe p, double& w) {
-    uint32_t i = p.i;
-    uint4 s = p.s;
-    while (true) {
-        uint64_t sfp = (uint64_t)s.x | ((uint64_t)s.y << 32);
-        if (sfp == k.k2) {
-            w = __hiloint2double((int)s.w, (int)s.z);
-            return true;
-        }
-        if (sfp == 0) return false;
-        i = (i + 1) & (uint32_t)T.feat_mask;
-        s = ldg16(T.feat + i);
-    }
+    const uint32_t flo = (uint32_t)k.k2, fhi = (uint32_t)(k.k2 >> 32);
+    const bool in_s = (p.s.x == flo) && (p.s.y == fhi);
+    const bool in_t = (p.t.x == flo) && (p.t.y == fhi);
+    if (in_s || in_t) w = __hiloint2double((int)(in_s ? p.s.w : p.t.w), (int)(in_s ? p.s.z : p.t.z));   // a miss leaves w alone
+    return in_s || in_t;
 }
 
 __device__ __forceinline__ H2 pow_at(const DevTables& T, uint32_t n) {

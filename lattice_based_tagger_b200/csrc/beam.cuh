@@ -61,6 +61,7 @@ struct BeamArgs {
     unsigned long long* counters;   // [3]=T [4]=F [5]=Bk [6]=W
     unsigned int* queue;
     const uint32_t* order;      // queue position -> sentence index (longest first), or nullptr
+    int32_t trail_smem;         // back-pointers in shared memory (4 B) instead of `trail` (8 B)
 };
 
 // Prepared edges (shared memory, struct of arrays).  Slots [0, kEdgeRing): dictionary edges at
@@ -68,7 +69,7 @@ struct BeamArgs {
 // unknown word of (end position e, span).
 struct EdgeCache {
     H2* e0;            // word hash   * M0
-    H2* g0;            // morph0 hash * M0
+    H2* g0;            // morph0 hash * M0 (dictionary edges only: an unknown word is its own morpheme)
     double* kval;      // 2 doubles per scorer: score-program values that depend on the edge only
     uint32_t* meta;    // tag0 | len << 8 (16 bits) | flags << 24
     uint32_t* present; // bit f*2: template 4 present, bit f*2+1: template 5 present (scorer f); bits 24..31: min(255, e - b)
@@ -77,25 +78,34 @@ struct EdgeCache {
 // doubles per edge in kval (stride 2 * n_funcs): for scorer f: [2f] = REG / MPREF / WPREF value or
 // template-4 weight, [2f+1] = template-5 weight
 
-__host__ __device__ inline size_t beam_warp_smem(int lcap, int beam, int n_funcs) {
-    const size_t units = (size_t)lcap + 8;
+// The back-pointer trail takes 4 bytes per kept entry in shared memory when the host finds that it
+// does not cost residency (BeamArgs::trail_smem); otherwise 8-byte records go to HBM.
+// Per-warp shared memory, in this order so that most arrays sit at compile-time offsets:
+//   fixed part      edge cache (e0, g0, meta, present), selection pool, per-span tables, counters
+//   beam part       ring entries: score, p1, pp, c1, meta, non-unknown ranks        (kRing * beam each)
+//   sentence part   ha, hb, CSR row, syllables, back-pointers                       (lcap + 8 each)
+//   kval            edge-only score values, 2 doubles per scorer and cache slot
+constexpr size_t kBeamFixedBytes = (size_t)kCacheSlots * 16 + (size_t)kEdgeRing * 16 + 32 * 8 + 64 * 8 +
+                                   (size_t)kCacheSlots * 8 + (5 * 16 + 32 + 8) * 4;
+static_assert(kBeamFixedBytes % 16 == 0, "fixed part keeps 16-byte alignment");
+__host__ __device__ inline size_t beam_ring_bytes(int beam) {
+    return (((size_t)kRing * beam * (8 + 48 + 4 + 1)) + 15) & ~(size_t)15;
+}
+__host__ __device__ inline size_t beam_sentence_bytes(int lcap, int beam, bool trail_smem) {
+    const size_t units = (size_t)lcap + 8;                 // a multiple of 8
+    return units * (8 + 8 + 8 + 2) + (trail_smem ? units * beam * 4 : 0);
+}
+__host__ __device__ inline size_t beam_warp_smem(int lcap, int beam, int n_funcs, bool trail_smem) {
     const size_t nf = (size_t)(n_funcs > 0 ? n_funcs : 1);
-    size_t bytes = units * 8 * 2;                          // ha, hb
-    bytes += units * 8;                                    // pos (uint2)
-    bytes += (size_t)kRing * beam * (8 + 64);              // score, p1, pp, j2, c1
-    bytes += (size_t)kCacheSlots * (16 + 16 + 16 * nf);    // e0, g0, kval
-    bytes += 32 * 8;                                       // selected keys by rank
-    bytes += units * 2;                                    // chars
-    bytes = (bytes + 7) & ~(size_t)7;
-    bytes += (size_t)kRing * beam * 4;                     // meta
-    bytes += (size_t)kCacheSlots * 8;                      // cache meta, present
-    bytes += 6 * 16 * 4;                                   // per-span tables + ring sizes
-    bytes += 2 * 64 * 4 + 32 * 4;                          // selection pool (high / low words), selected payloads
-    bytes += (size_t)kRing * beam;                         // ranks of the entries that do not end in an unknown word
+    const size_t bytes = kBeamFixedBytes + beam_ring_bytes(beam) + beam_sentence_bytes(lcap, beam, trail_smem) +
+                         (size_t)kCacheSlots * 16 * nf;
     return (bytes + 15) & ~(size_t)15;
 }
 
-// trail entry: edge reference (global edge index, or kTrailUnk) | span << 32 | parent rank << 40
+// candidate payload = shared-memory trail entry: (LT_WINDOW - span) << 27 | parent rank << 20 | bucket-local edge index
+constexpr uint32_t kPayUnk = 0xFFFFFu;        // edge index of an unknown word
+
+// HBM trail entry: edge reference (global edge index, or kTrailUnk) | span << 32 | parent rank << 40
 constexpr uint32_t kTrailUnk = 0xFFFFFFFFu;
 
 struct DenseView {
@@ -334,7 +344,7 @@ __device__ __forceinline__ void prep_edge(const DevTables& T, const SentView& v,
         C.kval[slot * kvs + 2 * f + 1] = b2;
     }
     C.e0[slot] = e0;
-    C.g0[slot] = g0;
+    if (slot < (uint32_t)kEdgeRing) C.g0[slot] = g0;
     C.meta[slot] = k.tag0 | (k.len << 8) | (k.flags << 24);
     const uint32_t span = (uint32_t)(k.e - k.b);
     C.present[slot] = present | ((span < 255u ? span : 255u) << 24);
@@ -344,14 +354,14 @@ __device__ __forceinline__ void prep_edge(const DevTables& T, const SentView& v,
 //   2  rank by counting (beam <= kRankMaxBeam): every candidate counts the pool entries that beat it
 //   1  32-lane bitonic sorting network per chunk + bitonic merge with the kept list (beam <= 32)
 //   0  rounds of warp arg-max with two kept entries per lane (beam 33..64)
-template <int MODE>
+template <int MODE, int KT>      // KT: the beam size when known at compile time (array offsets become constants), 0 = A.beam
 __global__ void __launch_bounds__(kBeamWarps * 32, LT_BEAM_MINB) beam_kernel(const __grid_constant__ DevTables T, const __grid_constant__ BeamArgs A) {
     constexpr int KR = (MODE == 0) ? 2 : 1;      // kept entries per lane
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
-    const int K = A.beam;
+    const int K = KT ? KT : A.beam;
     const int NT = T.n_tags;
 
     // CTA-shared dense tables (tag x tag matrix, length vectors)
@@ -362,38 +372,42 @@ __global__ void __launch_bounds__(kBeamWarps * 32, LT_BEAM_MINB) beam_kernel(con
     __syncthreads();
     if (A.flags[kFlagEdgeOverflow] | A.flags[kFlagStageOverflow]) return;   // lattice incomplete: the host grows the buffer and reruns
 
+    const bool trail_smem = A.trail_smem != 0;
     const size_t units = (size_t)A.lcap + 8;
-    unsigned char* wbase = smem_raw + dense_bytes + (size_t)warp * beam_warp_smem(A.lcap, K, T.n_funcs);
-    uint64_t* ha = reinterpret_cast<uint64_t*>(wbase);
-    uint64_t* hb = ha + units;
-    uint2* spos = reinterpret_cast<uint2*>(hb + units);
-    double* e_score = reinterpret_cast<double*>(spos + units);
-    H2* e_p1 = reinterpret_cast<H2*>(e_score + kRing * K);     // wj * M1
-    H2* e_pp = e_p1 + kRing * K;                                // wj * M1 + wi * M2
-    H2* e_j2 = e_pp + kRing * K;                                // wj * M2
-    H2* e_c1 = e_j2 + kRing * K;                                // contextual morph * M1
+    const int RK = kRing * K;
+    unsigned char* wbase = smem_raw + dense_bytes + (size_t)warp * beam_warp_smem(A.lcap, K, T.n_funcs, trail_smem);
+    // fixed part
     EdgeCache C;
-    C.e0 = e_c1 + kRing * K;
+    C.e0 = reinterpret_cast<H2*>(wbase);
     C.g0 = C.e0 + kCacheSlots;
-    C.kval = reinterpret_cast<double*>(C.g0 + kCacheSlots);
-    const int kvs = 2 * (T.n_funcs > 0 ? T.n_funcs : 1);   // kval stride
-    uint64_t* s_newkey = reinterpret_cast<uint64_t*>(C.kval + (size_t)kCacheSlots * kvs);   // [32] selected keys by rank
-    uint16_t* ch = reinterpret_cast<uint16_t*>(s_newkey + 32);
-    uintptr_t after = (reinterpret_cast<uintptr_t>(ch + units) + 7) & ~(uintptr_t)7;
-    uint32_t* e_meta = reinterpret_cast<uint32_t*>(after);
-    C.meta = e_meta + kRing * K;
+    uint64_t* s_newkey = reinterpret_cast<uint64_t*>(C.g0 + kEdgeRing);   // [32] selected keys by rank
+    uint64_t* s_pool = s_newkey + 32;               // [64] selection pool: kept entries, then the chunk's lanes
+    C.meta = reinterpret_cast<uint32_t*>(s_pool + 64);
     C.present = C.meta + kCacheSlots;
     uint32_t* s_cnt = C.present + kCacheSlots;      // [9] edges per span
     uint32_t* s_gstart = s_cnt + 16;                // [9] bucket-local index of the span's first edge
-    uint32_t* s_ncand = s_gstart + 16;              // [9] candidates of the span
-    uint32_t* s_nbeam = s_ncand + 16;               // [kRing] entries per ring slot
+    uint32_t* s_tlist = s_gstart + 16;              // [8] spans that generate candidates, in generation order: first candidate << 4 | span
+    uint32_t* s_nbeam = s_tlist + 16;               // [kRing] entries per ring slot
     uint32_t* s_nnon = s_nbeam + 16;                // [kRing] entries per ring slot that do not end in an unknown word
-    uint32_t* p_hi = s_nnon + 32;                   // [64] selection pool, high words: kept entries, then the chunk's lanes
-    uint32_t* p_lo = p_hi + 64;                     // [64] low words
-    uint32_t* s_newpay = p_lo + 64;                 // [32] selected payloads by rank
-    uint8_t* s_nonunk = reinterpret_cast<uint8_t*>(s_newpay + 32);   // [kRing * K] ranks of the non-unknown entries, ascending
+    uint32_t* s_newpay = s_nnon + 16;               // [32] selected payloads by rank
+    uint32_t* s_acc = s_newpay + 32;                // [4] work counters of this warp: T, F, Bk, W (+ 4 spare)
+    // beam part
+    double* e_score = reinterpret_cast<double*>(wbase + kBeamFixedBytes);
+    H2* e_p1 = reinterpret_cast<H2*>(e_score + RK);             // wj * M1
+    H2* e_pp = e_p1 + RK;                                       // wj * M1 + wi * M2
+    H2* e_c1 = e_pp + RK;                                       // contextual morph * M1
+    uint32_t* e_meta = reinterpret_cast<uint32_t*>(e_c1 + RK);
+    uint8_t* s_nonunk = reinterpret_cast<uint8_t*>(e_meta + RK);   // [kRing * K] ranks of the non-unknown entries, ascending
+    // sentence part
+    uint64_t* ha = reinterpret_cast<uint64_t*>(wbase + kBeamFixedBytes + beam_ring_bytes(K));
+    uint64_t* hb = ha + units;
+    uint2* spos = reinterpret_cast<uint2*>(hb + units);
+    uint16_t* ch = reinterpret_cast<uint16_t*>(spos + units);
+    uint32_t* s_trail = reinterpret_cast<uint32_t*>(ch + units);   // [units * K] when trail_smem
+    C.kval = reinterpret_cast<double*>(wbase + kBeamFixedBytes + beam_ring_bytes(K) + beam_sentence_bytes(A.lcap, K, trail_smem));
+    const int kvs = 2 * (T.n_funcs > 0 ? T.n_funcs : 1);   // kval stride
 
-    uint32_t acc_T = 0, acc_F = 0, acc_B = 0, acc_W = 0;     // per lane and launch: far below 2^32
+    if (lane < 4) s_acc[lane] = 0;
 
     bool need_m1 = false;
     for (int f = 0; f < T.n_funcs; ++f) need_m1 |= (T.funcs[f].kind == LT_FUNC_MPREF);
@@ -431,7 +445,6 @@ __global__ void __launch_bounds__(kBeamWarps * 32, LT_BEAM_MINB) beam_kernel(con
         if (lane == 0) {
             e_score[0] = 0.0;
             e_p1[0] = h2_mul(T.bos, kM1a, kM1b);
-            e_j2[0] = h2_mul(T.bos, kM2a, kM2b);
             e_pp[0] = H2{0, 0};
             e_c1[0] = H2{0, 0};
             e_meta[0] = (uint32_t)LT_TAG_BOS;
@@ -520,18 +533,28 @@ __global__ void __launch_bounds__(kBeamWarps * 32, LT_BEAM_MINB) beam_kernel(con
                 }
                 __syncwarp();
             }
+            // lane t < 8 owns span LT_WINDOW - t: generation order (begin ascending) is lane order
+            uint32_t span_nc = 0, span_c0 = 0;      // candidates of the lane's span, index of its first candidate
             uint32_t N;
             {
-                uint32_t nc = 0;
-                if (lane >= 1 && lane <= jmax) {
-                    const uint32_t c = s_cnt[lane];
-                    const int ps = (e - lane) % kRing;
+                const int jj = LT_WINDOW - lane;
+                if (lane < LT_WINDOW && jj <= jmax) {
+                    const uint32_t c = s_cnt[jj];
+                    const int ps = (e - jj) % kRing;
                     // an unknown word may follow an unknown word only from the window's first begin (beam.py:44-45):
                     // elsewhere only the parents that do not end in an unknown word generate a candidate
-                    nc = c ? s_nbeam[ps] * c : ((lane < jmax) ? s_nnon[ps] : s_nbeam[ps]);
+                    span_nc = c ? s_nbeam[ps] * c : ((jj < jmax) ? s_nnon[ps] : s_nbeam[ps]);
                 }
-                if (lane >= 1 && lane <= LT_WINDOW) s_ncand[lane] = nc;
-                N = __reduce_add_sync(kFull, nc);
+                uint32_t incl = span_nc;
+                #pragma unroll
+                for (int d = 1; d < LT_WINDOW; d <<= 1) {
+                    const uint32_t t = __shfl_up_sync(kFull, incl, d);
+                    if (lane >= d) incl += t;
+                }
+                span_c0 = incl - span_nc;
+                N = __shfl_sync(kFull, incl, LT_WINDOW - 1);
+                const unsigned gen = __ballot_sync(kFull, span_nc > 0);
+                if (span_nc > 0) s_tlist[__popc(gen & lt_mask)] = (span_c0 << 4) | (uint32_t)jj;
             }
             __syncwarp();
 
@@ -545,19 +568,20 @@ __global__ void __launch_bounds__(kBeamWarps * 32, LT_BEAM_MINB) beam_kernel(con
             for (uint32_t c0 = 0; c0 < N; c0 += 32) {
                 const uint32_t c = c0 + lane;
                 bool valid = c < N;
+                // the span of candidate c: spans that start inside this chunk vote their first lane
+                const bool gen = span_nc > 0;
+                const unsigned starts = __reduce_or_sync(kFull, (gen && span_c0 >= c0 && span_c0 < c0 + 32u) ? (1u << (span_c0 - c0)) : 0u);
+                const uint32_t before = __popc(__ballot_sync(kFull, gen && span_c0 < c0));
                 int j = 0;
-                uint32_t rem = c;
+                uint32_t rem = 0;
                 if (valid) {
-                    #pragma unroll
-                    for (int jj = LT_WINDOW; jj >= 1; --jj) {
-                        if (j == 0) {
-                            const uint32_t nc = s_ncand[jj];
-                            if (rem < nc) j = jj; else rem -= nc;
-                        }
-                    }
+                    const uint32_t tl = s_tlist[before + __popc(starts & (0xFFFFFFFFu >> (31 - lane))) - 1];
+                    j = (int)(tl & 15u);
+                    rem = c - (tl >> 4);
                 }
                 uint64_t ckey = 0;
                 uint32_t cpay = 0;
+                uint32_t cand_F = 0;        // feature tuples this candidate generates
                 if (valid) {
                     const uint32_t cj = s_cnt[j];
                     const bool unk_edge = (cj == 0);
@@ -587,7 +611,7 @@ __global__ void __launch_bounds__(kBeamWarps * 32, LT_BEAM_MINB) beam_kernel(con
                         emeta = kfly.tag0 | (kfly.len << 8) | (kfly.flags << 24);
                     } else {
                         e0 = C.e0[slot];
-                        g0 = C.g0[slot];
+                        g0 = unk_edge ? e0 : C.g0[slot];
                         emeta = C.meta[slot];
                         epresent = C.present[slot];
                     }
@@ -612,7 +636,7 @@ __global__ void __launch_bounds__(kBeamWarps * 32, LT_BEAM_MINB) beam_kernel(con
                         if (T.funcs[f].kind == LT_FUNC_TRIGRAM) {
                             // SimpleTrigramFeatureScore.score (score_funcs.py:137-144)
                             const DenseView D = dense_view(dense_smem + (size_t)T.func_dense[f] * dense_block_bytes(NT), NT);
-                            acc_F += valid ? 6u + (j_unk ? 1u : 0u) + (has_i ? 1u : 0u) + (ctx8 ? 1u : 0u) : 0u;
+                            cand_F += valid ? 6u + (j_unk ? 1u : 0u) + (has_i ? 1u : 0u) + (ctx8 ? 1u : 0u) : 0u;
                             const H2 pp = has_i ? e_pp[pslot] : H2{0, 0};
                             const H2 c1v = ctx8 ? e_c1[pslot] : H2{0, 0};
                             const uint32_t hk = feature_head32(tk, 0);
@@ -657,64 +681,42 @@ __global__ void __launch_bounds__(kBeamWarps * 32, LT_BEAM_MINB) beam_kernel(con
                     double newscore = __dadd_rn(pscore, inc);        // Sequence.add, beam.py:115
                     newscore = __dadd_rn(newscore, 0.0);             // -0.0 sorts as 0.0
                     ckey = valid ? sortable(newscore) : 0ull;
-                    acc_T += valid ? 1u : 0u;
                     // payload doubles as the generation ordinal: begin ascending (= span descending), parent
                     // rank ascending, edge order ascending (beam.py:30-48)
-                    cpay = ((uint32_t)(LT_WINDOW - j) << 27) | (prank << 20) | bidx;
+                    cpay = ((uint32_t)(LT_WINDOW - j) << 27) | (prank << 20) | (unk_edge ? kPayUnk : bidx);
+                }
+                // work counters: scored transitions and generated feature tuples of this chunk
+                const uint32_t chunk_T = __popc(__ballot_sync(kFull, ckey != 0));
+                {
+                    const uint32_t chunk_F = __reduce_add_sync(kFull, cand_F);
+                    if (lane == 0) { s_acc[0] += chunk_T; s_acc[1] += chunk_F; }
                 }
                 if constexpr (MODE == 2) {
                     // ---- top-K by rank counting: an entry's rank = number of pool entries that beat it ----
                     // pool = kept entries (earlier candidates, they win ties) + this chunk's lanes in generation order
                     const uint32_t nc = (N - c0 < 32u) ? (N - c0) : 32u;
-                    const uint32_t chi = (uint32_t)(ckey >> 32);
                     const uint64_t kkey = keep_key[0];
-                    const uint32_t khi = (uint32_t)(kkey >> 32);
-                    p_hi[32 + lane] = chi;
-                    p_lo[32 + lane] = (uint32_t)ckey;
-                    if ((uint32_t)lane < nk) { p_hi[lane] = khi; p_lo[lane] = (uint32_t)kkey; }
+                    s_pool[32 + lane] = ckey;
+                    if ((uint32_t)lane < nk) s_pool[lane] = kkey;
                     __syncwarp();
-                    // fast pass on the high words; any equal pair of high words falls back to the full keys
-                    uint32_t gt_c = 0, eq_c = 0, gt_k = 0, eq_k = 0;
+                    uint32_t gt_c = 0, gt_k = 0;
                     if (nk == 0) {
                         #pragma unroll 4
-                        for (uint32_t l = 0; l < nc; ++l) {
-                            const uint32_t h = p_hi[32 + l];
-                            gt_c += (h > chi) ? 1u : 0u;
-                            eq_c += (h == chi) ? 1u : 0u;
-                        }
+                        for (uint32_t l = 0; l < nc; ++l) gt_c += (s_pool[32 + l] > ckey) ? 1u : 0u;
                     } else {
                         #pragma unroll 4
                         for (uint32_t l = 0; l < nc; ++l) {
-                            const uint32_t h = p_hi[32 + l];
-                            gt_c += (h > chi) ? 1u : 0u;
-                            eq_c += (h == chi) ? 1u : 0u;
-                            gt_k += (h > khi) ? 1u : 0u;
-                            eq_k += (h == khi) ? 1u : 0u;
-                        }
-                        #pragma unroll 4
-                        for (uint32_t r = 0; r < nk; ++r) {
-                            const uint32_t h = p_hi[r];
-                            gt_c += (h > chi) ? 1u : 0u;
-                            eq_c += (h == chi) ? 1u : 0u;
-                        }
-                    }
-                    const bool ambiguous = (ckey != 0 && eq_c > 1u) || ((uint32_t)lane < nk && eq_k > 0u);
-                    if (__any_sync(kFull, ambiguous)) {
-                        gt_c = 0;
-                        gt_k = 0;
-                        #pragma unroll 1
-                        for (uint32_t l = 0; l < nc; ++l) {
-                            const uint64_t o = ((uint64_t)p_hi[32 + l] << 32) | p_lo[32 + l];
-                            gt_c += (o > ckey || (o == ckey && l < (uint32_t)lane)) ? 1u : 0u;
+                            const uint64_t o = s_pool[32 + l];
+                            gt_c += (o > ckey) ? 1u : 0u;
                             gt_k += (o > kkey) ? 1u : 0u;
                         }
-                        #pragma unroll 1
-                        for (uint32_t r = 0; r < nk; ++r) {
-                            const uint64_t o = ((uint64_t)p_hi[r] << 32) | p_lo[r];
-                            gt_c += (o >= ckey) ? 1u : 0u;
-                        }
+                        const uint64_t cm1 = ckey - 1;        // a kept entry with an equal key is the earlier candidate
+                        #pragma unroll 4
+                        for (uint32_t r = 0; r < nk; ++r) gt_c += (s_pool[r] > cm1) ? 1u : 0u;
                     }
-                    const uint32_t nvalid = __popc(__ballot_sync(kFull, ckey != 0));
+                    // equal keys inside the chunk: the earlier lane first
+                    gt_c += __popc(__match_any_sync(kFull, ckey) & lt_mask);
+                    const uint32_t nvalid = chunk_T;
                     if (ckey != 0 && gt_c < (uint32_t)K) { s_newkey[gt_c] = ckey; s_newpay[gt_c] = cpay; }
                     if ((uint32_t)lane < nk && lane + gt_k < (uint32_t)K) { s_newkey[lane + gt_k] = kkey; s_newpay[lane + gt_k] = keep_pay[0]; }
                     __syncwarp();
@@ -839,7 +841,7 @@ __global__ void __launch_bounds__(kBeamWarps * 32, LT_BEAM_MINB) beam_kernel(con
                     if (!unk_edge) eref = es + bidx;
                     if (cached) {
                         const uint32_t cslot = unk_edge ? unk_base + (uint32_t)j : (eref & (kEdgeRing - 1));
-                        const H2 e0 = C.e0[cslot], g0 = C.g0[cslot];
+                        const H2 e0 = C.e0[cslot], g0 = unk_edge ? e0 : C.g0[cslot];
                         const uint32_t em = C.meta[cslot];
                         tag0 = em & 0xFFu;
                         len = (em >> 8) & 0xFFFFu;
@@ -863,13 +865,12 @@ __global__ void __launch_bounds__(kBeamWarps * 32, LT_BEAM_MINB) beam_kernel(con
                     const int dst = slot_e * K + rank;
                     e_score[dst] = unsortable(keep_key[r]);
                     e_p1[dst] = wk1;
-                    e_pp[dst] = h2_add(wk1, e_j2[pslot]);
-                    e_j2[dst] = wk2;
+                    e_pp[dst] = h2_add(wk1, h2_mul(e_p1[pslot], kM2over1a, kM2over1b));     // wk * M1 + wj * M2
                     e_c1[dst] = k_ctx ? mk1 : (j_ctx ? e_c1[pslot] : H2{0, 0});
                     const uint32_t ul = len < 8u ? len : 8u;
                     e_meta[dst] = tag0 | kMetaHasI | ((k_ctx || j_ctx) ? kMetaHasCtx : 0u) | (ul << kMetaUnkLenShift);
-                    A.trail[(size_t)(s0 + e - 1) * K + rank] =
-                        (uint64_t)eref | ((uint64_t)j << 32) | ((uint64_t)prank << 40);
+                    if (trail_smem) s_trail[(e - 1) * K + rank] = kp;
+                    else A.trail[(size_t)(s0 + e - 1) * K + rank] = (uint64_t)eref | ((uint64_t)j << 32) | ((uint64_t)prank << 40);
                 }
                 // ranks of the entries that may be followed by an unknown word, ascending
                 const unsigned m_have = __ballot_sync(kFull, have);
@@ -878,52 +879,62 @@ __global__ void __launch_bounds__(kBeamWarps * 32, LT_BEAM_MINB) beam_kernel(con
                 nl += __popc(m_have);
                 nn += __popc(m_non);
             }
-            if (lane == 0) { s_nbeam[slot_e] = (uint32_t)nl; s_nnon[slot_e] = (uint32_t)nn; }
-            acc_B += (lane == 0) ? (uint32_t)nl : 0u;
+            if (lane == 0) { s_nbeam[slot_e] = (uint32_t)nl; s_nnon[slot_e] = (uint32_t)nn; s_acc[2] += (uint32_t)nl; }
             __syncwarp();
         }
 
         // ---- best path: matures[0] (tagger.py:78) ----
-        if (lane == 0 && L > 0) {
-            A.scores[s] = e_score[(L % kRing) * K + 0];
-            int e = L, r = 0, W = 0;
-            while (e > 0) {
-                const uint64_t t = A.trail[(size_t)(s0 + e - 1) * K + r];
+        // lane 0 follows the back-pointers (a dependent chain) and lists (end, edge reference); then the
+        // lanes fetch the edge records side by side
+        if (L > 0) {
+            uint64_t* s_path = ha;              // the prefix hashes are no longer needed
+            int W = 0;
+            if (lane == 0) {
+                A.scores[s] = e_score[(L % kRing) * K + 0];
+                int e = L, r = 0;
+                while (e > 0) {
+                    uint32_t eref, span;
+                    if (trail_smem) {
+                        const uint32_t t = s_trail[(e - 1) * K + r];
+                        span = (uint32_t)LT_WINDOW - (t >> 27);
+                        const uint32_t bidx = t & kPayUnk;
+                        eref = (bidx == kPayUnk) ? kTrailUnk : spos[e - 1].x + bidx;
+                        r = (int)((t >> 20) & 0x7Fu);
+                    } else {
+                        const uint64_t t = A.trail[(size_t)(s0 + e - 1) * K + r];
+                        eref = (uint32_t)t;
+                        span = (uint32_t)((t >> 32) & 0xFFu);
+                        r = (int)((t >> 40) & 0xFFu);
+                    }
+                    s_path[W] = (uint64_t)eref | ((uint64_t)e << 32) | ((uint64_t)span << 48);
+                    ++W;
+                    e -= (int)span;
+                }
+                A.path_len[s] = W;
+                s_acc[3] += (uint32_t)W;
+            }
+            W = __shfl_sync(kFull, W, 0);
+            __syncwarp();
+            for (int w = lane; w < W; w += 32) {
+                const uint64_t t = s_path[w];
                 const uint32_t eref = (uint32_t)t;
-                const int span = (int)((t >> 32) & 0xFFu);
                 lt_edge ed;
                 if (eref == kTrailUnk) {
+                    const uint32_t e = (uint32_t)(t >> 32) & 0xFFFFu, span = (uint32_t)(t >> 48);
                     ed.b = (uint16_t)(e - span); ed.e = (uint16_t)e; ed.len = (uint16_t)span;
                     ed.tag0 = LT_TAG_UNK; ed.tag1 = LT_NO_TAG; ed.rule = LT_NO_RULE; ed.split = 0;
                     ed.flags = LT_EDGE_UNK; ed.reserved = 0;
                 } else {
                     ed = A.edges[eref];
                 }
-                A.path_tmp[s0 + W] = ed;
-                ++W;
-                r = (int)((t >> 40) & 0xFFu);
-                e -= span;
+                A.path_tmp[s0 + w] = ed;
             }
-            A.path_len[s] = W;
-            acc_W += (uint32_t)W;
         }
         __syncwarp();
     }
-    // counters
-    unsigned long long t64 = acc_T, f64 = acc_F, b64 = acc_B, w64 = acc_W;
-    #pragma unroll
-    for (int d = 16; d; d >>= 1) {
-        t64 += __shfl_xor_sync(kFull, t64, d);
-        f64 += __shfl_xor_sync(kFull, f64, d);
-        b64 += __shfl_xor_sync(kFull, b64, d);
-        w64 += __shfl_xor_sync(kFull, w64, d);
-    }
-    if (lane == 0) {
-        atomicAdd(A.counters + 3, t64);
-        atomicAdd(A.counters + 4, f64);
-        atomicAdd(A.counters + 5, b64);
-        atomicAdd(A.counters + 6, w64);
-    }
+    // counters (per warp and launch each stays far below 2^32)
+    __syncwarp();
+    if (lane < 4) atomicAdd(A.counters + 3 + lane, (unsigned long long)s_acc[lane]);
 }
 
 }  // namespace lt

@@ -105,6 +105,7 @@ constexpr uint64_t inv64(uint64_t a) {
 }
 constexpr uint64_t kM1over0a = kM1a * inv64(kM0a), kM1over0b = kM1b * inv64(kM0b);
 constexpr uint64_t kM2over0a = kM2a * inv64(kM0a), kM2over0b = kM2b * inv64(kM0b);
+constexpr uint64_t kM2over1a = kM2a * inv64(kM1a), kM2over1b = kM2b * inv64(kM1b);
 static_assert(kM0a * inv64(kM0a) == 1 && kM0b * inv64(kM0b) == 1, "inv64");
 LT_HD H2 h2_add(H2 x, H2 y) { return H2{x.a + y.a, x.b + y.b}; }
 

@@ -533,7 +533,6 @@ static int launch_beam(lt_batch* b, cudaStream_t st) {
     const int n_sent = b->n_sent;
     const size_t nu = (size_t)b->n_units + 1;
 
-    if (int rc = ensure(b->trail, nu * (size_t)beam_size * 8)) return rc;
     if (int rc = ensure(b->path_tmp, nu * sizeof(lt_edge))) return rc;
     if (int rc = ensure(b->path_out, nu * sizeof(lt_edge))) return rc;
     if (int rc = ensure(b->path_len, (size_t)(n_sent + 1) * 4)) return rc;
@@ -541,7 +540,21 @@ static int launch_beam(lt_batch* b, cudaStream_t st) {
     if (int rc = ensure(b->scores, (size_t)std::max(1, n_sent) * 8)) return rc;
 
     const size_t dense_bytes = ((size_t)t->dev.n_tri * dense_block_bytes(t->dev.n_tags) + 15) & ~(size_t)15;
-    const size_t group_smem = beam_warp_smem(b->lcap, beam_size, t->dev.n_funcs);
+    // resident warps per SM for a per-warp footprint (the kernel's 128 registers allow 4 CTAs of 4 warps)
+    auto resident_warps = [&](size_t warp_smem) -> int {
+        if (dense_bytes + warp_smem > kSmemBudget) return 0;
+        const int w = (int)std::min<size_t>(kBeamWarps, (kSmemBudget - dense_bytes) / warp_smem);
+        const size_t cta = dense_bytes + warp_smem * w + 1024;
+        return w * (int)std::min<size_t>(4, (size_t)228 * 1024 / cta);
+    };
+    // back-pointers live in shared memory when that does not lower the residency
+    const size_t smem_hbm_trail = beam_warp_smem(b->lcap, beam_size, t->dev.n_funcs, false);
+    const size_t smem_own_trail = beam_warp_smem(b->lcap, beam_size, t->dev.n_funcs, true);
+    bool trail_smem = resident_warps(smem_own_trail) > 0 && resident_warps(smem_own_trail) >= resident_warps(smem_hbm_trail);
+    if (const char* env = getenv("LT_TRAIL_SMEM")) trail_smem = trail_smem && atoi(env) != 0;
+    if (!trail_smem)
+        if (int rc = ensure(b->trail, nu * (size_t)beam_size * 8)) return rc;
+    const size_t group_smem = trail_smem ? smem_own_trail : smem_hbm_trail;
     if (dense_bytes + group_smem > kSmemBudget)
         return fail(LT_ERR_INVALID, "sentence length %d with beam %d does not fit the beam kernel's shared memory", b->lcap, beam_size);
     const int warps = (int)std::min<size_t>(kBeamWarps, (kSmemBudget - dense_bytes) / group_smem);
@@ -566,14 +579,23 @@ static int launch_beam(lt_batch* b, cudaStream_t st) {
     A.counters = static_cast<unsigned long long*>(b->counters.p);
     A.queue = ctl + kCtlBeamQueue;
     A.order = (b->sort_by_length && n_sent > 1) ? static_cast<const uint32_t*>(b->order.p) : nullptr;
+    A.trail_smem = trail_smem ? 1 : 0;
 
-    auto kernel = beam_size <= kRankMaxBeam ? beam_kernel<2> : (beam_size <= 32 ? beam_kernel<1> : beam_kernel<0>);
+    // common beam sizes get their own instantiation (compile-time array offsets)
+    auto kernel = beam_size == 5 ? beam_kernel<2, 5>
+                  : beam_size == 10 ? beam_kernel<2, 10>
+                  : beam_size <= kRankMaxBeam ? beam_kernel<2, 0>
+                  : beam_size == 32 ? beam_kernel<1, 32>
+                  : beam_size <= 32 ? beam_kernel<1, 0> : beam_kernel<0, 0>;
     CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, warps * 32, smem));
     per_sm = std::max(1, per_sm);
     const int64_t want_blocks = ((int64_t)n_sent + warps - 1) / warps;
     const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(want_blocks, (int64_t)t->sm_count * per_sm));
+    if (getenv("LT_DEBUG"))
+        fprintf(stderr, "[lt] beam kernel: beam %d lcap %d, %zu B/warp, %d warps/CTA, %zu B/CTA, %d CTAs/SM, trail in %s\n", beam_size,
+                b->lcap, group_smem, warps, smem, per_sm, trail_smem ? "shared memory" : "HBM");
 
     CU(cudaMemsetAsync(ctl + kCtlBeamQueue, 0, sizeof(unsigned int), st));
     CU(cudaMemsetAsync(static_cast<unsigned long long*>(b->counters.p) + 3, 0, 4 * sizeof(unsigned long long), st));

@@ -47,7 +47,7 @@ struct BeamArgs {
     const uint16_t* text;
     const int32_t* sent_off;
     int32_t n_sent;
-    int32_t lcap;
+    int32_t units;              // shared-memory elements per sentence array: >= longest sentence + 8, a multiple of 8
     int32_t beam;
     int32_t warps;              // warps per CTA
     const uint2* pos;           // [n_units] (first edge, edge count) per (sentence, end position)
@@ -83,23 +83,28 @@ struct EdgeCache {
 // Per-warp shared memory, in this order so that most arrays sit at compile-time offsets:
 //   fixed part      edge cache (e0, g0, meta, present), selection pool, per-span tables, counters
 //   beam part       ring entries: score, p1, pp, c1, meta, non-unknown ranks        (kRing * beam each)
-//   sentence part   ha, hb, CSR row, syllables, back-pointers                       (lcap + 8 each)
+//   sentence part   ha, hb, CSR row, syllables                                       (units each)
 //   kval            edge-only score values, 2 doubles per scorer and cache slot
+//   trail           back-pointers, units * beam (when they live in shared memory)
+// `units` >= longest sentence of the batch + 8 (a multiple of 8); the common sizes are template
+// parameters of the kernel, so that every array but the trail sits at a constant offset.
 constexpr size_t kBeamFixedBytes = (size_t)kCacheSlots * 16 + (size_t)kEdgeRing * 16 + 32 * 8 + 64 * 8 +
                                    (size_t)kCacheSlots * 8 + (5 * 16 + 32 + 8) * 4;
 static_assert(kBeamFixedBytes % 16 == 0, "fixed part keeps 16-byte alignment");
 __host__ __device__ inline size_t beam_ring_bytes(int beam) {
     return (((size_t)kRing * beam * (8 + 48 + 4 + 1)) + 15) & ~(size_t)15;
 }
-__host__ __device__ inline size_t beam_sentence_bytes(int lcap, int beam, bool trail_smem) {
-    const size_t units = (size_t)lcap + 8;                 // a multiple of 8
-    return units * (8 + 8 + 8 + 2) + (trail_smem ? units * beam * 4 : 0);
-}
-__host__ __device__ inline size_t beam_warp_smem(int lcap, int beam, int n_funcs, bool trail_smem) {
+__host__ __device__ inline size_t beam_sentence_bytes(int units) { return (size_t)units * (8 + 8 + 8 + 2); }
+__host__ __device__ inline size_t beam_warp_smem(int units, int beam, int n_funcs, bool trail_smem) {
     const size_t nf = (size_t)(n_funcs > 0 ? n_funcs : 1);
-    const size_t bytes = kBeamFixedBytes + beam_ring_bytes(beam) + beam_sentence_bytes(lcap, beam, trail_smem) +
-                         (size_t)kCacheSlots * 16 * nf;
+    const size_t bytes = kBeamFixedBytes + beam_ring_bytes(beam) + beam_sentence_bytes(units) + (size_t)kCacheSlots * 16 * nf +
+                         (trail_smem ? (size_t)units * beam * 4 : 0);
     return (bytes + 15) & ~(size_t)15;
+}
+// sentence-array sizes with their own kernel instantiation
+__host__ __device__ inline int beam_units_class(int lcap) {
+    const int need = lcap + 8;
+    return need <= 64 ? 64 : (need <= 128 ? 128 : 0);
 }
 
 // candidate payload = shared-memory trail entry: (LT_WINDOW - span) << 27 | parent rank << 20 | bucket-local edge index
@@ -249,9 +254,10 @@ __device__ __noinline__ uint32_t edge_score(const DevTables& T, const unsigned c
 
 // numpy's association from eight surviving weights on: rare, so the nine weights are
 // simply gathered again and summed by numpy_order_sum9.
-__device__ __noinline__ double trigram_sum_tree(const DevTables& T, const DenseView& D, int NT, int f, FKey q0, FKey q1,
+__device__ __noinline__ double trigram_sum_tree(const DevTables& T, const unsigned char* dense_blk, int NT, int f, FKey q0, FKey q1,
                                                 FKey q2, FKey q7, FKey q8, uint32_t tj, uint32_t tk, uint32_t epresent,
                                                 double val4, double val5, bool j_unk, uint32_t ul, bool has_i, bool ctx8) {
+    const DenseView D = dense_view(dense_blk, NT);
     double w[9];
     uint32_t present = 0;
     #pragma unroll
@@ -354,7 +360,9 @@ __device__ __forceinline__ void prep_edge(const DevTables& T, const SentView& v,
 //   2  rank by counting (beam <= kRankMaxBeam): every candidate counts the pool entries that beat it
 //   1  32-lane bitonic sorting network per chunk + bitonic merge with the kept list (beam <= 32)
 //   0  rounds of warp arg-max with two kept entries per lane (beam 33..64)
-template <int MODE, int KT>      // KT: the beam size when known at compile time (array offsets become constants), 0 = A.beam
+// KT: the beam size, UC: the sentence-array size when known at compile time (array offsets become
+// constants, which is what keeps the kernel's address arithmetic out of registers); 0 = A.beam / A.units
+template <int MODE, int KT, int UC>
 __global__ void __launch_bounds__(kBeamWarps * 32, LT_BEAM_MINB) beam_kernel(const __grid_constant__ DevTables T, const __grid_constant__ BeamArgs A) {
     constexpr int KR = (MODE == 0) ? 2 : 1;      // kept entries per lane
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -373,9 +381,9 @@ __global__ void __launch_bounds__(kBeamWarps * 32, LT_BEAM_MINB) beam_kernel(con
     if (A.flags[kFlagEdgeOverflow] | A.flags[kFlagStageOverflow]) return;   // lattice incomplete: the host grows the buffer and reruns
 
     const bool trail_smem = A.trail_smem != 0;
-    const size_t units = (size_t)A.lcap + 8;
+    const int units = UC ? UC : A.units;
     const int RK = kRing * K;
-    unsigned char* wbase = smem_raw + dense_bytes + (size_t)warp * beam_warp_smem(A.lcap, K, T.n_funcs, trail_smem);
+    unsigned char* wbase = smem_raw + dense_bytes + (size_t)warp * beam_warp_smem(units, K, T.n_funcs, trail_smem);
     // fixed part
     EdgeCache C;
     C.e0 = reinterpret_cast<H2*>(wbase);
@@ -403,9 +411,9 @@ __global__ void __launch_bounds__(kBeamWarps * 32, LT_BEAM_MINB) beam_kernel(con
     uint64_t* hb = ha + units;
     uint2* spos = reinterpret_cast<uint2*>(hb + units);
     uint16_t* ch = reinterpret_cast<uint16_t*>(spos + units);
-    uint32_t* s_trail = reinterpret_cast<uint32_t*>(ch + units);   // [units * K] when trail_smem
-    C.kval = reinterpret_cast<double*>(wbase + kBeamFixedBytes + beam_ring_bytes(K) + beam_sentence_bytes(A.lcap, K, trail_smem));
+    C.kval = reinterpret_cast<double*>(ch + units);
     const int kvs = 2 * (T.n_funcs > 0 ? T.n_funcs : 1);   // kval stride
+    uint32_t* s_trail = reinterpret_cast<uint32_t*>(C.kval + kCacheSlots * kvs);   // [units * K] when trail_smem
 
     if (lane < 4) s_acc[lane] = 0;
 
@@ -628,14 +636,18 @@ __global__ void __launch_bounds__(kBeamWarps * 32, LT_BEAM_MINB) beam_kernel(con
                     for (int f = 0; f < nf; ++f) {
                         double val, val5;
                         if (uncached) {
-                            epresent |= edge_score(T, dense_smem, kfly, e0, g0, f, val, val5) << (2 * f);
+                            double uv, uv5;      // (by reference to a call: keep val / val5 themselves in registers)
+                            epresent |= edge_score(T, dense_smem, kfly, e0, g0, f, uv, uv5) << (2 * f);
+                            val = uv;
+                            val5 = uv5;
                         } else {
                             val = C.kval[slot * kvs + 2 * f];
                             val5 = C.kval[slot * kvs + 2 * f + 1];
                         }
                         if (T.funcs[f].kind == LT_FUNC_TRIGRAM) {
                             // SimpleTrigramFeatureScore.score (score_funcs.py:137-144)
-                            const DenseView D = dense_view(dense_smem + (size_t)T.func_dense[f] * dense_block_bytes(NT), NT);
+                            const unsigned char* dense_blk = dense_smem + (size_t)T.func_dense[f] * dense_block_bytes(NT);
+                            const DenseView D = dense_view(dense_blk, NT);
                             cand_F += valid ? 6u + (j_unk ? 1u : 0u) + (has_i ? 1u : 0u) + (ctx8 ? 1u : 0u) : 0u;
                             const H2 pp = has_i ? e_pp[pslot] : H2{0, 0};
                             const H2 c1v = ctx8 ? e_c1[pslot] : H2{0, 0};
@@ -672,7 +684,7 @@ __global__ void __launch_bounds__(kBeamWarps * 32, LT_BEAM_MINB) beam_kernel(con
                             if (has_i && feat_resolve(T, q7, s7, w)) { acc = __dadd_rn(acc, w); ++n; }
                             if (ctx8 && feat_resolve(T, q8, s8, w)) { acc = __dadd_rn(acc, w); ++n; }
                             if (n >= 8)   // numpy switches to an 8-lane tree: redo the gather and add in that order (rare)
-                                acc = trigram_sum_tree(T, D, NT, f, q0, q1, q2, q7, q8, tj, tk, epresent, val, val5, j_unk, ul,
+                                acc = trigram_sum_tree(T, dense_blk, NT, f, q0, q1, q2, q7, q8, tj, tk, epresent, val, val5, j_unk, ul,
                                                        has_i, ctx8);
                             val = n ? acc : 0.0;
                         }

@@ -548,8 +548,12 @@ static int launch_beam(lt_batch* b, cudaStream_t st) {
         return w * (int)std::min<size_t>(4, (size_t)228 * 1024 / cta);
     };
     // back-pointers live in shared memory when that does not lower the residency
-    const size_t smem_hbm_trail = beam_warp_smem(b->lcap, beam_size, t->dev.n_funcs, false);
-    const size_t smem_own_trail = beam_warp_smem(b->lcap, beam_size, t->dev.n_funcs, true);
+    // sentence arrays: common sizes are template parameters of the kernel (for beams 5 and 10)
+    int units = b->lcap + 8;
+    const int uclass = (beam_size == 5 || beam_size == 10) ? beam_units_class(b->lcap) : 0;
+    if (uclass) units = uclass;
+    const size_t smem_hbm_trail = beam_warp_smem(units, beam_size, t->dev.n_funcs, false);
+    const size_t smem_own_trail = beam_warp_smem(units, beam_size, t->dev.n_funcs, true);
     bool trail_smem = resident_warps(smem_own_trail) > 0 && resident_warps(smem_own_trail) >= resident_warps(smem_hbm_trail);
     if (const char* env = getenv("LT_TRAIL_SMEM")) trail_smem = trail_smem && atoi(env) != 0;
     if (!trail_smem)
@@ -565,7 +569,7 @@ static int launch_beam(lt_batch* b, cudaStream_t st) {
     A.text = b->d_text;
     A.sent_off = b->d_sent_off;
     A.n_sent = n_sent;
-    A.lcap = b->lcap;
+    A.units = units;
     A.beam = beam_size;
     A.warps = warps;
     A.pos = static_cast<const uint2*>(b->pos.p);
@@ -581,12 +585,14 @@ static int launch_beam(lt_batch* b, cudaStream_t st) {
     A.order = (b->sort_by_length && n_sent > 1) ? static_cast<const uint32_t*>(b->order.p) : nullptr;
     A.trail_smem = trail_smem ? 1 : 0;
 
-    // common beam sizes get their own instantiation (compile-time array offsets)
-    auto kernel = beam_size == 5 ? beam_kernel<2, 5>
-                  : beam_size == 10 ? beam_kernel<2, 10>
-                  : beam_size <= kRankMaxBeam ? beam_kernel<2, 0>
-                  : beam_size == 32 ? beam_kernel<1, 32>
-                  : beam_size <= 32 ? beam_kernel<1, 0> : beam_kernel<0, 0>;
+    // common beam sizes and sentence-array sizes get their own instantiation (compile-time array offsets)
+    void (*kernel)(const DevTables, const BeamArgs);
+    if (beam_size == 5) kernel = uclass == 64 ? beam_kernel<2, 5, 64> : (uclass == 128 ? beam_kernel<2, 5, 128> : beam_kernel<2, 5, 0>);
+    else if (beam_size == 10) kernel = uclass == 64 ? beam_kernel<2, 10, 64> : (uclass == 128 ? beam_kernel<2, 10, 128> : beam_kernel<2, 10, 0>);
+    else if (beam_size <= kRankMaxBeam) kernel = beam_kernel<2, 0, 0>;
+    else if (beam_size == 32) kernel = beam_kernel<1, 32, 0>;
+    else if (beam_size <= 32) kernel = beam_kernel<1, 0, 0>;
+    else kernel = beam_kernel<0, 0, 0>;
     CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, warps * 32, smem));
@@ -594,8 +600,8 @@ static int launch_beam(lt_batch* b, cudaStream_t st) {
     const int64_t want_blocks = ((int64_t)n_sent + warps - 1) / warps;
     const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(want_blocks, (int64_t)t->sm_count * per_sm));
     if (getenv("LT_DEBUG"))
-        fprintf(stderr, "[lt] beam kernel: beam %d lcap %d, %zu B/warp, %d warps/CTA, %zu B/CTA, %d CTAs/SM, trail in %s\n", beam_size,
-                b->lcap, group_smem, warps, smem, per_sm, trail_smem ? "shared memory" : "HBM");
+        fprintf(stderr, "[lt] beam kernel: beam %d units %d, %zu B/warp, %d warps/CTA, %zu B/CTA, %d CTAs/SM, trail in %s\n", beam_size,
+                units, group_smem, warps, smem, per_sm, trail_smem ? "shared memory" : "HBM");
 
     CU(cudaMemsetAsync(ctl + kCtlBeamQueue, 0, sizeof(unsigned int), st));
     CU(cudaMemsetAsync(static_cast<unsigned long long*>(b->counters.p) + 3, 0, 4 * sizeof(unsigned long long), st));

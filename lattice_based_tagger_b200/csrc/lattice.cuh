@@ -32,6 +32,7 @@
 namespace lt {
 
 constexpr int kLatWarps = 4;                 // warps per CTA of the lattice kernel
+constexpr int kRuleQueue = 256;              // rule-work descriptors per warp (drained when more than half full)
 constexpr unsigned kFull = 0xFFFFFFFFu;
 
 // flags[] written by the lattice kernel, read by the beam kernel and the host
@@ -72,7 +73,9 @@ __host__ __device__ inline size_t lattice_warp_smem(int lcap, int hcap, int max_
     bytes += units * 2 * 2;                        // chars, eojeol starts
     bytes += units;                                // nend
     bytes += 64;                                   // counters
-    return (bytes + 15) & ~(size_t)15;
+    bytes = (bytes + 15) & ~(size_t)15;
+    bytes += (size_t)kRuleQueue * 16;              // rule-work queue
+    return bytes;
 }
 
 struct SentView {
@@ -193,6 +196,8 @@ struct Enum {
     uint32_t* tcnt;          // hits per task of the current eojeol
     uint32_t* nh;            // staged entries (shared counter)
     int hcap;
+    uint4* rq;               // rule-work queue: (word, split, conjugation key) triples waiting for their rules to be applied
+    uint32_t* rqn;           // queued descriptors (shared counter)
 };
 
 __device__ __forceinline__ uint32_t sub_get(const Enum& E, int x, int y) {
@@ -250,33 +255,67 @@ __device__ __forceinline__ void rule_candidate(const DevTables& T, const Enum& E
     }
 }
 
+// Rule work is QUEUED, not done in place: the items of an eojeol that meet a conjugation key are a
+// minority of the lanes, so applying the rules inside the item loop runs the most expensive code of
+// the kernel (rule records, hash composition, two dictionary probes per rule) on a handful of lanes.
+// An item pushes one descriptor per (word, split, key); drain_rules() then gives every lane one.
+//   x = b | p << 12 | suffix code << 24 (0: p+1, 1: p+2, 2: e) | reps_is_count << 26 | is_l << 27 | skip2 << 28
+//   y = e | task << 12        z = first candidate index | rule count << 19        w = first rule
+__device__ __forceinline__ void push_rules(const Enum& E, uint2 ref, int b, int p, int e, uint32_t suffix_code, bool skip2,
+                                           bool is_l, uint32_t cand0, bool reps_is_count, uint32_t task) {
+    const uint32_t count = ref.y & 0xFFFFu;
+    if (count == 0) return;
+    const uint32_t slot = atomicAdd(E.rqn, 1u);
+    E.rq[slot] = make_uint4((uint32_t)b | ((uint32_t)p << 12) | (suffix_code << 24) | (reps_is_count ? 1u << 26 : 0u) |
+                                (is_l ? 1u << 27 : 0u) | (skip2 ? 1u << 28 : 0u),
+                            (uint32_t)e | (task << 12), cand0 | (count << 19), ref.x);
+}
+
 // Rules of one key applied at split p of the word [b, e): stem = word[:p-b] + rule.stem,
 // eomi = rule.eomi + word[suffix_from - b:]  (lemmatizer.py:100-102, :107-111).  `cand0` is the
 // candidate index of the key's first rule inside this split; with reps > 1 the whole list repeats
 // (the nested duplicate loop of lemmatizer.py:100-102) at stride `count`.
-__device__ __noinline__ void apply_rules(const DevTables& T, const SentView& v, const Enum& E, uint2 ref, int b, int p,
-                                         int e, int suffix_from, lt_edge proto, uint32_t cand0, uint32_t reps,
-                                         uint32_t task) {
-    const uint32_t count = ref.y & 0xFFFFu;
-    if (count == 0) return;
-    H2 suf{0, 0};
-    uint32_t suf_len = 0;
-    if (suffix_from < e) {
-        suf = sub_hash(T, v, suffix_from, e);
-        suf_len = (uint32_t)(e - suffix_from);
+__device__ __noinline__ void drain_rules(const DevTables& T, const SentView& v, const Enum& E, int lane) {
+    __syncwarp();
+    const uint32_t n = *E.rqn;
+    for (uint32_t i = lane; i < n; i += 32) {
+        const uint4 d = E.rq[i];
+        const int b = (int)(d.x & 0xFFFu), p = (int)((d.x >> 12) & 0xFFFu), e = (int)(d.y & 0xFFFu);
+        const uint32_t code = (d.x >> 24) & 3u;
+        const int suffix_from = (code == 0) ? p + 1 : (code == 1 ? p + 2 : e);
+        const uint32_t count = d.z >> 19, cand0 = d.z & 0x7FFFFu, task = d.y >> 12;
+        const uint32_t reps = ((d.x >> 26) & 1u) ? count : 1u;
+        lt_edge proto;
+        proto.b = (uint16_t)b;
+        proto.e = (uint16_t)e;
+        proto.len = (uint16_t)(e - b);
+        proto.tag0 = 0;
+        proto.tag1 = LT_TAG_EOMI;
+        proto.split = (uint16_t)(p - b);
+        proto.flags = (uint8_t)(LT_EDGE_LEMMA | (((d.x >> 27) & 1u) ? LT_EDGE_IS_L : 0) | (((d.x >> 28) & 1u) ? LT_EDGE_SKIP2 : 0));
+        proto.reserved = 0;
+        H2 suf{0, 0};
+        uint32_t suf_len = 0;
+        if (suffix_from < e) {
+            suf = sub_hash(T, v, suffix_from, e);
+            suf_len = (uint32_t)(e - suffix_from);
+        }
+        const H2 pre = (p > b) ? sub_hash(T, v, b, p) : H2{0, 0};
+        const H2 pw_suf = pow_at(T, suf_len);
+        for (uint32_t r = 0; r < count; ++r) {
+            const RuleRec rec = rule_load(T, d.w + r);
+            // no dictionary string is longer than max_str: most candidates die here, before any hashing
+            if (rec.eomi_len + suf_len > (uint32_t)E.max_str || (uint32_t)(p - b) + rec.stem_len > (uint32_t)E.max_str) continue;
+            const H2 stem = h2_concat(pre, rec.stem, pow_at(T, rec.stem_len));
+            const H2 eomi = h2_concat(rec.eomi, suf, pw_suf);
+            proto.rule = d.w + r;
+            rule_candidate(T, E, stem, (uint32_t)(p - b) + rec.stem_len, eomi, rec.eomi_len + suf_len, proto,
+                           (uint32_t)(p - b), cand0 + r, reps, count, task);
+        }
     }
-    const H2 pre = (p > b) ? sub_hash(T, v, b, p) : H2{0, 0};
-    const H2 pw_suf = pow_at(T, suf_len);
-    for (uint32_t r = 0; r < count; ++r) {
-        const RuleRec rec = rule_load(T, ref.x + r);
-        // no dictionary string is longer than max_str: most candidates die here, before any hashing
-        if (rec.eomi_len + suf_len > (uint32_t)E.max_str || (uint32_t)(p - b) + rec.stem_len > (uint32_t)E.max_str) continue;
-        const H2 stem = h2_concat(pre, rec.stem, pow_at(T, rec.stem_len));
-        const H2 eomi = h2_concat(rec.eomi, suf, pw_suf);
-        proto.rule = ref.x + r;
-        rule_candidate(T, E, stem, (uint32_t)(p - b) + rec.stem_len, eomi, rec.eomi_len + suf_len, proto,
-                       (uint32_t)(p - b), cand0 + r, reps, count, task);
-    }
+    __syncwarp();
+    if (lane == 0) *E.rqn = 0;
+    __syncwarp();
 }
 
 // Lemma candidates of the word [b, e) at split position p, in get_lemma_candidates order
@@ -309,27 +348,26 @@ __device__ LT_ITEM_ATTR uint32_t lemma_item(const DevTables& T, const SentView& 
     const uint2 r3 = (p + 3 <= e) ? v.rref[3 * p + 2] : make_uint2(0u, 0u);
     const uint32_t c1 = r1.y & 0xFFFFu, c2 = r2.y & 0xFFFFu, c3 = r3.y & 0xFFFFu;
     if (!(c1 | c2 | c3)) return ncand;
+    const bool is_l = base_flags != 0;
     // one-syllable key: the whole rule list once per rule of the key (lemmatizer.py:100-102)
     if (c1) {
-        proto.flags = base_flags | LT_EDGE_LEMMA;
-        apply_rules(T, v, E, r1, b, p, e, p + 1, proto, 1u, c1, task);
+        push_rules(E, r1, b, p, e, 0u, false, is_l, 1u, true, task);
         ncand += c1 * c1;
     }
     // {word[i:i+2], word[i:i+3]} in set order; the eomi continues at word[i+2:] for both
-    proto.flags = base_flags | LT_EDGE_LEMMA | LT_EDGE_SKIP2;
     const uint32_t after1 = 1u + c1 * c1;
     if (p == e - 1) {
         // both slices are the last syllable itself: its rules once more, empty suffix
         if (c1) {
-            apply_rules(T, v, E, r1, b, p, e, e, proto, after1, 1u, task);
+            push_rules(E, r1, b, p, e, 2u, true, is_l, after1, false, task);
             ncand += c1;
         }
     } else {
         const bool k3_first = (r3.y >> 31) != 0;
         const uint2 first = k3_first ? r3 : r2;
         const uint2 second = k3_first ? r2 : r3;
-        apply_rules(T, v, E, first, b, p, e, p + 2, proto, after1, 1u, task);
-        apply_rules(T, v, E, second, b, p, e, p + 2, proto, after1 + (first.y & 0xFFFFu), 1u, task);
+        push_rules(E, first, b, p, e, 1u, true, is_l, after1, false, task);
+        push_rules(E, second, b, p, e, 1u, true, is_l, after1 + (first.y & 0xFFFFu), false, task);
         ncand += c2 + c3;
     }
     return ncand;
@@ -402,6 +440,8 @@ __global__ void __launch_bounds__(kLatWarps * 32, LT_LAT_MINB) lattice_kernel(co
     uint16_t* eoj = ch + units;
     uint8_t* nend = reinterpret_cast<uint8_t*>(eoj + units);
     uint32_t* nh = reinterpret_cast<uint32_t*>((reinterpret_cast<uintptr_t>(nend + units) + 3) & ~(uintptr_t)3);
+    uint32_t* rqn = nh + 1;
+    uint4* rq = reinterpret_cast<uint4*>(base + lattice_warp_smem(A.lcap, HC, DM) - (size_t)kRuleQueue * 16);
 
     unsigned long long acc_L = 0, acc_P = 0, acc_E = 0;
     const int n_order = T.n_tag_order;
@@ -417,7 +457,7 @@ __global__ void __launch_bounds__(kLatWarps * 32, LT_LAT_MINB) lattice_kernel(co
         bool bad;
         const int L = stage_sentence(A.text, s0, s1, lane, ch, eoj, ha, hb, n_eoj, bad);
         SentView v{ch, ha, hb, rref};
-        Enum E{sub, DM, hkey, hrec, htask, tcnt, nh, HC};
+        Enum E{sub, DM, hkey, hrec, htask, tcnt, nh, HC, rq, rqn};
 
         // conjugation-rule lists of the keys starting at every syllable
         for (int p = lane; p < L; p += 32) {
@@ -438,7 +478,7 @@ __global__ void __launch_bounds__(kLatWarps * 32, LT_LAT_MINB) lattice_kernel(co
         }
         #pragma unroll 1
         for (int p = lane; p < s1 - s0; p += 32) { pstart[p] = 0xFFFFFFFFu; pcnt[p] = 0; }
-        if (lane == 0) *nh = 0;
+        if (lane == 0) { *nh = 0; *rqn = 0; }
         __syncwarp();
 
         uint32_t ncand = 0;      // lemma candidates the reference generates (lane-local)
@@ -502,8 +542,10 @@ __global__ void __launch_bounds__(kLatWarps * 32, LT_LAT_MINB) lattice_kernel(co
                         if (!special)
                             ncand_try += lemma_item(T, v, E, b, e, p, edge_proto(b, e, (uint32_t)(e - b), b == o), task);
                     }
+                    __syncwarp();
+                    if (*rqn > (uint32_t)(kRuleQueue - 128)) drain_rules(T, v, E, lane);     // a pass queues at most 4 per lane
                 }
-                __syncwarp();
+                drain_rules(T, v, E, lane);
                 // ---- a split survives only when both sides found something (lookup.py:205-209) ----
                 uint32_t nstaged = *nh;
                 bool too_many = nstaged > (uint32_t)HC;
@@ -569,8 +611,10 @@ __global__ void __launch_bounds__(kLatWarps * 32, LT_LAT_MINB) lattice_kernel(co
                                 ncand_try += lemma_item(T, v, E, b, e, p, rec, 0u);
                             }
                         }
+                        __syncwarp();
+                        if (*rqn > (uint32_t)(kRuleQueue - 128)) drain_rules(T, v, E, lane);
                     }
-                    __syncwarp();
+                    drain_rules(T, v, E, lane);
                     nstaged = *nh;
                     too_many = nstaged > (uint32_t)HC;
                     alive_here = nstaged - slots;             // every stage-2 hit survives

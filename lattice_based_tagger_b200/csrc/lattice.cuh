@@ -238,6 +238,7 @@ __device__ __forceinline__ void rule_candidate(const DevTables& T, const Enum& E
                                                uint32_t eomi_len, lt_edge proto, uint32_t split, uint32_t cand,
                                                uint32_t reps, uint32_t rep_stride, uint32_t task) {
     if (eomi_len > (uint32_t)E.max_str || stem_len > (uint32_t)E.max_str) return;    // longer than any entry
+    // both probes in flight together: the stem's is wasted when the eomi misses, but a lane never waits twice
     const uint64_t pe = dict_probe(T, eomi, eomi_len);
     if (!((uint32_t)(pe >> 32) & kLemEomi)) return;
     const uint32_t ps = (uint32_t)(dict_probe(T, stem, stem_len) >> 32);
@@ -302,8 +303,10 @@ __device__ __noinline__ void drain_rules(const DevTables& T, const SentView& v, 
         }
         const H2 pre = (p > b) ? sub_hash(T, v, b, p) : H2{0, 0};
         const H2 pw_suf = pow_at(T, suf_len);
+        RuleRec next = rule_load(T, d.w);
         for (uint32_t r = 0; r < count; ++r) {
-            const RuleRec rec = rule_load(T, d.w + r);
+            const RuleRec rec = next;
+            if (r + 1 < count) next = rule_load(T, d.w + r + 1);      // in flight while this rule is probed
             // no dictionary string is longer than max_str: most candidates die here, before any hashing
             if (rec.eomi_len + suf_len > (uint32_t)E.max_str || (uint32_t)(p - b) + rec.stem_len > (uint32_t)E.max_str) continue;
             const H2 stem = h2_concat(pre, rec.stem, pow_at(T, rec.stem_len));
@@ -462,9 +465,18 @@ __global__ void __launch_bounds__(kLatWarps * 32, LT_LAT_MINB) lattice_kernel(co
         // conjugation-rule lists of the keys starting at every syllable
         for (int p = lane; p < L; p += 32) {
             uint32_t c0 = ch[p], c1 = (p + 1 < L) ? ch[p + 1] : 0u, c2 = (p + 2 < L) ? ch[p + 2] : 0u;
-            rref[3 * p + 0] = rule_probe(T, rule_key(c0, 0, 0, 1));
-            rref[3 * p + 1] = (p + 1 < L) ? rule_probe(T, rule_key(c0, c1, 0, 2)) : make_uint2(0u, 0u);
-            rref[3 * p + 2] = (p + 2 < L) ? rule_probe(T, rule_key(c0, c1, c2, 3)) : make_uint2(0u, 0u);
+            // (keys past the sentence end are probed too — c1 / c2 are 0 there — and discarded)
+            const uint64_t k1 = rule_key(c0, 0, 0, 1), k2 = rule_key(c0, c1, 0, 2), k3 = rule_key(c0, c1, c2, 3);
+            uint2 r1 = make_uint2(0u, 0u), r2 = r1, r3 = r1;
+            if (T.has_rules) {
+                const RuleProbe q1 = rule_first(T, k1), q2 = rule_first(T, k2), q3 = rule_first(T, k3);
+                r1 = rule_resolve(q1, k1);
+                if (p + 1 < L) r2 = rule_resolve(q2, k2);
+                if (p + 2 < L) r3 = rule_resolve(q3, k3);
+            }
+            rref[3 * p + 0] = r1;
+            rref[3 * p + 1] = r2;
+            rref[3 * p + 2] = r3;
         }
         // substring table: every substring of at most max_str syllables, one wave of probes
         for (int q = lane; q < L * DM; q += 32) {

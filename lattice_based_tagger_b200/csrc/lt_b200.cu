@@ -196,8 +196,7 @@ static int build_tables(const lt_tables_desc* d, lt_tables* t) {
             recs[r].pad = 0;
         }
         if (int rc = upload(t, recs, &D.rrec)) return rc;
-        const uint64_t slots = next_pow2((uint64_t)d->n_rule_keys * 4);
-        std::vector<RuleSlot> table(slots, RuleSlot{0, 0, 0});
+        std::vector<CuckooItem> items((size_t)d->n_rule_keys);
         for (int64_t k = 0; k < d->n_rule_keys; ++k) {
             const uint32_t len = d->rule_key_len[k];
             if (len < 1 || len > 3) return fail(LT_ERR_INVALID, "rule key %lld has length %u (1..3 expected)", (long long)k, len);
@@ -205,16 +204,15 @@ static int build_tables(const lt_tables_desc* d, lt_tables* t) {
             const uint64_t key = rule_key(c[0], len > 1 ? c[1] : 0, len > 2 ? c[2] : 0, len);
             const int64_t first = d->rule_first[k], count = d->rule_first[k + 1] - first;
             if (count < 0 || count > 255) return fail(LT_ERR_INVALID, "rule key %lld has %lld rules (at most 255)", (long long)k, (long long)count);
-            uint64_t s = fmix64(key) & (slots - 1);
-            while (table[s].key != 0) {
-                if (table[s].key == key) return fail(LT_ERR_INVALID, "duplicate rule key %lld", (long long)k);
-                s = (s + 1) & (slots - 1);
-            }
-            table[s].key = key;
-            table[s].first = (uint32_t)first;
-            table[s].count = (uint32_t)count | (d->rule_k3_first[k] ? 0x80000000u : 0u);
+            items[k] = CuckooItem{fmix64(key), key, (uint64_t)(uint32_t)first |
+                                  ((uint64_t)((uint32_t)count | (d->rule_k3_first[k] ? 0x80000000u : 0u)) << 32)};
         }
-        D.rule_mask = slots - 1;
+        std::vector<CuckooSlot> slots;
+        if (int rc = build_cuckoo(items, next_pow2((uint64_t)d->n_rule_keys * 4), &slots, &D.rule_bits, "rule keys")) return rc;
+        static_assert(sizeof(CuckooSlot) == sizeof(RuleSlot), "slot layout");
+        std::vector<RuleSlot> table(slots.size());
+        for (size_t i = 0; i < slots.size(); ++i)
+            table[i] = RuleSlot{slots[i].fp, (uint32_t)slots[i].payload, (uint32_t)(slots[i].payload >> 32)};
         D.has_rules = d->n_rule_keys > 0;
         if (int rc = upload(t, table, &D.rules)) return rc;
     }

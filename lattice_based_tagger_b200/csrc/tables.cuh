@@ -68,7 +68,8 @@ struct DevTables {
     uint32_t dict_bits;           // log2(slots)
     uint32_t reserved3;
     const RuleSlot* rules;
-    uint64_t rule_mask;
+    uint32_t rule_bits;           // log2(slots)
+    uint32_t reserved4;
     const RuleRec* rrec;
     const FeatSlot* feat;
     uint64_t feat_mask;
@@ -97,29 +98,45 @@ __device__ __forceinline__ uint4 ldg16(const void* p) {
     return __ldg(reinterpret_cast<const uint4*>(p));
 }
 
-// dictionary probe: returns the 64-bit payload (tagmask | lemma << 32), 0 when absent
-__device__ __forceinline__ uint64_t dict_probe(const DevTables& T, H2 h, uint32_t len) {
+// dictionary probe, split so that callers can put several probes in flight: both slots of the key
+// are loaded at once; the payload is (tagmask | lemma << 32), 0 when absent
+struct DictProbe {
+    uint4 s, t;
+};
+__device__ __forceinline__ DictProbe dict_first(const DevTables& T, H2 h, uint32_t len) {
     const uint64_t x = dict_slot_hash(h, len);
+    DictProbe p;
+    p.s = ldg16(T.dict + cuckoo_slot1(x, T.dict_bits));
+    p.t = ldg16(T.dict + cuckoo_slot2(x, T.dict_bits));
+    return p;
+}
+__device__ __forceinline__ uint64_t dict_resolve(const DictProbe& p, H2 h, uint32_t len) {
     const uint64_t fp = dict_fp(h, len);
-    const uint4 s = ldg16(T.dict + cuckoo_slot1(x, T.dict_bits));
-    const uint4 t = ldg16(T.dict + cuckoo_slot2(x, T.dict_bits));
     const uint32_t flo = (uint32_t)fp, fhi = (uint32_t)(fp >> 32);
-    if (s.x == flo && s.y == fhi) return (uint64_t)s.z | ((uint64_t)s.w << 32);
-    if (t.x == flo && t.y == fhi) return (uint64_t)t.z | ((uint64_t)t.w << 32);
+    if (p.s.x == flo && p.s.y == fhi) return (uint64_t)p.s.z | ((uint64_t)p.s.w << 32);
+    if (p.t.x == flo && p.t.y == fhi) return (uint64_t)p.t.z | ((uint64_t)p.t.w << 32);
     return 0;
 }
+__device__ __forceinline__ uint64_t dict_probe(const DevTables& T, H2 h, uint32_t len) {
+    return dict_resolve(dict_first(T, h, len), h, len);
+}
 
-// rule probe: (first, count|flag) of an exact 1..3 syllable key; count = 0 when absent
-__device__ __forceinline__ uint2 rule_probe(const DevTables& T, uint64_t key) {
-    if (!T.has_rules) return make_uint2(0u, 0u);
-    uint64_t i = fmix64(key) & T.rule_mask;
-    while (true) {
-        uint4 s = ldg16(T.rules + i);
-        uint64_t skey = (uint64_t)s.x | ((uint64_t)s.y << 32);
-        if (skey == key) return make_uint2(s.z, s.w);
-        if (skey == 0) return make_uint2(0u, 0u);
-        i = (i + 1) & T.rule_mask;
-    }
+// rule probe: (first, count|flag) of an exact 1..3 syllable key; count = 0 when absent (cuckoo table)
+struct RuleProbe {
+    uint4 s, t;
+};
+__device__ __forceinline__ RuleProbe rule_first(const DevTables& T, uint64_t key) {
+    const uint64_t x = fmix64(key);
+    RuleProbe p;
+    p.s = ldg16(T.rules + cuckoo_slot1(x, T.rule_bits));
+    p.t = ldg16(T.rules + cuckoo_slot2(x, T.rule_bits));
+    return p;
+}
+__device__ __forceinline__ uint2 rule_resolve(const RuleProbe& p, uint64_t key) {
+    const uint32_t klo = (uint32_t)key, khi = (uint32_t)(key >> 32);
+    if (p.s.x == klo && p.s.y == khi) return make_uint2(p.s.z, p.s.w);
+    if (p.t.x == klo && p.t.y == khi) return make_uint2(p.t.z, p.t.w);
+    return make_uint2(0u, 0u);
 }
 
 __device__ __forceinline__ RuleRec rule_load(const DevTables& T, uint32_t idx) {

@@ -288,6 +288,8 @@ def run_gpu(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
     if world > 1:
+        if os.environ.get('NCCL_DEBUG', '').upper() == 'VERSION':
+            os.environ['NCCL_DEBUG'] = 'WARN'      # NCCL prints its version on stdout otherwise; stdout carries the JSON line
         dist.init_process_group('nccl', device_id=dev)
 
     cfg, dictionary, sents = synth.build_workload(args.config, rank=rank, n_sent=args.sentences)

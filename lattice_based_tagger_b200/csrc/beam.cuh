@@ -285,12 +285,13 @@ __device__ __forceinline__ double unsortable(uint64_t key) {
 }
 
 #ifndef LT_BEAM_MINB
-#define LT_BEAM_MINB 4
+#define LT_BEAM_MINB 2
 #endif
 #ifndef LT_PROBE_SPLIT
 #define LT_PROBE_SPLIT 1       // 1: the loads of templates 7 and 8 are issued after templates 0..2 are consumed
 #endif
-constexpr int kBeamWarps = 4;                 // warps per CTA of the beam kernel
+constexpr int kBeamWarps = 4;                 // preferred warps per CTA of the beam kernel
+constexpr int kBeamMaxWarps = 8;              // largest CTA (128 registers per thread either way: 8 warps x 2 CTAs = 4 warps x 4 CTAs)
 
 // Prefix hashes of the staged syllables by warp scan: H[0] = 0, H[i+1] = H[i] * B + (c_i + 1).
 __device__ __forceinline__ void beam_prefix_hashes(const uint16_t* ch, int L, int lane, uint64_t* ha, uint64_t* hb) {
@@ -363,7 +364,7 @@ __device__ __forceinline__ void prep_edge(const DevTables& T, const SentView& v,
 // KT: the beam size, UC: the sentence-array size when known at compile time (array offsets become
 // constants, which is what keeps the kernel's address arithmetic out of registers); 0 = A.beam / A.units
 template <int MODE, int KT, int UC>
-__global__ void __launch_bounds__(kBeamWarps * 32, LT_BEAM_MINB) beam_kernel(const __grid_constant__ DevTables T, const __grid_constant__ BeamArgs A) {
+__global__ void __launch_bounds__(kBeamMaxWarps * 32, LT_BEAM_MINB) beam_kernel(const __grid_constant__ DevTables T, const __grid_constant__ BeamArgs A) {
     constexpr int KR = (MODE == 0) ? 2 : 1;      // kept entries per lane
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;

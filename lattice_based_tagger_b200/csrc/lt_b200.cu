@@ -538,28 +538,37 @@ static int launch_beam(lt_batch* b, cudaStream_t st) {
     if (int rc = ensure(b->scores, (size_t)std::max(1, n_sent) * 8)) return rc;
 
     const size_t dense_bytes = ((size_t)t->dev.n_tri * dense_block_bytes(t->dev.n_tags) + 15) & ~(size_t)15;
-    // resident warps per SM for a per-warp footprint (the kernel's 128 registers allow 4 CTAs of 4 warps)
-    auto resident_warps = [&](size_t warp_smem) -> int {
-        if (dense_bytes + warp_smem > kSmemBudget) return 0;
-        const int w = (int)std::min<size_t>(kBeamWarps, (kSmemBudget - dense_bytes) / warp_smem);
-        const size_t cta = dense_bytes + warp_smem * w + 1024;
-        return w * (int)std::min<size_t>(4, (size_t)228 * 1024 / cta);
+    // CTA shape: the warps per CTA (1..8) that keep the most warps resident on an SM under the kernel's
+    // 128 registers per thread (16 warps) and the per-warp shared memory; ties go to 4-warp CTAs
+    auto resident_warps = [&](size_t warp_smem, int w) -> int {
+        const size_t cta = dense_bytes + warp_smem * w;
+        if (cta > kSmemBudget) return 0;
+        return w * (int)std::min<size_t>(16 / w, (size_t)228 * 1024 / (cta + 1024));
     };
-    // back-pointers live in shared memory when that does not lower the residency
+    auto best_warps = [&](size_t warp_smem) -> int {
+        int best = 0, best_res = 0;
+        for (int w : {kBeamWarps, 8, 6, 5, 3, 2, 1}) {
+            const int r = resident_warps(warp_smem, w);
+            if (r > best_res) { best_res = r; best = w; }
+        }
+        return best;
+    };
     // sentence arrays: common sizes are template parameters of the kernel (for beams 5 and 10)
     int units = b->lcap + 8;
     const int uclass = (beam_size == 5 || beam_size == 10) ? beam_units_class(b->lcap) : 0;
     if (uclass) units = uclass;
+    // back-pointers live in shared memory when that does not lower the residency
     const size_t smem_hbm_trail = beam_warp_smem(units, beam_size, t->dev.n_funcs, false);
     const size_t smem_own_trail = beam_warp_smem(units, beam_size, t->dev.n_funcs, true);
-    bool trail_smem = resident_warps(smem_own_trail) > 0 && resident_warps(smem_own_trail) >= resident_warps(smem_hbm_trail);
+    const int w_hbm = best_warps(smem_hbm_trail), w_own = best_warps(smem_own_trail);
+    if (w_hbm == 0)
+        return fail(LT_ERR_INVALID, "sentence length %d with beam %d does not fit the beam kernel's shared memory", b->lcap, beam_size);
+    bool trail_smem = w_own > 0 && resident_warps(smem_own_trail, w_own) >= resident_warps(smem_hbm_trail, w_hbm);
     if (const char* env = getenv("LT_TRAIL_SMEM")) trail_smem = trail_smem && atoi(env) != 0;
     if (!trail_smem)
         if (int rc = ensure(b->trail, nu * (size_t)beam_size * 8)) return rc;
     const size_t group_smem = trail_smem ? smem_own_trail : smem_hbm_trail;
-    if (dense_bytes + group_smem > kSmemBudget)
-        return fail(LT_ERR_INVALID, "sentence length %d with beam %d does not fit the beam kernel's shared memory", b->lcap, beam_size);
-    const int warps = (int)std::min<size_t>(kBeamWarps, (kSmemBudget - dense_bytes) / group_smem);
+    const int warps = trail_smem ? w_own : w_hbm;
     const size_t smem = dense_bytes + group_smem * warps;
 
     unsigned int* ctl = static_cast<unsigned int*>(b->ctl.p);

@@ -93,6 +93,8 @@ def main():
     for (fn, ln), (inst, samp) in sorted(by_line.items(), key=lambda kv: -kv[1][0])[:top]:
         if fn not in srcs:
             path = os.path.join(os.path.dirname(os.path.abspath(lib)), 'csrc', fn)
+            if not os.path.exists(path):     # a copy of the library kept elsewhere: use this repo's sources
+                path = os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', '..', 'lattice_based_tagger_b200', 'csrc', fn)
             srcs[fn] = open(path).read().split('\n') if os.path.exists(path) else []
         text = srcs[fn][ln - 1].strip()[:90] if 0 < ln <= len(srcs[fn]) else ''
         print('%5.2f%% inst %5.2f%% stall  %s:%d  %s' % (100 * inst / tot_i, 100 * samp / max(1, tot_s), fn, ln, text))

@@ -206,3 +206,74 @@ def test_rejected_inputs():
         pkg.Tagger(dictionary, score_funcs=pkg.beam.BeamScoreFunctions(Custom()))
     with pytest.raises(ValueError):
         pkg.Tagger(object(), score_funcs=funcs)              # not a morpheme dictionary
+
+
+def _check_against_oracle(tagger, oracle, sents, beams):
+    for sent, (words, bindex) in zip(sents, tagger.lattice_batch(sents)):
+        assert [tuple(w) for w in words[1:-1]] == _lattice_key(oracle.lattice(sent)), sent
+    for k in beams:
+        got = tagger.tag_batch(sents, beam_size=k, errors='none')
+        for sent, seq in zip(sents, got):
+            try:
+                want = oracle.tag(sent, k)
+            except IndexError:
+                assert seq is None, sent
+                continue
+            assert [tuple(w) for w in seq.sequences] == want.words, (sent, k)
+            assert seq.score == want.score, (sent, k)
+
+
+def _dense_case(seed):
+    """One long eojeol whose every prefix and suffix is a dictionary word under many tags: the
+    bucket of the eojeol's last syllable holds far more than the 32 edges the beam kernel caches,
+    and most of them span more than the 8-syllable window."""
+    import random
+    rng = random.Random(seed)
+    alphabet = ['가', '나', '다']
+    word = ''.join(rng.choice(alphabet) for _ in range(14))
+    tags = ['Noun', 'Adverb', 'Exclamation', 'Determiner', 'Number', 'Pronoun', 'Josa', 'Eomi', 'Verb', 'Adjective']
+    tag_to_morphs = {t: set() for t in tags}
+    for i in range(1, len(word)):
+        for piece in (word[:i], word[i:]):
+            for t in rng.sample(tags[:6], 5):
+                tag_to_morphs[t].add(piece)
+    for t in ('Josa', 'Eomi', 'Verb', 'Adjective'):
+        tag_to_morphs[t].update({word[-1], word[-2:], word[:2]})
+    case = {'seed': seed, 'tags': tags, 'tag_to_morphs': {t: sorted(m) for t, m in tag_to_morphs.items()},
+            'rules': {word[3]: [(word[3], word[-1])], word[5:7]: [(word[5], word[-2:])]},
+            'sentences': [word, word + ' ' + word[:5], word[2:] + word, word[:9] + ' ' + word[4:]],
+            'funcs': [{'kind': 'reg', 'unknown_penalty': -0.5, 'known_preference': 0.5, 'syllable_penalty': -0.2},
+                      {'kind': 'trigram'}],
+            'feature_keys': [], 'coefficients': []}
+    return case
+
+
+@pytest.mark.parametrize('seed', [7, 8])
+def test_buckets_beyond_the_edge_cache(seed):
+    case = _dense_case(seed)
+    _cases.add_features(case, _cases.observed_features(case, lo, seed=seed), seed)
+    dictionary, funcs = _cases.build_objects(case, pkg)
+    tagger = pkg.Tagger(dictionary, score_funcs=funcs)
+    oracle = lo.OracleTagger(dictionary, funcs)
+    sents = case['sentences']
+    words, bindex = tagger.lattice_batch(sents[:1])[0]
+    last = [w for w in words[1:-1] if w.e == len(sents[0])]
+    assert len(last) > 40 and max(w.e - w.b for w in last) > 8       # the case does what it is built for
+    _check_against_oracle(tagger, oracle, sents, (1, 5, 10, 20, 32, 40))
+
+
+def test_trail_in_hbm_and_generic_array_sizes(monkeypatch):
+    """Long sentences (sentence arrays beyond the templated 64 / 128 elements) and the HBM
+    back-pointer trail forced for short ones."""
+    case = _cases.random_case(5151, n_sent=16, features=True, prefs=True, max_sent_len=180)
+    _cases.add_features(case, _cases.observed_features(case, lo, seed=5), 5)
+    dictionary, funcs = _cases.build_objects(case, pkg)
+    oracle = lo.OracleTagger(dictionary, funcs)
+    sents = case['sentences']
+    assert max(len(s) for s in sents) > 128
+    tagger = pkg.Tagger(dictionary, score_funcs=funcs)
+    _check_against_oracle(tagger, oracle, sents, (5, 10, 12))
+    short = [s for s in sents if len(s) <= 40]
+    _check_against_oracle(tagger, oracle, short, (5, 10))              # 64-element arrays, trail in shared memory
+    monkeypatch.setenv('LT_TRAIL_SMEM', '0')
+    _check_against_oracle(tagger, oracle, short, (5, 10, 12))          # same kernels, trail in HBM

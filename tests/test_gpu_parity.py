@@ -277,3 +277,24 @@ def test_trail_in_hbm_and_generic_array_sizes(monkeypatch):
     _check_against_oracle(tagger, oracle, short, (5, 10))              # 64-element arrays, trail in shared memory
     monkeypatch.setenv('LT_TRAIL_SMEM', '0')
     _check_against_oracle(tagger, oracle, short, (5, 10, 12))          # same kernels, trail in HBM
+
+
+def test_dictionary_mutation_and_refresh():
+    """`add` / `remove_words` on the host dictionary (reference
+    `dictionary.py:244-262`) + `Tagger.refresh()` recompiles the device tables; results follow the
+    oracle on the mutated dictionary, including the stale `verbs/adjectives/eomis` views the
+    reference keeps after `remove_words`."""
+    dictionary = pkg.dictionary.DemoMorphemeDictionary()
+    funcs = pkg.beam.BeamScoreFunctions(pkg.beam.RegularizationScore(unknown_penalty=-.1, known_preference=0.5))
+    tagger = pkg.Tagger(dictionary, score_funcs=funcs)
+    sents = ['트와이스의 노래 입니다', '아이오아이는 노래를 했다', '노래 입니다']
+    first = tagger.tag_batch(sents, errors='none')
+    assert [w.tag0 for w in first[0].sequences[1:3]] == ['Unknown', 'Josa'] or first[0].sequences[1].tag0 == 'Unknown'
+    dictionary.add({'트와이스'}, 'Noun')
+    dictionary.add('짱', 'Suffix', force=True)
+    dictionary.remove_words({'입니다', '이'}, 'Adjective')
+    with pytest.raises(ValueError):
+        dictionary.add('x', 'NoSuchTag')
+    tagger.refresh()
+    _check_against_oracle(tagger, lo.OracleTagger(dictionary, funcs), sents + ['트와이스짱'], (1, 5))
+    assert tagger.tag(sents[0]).sequences[1].tag0 == 'Noun'

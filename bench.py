@@ -260,7 +260,7 @@ def run_reference(args):
         'edges_per_sec': counters.get('E', 0) * args.steps / total if total else None,
         'transitions_per_sec': counters.get('T', 0) * args.steps / total if total else None,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(name, cfg, n_sent):
@@ -288,8 +288,6 @@ def run_gpu(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
     if world > 1:
-        if os.environ.get('NCCL_DEBUG', '').upper() == 'VERSION':
-            os.environ['NCCL_DEBUG'] = 'WARN'      # NCCL prints its version on stdout otherwise; stdout carries the JSON line
         dist.init_process_group('nccl', device_id=dev)
 
     cfg, dictionary, sents = synth.build_workload(args.config, rank=rank, n_sent=args.sentences)
@@ -446,7 +444,7 @@ def run_gpu(args):
         }
         if world == 1 and not args.no_cpu_baseline:
             line.update(cpu_baseline(args, cfg, sents, feature_dic, coef, beam, h_poff, h_edges, h_scores, h_status, n, tagger))
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -493,6 +491,27 @@ def cpu_baseline(args, cfg, sents, feature_dic, coef, beam, h_poff, h_edges, h_s
                        'what': 'segmentation, tags, lemmas and fp64 score bit-exact vs the CPU sample'}}
 
 
+_RESULT_FD = None
+
+
+def capture_stdout():
+    """Everything libraries print on stdout (NCCL's version banner, for one) goes to stderr, so that
+    stdout carries exactly the one JSON line."""
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + '\n').encode()
+    sys.stdout.flush()
+    if _RESULT_FD is None:
+        os.write(1, data)
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -504,6 +523,7 @@ def main():
     ap.add_argument('--beam', type=int, default=None)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
+    capture_stdout()
     if args.impl == 'reference':
         run_reference(args)
     else:

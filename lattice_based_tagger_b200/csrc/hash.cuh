@@ -50,20 +50,27 @@ LT_HD H2 h2_sub(H2 pre_b, H2 pre_e, H2 pow_len) {
 }
 
 // ---- dictionary key: (string, length) -------------------------------------------------------
-// slot: multiply-shift of hash a (top bits of a product depend on every input bit);
-// fingerprint: hash b combined with the length (compared in full, so it needs no mixing).
-LT_HD uint64_t dict_slot_hash(H2 h, uint32_t len) {
-    return (h.a + (uint64_t)len * 0xA24BAED4963EE407ull) * 0x9E3779B97F4A7C15ull;
-}
-LT_HD uint64_t dict_slot(H2 h, uint32_t len, uint32_t bits) { return dict_slot_hash(h, len) >> (64 - bits); }
+// slot hash: hash a combined with the length; fingerprint: hash b combined with the length
+// (compared in full, so it needs no mixing).
+LT_HD uint64_t dict_slot_hash(H2 h, uint32_t len) { return h.a + (uint64_t)len * 0xA24BAED4963EE407ull; }
 
 // ---- cuckoo placement --------------------------------------------------------------------------
-// The dictionary and the feature table are cuckoo tables: a key lives in one of TWO slots, both
-// derived from the same 64-bit slot hash x.  A lookup loads both slots at once and never follows a
-// chain, so a warp's probe costs one memory round trip whatever the other lanes hit.
-constexpr uint64_t kSlotMul2 = 0xC2B2AE3D27D4EB4Full;   // odd
-LT_HD uint64_t cuckoo_slot1(uint64_t x, uint32_t bits) { return x >> (64 - bits); }
-LT_HD uint64_t cuckoo_slot2(uint64_t x, uint32_t bits) { return ((x ^ (x >> 32)) * kSlotMul2) >> (64 - bits); }
+// The dictionary, the rule keys and the feature table are cuckoo tables: a key lives in one of
+// TWO slots, both derived from the same 64-bit slot hash x.  A lookup loads both slots at once and
+// never follows a chain, so a warp's probe costs one memory round trip whatever the other lanes hit.
+// The slots come from two different 32-bit folds of x by multiply-shift (the top bits of a
+// product depend on every bit of the fold): three 32-bit instructions each on the device instead
+// of a 64-bit multiplication.  Tables hold at most 2^32 slots.
+constexpr uint32_t kSlotMulA = 0x9E3779B1u, kSlotMulB = 0x85EBCA77u;   // odd
+LT_HD uint64_t cuckoo_slot1(uint64_t x, uint32_t bits) {
+    const uint32_t f = (uint32_t)x ^ (uint32_t)(x >> 32);
+    return (uint64_t)((f * kSlotMulA) >> (32 - bits));
+}
+LT_HD uint64_t cuckoo_slot2(uint64_t x, uint32_t bits) {
+    const uint32_t hi = (uint32_t)(x >> 32);
+    const uint32_t f = (uint32_t)x + ((hi << 15) | (hi >> 17));
+    return (uint64_t)((f * kSlotMulB) >> (32 - bits));
+}
 LT_HD uint64_t dict_fp(H2 h, uint32_t len) {
     uint64_t f = h.b ^ ((uint64_t)len * 0x9FB21C651E98DF25ull);
     return f ? f : 1;
@@ -84,7 +91,7 @@ LT_HD uint64_t rule_key(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t len) {
 //     kb = seed_b(kind, func) + head * Tb + s0.b * M0b + s1.b * M1b + s2.b * M2b
 // so the beam kernel keeps the products of a word's hashes with the slot multipliers (once per
 // lattice edge, once per surviving hypothesis) and forms a transition's keys with additions only.
-// ka picks the slot by multiply-shift (top bits of ka * kSlotMul), kb is the stored fingerprint.
+// ka is the slot hash (cuckoo_slot1 / cuckoo_slot2), kb is the stored fingerprint.
 struct FKey {
     uint64_t k1, k2;     // k1 = ka (slot source), k2 = kb (fingerprint, never 0)
 };
@@ -92,7 +99,6 @@ struct FKey {
 constexpr uint64_t kM0a = 0xE7037ED1A0B428DBull, kM1a = 0x1D8E4E27C47D124Full, kM2a = 0xEB44ACCAB455D165ull;
 constexpr uint64_t kM0b = 0x2D358DCCAA6C78A5ull, kM1b = 0x8BB84B93962EACC9ull, kM2b = 0x4B33A62ED433D4A3ull;
 constexpr uint64_t kTa = 0x8CB92BA72F3D8DD7ull, kTb = 0xA0761D6478BD642Full;
-constexpr uint64_t kSlotMul = 0x9E3779B97F4A7C15ull;
 
 LT_HD H2 h2_mul(H2 h, uint64_t ma, uint64_t mb) { return H2{h.a * ma, h.b * mb}; }
 
@@ -142,7 +148,7 @@ LT_HD FKey feature_key(uint32_t kind, uint32_t func, H2 s0, H2 s1, H2 s2, uint32
 }
 
 // slot hash of a key (cuckoo_slot1 / cuckoo_slot2 turn it into the key's two slots)
-LT_HD uint64_t feature_slot_hash(uint64_t k1) { return k1 * kSlotMul; }
+LT_HD uint64_t feature_slot_hash(uint64_t k1) { return k1; }
 
 constexpr uint32_t kKindMPref = 16;
 constexpr uint32_t kKindWPref = 17;

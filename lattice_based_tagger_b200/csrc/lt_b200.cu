@@ -84,7 +84,7 @@ static int build_cuckoo(const std::vector<CuckooItem>& items, uint64_t min_slots
                         uint32_t* bits_out, const char* what) {
     uint32_t bits = 4;
     while ((1ull << bits) < min_slots) ++bits;
-    for (; bits <= 40; ++bits) {
+    for (; bits <= 32; ++bits) {
         const uint64_t slots = 1ull << bits;
         std::vector<int64_t> owner(slots, -1);
         bool placed_all = true;

@@ -362,8 +362,10 @@ __device__ __forceinline__ void prep_edge(const DevTables& T, const SentView& v,
 //   1  32-lane bitonic sorting network per chunk + bitonic merge with the kept list (beam <= 32)
 //   0  rounds of warp arg-max with two kept entries per lane (beam 33..64)
 // KT: the beam size, UC: the sentence-array size when known at compile time (array offsets become
-// constants, which is what keeps the kernel's address arithmetic out of registers); 0 = A.beam / A.units
-template <int MODE, int KT, int UC>
+// constants, which is what keeps the kernel's address arithmetic out of registers); 0 = A.beam / A.units.
+// PROG: 1 = the score program is exactly (RegularizationScore, SimpleTrigramFeatureScore) — the
+// scorer loop of a candidate unrolls, the template seeds become immediates; 0 = read it from T.
+template <int MODE, int KT, int UC, int PROG>
 __global__ void __launch_bounds__(kBeamMaxWarps * 32, LT_BEAM_MINB) beam_kernel(const __grid_constant__ DevTables T, const __grid_constant__ BeamArgs A) {
     constexpr int KR = (MODE == 0) ? 2 : 1;      // kept entries per lane
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -413,14 +415,14 @@ __global__ void __launch_bounds__(kBeamMaxWarps * 32, LT_BEAM_MINB) beam_kernel(
     uint2* spos = reinterpret_cast<uint2*>(hb + units);
     uint16_t* ch = reinterpret_cast<uint16_t*>(spos + units);
     C.kval = reinterpret_cast<double*>(ch + units);
-    const int kvs = 2 * (T.n_funcs > 0 ? T.n_funcs : 1);   // kval stride
+    const int kvs = PROG == 1 ? 4 : 2 * (T.n_funcs > 0 ? T.n_funcs : 1);   // kval stride
     uint32_t* s_trail = reinterpret_cast<uint32_t*>(C.kval + kCacheSlots * kvs);   // [units * K] when trail_smem
 
     if (lane < 4) s_acc[lane] = 0;
 
     bool need_m1 = false;
     for (int f = 0; f < T.n_funcs; ++f) need_m1 |= (T.funcs[f].kind == LT_FUNC_MPREF);
-    const int nf = T.n_funcs;
+    const int nf = PROG == 1 ? 2 : T.n_funcs;
 
     while (true) {
         unsigned int s = 0;
@@ -633,8 +635,9 @@ __global__ void __launch_bounds__(kBeamMaxWarps * 32, LT_BEAM_MINB) beam_kernel(
                     const bool j_unk = (tj == LT_TAG_UNK);
                     const bool ctx8 = ((kCtxMask >> tk) & 1u) && (pmeta & kMetaHasCtx);
                     double inc = 0.0;
-                    #pragma unroll 1
+                    #pragma unroll (PROG == 1 ? 2 : 1)
                     for (int f = 0; f < nf; ++f) {
+                        const int kind = PROG == 1 ? (f == 0 ? LT_FUNC_REG : LT_FUNC_TRIGRAM) : T.funcs[f].kind;
                         double val, val5;
                         if (uncached) {
                             double uv, uv5;      // (by reference to a call: keep val / val5 themselves in registers)
@@ -645,19 +648,24 @@ __global__ void __launch_bounds__(kBeamMaxWarps * 32, LT_BEAM_MINB) beam_kernel(
                             val = C.kval[slot * kvs + 2 * f];
                             val5 = C.kval[slot * kvs + 2 * f + 1];
                         }
-                        if (T.funcs[f].kind == LT_FUNC_TRIGRAM) {
+                        if (kind == LT_FUNC_TRIGRAM) {
                             // SimpleTrigramFeatureScore.score (score_funcs.py:137-144)
-                            const unsigned char* dense_blk = dense_smem + (size_t)T.func_dense[f] * dense_block_bytes(NT);
+                            const unsigned char* dense_blk = dense_smem + (PROG == 1 ? 0 : (size_t)T.func_dense[f] * dense_block_bytes(NT));
+                            const H2 sd0 = PROG == 1 ? feature_seed(0u, (uint32_t)f) : T.seeds[f][0];
+                            const H2 sd1 = PROG == 1 ? feature_seed(1u, (uint32_t)f) : T.seeds[f][1];
+                            const H2 sd2 = PROG == 1 ? feature_seed(2u, (uint32_t)f) : T.seeds[f][2];
+                            const H2 sd7 = PROG == 1 ? feature_seed(7u, (uint32_t)f) : T.seeds[f][7];
+                            const H2 sd8 = PROG == 1 ? feature_seed(8u, (uint32_t)f) : T.seeds[f][8];
                             const DenseView D = dense_view(dense_blk, NT);
                             cand_F += valid ? 6u + (j_unk ? 1u : 0u) + (has_i ? 1u : 0u) + (ctx8 ? 1u : 0u) : 0u;
                             const H2 pp = has_i ? e_pp[pslot] : H2{0, 0};
                             const H2 c1v = ctx8 ? e_c1[pslot] : H2{0, 0};
                             const uint32_t hk = feature_head32(tk, 0);
-                            const FKey q0 = feature_key_sum32(T.seeds[f][0], hk, h2_add(e0, p1));
-                            const FKey q1 = feature_key_sum32(T.seeds[f][1], hk, p1);
-                            const FKey q2 = feature_key_sum32(T.seeds[f][2], feature_head32(tj, tk), e0);
-                            const FKey q7 = feature_key_sum32(T.seeds[f][7], 0u, h2_add(e0, pp));
-                            const FKey q8 = feature_key_sum32(T.seeds[f][8], 0u, h2_add(g0, c1v));
+                            const FKey q0 = feature_key_sum32(sd0, hk, h2_add(e0, p1));
+                            const FKey q1 = feature_key_sum32(sd1, hk, p1);
+                            const FKey q2 = feature_key_sum32(sd2, feature_head32(tj, tk), e0);
+                            const FKey q7 = feature_key_sum32(sd7, 0u, h2_add(e0, pp));
+                            const FKey q8 = feature_key_sum32(sd8, 0u, h2_add(g0, c1v));
                             // all first-slot loads in flight before any is consumed
                             const FeatProbe s0 = feat_first(T, q0);
                             const FeatProbe s1 = feat_first(T, q1);

@@ -592,14 +592,20 @@ static int launch_beam(lt_batch* b, cudaStream_t st) {
     A.order = (b->sort_by_length && n_sent > 1) ? static_cast<const uint32_t*>(b->order.p) : nullptr;
     A.trail_smem = trail_smem ? 1 : 0;
 
-    // common beam sizes and sentence-array sizes get their own instantiation (compile-time array offsets)
+    // common beam sizes, sentence-array sizes and the (RegularizationScore, SimpleTrigramFeatureScore)
+    // score program get their own instantiation (compile-time array offsets, unrolled scorer loop)
+    const bool reg_tri = t->dev.n_funcs == 2 && t->dev.funcs[0].kind == LT_FUNC_REG && t->dev.funcs[1].kind == LT_FUNC_TRIGRAM;
     void (*kernel)(const DevTables, const BeamArgs);
-    if (beam_size == 5) kernel = uclass == 64 ? beam_kernel<2, 5, 64> : (uclass == 128 ? beam_kernel<2, 5, 128> : beam_kernel<2, 5, 0>);
-    else if (beam_size == 10) kernel = uclass == 64 ? beam_kernel<2, 10, 64> : (uclass == 128 ? beam_kernel<2, 10, 128> : beam_kernel<2, 10, 0>);
-    else if (beam_size <= kRankMaxBeam) kernel = beam_kernel<2, 0, 0>;
-    else if (beam_size == 32) kernel = beam_kernel<1, 32, 0>;
-    else if (beam_size <= 32) kernel = beam_kernel<1, 0, 0>;
-    else kernel = beam_kernel<0, 0, 0>;
+    if (beam_size == 5 && uclass == 64) kernel = reg_tri ? beam_kernel<2, 5, 64, 1> : beam_kernel<2, 5, 64, 0>;
+    else if (beam_size == 5 && uclass == 128) kernel = reg_tri ? beam_kernel<2, 5, 128, 1> : beam_kernel<2, 5, 128, 0>;
+    else if (beam_size == 5) kernel = reg_tri ? beam_kernel<2, 5, 0, 1> : beam_kernel<2, 5, 0, 0>;
+    else if (beam_size == 10 && uclass == 64) kernel = reg_tri ? beam_kernel<2, 10, 64, 1> : beam_kernel<2, 10, 64, 0>;
+    else if (beam_size == 10 && uclass == 128) kernel = reg_tri ? beam_kernel<2, 10, 128, 1> : beam_kernel<2, 10, 128, 0>;
+    else if (beam_size == 10) kernel = reg_tri ? beam_kernel<2, 10, 0, 1> : beam_kernel<2, 10, 0, 0>;
+    else if (beam_size <= kRankMaxBeam) kernel = reg_tri ? beam_kernel<2, 0, 0, 1> : beam_kernel<2, 0, 0, 0>;
+    else if (beam_size == 32) kernel = reg_tri ? beam_kernel<1, 32, 0, 1> : beam_kernel<1, 32, 0, 0>;
+    else if (beam_size <= 32) kernel = reg_tri ? beam_kernel<1, 0, 0, 1> : beam_kernel<1, 0, 0, 0>;
+    else kernel = reg_tri ? beam_kernel<0, 0, 0, 1> : beam_kernel<0, 0, 0, 0>;
     CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, warps * 32, smem));

@@ -43,7 +43,7 @@ struct LatticeArgs {
     const uint16_t* text;       // raw UTF-16 units, spaces included
     const int32_t* sent_off;    // n_sent + 1
     int32_t n_sent;
-    int32_t lcap;               // max raw units of one sentence (shared-memory sizing)
+    int32_t units;              // shared-memory elements per sentence array (>= longest sentence + 8)
     int32_t hcap;               // staging capacity (hits) per warp
     int32_t max_str;            // longest dictionary string (syllables), >= 1
     uint2* pos;                 // [n_units] out: (first edge, count) per (sentence, end position)
@@ -60,22 +60,26 @@ struct LatticeArgs {
     const uint32_t* order;      // queue position -> sentence index (longest first), or nullptr
 };
 
-__host__ __device__ inline size_t lattice_warp_smem(int lcap, int hcap, int max_str) {
-    size_t units = (size_t)lcap + 8;
-    size_t bytes = units * 8 * 2;                  // ha, hb
-    bytes += units * 8 * 3;                        // rref
-    bytes += (size_t)hcap * 8;                     // staged keys
-    bytes += (size_t)hcap * 16;                    // staged edge records
-    bytes += units * 4 * (size_t)max_str;          // substring table
-    bytes += units * 4 * 2;                        // pstart, pcnt
-    bytes += units * 4 * 2;                        // tcnt (2 tasks per syllable of an eojeol)
-    bytes += (size_t)hcap * 4;                     // staged task id, later final rank
-    bytes += units * 2 * 2;                        // chars, eojeol starts
-    bytes += units;                                // nend
+// Per-warp shared memory.  `units` = elements per sentence array (>= longest sentence + 8, a
+// multiple of 8), `hcap` = staging capacity; the substring table (units * max_str words) comes last,
+// so that with `units` and `hcap` known at compile time every array sits at a constant offset.
+__host__ __device__ inline size_t lattice_fixed_smem(int units, int hcap) {
+    size_t bytes = (size_t)kRuleQueue * 16;        // rule-work queue
+    bytes += (size_t)hcap * (8 + 16 + 4);          // staged keys, edge records, task id / final rank
+    bytes += (size_t)units * (8 * 2 + 8 * 3);      // ha, hb, rref
+    bytes += (size_t)units * 4 * 4;                // pstart, pcnt, tcnt (2 tasks per syllable of an eojeol)
+    bytes += (size_t)units * (2 * 2 + 1);          // chars, eojeol starts, nend
     bytes += 64;                                   // counters
-    bytes = (bytes + 15) & ~(size_t)15;
-    bytes += (size_t)kRuleQueue * 16;              // rule-work queue
-    return bytes;
+    return (bytes + 15) & ~(size_t)15;
+}
+__host__ __device__ inline size_t lattice_warp_smem(int units, int hcap, int max_str) {
+    return lattice_fixed_smem(units, hcap) + (((size_t)units * 4 * (size_t)max_str + 15) & ~(size_t)15);
+}
+// sentence-array sizes with their own kernel instantiation (together with the default staging capacity)
+constexpr int kLatDefaultHcap = 128;
+__host__ __device__ inline int lattice_units_class(int lcap) {
+    const int need = lcap + 8;
+    return need <= 64 ? 64 : (need <= 128 ? 128 : 0);
 }
 
 struct SentView {
@@ -420,31 +424,33 @@ __device__ LT_FLUSH_ATTR void flush_staged(const LatticeArgs& A, int lane, uint3
 #ifndef LT_LAT_MINB
 #define LT_LAT_MINB 4
 #endif
+// UC / HCT: sentence-array size and staging capacity when known at compile time (0 = A.units / A.hcap)
+template <int UC, int HCT>
 __global__ void __launch_bounds__(kLatWarps * 32, LT_LAT_MINB) lattice_kernel(const __grid_constant__ DevTables T,
                                                                 const __grid_constant__ LatticeArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const size_t units = (size_t)A.lcap + 8;
-    const int HC = A.hcap;
+    const int units = UC ? UC : A.units;
+    const int HC = HCT ? HCT : A.hcap;
     const int DM = A.max_str;
-    unsigned char* base = smem_raw + (size_t)warp * lattice_warp_smem(A.lcap, HC, DM);
-    uint64_t* ha = reinterpret_cast<uint64_t*>(base);
+    unsigned char* base = smem_raw + (size_t)warp * lattice_warp_smem(units, HC, DM);
+    uint4* rq = reinterpret_cast<uint4*>(base);
+    uint64_t* hkey = reinterpret_cast<uint64_t*>(rq + kRuleQueue);
+    lt_edge* hrec = reinterpret_cast<lt_edge*>(hkey + HC);
+    uint32_t* htask = reinterpret_cast<uint32_t*>(hrec + HC);
+    uint64_t* ha = reinterpret_cast<uint64_t*>(htask + HC);          // (kRuleQueue * 16 + HC * 28 is a multiple of 8 for even HC)
     uint64_t* hb = ha + units;
     uint2* rref = reinterpret_cast<uint2*>(hb + units);
-    uint64_t* hkey = reinterpret_cast<uint64_t*>(rref + 3 * units);
-    lt_edge* hrec = reinterpret_cast<lt_edge*>(hkey + HC);
-    uint32_t* sub = reinterpret_cast<uint32_t*>(hrec + HC);
-    uint32_t* pstart = sub + units * DM;
+    uint32_t* pstart = reinterpret_cast<uint32_t*>(rref + 3 * units);
     uint32_t* pcnt = pstart + units;
     uint32_t* tcnt = pcnt + units;
-    uint32_t* htask = tcnt + 2 * units;
-    uint16_t* ch = reinterpret_cast<uint16_t*>(htask + HC);
+    uint16_t* ch = reinterpret_cast<uint16_t*>(tcnt + 2 * units);
     uint16_t* eoj = ch + units;
     uint8_t* nend = reinterpret_cast<uint8_t*>(eoj + units);
-    uint32_t* nh = reinterpret_cast<uint32_t*>((reinterpret_cast<uintptr_t>(nend + units) + 3) & ~(uintptr_t)3);
+    uint32_t* nh = reinterpret_cast<uint32_t*>(nend + units);          // units is a multiple of 8
     uint32_t* rqn = nh + 1;
-    uint4* rq = reinterpret_cast<uint4*>(base + lattice_warp_smem(A.lcap, HC, DM) - (size_t)kRuleQueue * 16);
+    uint32_t* sub = reinterpret_cast<uint32_t*>(base + lattice_fixed_smem(units, HC));
 
     unsigned long long acc_L = 0, acc_P = 0, acc_E = 0;
     const int n_order = T.n_tag_order;

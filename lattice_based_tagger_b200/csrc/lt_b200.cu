@@ -459,7 +459,11 @@ static int launch_lattice(lt_batch* b, cudaStream_t st) {
     const int lcap = b->lcap;
     const int max_str = std::max(1, t->dev.max_str);
     int hcap = b->hcap;
-    size_t warp_smem = lattice_warp_smem(lcap, hcap, max_str);
+    if (hcap & 1) ++hcap;                               // keeps the arrays behind the staging area 8-byte aligned
+    // common sentence-array sizes (with the default staging capacity) have their own instantiation
+    const int uclass = hcap == kLatDefaultHcap ? lattice_units_class(lcap) : 0;
+    const int units = uclass ? uclass : lcap + 8;
+    size_t warp_smem = lattice_warp_smem(units, hcap, max_str);
     int warps = (int)std::min<size_t>(kLatWarps, kSmemBudget / warp_smem);
     if (warps < 1)
         return fail(LT_ERR_INVALID, "a sentence of %d code units (dictionary strings up to %d) does not fit the lattice "
@@ -485,7 +489,7 @@ static int launch_lattice(lt_batch* b, cudaStream_t st) {
     A.text = b->d_text;
     A.sent_off = b->d_sent_off;
     A.n_sent = n_sent;
-    A.lcap = lcap;
+    A.units = units;
     A.hcap = hcap;
     A.max_str = max_str;
     A.pos = static_cast<uint2*>(b->pos.p);
@@ -508,6 +512,8 @@ static int launch_lattice(lt_batch* b, cudaStream_t st) {
     }
 
     const size_t smem = warp_smem * warps;
+    void (*lattice_kernel)(const DevTables, const LatticeArgs) =
+        uclass == 64 ? lt::lattice_kernel<64, kLatDefaultHcap> : (uclass == 128 ? lt::lattice_kernel<128, kLatDefaultHcap> : lt::lattice_kernel<0, 0>);
     CU(cudaFuncSetAttribute(lattice_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lattice_kernel, warps * 32, smem));
@@ -663,7 +669,7 @@ static int resolve(lt_batch* b) {
         if (stage_over) {
             const int max_str = std::max(1, b->tables->dev.max_str);
             const int next = b->hcap * 2;
-            if (lattice_warp_smem(b->lcap, next, max_str) > kSmemBudget)
+            if (lattice_warp_smem(b->lcap + 8, next, max_str) > kSmemBudget)
                 return fail(LT_ERR_CAPACITY, "one eojeol yields more than %d lattice candidates; the staging buffer cannot grow further", b->hcap);
             b->hcap = next;
         }

@@ -435,7 +435,9 @@ def run_gpu(args):
                     'ms_per_step': host_ms_per_step,
                     'h2d_bytes_per_step': int(text.nbytes + offsets.nbytes),
                     'd2h_bytes_per_step': int(4 * (n + 1) + 16 * n_words + 8 * n + 4 * n)},
-            'gpu_launches': 7 * args.steps,   # length order, lattice, beam, 3 scan passes, pack
+            # per step: batch prologue (zeroing + work order), lattice, beam, path-offset scan (one launch up to
+            # 64 Ki sentences, else three), pack
+            'gpu_launches': (5 if n + 1 <= 65536 else 7) * args.steps,
             'stage_ms_per_step': {k: v / args.steps for k, v in stage.items()},
             'counters_per_step': counters,
             'roofline': roofline,

@@ -381,7 +381,14 @@ __global__ void __launch_bounds__(kBeamMaxWarps * 32, LT_BEAM_MINB) beam_kernel(
     for (size_t i = threadIdx.x * 4; i < (size_t)T.n_tri * dense_block_bytes(NT); i += blockDim.x * 4)
         *reinterpret_cast<uint32_t*>(dense_smem + i) = *reinterpret_cast<const uint32_t*>(T.dense + i);
     __syncthreads();
-    if (A.flags[kFlagEdgeOverflow] | A.flags[kFlagStageOverflow]) return;   // lattice incomplete: the host grows the buffer and reruns
+    if (A.flags[kFlagEdgeOverflow] | A.flags[kFlagStageOverflow]) {
+        // lattice incomplete: the host grows the buffer and reruns; the path lengths the scan / pack kernels
+        // behind this launch read must still be defined
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= A.n_sent; i += (int64_t)gridDim.x * blockDim.x)
+            A.path_len[i] = 0;
+        return;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) A.path_len[A.n_sent] = 0;      // the scan runs over n_sent + 1 entries
 
     const bool trail_smem = A.trail_smem != 0;
     const int units = UC ? UC : A.units;

@@ -387,6 +387,7 @@ struct lt_batch {
     bool edge_cap_fixed = false;   // LT_EDGE_CAP given: start there instead of the size guess (tests)
     int64_t n_edges = 0;
     bool have_lattice = false, have_paths = false, resolved = false;
+    bool beam_state_clean = false;   // beam queue cursor / counters still zero from the batch prologue
     cudaEvent_t ev[10]{};
     bool timed = false;
     int reruns = 0;
@@ -439,6 +440,11 @@ extern "C" void lt_batch_destroy(lt_batch* b) {
 }
 
 static int scan_u32(lt_batch* b, const uint32_t* in, uint32_t* out, int64_t n, cudaStream_t st) {
+    if (n <= kScanSmallMax) {
+        scan_small<<<1, kScanSmallThreads, 0, st>>>(in, out, n);
+        CU(cudaGetLastError());
+        return LT_OK;
+    }
     const int64_t tiles = (n + kScanTile - 1) / kScanTile;
     if (int rc = ensure(b->scan_tmp, (size_t)tiles * 4)) return rc;
     uint32_t* sums = static_cast<uint32_t*>(b->scan_tmp.p);
@@ -482,8 +488,6 @@ static int launch_lattice(lt_batch* b, cudaStream_t st) {
     }
     if (int rc = ensure(b->edges, (size_t)b->edge_cap * sizeof(lt_edge))) return rc;
 
-    CU(cudaMemsetAsync(b->counters.p, 0, 8 * sizeof(unsigned long long), st));
-    CU(cudaMemsetAsync(b->ctl.p, 0, kCtlWords * sizeof(unsigned int), st));
 
     LatticeArgs A{};
     A.text = b->d_text;
@@ -504,12 +508,17 @@ static int launch_lattice(lt_batch* b, cudaStream_t st) {
     A.counters = static_cast<unsigned long long*>(b->counters.p);
     A.queue = ctl + kCtlLatticeQueue;
     A.order = nullptr;
+    // prologue: control words and counters zeroed, work order (longest sentences first)
+    uint32_t* order = nullptr;
     if (b->sort_by_length && n_sent > 1) {
         if (int rc = ensure(b->order, (size_t)n_sent * 4)) return rc;
-        length_order<<<1, 1024, 0, st>>>(b->d_sent_off, n_sent, static_cast<uint32_t*>(b->order.p));
-        CU(cudaGetLastError());
-        A.order = static_cast<const uint32_t*>(b->order.p);
+        order = static_cast<uint32_t*>(b->order.p);
     }
+    batch_prologue<<<1, 1024, 0, st>>>(b->d_sent_off, n_sent, order, ctl, kCtlWords,
+                                       static_cast<unsigned long long*>(b->counters.p), 8);
+    CU(cudaGetLastError());
+    A.order = order;
+    b->beam_state_clean = true;
 
     const size_t smem = warp_smem * warps;
     void (*lattice_kernel)(const DevTables, const LatticeArgs) =
@@ -622,9 +631,13 @@ static int launch_beam(lt_batch* b, cudaStream_t st) {
         fprintf(stderr, "[lt] beam kernel: beam %d units %d, %zu B/warp, %d warps/CTA, %zu B/CTA, %d CTAs/SM, trail in %s\n", beam_size,
                 units, group_smem, warps, smem, per_sm, trail_smem ? "shared memory" : "HBM");
 
-    CU(cudaMemsetAsync(ctl + kCtlBeamQueue, 0, sizeof(unsigned int), st));
-    CU(cudaMemsetAsync(static_cast<unsigned long long*>(b->counters.p) + 3, 0, 4 * sizeof(unsigned long long), st));
-    CU(cudaMemsetAsync(b->path_len.p, 0, (size_t)(n_sent + 1) * 4, st));
+    // queue cursor and counters of this stage are zero after the batch prologue; a second search of the
+    // same lattice resets them (path_len needs no clearing: the kernel writes every entry)
+    if (!b->beam_state_clean) {
+        beam_reset<<<1, 32, 0, st>>>(ctl + kCtlBeamQueue, static_cast<unsigned long long*>(b->counters.p) + 3, 4);
+        CU(cudaGetLastError());
+    }
+    b->beam_state_clean = false;
     if (b->timed) CU(cudaEventRecord(b->ev[5], st));
     if (n_sent > 0) kernel<<<grid, warps * 32, smem, st>>>(t->dev, A);
     CU(cudaGetLastError());

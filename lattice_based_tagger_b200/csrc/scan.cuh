@@ -88,41 +88,100 @@ __global__ void __launch_bounds__(kScanThreads) scan_apply(const uint32_t* __res
     }
 }
 
-// Work order: sentence indices sorted by raw length, longest first, so that the persistent warps of
-// the lattice / beam kernels pull the expensive sentences early and the launch tail stays short.
-// One CTA: histogram of lengths (clamped), descending scan, scatter.  The order inside a length
-// bucket is arbitrary (atomics); results do not depend on it.
-constexpr int kOrderBins = 1024;
-__global__ void __launch_bounds__(1024) length_order(const int32_t* __restrict__ sent_off, int32_t n_sent,
-                                                     uint32_t* __restrict__ order) {
-    __shared__ uint32_t bins[kOrderBins];
-    for (int i = threadIdx.x; i < kOrderBins; i += blockDim.x) bins[i] = 0;
+// Small inputs: the whole exclusive scan by one CTA (one launch instead of three).
+constexpr int kScanSmallThreads = 1024;
+constexpr int64_t kScanSmallMax = 64 * 1024;
+__global__ void __launch_bounds__(kScanSmallThreads) scan_small(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int64_t n) {
+    __shared__ uint32_t warp_sums[33];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t per = (n + kScanSmallThreads - 1) / kScanSmallThreads;
+    const int64_t lo = (int64_t)threadIdx.x * per, hi = (lo + per < n) ? lo + per : n;
+    uint32_t local = 0;
+    for (int64_t i = lo; i < hi; ++i) local += in[i];
+    uint32_t incl = local;
+    #pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if (lane >= d) incl += t;
+    }
+    if (lane == 31) warp_sums[warp] = incl;
     __syncthreads();
-    for (int s = threadIdx.x; s < n_sent; s += blockDim.x) {
+    if (warp == 0) {
+        const uint32_t w = warp_sums[lane];
+        uint32_t wi = w;
+        #pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, wi, d);
+            if (lane >= d) wi += t;
+        }
+        warp_sums[lane] = wi - w;
+    }
+    __syncthreads();
+    uint32_t run = warp_sums[warp] + incl - local;
+    for (int64_t i = lo; i < hi; ++i) {
+        const uint32_t v = in[i];
+        out[i] = run;
+        run += v;
+    }
+}
+
+// Prologue of a batch, one CTA: zeroes the control words and work counters (instead of separate
+// memsets) and computes the WORK ORDER — sentence indices sorted by raw length, longest first, so
+// that the persistent warps of the lattice / beam kernels pull the expensive sentences early and
+// the launch tail stays short.  Histogram of lengths (clamped), scan, scatter; the order inside a
+// length bucket is arbitrary (atomics) and results do not depend on it.
+constexpr int kOrderBins = 1024;
+__global__ void __launch_bounds__(1024) batch_prologue(const int32_t* __restrict__ sent_off, int32_t n_sent,
+                                                       uint32_t* __restrict__ order, unsigned int* __restrict__ ctl, int n_ctl,
+                                                       unsigned long long* __restrict__ counters, int n_counters) {
+    if ((int)threadIdx.x < n_ctl) ctl[threadIdx.x] = 0;
+    if ((int)threadIdx.x < n_counters) counters[threadIdx.x] = 0;
+    if (order == nullptr) return;
+    __shared__ uint32_t bins[kOrderBins];
+    __shared__ uint32_t warp_sums[32];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    bins[t] = 0;
+    __syncthreads();
+    for (int s = t; s < n_sent; s += blockDim.x) {
         int len = sent_off[s + 1] - sent_off[s];
         len = len < 0 ? 0 : (len >= kOrderBins ? kOrderBins - 1 : len);
         atomicAdd(&bins[kOrderBins - 1 - len], 1u);          // bin 0 = longest
     }
     __syncthreads();
-    // exclusive scan of 1024 bins by 1024 threads (Hillis-Steele in shared memory)
-    __shared__ uint32_t tmp[kOrderBins];
-    const int t = threadIdx.x;
-    uint32_t v = (t < kOrderBins) ? bins[t] : 0u;
-    tmp[t] = v;
-    __syncthreads();
-    for (int d = 1; d < kOrderBins; d <<= 1) {
-        uint32_t add = (t >= d) ? tmp[t - d] : 0u;
-        __syncthreads();
-        tmp[t] += add;
-        __syncthreads();
+    // exclusive scan of the 1024 bins: warp scans + scan of the warp totals
+    const uint32_t v = bins[t];
+    uint32_t incl = v;
+    #pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if (lane >= d) incl += u;
     }
-    bins[t] = tmp[t] - v;           // start of every bin
+    if (lane == 31) warp_sums[warp] = incl;
     __syncthreads();
-    for (int s = threadIdx.x; s < n_sent; s += blockDim.x) {
+    if (warp == 0) {
+        const uint32_t w = warp_sums[lane];
+        uint32_t wi = w;
+        #pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, wi, d);
+            if (lane >= d) wi += u;
+        }
+        warp_sums[lane] = wi - w;
+    }
+    __syncthreads();
+    bins[t] = warp_sums[warp] + incl - v;           // start of every bin
+    __syncthreads();
+    for (int s = t; s < n_sent; s += blockDim.x) {
         int len = sent_off[s + 1] - sent_off[s];
         len = len < 0 ? 0 : (len >= kOrderBins ? kOrderBins - 1 : len);
         order[atomicAdd(&bins[kOrderBins - 1 - len], 1u)] = (uint32_t)s;
     }
+}
+
+// zeroes the beam stage's queue cursor and counters when a lattice is searched a second time
+__global__ void beam_reset(unsigned int* __restrict__ queue, unsigned long long* __restrict__ counters, int n_counters) {
+    if (threadIdx.x == 0) *queue = 0;
+    if ((int)threadIdx.x < n_counters) counters[threadIdx.x] = 0;
 }
 
 // best paths: reversed per-sentence scratch -> contiguous forward order

@@ -204,43 +204,44 @@ __device__ __noinline__ void edge_hashes(const DevTables& T, const SentView& v, 
 // Everything of a transition's score that depends on the edge alone, for scorer f:
 //   REG / MPREF / WPREF: a = the scorer's value;  TRIGRAM: a = template 4 weight, b2 = template 5
 //   weight, presence bits 0 / 1.
-__device__ __noinline__ uint32_t edge_score(const DevTables& T, const unsigned char* dense_smem, const EdgeView& k,
-                                            H2 e0, H2 g0, int f, double& a, double& b2) {
+__device__ __forceinline__ uint32_t edge_score_body(const DevTables& T, const unsigned char* dense_blk, const EdgeView& k,
+                                                    H2 e0, H2 g0, int f, int kind, H2 seed4, H2 seed5, H2 seed_pref,
+                                                    double& a, double& b2) {
     uint32_t present = 0;
     const uint32_t tk = k.tag0;
     const lt_func& fn = T.funcs[f];
     a = 0.0;
     b2 = 0.0;
-    if (fn.kind == LT_FUNC_REG) {
+    if (kind == LT_FUNC_REG) {
         // score_funcs.py:65-73
         if (tk == LT_TAG_UNK) a = __dmul_rn(fn.p[0], __dadd_rn((double)k.len, 0.1));
         else a = __dmul_rn(fn.p[1], (double)k.len);
         a = __dadd_rn(0.0, a);
         if (k.len == 1 && tk == LT_TAG_NOUN) a = __dadd_rn(a, fn.p[2]);
-    } else if (fn.kind == LT_FUNC_MPREF) {
+    } else if (kind == LT_FUNC_MPREF) {
         // score_funcs.py:84-88
-        FKey k0 = feature_key_sum32(T.seeds[f][9], feature_head32(tk, 0), g0);
+        FKey k0 = feature_key_sum32(seed_pref, feature_head32(tk, 0), g0);
         FeatProbe s0 = feat_first(T, k0);
         if (k.tag1 != LT_NO_TAG) {
-            FKey k1 = feature_key_sum32(T.seeds[f][9], feature_head32(k.tag1, 0), h2_mul(k.m1, kM0a, kM0b));
+            FKey k1 = feature_key_sum32(seed_pref, feature_head32(k.tag1, 0), h2_mul(k.m1, kM0a, kM0b));
             FeatProbe s1 = feat_first(T, k1);
             feat_resolve(T, k1, s1, b2);
         }
         feat_resolve(T, k0, s0, a);
         if (k.tag1 != LT_NO_TAG) a = __dadd_rn(a, b2);
         b2 = 0.0;
-    } else if (fn.kind == LT_FUNC_WPREF) {
+    } else if (kind == LT_FUNC_WPREF) {
         // score_funcs.py:99-100
-        FKey k0 = feature_key_sum32(T.seeds[f][9], feature_head32(tk, 0), e0);
+        FKey k0 = feature_key_sum32(seed_pref, feature_head32(tk, 0), e0);
         FeatProbe s0 = feat_first(T, k0);
         feat_resolve(T, k0, s0, a);
     } else {
         // templates 4 (wk.len) and 5 (wk.word, wk.tag0, wk.is_l), features/feature.py:100,104
-        const DenseView D = dense_view(dense_smem + (size_t)T.func_dense[f] * dense_block_bytes(T.n_tags), T.n_tags);
-        FKey q5 = feature_key_sum32(T.seeds[f][5], feature_head32(tk, (k.flags & LT_EDGE_IS_L) ? 1u : 0u), e0);
+        const DenseView D = dense_view(dense_blk, T.n_tags);
+        FKey q5 = feature_key_sum32(seed5, feature_head32(tk, (k.flags & LT_EDGE_IS_L) ? 1u : 0u), e0);
         FeatProbe s5 = feat_first(T, q5);
         if (k.len >= (uint32_t)kT4Dense) {
-            FKey q4 = feature_key_sum(T.seeds[f][4], feature_head(k.len, 0), H2{0, 0});
+            FKey q4 = feature_key_sum(seed4, feature_head(k.len, 0), H2{0, 0});
             FeatProbe s4 = feat_first(T, q4);
             if (feat_resolve(T, q4, s4, a)) present |= 1u;
         } else if ((D.m4[k.len >> 5] >> (k.len & 31)) & 1u) {
@@ -250,6 +251,15 @@ __device__ __noinline__ uint32_t edge_score(const DevTables& T, const unsigned c
         if (feat_resolve(T, q5, s5, b2)) present |= 2u;
     }
     return present;
+}
+
+// any score program: kind, dense block and seeds of scorer f read from the tables
+__device__ __noinline__ uint32_t edge_score(const DevTables& T, const unsigned char* dense_smem, const EdgeView& k,
+                                            H2 e0, H2 g0, int f, double& a, double& b2) {
+    const int kind = T.funcs[f].kind;
+    const unsigned char* dense_blk = dense_smem;
+    if (kind == LT_FUNC_TRIGRAM) dense_blk += (size_t)T.func_dense[f] * dense_block_bytes(T.n_tags);
+    return edge_score_body(T, dense_blk, k, e0, g0, f, kind, T.seeds[f][4], T.seeds[f][5], T.seeds[f][9], a, b2);
 }
 
 // numpy's association from eight surviving weights on: rare, so the nine weights are
@@ -338,17 +348,32 @@ __device__ __forceinline__ void beam_prefix_hashes(const uint16_t* ch, int L, in
 }
 
 // Edge prep: hash products and the edge-only part of the score program into cache slot `slot`.
+template <int PROG>
 __device__ __forceinline__ void prep_edge(const DevTables& T, const SentView& v, const unsigned char* dense_smem,
                                           EdgeView& k, bool need_m1, int nf, int kvs, const EdgeCache& C, uint32_t slot) {
     edge_hashes(T, v, k, need_m1);
     const H2 e0 = h2_mul(k.wk, kM0a, kM0b), g0 = h2_mul(k.mk, kM0a, kM0b);
     uint32_t present = 0;
-    #pragma unroll 1
-    for (int f = 0; f < nf; ++f) {
-        double a, b2;
-        present |= edge_score(T, dense_smem, k, e0, g0, f, a, b2) << (2 * f);
-        C.kval[slot * kvs + 2 * f] = a;
-        C.kval[slot * kvs + 2 * f + 1] = b2;
+    if (PROG == 1) {
+        // (RegularizationScore, SimpleTrigramFeatureScore): both scorers inline, the trigram seeds as immediates,
+        // the regulariser computed while the template-5 probe is in flight
+        double reg, unused, w4, w5;
+        const uint32_t tri = edge_score_body(T, dense_smem, k, e0, g0, 1, LT_FUNC_TRIGRAM, feature_seed(4u, 1u), feature_seed(5u, 1u),
+                                             H2{0, 0}, w4, w5);
+        edge_score_body(T, dense_smem, k, e0, g0, 0, LT_FUNC_REG, H2{0, 0}, H2{0, 0}, H2{0, 0}, reg, unused);
+        present = tri << 2;
+        C.kval[slot * 4 + 0] = reg;
+        C.kval[slot * 4 + 1] = 0.0;
+        C.kval[slot * 4 + 2] = w4;
+        C.kval[slot * 4 + 3] = w5;
+    } else {
+        #pragma unroll 1
+        for (int f = 0; f < nf; ++f) {
+            double a, b2;
+            present |= edge_score(T, dense_smem, k, e0, g0, f, a, b2) << (2 * f);
+            C.kval[slot * kvs + 2 * f] = a;
+            C.kval[slot * kvs + 2 * f + 1] = b2;
+        }
     }
     C.e0[slot] = e0;
     if (slot < (uint32_t)kEdgeRing) C.g0[slot] = g0;
@@ -507,7 +532,7 @@ __global__ void __launch_bounds__(kBeamMaxWarps * 32, LT_BEAM_MINB) beam_kernel(
                         const uint32_t gi = start + lane;
                         EdgeView k;
                         unpack_edge(ldg16(A.edges + gi), k);
-                        prep_edge(T, v, dense_smem, k, need_m1, nf, kvs, C, gi & (kEdgeRing - 1));
+                        prep_edge<PROG>(T, v, dense_smem, k, need_m1, nf, kvs, C, gi & (kEdgeRing - 1));
                     }
                     ring_hi = start + n;
                     if (ring_hi - ring_lo > (uint32_t)kEdgeRing) ring_lo = ring_hi - kEdgeRing;
@@ -521,7 +546,7 @@ __global__ void __launch_bounds__(kBeamMaxWarps * 32, LT_BEAM_MINB) beam_kernel(
                 if (pe <= L && j <= pe) {
                     EdgeView k;
                     unknown_edge(pe - j, pe, k);
-                    prep_edge(T, v, dense_smem, k, need_m1, nf, kvs, C, (uint32_t)(kEdgeRing + lane));
+                    prep_edge<PROG>(T, v, dense_smem, k, need_m1, nf, kvs, C, (uint32_t)(kEdgeRing + lane));
                 }
                 __syncwarp();
             }

@@ -204,6 +204,46 @@ struct Enum {
     uint32_t* rqn;           // queued descriptors (shared counter)
 };
 
+// The per-warp shared-memory arrays as views (layout: lattice_fixed_smem / lattice_warp_smem).
+struct LatticeViews {
+    SentView v;
+    Enum E;
+    uint32_t* pstart;
+    uint32_t* pcnt;
+    uint16_t* ch;
+    uint16_t* eoj;
+    uint8_t* nend;
+    uint64_t* ha;
+    uint64_t* hb;
+    uint2* rref;
+};
+template <int UC, int HCT>
+__device__ __forceinline__ LatticeViews lattice_views(unsigned char* base, int units_rt, int hcap_rt, int max_str) {
+    const int units = UC ? UC : units_rt;
+    const int HC = HCT ? HCT : hcap_rt;
+    uint4* rq = reinterpret_cast<uint4*>(base);
+    uint64_t* hkey = reinterpret_cast<uint64_t*>(rq + kRuleQueue);
+    lt_edge* hrec = reinterpret_cast<lt_edge*>(hkey + HC);
+    uint32_t* htask = reinterpret_cast<uint32_t*>(hrec + HC);
+    uint64_t* ha = reinterpret_cast<uint64_t*>(htask + HC);          // (kRuleQueue * 16 + HC * 28 is a multiple of 8 for even HC)
+    uint64_t* hb = ha + units;
+    uint2* rref = reinterpret_cast<uint2*>(hb + units);
+    uint32_t* pstart = reinterpret_cast<uint32_t*>(rref + 3 * units);
+    uint32_t* pcnt = pstart + units;
+    uint32_t* tcnt = pcnt + units;
+    uint16_t* ch = reinterpret_cast<uint16_t*>(tcnt + 2 * units);
+    uint16_t* eoj = ch + units;
+    uint8_t* nend = reinterpret_cast<uint8_t*>(eoj + units);
+    uint32_t* nh = reinterpret_cast<uint32_t*>(nend + units);          // units is a multiple of 8
+    uint32_t* rqn = nh + 1;
+    uint32_t* sub = reinterpret_cast<uint32_t*>(base + lattice_fixed_smem(units, HC));
+    LatticeViews W;
+    W.v = SentView{ch, ha, hb, rref};
+    W.E = Enum{sub, max_str, hkey, hrec, htask, tcnt, nh, HC, rq, rqn};
+    W.pstart = pstart; W.pcnt = pcnt; W.ch = ch; W.eoj = eoj; W.nend = nend; W.ha = ha; W.hb = hb; W.rref = rref;
+    return W;
+}
+
 __device__ __forceinline__ uint32_t sub_get(const Enum& E, int x, int y) {
     const int len = y - x;
     if (len <= 0 || len > E.max_str) return 0u;
@@ -280,7 +320,14 @@ __device__ __forceinline__ void push_rules(const Enum& E, uint2 ref, int b, int 
 // eomi = rule.eomi + word[suffix_from - b:]  (lemmatizer.py:100-102, :107-111).  `cand0` is the
 // candidate index of the key's first rule inside this split; with reps > 1 the whole list repeats
 // (the nested duplicate loop of lemmatizer.py:100-102) at stride `count`.
-__device__ __noinline__ void drain_rules(const DevTables& T, const SentView& v, const Enum& E, int lane) {
+// (Out of line; its arguments are the warp's shared-memory base and sizes by value, from which it
+// rebuilds the array views — passing the views by reference would force the caller's copies into
+// local memory for the whole kernel.)
+template <int UC, int HCT>
+__device__ __noinline__ void drain_rules(const DevTables& T, unsigned char* base, int units_rt, int hcap_rt, int max_str, int lane) {
+    const LatticeViews W = lattice_views<UC, HCT>(base, units_rt, hcap_rt, max_str);
+    const SentView v = W.v;
+    const Enum E = W.E;
     __syncwarp();
     const uint32_t n = *E.rqn;
     for (uint32_t i = lane; i < n; i += 32) {
@@ -435,22 +482,22 @@ __global__ void __launch_bounds__(kLatWarps * 32, LT_LAT_MINB) lattice_kernel(co
     const int HC = HCT ? HCT : A.hcap;
     const int DM = A.max_str;
     unsigned char* base = smem_raw + (size_t)warp * lattice_warp_smem(units, HC, DM);
-    uint4* rq = reinterpret_cast<uint4*>(base);
-    uint64_t* hkey = reinterpret_cast<uint64_t*>(rq + kRuleQueue);
-    lt_edge* hrec = reinterpret_cast<lt_edge*>(hkey + HC);
-    uint32_t* htask = reinterpret_cast<uint32_t*>(hrec + HC);
-    uint64_t* ha = reinterpret_cast<uint64_t*>(htask + HC);          // (kRuleQueue * 16 + HC * 28 is a multiple of 8 for even HC)
-    uint64_t* hb = ha + units;
-    uint2* rref = reinterpret_cast<uint2*>(hb + units);
-    uint32_t* pstart = reinterpret_cast<uint32_t*>(rref + 3 * units);
-    uint32_t* pcnt = pstart + units;
-    uint32_t* tcnt = pcnt + units;
-    uint16_t* ch = reinterpret_cast<uint16_t*>(tcnt + 2 * units);
-    uint16_t* eoj = ch + units;
-    uint8_t* nend = reinterpret_cast<uint8_t*>(eoj + units);
-    uint32_t* nh = reinterpret_cast<uint32_t*>(nend + units);          // units is a multiple of 8
-    uint32_t* rqn = nh + 1;
-    uint32_t* sub = reinterpret_cast<uint32_t*>(base + lattice_fixed_smem(units, HC));
+    const LatticeViews W = lattice_views<UC, HCT>(base, units, HC, DM);
+    uint64_t* ha = W.ha;
+    uint64_t* hb = W.hb;
+    uint2* rref = W.rref;
+    uint64_t* hkey = W.E.hkey;
+    lt_edge* hrec = W.E.hrec;
+    uint32_t* htask = W.E.htask;
+    uint32_t* pstart = W.pstart;
+    uint32_t* pcnt = W.pcnt;
+    uint32_t* tcnt = W.E.tcnt;
+    uint16_t* ch = W.ch;
+    uint16_t* eoj = W.eoj;
+    uint8_t* nend = W.nend;
+    uint32_t* nh = W.E.nh;
+    uint32_t* rqn = W.E.rqn;
+    uint32_t* sub = const_cast<uint32_t*>(W.E.sub);
 
     unsigned long long acc_L = 0, acc_P = 0, acc_E = 0;
     const int n_order = T.n_tag_order;
@@ -465,8 +512,8 @@ __global__ void __launch_bounds__(kLatWarps * 32, LT_LAT_MINB) lattice_kernel(co
         int n_eoj;
         bool bad;
         const int L = stage_sentence(A.text, s0, s1, lane, ch, eoj, ha, hb, n_eoj, bad);
-        SentView v{ch, ha, hb, rref};
-        Enum E{sub, DM, hkey, hrec, htask, tcnt, nh, HC, rq, rqn};
+        const SentView v = W.v;
+        const Enum E = W.E;
 
         // conjugation-rule lists of the keys starting at every syllable
         for (int p = lane; p < L; p += 32) {
@@ -561,9 +608,9 @@ __global__ void __launch_bounds__(kLatWarps * 32, LT_LAT_MINB) lattice_kernel(co
                             ncand_try += lemma_item(T, v, E, b, e, p, edge_proto(b, e, (uint32_t)(e - b), b == o), task);
                     }
                     __syncwarp();
-                    if (*rqn > (uint32_t)(kRuleQueue - 128)) drain_rules(T, v, E, lane);     // a pass queues at most 4 per lane
+                    if (*rqn > (uint32_t)(kRuleQueue - 128)) drain_rules<UC, HCT>(T, base, units, HC, DM, lane);     // a pass queues at most 4 per lane
                 }
-                drain_rules(T, v, E, lane);
+                drain_rules<UC, HCT>(T, base, units, HC, DM, lane);
                 // ---- a split survives only when both sides found something (lookup.py:205-209) ----
                 uint32_t nstaged = *nh;
                 bool too_many = nstaged > (uint32_t)HC;
@@ -630,9 +677,9 @@ __global__ void __launch_bounds__(kLatWarps * 32, LT_LAT_MINB) lattice_kernel(co
                             }
                         }
                         __syncwarp();
-                        if (*rqn > (uint32_t)(kRuleQueue - 128)) drain_rules(T, v, E, lane);
+                        if (*rqn > (uint32_t)(kRuleQueue - 128)) drain_rules<UC, HCT>(T, base, units, HC, DM, lane);
                     }
-                    drain_rules(T, v, E, lane);
+                    drain_rules<UC, HCT>(T, base, units, HC, DM, lane);
                     nstaged = *nh;
                     too_many = nstaged > (uint32_t)HC;
                     alive_here = nstaged - slots;             // every stage-2 hit survives

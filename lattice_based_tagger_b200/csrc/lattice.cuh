@@ -500,7 +500,6 @@ __global__ void __launch_bounds__(kLatWarps * 32, LT_LAT_MINB) lattice_kernel(co
     uint32_t* sub = const_cast<uint32_t*>(W.E.sub);
 
     unsigned long long acc_L = 0, acc_P = 0, acc_E = 0;
-    const int n_order = T.n_tag_order;
 
     while (true) {
         unsigned int s = 0;
@@ -590,16 +589,17 @@ __global__ void __launch_bounds__(kLatWarps * 32, LT_LAT_MINB) lattice_kernel(co
                                 rec.tag0 = left ? LT_TAG_NOUN : LT_TAG_JOSA;
                                 stage_hit(E, rec, hit_key(e, b, 0, 0, 0), task);
                             } else {
-                                const uint32_t mask = sub_get(E, b, e) & kSubTagMask;
+                                // one hit per tag of the string; the sort key carries the tag's position in the
+                                // dictionary's tag order (get_tags, dictionary.py:238-242), so set bits are simply walked
+                                uint32_t mask = sub_get(E, b, e) & kSubTagMask & T.order_mask;
                                 if (mask) {
                                     lt_edge rec = edge_proto(b, e, (uint32_t)(e - b), b == o);
                                     #pragma unroll 1
-                                    for (int k = 0; k < n_order; ++k) {
-                                        const uint32_t t = T.tag_order[k];
-                                        if ((mask >> t) & 1u) {
-                                            rec.tag0 = (uint8_t)t;
-                                            stage_hit(E, rec, hit_key(e, b, 0, 0, (uint32_t)k), task);
-                                        }
+                                    while (mask) {
+                                        const uint32_t t = (uint32_t)__ffs(mask) - 1u;
+                                        mask &= mask - 1u;
+                                        rec.tag0 = (uint8_t)t;
+                                        stage_hit(E, rec, hit_key(e, b, 0, 0, (uint32_t)T.tag_pos[t]), task);
                                     }
                                 }
                             }
@@ -658,15 +658,18 @@ __global__ void __launch_bounds__(kLatWarps * 32, LT_LAT_MINB) lattice_kernel(co
                                 if (t == 0) {
                                     const uint32_t m = sub_get(E, b, e);
                                     // stand-alone tags in list order (lookup.py:104-105), then Josa after a Noun
-                                    constexpr uint32_t order = LT_TAG_NOUN | (LT_TAG_ADVERB << 4) | (LT_TAG_EXCLAMATION << 8) |
-                                                               (LT_TAG_DETERMINER << 12) | (LT_TAG_NUMBER << 16);
+                                    constexpr uint32_t standalone = (1u << LT_TAG_NOUN) | (1u << LT_TAG_ADVERB) | (1u << LT_TAG_EXCLAMATION) |
+                                                                    (1u << LT_TAG_DETERMINER) | (1u << LT_TAG_NUMBER);
+                                    constexpr uint64_t pos_of = (0ull << (4 * LT_TAG_NOUN)) | (1ull << (4 * LT_TAG_ADVERB)) |
+                                                                (2ull << (4 * LT_TAG_EXCLAMATION)) | (3ull << (4 * LT_TAG_DETERMINER)) |
+                                                                (4ull << (4 * LT_TAG_NUMBER));
+                                    uint32_t sm = m & standalone;
                                     #pragma unroll 1
-                                    for (int k = 0; k < 5; ++k) {
-                                        const uint32_t t = (order >> (4 * k)) & 0xFu;
-                                        if ((m >> t) & 1u) {
-                                            rec.tag0 = (uint8_t)t;
-                                            stage_hit(E, rec, hit_key(e, b, 0, 0, (uint32_t)k), 0u);
-                                        }
+                                    while (sm) {
+                                        const uint32_t t = (uint32_t)__ffs(sm) - 1u;
+                                        sm &= sm - 1u;
+                                        rec.tag0 = (uint8_t)t;
+                                        stage_hit(E, rec, hit_key(e, b, 0, 0, (uint32_t)((pos_of >> (4 * t)) & 0xFu)), 0u);
                                     }
                                     if (nend[b] && ((m >> LT_TAG_JOSA) & 1u)) {
                                         rec.tag0 = LT_TAG_JOSA;

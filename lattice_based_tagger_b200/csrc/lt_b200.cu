@@ -148,7 +148,15 @@ static int build_tables(const lt_tables_desc* d, lt_tables* t) {
     D.n_tags = d->n_tags;
     D.n_tag_order = d->n_tag_order;
     D.max_len = d->max_len;
-    for (int i = 0; i < d->n_tag_order; ++i) D.tag_order[i] = d->tag_order[i];
+    D.order_mask = 0;
+    for (int i = 0; i < 32; ++i) D.tag_pos[i] = 0xFF;
+    for (int i = 0; i < d->n_tag_order; ++i) {
+        const uint8_t t = d->tag_order[i];
+        if (t >= LT_MAX_TAGS) return fail(LT_ERR_INVALID, "tag_order[%d] = %d out of range", i, (int)t);
+        D.tag_order[i] = t;
+        if (!((D.order_mask >> t) & 1u)) D.tag_pos[t] = (uint8_t)i;      // a repeated tag keeps its first position
+        D.order_mask |= 1u << t;
+    }
 
     // ---- powers of the hash bases ----
     int64_t max_str = 1;

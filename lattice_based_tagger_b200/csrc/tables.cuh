@@ -86,6 +86,8 @@ struct DevTables {
     int32_t has_rules;
     int32_t max_str;              // longest dictionary string (syllables)
     uint8_t tag_order[LT_MAX_TAGS];
+    uint8_t tag_pos[32];           // position of a tag id in tag_order (the emission order of a string's tags)
+    uint32_t order_mask;           // tag ids that appear in tag_order
     lt_func funcs[LT_MAX_FUNCS];
     int8_t  func_dense[LT_MAX_FUNCS];   // dense block index of a trigram scorer, -1 otherwise
     H2 bos;                        // hash of the literal 'BOS' (beam.py:21)

@@ -2,7 +2,7 @@
 //
 // HBM layout (all built once by lt_tables_create, read-only afterwards):
 //   dict   cuckoo table (two slots per key), 16 B slots {fp, tagmask, lemma bits}; key = (string, length)
-//   rules  open-addressing table, 16 B slots {exact 1..3-syllable key, first rule, count|k3_first}
+//   rules  cuckoo table, 16 B slots {exact 1..3-syllable key, first rule, count|k3_first}
 //   rrec   one 48 B record per (stem, eomi) rule: hashes and lengths of both strings
 //   feat   cuckoo table (two slots per key), 16 B slots {fp, fp64 weight}; key = feature tuple / preference
 //   dense  per trigram scorer: tag x tag matrix (template 3), length vectors (templates 4, 6)

@@ -210,7 +210,10 @@ def oracle_feature_inputs(config, sample):
 
     cfg = synth.CONFIGS[config]
     tags = list(tagger.view.tag_to_morphs)
-    return synth.make_features(sample, tag_fn, lattice_fn, cfg['n_feat'], tags, seed=3)
+    vocab = None
+    if cfg['n_feat'] > 1_000_000:
+        vocab = [(m, t) for t, ms in tagger.view.tag_to_morphs.items() for m in sorted(ms)]
+    return synth.make_features(sample, tag_fn, lattice_fn, cfg['n_feat'], tags, seed=3, vocab=vocab)
 
 
 def feature_sample(sents):
@@ -303,9 +306,14 @@ def run_gpu(args):
     # features: rank 0's sample defines them for every rank (same tables everywhere)
     base_sents = sents if rank == 0 else synth.build_workload(args.config, rank=0, n_sent=args.sentences)[2]
     sample = feature_sample(base_sents)
+    # (configurations whose feature target exceeds what lattice chains of the sample yield — C5 — are padded
+    # with word n-grams over the dictionary)
+    vocab = None
+    if cfg['n_feat'] > 1_000_000:
+        vocab = [(m, t) for t, ms in dictionary.tag_to_morphs.items() for m in sorted(ms)]
     feature_dic, coef = synth.make_features(
         sample, lambda s: reg_tagger.tag_batch(s, beam, errors='none'), reg_tagger.lattice_batch,
-        cfg['n_feat'], list(dictionary.tag_to_morphs), seed=3)
+        cfg['n_feat'], list(dictionary.tag_to_morphs), seed=3, vocab=vocab)
     reg_tagger.close()
     funcs = pkg.beam.BeamScoreFunctions(
         pkg.beam.RegularizationScore(),
@@ -428,7 +436,7 @@ def run_gpu(args):
             'metric': METRIC, 'value': total_counters['sentences'] / (ms_per_step * 1e-3), 'unit': UNIT,
             'n_gpus': world, 'steps': args.steps, 'warmup': max(3, args.warmup), 'ms_per_step': ms_per_step,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-            'config': workload_config(args.config, cfg, n),
+            'config': dict(workload_config(args.config, cfg, n), features=len(feature_dic)),
             'edges_per_sec': total_counters['E'] / (ms_per_step * 1e-3),
             'transitions_per_sec': total_counters['T'] / (ms_per_step * 1e-3),
             'e2e': {'value': total_counters['sentences'] / (host_ms_per_step * 1e-3), 'unit': UNIT,

@@ -179,12 +179,15 @@ def make_sentences(tag_to_morphs, rules, n_sent, mean_len, alphabet, seed=2, fix
     return sents
 
 
-def make_features(sample_sents, tag_fn, lattice_fn, n_features, tags, seed=3):
+def make_features(sample_sents, tag_fn, lattice_fn, n_features, tags, seed=3, vocab=None):
     """`feature_dic` (tuple -> index, insertion order) and fp64 `coefficients`.
 
     `tag_fn(sents) -> [Sequence | None]` gives best paths (features that really fire);
     `lattice_fn(sents) -> [(words, bindex)]` gives lattices from which random (i, j, k) chains pad
     the dictionary up to `n_features`.  All (3, ti, tj), (4, 1..8) and (6, 1..8) are included.
+    When the lattice chains run dry before the target (the 10 M-weight table of C5), word n-grams
+    over `vocab` = [(word, tag)] fill the rest: they rarely fire, they make the table as large as
+    the configuration says.
     """
     rng = np.random.default_rng(seed)
     feature_dic = {}
@@ -254,6 +257,29 @@ def make_features(sample_sents, tag_fn, lattice_fn, n_features, tags, seed=3):
                         add(f)
         if len(feature_dic) == before:
             break
+    if vocab and len(feature_dic) < n_features:
+        words = [w for w, _ in vocab]
+        wtags = [t for _, t in vocab]
+        nv = len(words)
+        while len(feature_dic) < n_features:
+            m = min(1 << 20, (n_features - len(feature_dic)) * 5 // 4 + 16)
+            a = rng.integers(0, nv, m)
+            b = rng.integers(0, nv, m)
+            c = rng.integers(0, nv, m)
+            tmpl = rng.integers(0, 4, m)
+            for x, y, z, t in zip(a.tolist(), b.tolist(), c.tolist(), tmpl.tolist()):
+                if t == 0:
+                    f = (0, words[x], words[y], wtags[y])
+                elif t == 1:
+                    f = (7, words[x], words[y], words[z])
+                elif t == 2:
+                    f = (2, wtags[x], words[y], wtags[y])
+                else:
+                    f = (8, words[x], words[y])
+                if f not in feature_dic:
+                    feature_dic[f] = len(feature_dic)
+                    if len(feature_dic) >= n_features:
+                        break
     coefficients = rng.standard_normal(len(feature_dic)).astype(np.float64)
     return feature_dic, coefficients
 

@@ -31,7 +31,8 @@
 
 namespace lt {
 
-constexpr int kLatWarps = 4;                 // warps per CTA of the lattice kernel
+constexpr int kLatWarps = 4;                 // preferred warps per CTA of the lattice kernel
+constexpr int kLatMaxWarps = 8;              // largest CTA (128 registers per thread either way)
 constexpr int kRuleQueue = 256;              // rule-work descriptors per warp (drained when more than half full)
 constexpr unsigned kFull = 0xFFFFFFFFu;
 
@@ -58,6 +59,12 @@ struct LatticeArgs {
     unsigned long long* counters;   // [0]=L [1]=P [2]=E
     unsigned int* queue;        // work-queue cursor
     const uint32_t* order;      // queue position -> sentence index (longest first), or nullptr
+    // Two-pass staging: when `retry_list` is set, a sentence whose eojeol outgrows the staging area of the
+    // main pass is appended to it instead of raising the overflow flag; the retry pass (retry_pass = 1, a
+    // small launch with a larger staging area) takes its sentences from that list.
+    uint32_t* retry_list;
+    unsigned int* retry_count;
+    int32_t retry_pass;
 };
 
 // Per-warp shared memory.  `units` = elements per sentence array (>= longest sentence + 8, a
@@ -469,11 +476,11 @@ __device__ LT_FLUSH_ATTR void flush_staged(const LatticeArgs& A, int lane, uint3
 // ---- the kernel -----------------------------------------------------------------------------------
 
 #ifndef LT_LAT_MINB
-#define LT_LAT_MINB 4
+#define LT_LAT_MINB 2
 #endif
 // UC / HCT: sentence-array size and staging capacity when known at compile time (0 = A.units / A.hcap)
 template <int UC, int HCT>
-__global__ void __launch_bounds__(kLatWarps * 32, LT_LAT_MINB) lattice_kernel(const __grid_constant__ DevTables T,
+__global__ void __launch_bounds__(kLatMaxWarps * 32, LT_LAT_MINB) lattice_kernel(const __grid_constant__ DevTables T,
                                                                 const __grid_constant__ LatticeArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
@@ -505,8 +512,13 @@ __global__ void __launch_bounds__(kLatWarps * 32, LT_LAT_MINB) lattice_kernel(co
         unsigned int s = 0;
         if (lane == 0) s = atomicAdd(A.queue, 1u);
         s = __shfl_sync(kFull, s, 0);
-        if (s >= (unsigned)A.n_sent) break;
-        if (A.order) s = __ldg(A.order + s);
+        if (A.retry_pass) {
+            if (s >= *A.retry_count) break;
+            s = A.retry_list[s];
+        } else {
+            if (s >= (unsigned)A.n_sent) break;
+            if (A.order) s = __ldg(A.order + s);
+        }
         const int s0 = __ldg(A.sent_off + s), s1 = __ldg(A.sent_off + s + 1);
         int n_eoj;
         bool bad;
@@ -723,6 +735,12 @@ __global__ void __launch_bounds__(kLatWarps * 32, LT_LAT_MINB) lattice_kernel(co
             }
         }
         if (overflow) {
+            if (!A.retry_pass && A.retry_list != nullptr) {
+                // the retry pass redoes this sentence from scratch (edges already flushed stay unreferenced)
+                if (lane == 0) A.retry_list[atomicAdd(A.retry_count, 1u)] = s;
+                __syncwarp();
+                continue;
+            }
             if (lane == 0) atomicOr(A.flags + kFlagStageOverflow, 1u);
         } else {
             flush();

@@ -372,7 +372,7 @@ struct DevBuf {
 };
 
 // control words on the device: work-queue cursors, edge cursor, overflow flags
-enum { kCtlLatticeQueue = 0, kCtlBeamQueue = 1, kCtlCursor = 2, kCtlFlags = 4, kCtlWords = 8 };
+enum { kCtlLatticeQueue = 0, kCtlBeamQueue = 1, kCtlCursor = 2, kCtlRetryCount = 3, kCtlFlags = 4, kCtlRetryQueue = 6, kCtlWords = 8 };
 
 struct lt_batch {
     lt_tables* tables = nullptr;
@@ -381,7 +381,7 @@ struct lt_batch {
     // inputs (host entry point) and per-unit / per-sentence arrays
     DevBuf text, sent_off, pos, scan_tmp;
     DevBuf sent_len, sent_edges, status, path_len, path_off, scores;
-    DevBuf edges, trail, path_tmp, path_out, counters, ctl, order;
+    DevBuf edges, trail, path_tmp, path_out, counters, ctl, order, retry;
     const uint16_t* d_text = nullptr;
     const int32_t* d_sent_off = nullptr;
     int32_t n_sent = 0;
@@ -389,7 +389,9 @@ struct lt_batch {
     int32_t max_sent_units = 0;
     int32_t lcap = 0;
     int32_t beam = 0;
-    int32_t hcap = 128;            // lattice staging capacity per warp (grows on overflow, sticky)
+    int32_t hcap = 128;            // lattice staging capacity per warp of the main pass
+    bool use_retry = false;        // a batch outgrew `hcap`: such sentences go to a retry pass from now on (sticky)
+    int32_t retry_hcap = 0;        // staging capacity of the retry pass (grows on overflow, sticky)
     bool sort_by_length = true;    // persistent warps pull the longest sentences first (LT_SORT_BY_LENGTH=0 disables)
     uint32_t edge_cap = 0;         // edge buffer capacity (grows on overflow, sticky)
     bool edge_cap_fixed = false;   // LT_EDGE_CAP given: start there instead of the size guess (tests)
@@ -438,7 +440,7 @@ extern "C" void lt_batch_destroy(lt_batch* b) {
     cudaSetDevice(b->tables->device);
     DevBuf* bufs[] = {&b->text, &b->sent_off, &b->pos, &b->scan_tmp, &b->sent_len, &b->sent_edges, &b->status,
                       &b->path_len, &b->path_off, &b->scores, &b->edges, &b->trail, &b->path_tmp, &b->path_out,
-                      &b->counters, &b->ctl, &b->order};
+                      &b->counters, &b->ctl, &b->order, &b->retry};
     for (DevBuf* x : bufs)
         if (x->p) cudaFree(x->p);
     for (auto& e : b->ev)
@@ -475,10 +477,18 @@ static int launch_lattice(lt_batch* b, cudaStream_t st) {
     int hcap = b->hcap;
     if (hcap & 1) ++hcap;                               // keeps the arrays behind the staging area 8-byte aligned
     // common sentence-array sizes (with the default staging capacity) have their own instantiation
-    const int uclass = hcap == kLatDefaultHcap ? lattice_units_class(lcap) : 0;
+    const int uclass = (hcap == kLatDefaultHcap || hcap == 2 * kLatDefaultHcap) ? lattice_units_class(lcap) : 0;
     const int units = uclass ? uclass : lcap + 8;
     size_t warp_smem = lattice_warp_smem(units, hcap, max_str);
-    int warps = (int)std::min<size_t>(kLatWarps, kSmemBudget / warp_smem);
+    // CTA shape: the warps per CTA (1..8) that keep the most warps resident on an SM (128 registers per
+    // thread allow 16); ties go to 4-warp CTAs
+    int warps = 0, best_res = 0;
+    for (int w : {kLatWarps, 8, 6, 5, 3, 2, 1}) {
+        const size_t cta = warp_smem * w;
+        if (cta > kSmemBudget) continue;
+        const int res = w * (int)std::min<size_t>(16 / w, (size_t)228 * 1024 / (cta + 1024));
+        if (res > best_res) { best_res = res; warps = w; }
+    }
     if (warps < 1)
         return fail(LT_ERR_INVALID, "a sentence of %d code units (dictionary strings up to %d) does not fit the lattice "
                                     "kernel's shared memory", b->max_sent_units, max_str);
@@ -530,7 +540,11 @@ static int launch_lattice(lt_batch* b, cudaStream_t st) {
 
     const size_t smem = warp_smem * warps;
     void (*lattice_kernel)(const DevTables, const LatticeArgs) =
-        uclass == 64 ? lt::lattice_kernel<64, kLatDefaultHcap> : (uclass == 128 ? lt::lattice_kernel<128, kLatDefaultHcap> : lt::lattice_kernel<0, 0>);
+        (uclass == 64 && hcap == kLatDefaultHcap) ? lt::lattice_kernel<64, kLatDefaultHcap>
+        : (uclass == 128 && hcap == kLatDefaultHcap) ? lt::lattice_kernel<128, kLatDefaultHcap>
+        : (uclass == 64 && hcap == 2 * kLatDefaultHcap) ? lt::lattice_kernel<64, 2 * kLatDefaultHcap>
+        : (uclass == 128 && hcap == 2 * kLatDefaultHcap) ? lt::lattice_kernel<128, 2 * kLatDefaultHcap>
+        : lt::lattice_kernel<0, 0>;
     CU(cudaFuncSetAttribute(lattice_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lattice_kernel, warps * 32, smem));
@@ -538,9 +552,39 @@ static int launch_lattice(lt_batch* b, cudaStream_t st) {
     const int64_t want_blocks = ((int64_t)n_sent + warps - 1) / warps;
     const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(want_blocks, (int64_t)t->sm_count * per_sm));
 
+    if (getenv("LT_DEBUG"))
+        fprintf(stderr, "[lt] lattice kernel: units %d hcap %d max_str %d, %zu B/warp, %d warps/CTA, %zu B/CTA, %d CTAs/SM\n", units, hcap,
+                max_str, warp_smem, warps, smem, per_sm);
+    if (b->use_retry) {
+        if (int rc = ensure(b->retry, (size_t)std::max(1, n_sent) * 4)) return rc;
+        A.retry_list = static_cast<uint32_t*>(b->retry.p);
+        A.retry_count = ctl + kCtlRetryCount;
+    }
     if (b->timed) CU(cudaEventRecord(b->ev[0], st));
     if (n_sent > 0) lattice_kernel<<<grid, warps * 32, smem, st>>>(t->dev, A);
     CU(cudaGetLastError());
+    if (b->use_retry && n_sent > 0) {
+        // retry pass: the few sentences with an eojeol beyond `hcap` hits, with a staging area of their own size
+        int rh = b->retry_hcap;
+        if (rh & 1) ++rh;
+        const int r_units = lcap + 8;
+        const size_t r_warp = lattice_warp_smem(r_units, rh, max_str);
+        if (r_warp > kSmemBudget)
+            return fail(LT_ERR_CAPACITY, "one eojeol yields more than %d lattice candidates; the staging buffer cannot grow further", rh / 2);
+        const int r_warps = (int)std::max<size_t>(1, std::min<size_t>(2, kSmemBudget / r_warp));
+        const size_t r_smem = r_warp * r_warps;
+        void (*retry_kernel)(const DevTables, const LatticeArgs) = lt::lattice_kernel<0, 0>;
+        CU(cudaFuncSetAttribute(retry_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(r_smem, smem)));
+        LatticeArgs R = A;
+        R.units = r_units;
+        R.hcap = rh;
+        R.queue = ctl + kCtlRetryQueue;
+        R.retry_pass = 1;
+        int r_per_sm = 1;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r_per_sm, retry_kernel, r_warps * 32, r_smem));
+        retry_kernel<<<(unsigned)(t->sm_count * std::max(1, r_per_sm)), r_warps * 32, r_smem, st>>>(t->dev, R);
+        CU(cudaGetLastError());
+    }
     if (b->timed) CU(cudaEventRecord(b->ev[1], st));
     b->have_lattice = true;
     b->have_paths = false;
@@ -666,6 +710,13 @@ static int launch_beam(lt_batch* b, cudaStream_t st) {
     return LT_OK;
 }
 
+// The retry pass is meant for outliers: when more than 1 / 32 of a batch's sentences needed it, the main
+// pass's staging area doubles for the batches to come (as long as the retry pass's is larger).
+static void adapt_staging(lt_batch* b, unsigned int retried) {
+    if (!b->use_retry || b->n_sent < 64) return;
+    if ((uint64_t)retried * 32 > (uint64_t)b->n_sent && b->hcap * 2 < b->retry_hcap) b->hcap *= 2;
+}
+
 // Wait for the batch and, if the lattice outgrew a buffer (edge array or per-warp staging), enlarge
 // it and run the stages again — still on the device; capacities are sticky for later batches.
 static int resolve(lt_batch* b) {
@@ -680,6 +731,7 @@ static int resolve(lt_batch* b) {
         if (!edge_over && !stage_over) {
             b->n_edges = ctl[kCtlCursor];
             b->resolved = true;
+            adapt_staging(b, ctl[kCtlRetryCount]);
             return LT_OK;
         }
         if (edge_over) {
@@ -688,11 +740,15 @@ static int resolve(lt_batch* b) {
             b->edge_cap = (uint32_t)need;
         }
         if (stage_over) {
+            // first time: switch the two-pass scheme on (the main pass keeps its small staging area and its
+            // residency); afterwards the retry pass's staging area doubles
             const int max_str = std::max(1, b->tables->dev.max_str);
-            const int next = b->hcap * 2;
+            const int next = b->use_retry ? b->retry_hcap * 2 : std::max(512, b->hcap * 4);
             if (lattice_warp_smem(b->lcap + 8, next, max_str) > kSmemBudget)
-                return fail(LT_ERR_CAPACITY, "one eojeol yields more than %d lattice candidates; the staging buffer cannot grow further", b->hcap);
-            b->hcap = next;
+                return fail(LT_ERR_CAPACITY, "one eojeol yields more than %d lattice candidates; the staging buffer cannot grow further",
+                            b->use_retry ? b->retry_hcap : b->hcap);
+            b->use_retry = true;
+            b->retry_hcap = next;
         }
         ++b->reruns;
         const bool want_paths = b->have_paths;
@@ -790,6 +846,7 @@ static int fetch_paths(lt_batch* b, int32_t* path_off, lt_edge* path_edges, int6
         if (ctl[kCtlFlags + kFlagEdgeOverflow] == 0 && ctl[kCtlFlags + kFlagStageOverflow] == 0) {
             b->n_edges = ctl[kCtlCursor];
             b->resolved = true;
+            adapt_staging(b, ctl[kCtlRetryCount]);
             break;
         }
         b->resolved = false;

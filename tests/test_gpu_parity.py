@@ -298,3 +298,17 @@ def test_dictionary_mutation_and_refresh():
     tagger.refresh()
     _check_against_oracle(tagger, lo.OracleTagger(dictionary, funcs), sents + ['트와이스짱'], (1, 5))
     assert tagger.tag(sents[0]).sequences[1].tag0 == 'Noun'
+
+
+def test_retry_pass_and_adaptive_staging(monkeypatch):
+    """A staging area far too small for most eojeols: the sentences go through the retry pass, the
+    main pass's capacity adapts over successive batches (>= 64 sentences), results never change."""
+    case = _cases.random_case(777, n_sent=90, features=True, max_sent_len=50)
+    _cases.add_features(case, _cases.observed_features(case, lo, seed=2), 2)
+    dictionary, funcs = _cases.build_objects(case, pkg)
+    sents = list(case['sentences'])
+    oracle = lo.OracleTagger(dictionary, funcs)
+    monkeypatch.setenv('LT_HIT_CAP', '8')
+    tagger = pkg.Tagger(dictionary, score_funcs=funcs)
+    for _ in range(4):                       # capacities are sticky per tagger: 8 -> 16 -> 32 ...
+        _check_against_oracle(tagger, oracle, sents, (5,))

@@ -100,6 +100,13 @@ __device__ __forceinline__ H2 sub_hash(const DevTables& T, const SentView& v, in
     return h2_sub(H2{v.ha[b], v.hb[b]}, H2{v.ha[e], v.hb[e]}, pow_at(T, (uint32_t)(e - b)));
 }
 
+// q / d for the small flat item indices of the enumeration loops: exact through a float reciprocal
+// while q * 1 < 2^22 (the rounding error of (q + 0.5) * (1 / d) stays below the 0.5 / d margin), an
+// integer division otherwise.  `inv` = 1.0f / d, computed once per loop.
+__device__ __forceinline__ int small_div(int q, int d, float inv) {
+    return q < (1 << 22) ? __float2int_rz(((float)q + 0.5f) * inv) : q / d;
+}
+
 __device__ __forceinline__ bool is_py_space(uint32_t c) {
     // str.split() separators in the BMP
     return (c >= 0x09 && c <= 0x0D) || (c >= 0x1C && c <= 0x20) || c == 0x85 || c == 0xA0 || c == 0x1680 ||
@@ -543,8 +550,9 @@ __global__ void __launch_bounds__(kLatMaxWarps * 32, LT_LAT_MINB) lattice_kernel
             rref[3 * p + 2] = r3;
         }
         // substring table: every substring of at most max_str syllables, one wave of probes
+        const float inv_dm = 1.0f / (float)DM;
         for (int q = lane; q < L * DM; q += 32) {
-            const int x = q / DM, len = q - x * DM + 1;
+            const int x = small_div(q, DM, inv_dm), len = q - x * DM + 1;
             uint32_t payload = 0;
             if (x + len <= L) {
                 const uint64_t pl = dict_probe(T, sub_hash(T, v, x, x + len), (uint32_t)len);
@@ -580,10 +588,11 @@ __global__ void __launch_bounds__(kLatMaxWarps * 32, LT_LAT_MINB) lattice_kernel
                 for (int u = lane; u < 2 * n; u += 32) tcnt[u] = 0;
                 __syncwarp();
                 uint32_t ncand_try = 0;
+                const float inv_n = 1.0f / (float)n;
                 for (int q0 = 0; q0 < n * n; q0 += 32) {
                     const int q = q0 + lane;
                     if (q < n * n) {
-                        const int i = q / n, r = q - i * n;
+                        const int i = small_div(q, n, inv_n), r = q - i * n;
                         const int p = o + r;
                         // task: i == 0 whole; r < i: left_i = [o, o+i); else right_i = [o+i, oe)
                         const bool left = (i > 0) && (r < i);
@@ -657,10 +666,11 @@ __global__ void __launch_bounds__(kLatMaxWarps * 32, LT_LAT_MINB) lattice_kernel
                     __syncwarp();
                     const int tri = M * (M + 1) / 2;
                     const int items = (n - 1) * tri;
+                    const float inv_tri = 1.0f / (float)tri;
                     for (int q0 = 0; q0 < items; q0 += 32) {
                         const int q = q0 + lane;
                         if (q < items) {
-                            const int bl = 1 + q / tri;
+                            const int bl = 1 + small_div(q, tri, inv_tri);
                             int t = q - (bl - 1) * tri;
                             int span = 1;
                             while (t >= span) { t -= span; ++span; }       // t = split offset inside the span

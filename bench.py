@@ -399,10 +399,13 @@ def run_gpu(args):
 
     ms_per_step = dev_ms / args.steps
     host_ms_per_step = 1e3 * host_s / args.steps
+    rank_ms = [ms_per_step]
     if world > 1:
-        t = torch.tensor([ms_per_step, host_ms_per_step], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_per_step, host_ms_per_step = float(t[0]), float(t[1])
+        mine = torch.tensor([ms_per_step, host_ms_per_step], dtype=torch.float64, device=dev)
+        every = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(every, mine)
+        rank_ms = [float(x[0]) for x in every]                 # reported per rank; the line's time is the maximum
+        ms_per_step, host_ms_per_step = max(rank_ms), max(float(x[1]) for x in every)
         c = torch.tensor([counters[k] for k in ('sentences', 'L', 'P', 'E', 'T', 'F', 'Bk', 'W')], dtype=torch.float64, device=dev)
         dist.all_reduce(c, op=dist.ReduceOp.SUM)
         total_counters = dict(zip(('sentences', 'L', 'P', 'E', 'T', 'F', 'Bk', 'W'), [float(x) for x in c]))
@@ -447,6 +450,7 @@ def run_gpu(args):
             # 64 Ki sentences, else three), pack
             'gpu_launches': (5 if n + 1 <= 65536 else 7) * args.steps,
             'stage_ms_per_step': {k: v / args.steps for k, v in stage.items()},
+            'ms_per_step_by_rank': rank_ms,
             'counters_per_step': counters,
             'roofline': roofline,
             'clocks': clocks,

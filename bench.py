@@ -332,10 +332,10 @@ def run_gpu(args):
     stream = torch.cuda.current_stream(dev)
     sp = ctypes.c_void_p(stream.cuda_stream)
 
+    p_text, p_off = ctypes.c_void_p(d_text.data_ptr()), ctypes.c_void_p(d_off.data_ptr())
+
     def step_device():
-        _native.check(lib.lt_lattice(batch, ctypes.c_void_p(d_text.data_ptr()), ctypes.c_void_p(d_off.data_ptr()),
-                                     n, n_units, max_units, sp))
-        _native.check(lib.lt_beam(batch, beam, sp))
+        _native.check(lib.lt_tag_batch_device(batch, p_text, p_off, n, n_units, max_units, beam, sp))
 
     # pinned host buffers for the end-to-end path
     def pinned(nbytes):
@@ -405,6 +405,10 @@ def run_gpu(args):
         every = [torch.zeros_like(mine) for _ in range(world)]
         dist.all_gather(every, mine)
         rank_ms = [float(x[0]) for x in every]                 # reported per rank; the line's time is the maximum
+        mhz = torch.tensor([float(clocks['sm_mhz'] or 0.0)], dtype=torch.float64, device=dev)
+        all_mhz = [torch.zeros_like(mhz) for _ in range(world)]
+        dist.all_gather(all_mhz, mhz)
+        clocks['sm_mhz_by_rank'] = [float(x[0]) for x in all_mhz]
         ms_per_step, host_ms_per_step = max(rank_ms), max(float(x[1]) for x in every)
         c = torch.tensor([counters[k] for k in ('sentences', 'L', 'P', 'E', 'T', 'F', 'Bk', 'W')], dtype=torch.float64, device=dev)
         dist.all_reduce(c, op=dist.ReduceOp.SUM)

@@ -198,6 +198,11 @@ int  lt_tag_batch_host(lt_batch* batch, const uint16_t* text, const int32_t* sen
 int  lt_lattice(lt_batch* batch, const uint16_t* d_text, const int32_t* d_sent_off,
                 int32_t n_sent, int64_t n_units, int32_t max_sent_units, void* stream);
 int  lt_beam(lt_batch* batch, int32_t beam_size, void* stream);
+/* Both stages in one call (= lt_lattice then lt_beam): Tagger.tag for N sentences already in HBM
+ * (tagger.py:68-78), results fetched with lt_paths_fetch.                                     */
+int  lt_tag_batch_device(lt_batch* batch, const uint16_t* d_text, const int32_t* d_sent_off,
+                         int32_t n_sent, int64_t n_units, int32_t max_sent_units, int32_t beam_size,
+                         void* stream);
 
 /* Results of the last lt_lattice / lt_beam on this batch (these synchronise the stream). */
 int  lt_lattice_size(lt_batch* batch, int64_t* n_edges);

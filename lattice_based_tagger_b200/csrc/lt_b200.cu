@@ -787,6 +787,12 @@ extern "C" int lt_beam(lt_batch* b, int32_t beam_size, void* stream) {
     return launch_beam(b, st);
 }
 
+extern "C" int lt_tag_batch_device(lt_batch* b, const uint16_t* d_text, const int32_t* d_sent_off, int32_t n_sent,
+                                   int64_t n_units, int32_t max_sent_units, int32_t beam_size, void* stream) {
+    if (int rc = lt_lattice(b, d_text, d_sent_off, n_sent, n_units, max_sent_units, stream)) return rc;
+    return lt_beam(b, beam_size, stream);
+}
+
 extern "C" int lt_lattice_size(lt_batch* b, int64_t* n_edges) {
     if (!b || !b->have_lattice || !n_edges) return fail(LT_ERR_INVALID, "no lattice");
     CU(cudaSetDevice(b->tables->device));

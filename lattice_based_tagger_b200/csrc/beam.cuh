@@ -9,20 +9,32 @@
 // (hash.cuh: keys are additive), so a transition costs additions, not string hashing.
 //
 // Per end position e the warp
-//   1. reads the CSR bucket of e (sorted by begin) and counts edges per span;
-//   2. EDGE PREP, lanes = edges: per edge the word/morpheme hash products and everything of the
-//      score that depends on the edge alone — RegularizationScore, the preference scorers,
-//      templates 4 and 5 — into a shared-memory edge cache;
+//   1. makes sure the edges of e's CSR bucket are PREPARED: per edge the word/morpheme hash
+//      products and everything of the score that depends on the edge alone — RegularizationScore,
+//      the preference scorers, templates 4 and 5.  Dictionary edges are prepared
+//      32 consecutive edges at a time into a ring cache (the buckets of consecutive positions are
+//      adjacent in HBM, so one full-warp pass serves many positions), unknown words 4 positions x 8
+//      spans at a time;
+//   2. counts edges per span and candidates per span; an unknown word after an unknown word is
+//      allowed only from the window's first begin (beam.py:44-45), such candidates are never
+//      enumerated;
 //   3. enumerates candidates in the reference's generation order — begin ascending, parent rank
 //      ascending, edge order ascending (beam.py:30-48) — 32 at a time, one per lane, and scores
 //      each: score program in BeamScoreFunctions order, every fp64 add in the reference's
-//      association; templates 0,1,2,7,8 are gathered from the HBM feature table
-//      with all first-slot loads in flight together, template 3/6 come from shared memory;
-//   4. keeps the best `beam` candidates: repeated warp arg-max (redux.sync on the order-preserving
-//      integer image of the fp64 score) with ties resolved towards the earlier candidate, which is
-//      exactly the stable sort of Beam.append (beam.py:83-86);
-//   5. writes the survivors as new ring entries and one 8-byte back-pointer each to the HBM trail.
-// The best path is recovered from the trail and written as 16-byte edge records.
+//      association; templates 0,1,2,7,8 are gathered from the feature table
+//      (a cuckoo table: both slots of a key loaded at once), template 3/6 come from shared memory;
+//   4. keeps the best `beam` candidates on the order-preserving integer image of the fp64 score
+//      with ties resolved towards the earlier candidate, which is exactly the stable sort of
+//      Beam.append (beam.py:83-86): rank counting (beam <= 16), a sorting network (<= 32) or
+//      arg-max rounds (<= 64);
+//   5. writes the survivors as new ring entries and one back-pointer each (shared memory when the
+//      host finds room, HBM otherwise).
+// The best path is recovered from the back-pointers and written as 16-byte edge records.
+//
+// The kernel is instantiated per top-K method, beam size, sentence-array size and score program
+// (beam_kernel<MODE, KT, UC, PROG>): with those fixed every shared-memory array sits at a constant
+// offset and the scorer loop unrolls with its template seeds as immediates — in this latency-bound
+// kernel dynamically indexed constant loads and spilled address arithmetic were the largest costs.
 #pragma once
 #include "lattice.cuh"
 #include "tables.cuh"

@@ -17,9 +17,11 @@
 //   4. per eojeol, lanes = (task, split position) items in a flat index space, so lanes stay busy:
 //        stage 1 (lr_lookup): tasks {whole, left_i, right_i}, n items per pair -> n*n items
 //        stage 2 (sub-word scan, only when stage 1 found nothing): (begin, span, split) items
-//      an item tests its plain split in the table and probes the dictionary only for conjugation-rule
-//      candidates (prefix + stem, eomi + suffix).  Hits are staged in shared memory with a sort key
-//      (end, begin, class, split, candidate order) that encodes the reference's emission order.
+//      an item tests its plain split in the table; where a conjugation key starts at its split it
+//      QUEUES a descriptor, and drain_rules() applies the rules (prefix + stem, eomi + suffix: the
+//      only dictionary probes of the enumeration) with one descriptor per lane.  Hits are staged in
+//      shared memory with a sort key (end, begin, class, split, candidate order) that encodes the
+//      reference's emission order.
 //   5. the eojeol's hits are filtered (lr_lookup keeps a split only when both sides are non-empty,
 //      lookup.py:205-209) and ranked by key; staged edges go to HBM at their rank with one atomic
 //      reservation per flush (normally one per sentence).

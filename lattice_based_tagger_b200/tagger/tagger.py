@@ -23,6 +23,9 @@ from ..dictionary import BaseMorphemeDictionary, Word
 from ..tagset import BOS, EOS
 
 
+_BOS_WORD = Word(BOS, BOS, None, BOS, None, 0, 0, 0, False)
+
+
 class MorphemeLookup:
     """Descriptor of the eojeol lookup the tagger uses (reference `MorphemeLookup`,
     `dictionary/lookup.py:99-132`): `prefer_exact_match=True`, the default stand-alone tags and
@@ -137,9 +140,14 @@ class Tagger:
 
     def unpack(self, sents, packed, errors='raise'):
         path_off, path_edges, scores, status = packed
+        # one conversion for the whole batch (per-sentence numpy slicing dominates otherwise)
+        offs = path_off.tolist()
+        records = path_edges.tolist()
+        score_list = scores.tolist()
+        status_list = status.tolist()
         out = []
         for i, sent in enumerate(sents):
-            st = int(status[i])
+            st = status_list[i]
             if st != _native.LT_SENT_OK:
                 if errors == 'raise':
                     if st == _native.LT_SENT_NO_EDGES:
@@ -149,31 +157,36 @@ class Tagger:
                 continue
             chars = sent.replace(' ', '')
             n = len(chars)
-            words = [Word(BOS, BOS, None, BOS, None, 0, 0, 0, False)]
-            words += self.edges_to_words(chars, path_edges[int(path_off[i]):int(path_off[i + 1])])
+            words = [_BOS_WORD]
+            words += self._records_to_words(chars, records[offs[i]:offs[i + 1]])
             words.append(Word(EOS, EOS, None, EOS, None, 0, n, n, False))
             # adding EOS resets the trailing-unknown count (beam.py:113 with tag0 == EOS)
-            out.append(Sequence(words, float(scores[i]), 0))
+            out.append(Sequence(words, score_list[i], 0))
         return out
 
     def edges_to_words(self, chars, edges):
         """Packed `lt_edge` records -> `Word` tuples (include/lt_b200.h documents the encoding)."""
+        return self._records_to_words(chars, edges.tolist())
+
+    def _records_to_words(self, chars, records):
         names = self._tables.tag_names
         rules = self._tables.rules_flat
+        lemma_flag, is_l_flag = _native.LT_EDGE_LEMMA, _native.LT_EDGE_IS_L
+        new = tuple.__new__            # Word is a namedtuple: skips the per-call length check of _make
         words = []
-        for b, e, length, tag0, tag1, rule, split, flags, _ in edges.tolist():
+        for b, e, length, tag0, tag1, rule, split, flags, _ in records:
             surface = chars[b:e]
-            is_l = bool(flags & _native.LT_EDGE_IS_L)
-            if flags & _native.LT_EDGE_LEMMA:
+            is_l = (flags & is_l_flag) != 0
+            if flags & lemma_flag:
                 if rule == _native.LT_NO_RULE:
                     morph0, morph1 = surface[:split + 1], surface[split + 1:]
                 else:
                     stem, eomi = rules[rule]
                     skip = 2 if flags & _native.LT_EDGE_SKIP2 else 1
                     morph0, morph1 = surface[:split] + stem, eomi + surface[split + skip:]
-                words.append(Word(surface, morph0, morph1, names[tag0], names[tag1], length, b, e, is_l))
+                words.append(new(Word, (surface, morph0, morph1, names[tag0], names[tag1], length, b, e, is_l)))
             else:
-                words.append(Word(surface, surface, None, names[tag0], None, length, b, e, is_l))
+                words.append(new(Word, (surface, surface, None, names[tag0], None, length, b, e, is_l)))
         return words
 
     def lattice_batch(self, sents):

@@ -310,7 +310,7 @@ __device__ __forceinline__ double unsortable(uint64_t key) {
 #define LT_BEAM_MINB 2
 #endif
 #ifndef LT_PROBE_SPLIT
-#define LT_PROBE_SPLIT 1       // 1: the loads of templates 7 and 8 are issued after templates 0..2 are consumed
+#define LT_PROBE_SPLIT 1       // 1: generic kernels issue the loads of templates 7 and 8 after templates 0..2 are consumed
 #endif
 constexpr int kBeamWarps = 4;                 // preferred warps per CTA of the beam kernel
 constexpr int kBeamMaxWarps = 8;              // largest CTA (128 registers per thread either way: 8 warps x 2 CTAs = 4 warps x 4 CTAs)
@@ -715,20 +715,23 @@ __global__ void __launch_bounds__(kBeamMaxWarps * 32, LT_BEAM_MINB) beam_kernel(
                             const FeatProbe s1 = feat_first(T, q1);
                             const FeatProbe s2 = feat_first(T, q2);
                             FeatProbe s7, s8;
-#if !LT_PROBE_SPLIT
-                            if (has_i) s7 = feat_first(T, q7);
-                            if (ctx8) s8 = feat_first(T, q8);
-#endif
+                            // generic score programs issue templates 7 / 8 after 0..2 are consumed (all five at once
+                            // spill there); the specialised kernel has the registers for a single round trip
+                            constexpr bool kSplitProbes = LT_PROBE_SPLIT && PROG != 1;
+                            if constexpr (!kSplitProbes) {
+                                if (has_i) s7 = feat_first(T, q7);
+                                if (ctx8) s8 = feat_first(T, q8);
+                            }
                             // running left-to-right sum = numpy's order while fewer than 8 weights survive
                             double acc = 0.0, w;
                             int n = 0;
                             if (feat_resolve(T, q0, s0, w)) { acc = __dadd_rn(acc, w); ++n; }
                             if (feat_resolve(T, q1, s1, w)) { acc = __dadd_rn(acc, w); ++n; }
                             if (feat_resolve(T, q2, s2, w)) { acc = __dadd_rn(acc, w); ++n; }
-#if LT_PROBE_SPLIT
-                            if (has_i) s7 = feat_first(T, q7);
-                            if (ctx8) s8 = feat_first(T, q8);
-#endif
+                            if constexpr (kSplitProbes) {
+                                if (has_i) s7 = feat_first(T, q7);
+                                if (ctx8) s8 = feat_first(T, q8);
+                            }
                             if ((D.m3[tj] >> tk) & 1u) { acc = __dadd_rn(acc, D.t3[tj * NT + tk]); ++n; }
                             if ((epresent >> (2 * f)) & 1u) { acc = __dadd_rn(acc, val); ++n; }
                             if ((epresent >> (2 * f + 1)) & 1u) { acc = __dadd_rn(acc, val5); ++n; }

@@ -71,10 +71,9 @@ LT_HD uint64_t cuckoo_slot2(uint64_t x, uint32_t bits) {
     const uint32_t f = (uint32_t)x + ((hi << 15) | (hi >> 17));
     return (uint64_t)((f * kSlotMulB) >> (32 - bits));
 }
-LT_HD uint64_t dict_fp(H2 h, uint32_t len) {
-    uint64_t f = h.b ^ ((uint64_t)len * 0x9FB21C651E98DF25ull);
-    return f ? f : 1;
-}
+// Fingerprint 0 marks an empty slot: the table builder rejects a key whose fingerprint is 0 (2^-64
+// per key), and a lookup whose fingerprint is 0 reads an empty slot as "absent" (its payload is 0).
+LT_HD uint64_t dict_fp(H2 h, uint32_t len) { return h.b ^ ((uint64_t)len * 0x9FB21C651E98DF25ull); }
 
 // ---- rule key: up to three code units, exact -------------------------------------------------
 LT_HD uint64_t rule_key(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t len) {
@@ -93,7 +92,8 @@ LT_HD uint64_t rule_key(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t len) {
 // lattice edge, once per surviving hypothesis) and forms a transition's keys with additions only.
 // ka is the slot hash (cuckoo_slot1 / cuckoo_slot2), kb is the stored fingerprint.
 struct FKey {
-    uint64_t k1, k2;     // k1 = ka (slot source), k2 = kb (fingerprint, never 0)
+    uint64_t k1, k2;     // k1 = ka (slot source), k2 = kb (fingerprint; 0 is reserved for empty slots: the builder
+                         // rejects such a key, a lookup with it can at worst read an empty slot as weight 0.0)
 };
 
 constexpr uint64_t kM0a = 0xE7037ED1A0B428DBull, kM1a = 0x1D8E4E27C47D124Full, kM2a = 0xEB44ACCAB455D165ull;
@@ -128,7 +128,6 @@ LT_HD FKey feature_key_sum(H2 seed, uint64_t head, H2 sum) {
     FKey k;
     k.k1 = seed.a + head * kTa + sum.a;
     k.k2 = seed.b + head * kTb + sum.b;
-    if (k.k2 == 0) k.k2 = 1;
     return k;
 }
 
@@ -137,7 +136,6 @@ LT_HD FKey feature_key_sum32(H2 seed, uint32_t head, H2 sum) {
     FKey k;
     k.k1 = seed.a + (uint64_t)head * kTa + sum.a;
     k.k2 = seed.b + (uint64_t)head * kTb + sum.b;
-    if (k.k2 == 0) k.k2 = 1;
     return k;
 }
 LT_HD uint32_t feature_head32(uint32_t a0, uint32_t a1) { return (a0 << 24) | a1; }   // a0 < 256, a1 < 2^24

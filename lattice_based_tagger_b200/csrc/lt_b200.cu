@@ -84,6 +84,8 @@ static int build_cuckoo(const std::vector<CuckooItem>& items, uint64_t min_slots
                         uint32_t* bits_out, const char* what) {
     uint32_t bits = 4;
     while ((1ull << bits) < min_slots) ++bits;
+    for (const CuckooItem& it : items)
+        if (it.fp == 0) return fail(LT_ERR_COLLISION, "one of the %s hashes to the reserved fingerprint 0", what);
     for (; bits <= 32; ++bits) {
         const uint64_t slots = 1ull << bits;
         std::vector<int64_t> owner(slots, -1);

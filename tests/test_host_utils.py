@@ -59,3 +59,19 @@ def test_weight_format_round_trip():
     assert back['idx_to_feature'] == idx_to_feature and np.allclose(back['coefficient'], coef)
     with pytest.raises(ValueError):
         load_params({'idx_to_feature': idx_to_feature, 'coefficient': [0.0]})
+
+
+def test_feature_padding_with_vocabulary():
+    """C5's 10 M-weight target exceeds what lattice chains of the sample yield: the rest comes from
+    word n-grams over the dictionary (seeded, so every rank builds the same table)."""
+    import numpy as np
+    from lattice_based_tagger_b200 import synth
+    vocab = [('가%d' % i, 'Noun' if i % 2 else 'Verb') for i in range(500)]
+    fd1, c1 = synth.make_features([], lambda s: [], lambda s: [], 5000, ['Noun', 'Verb'], seed=3, vocab=vocab)
+    fd2, c2 = synth.make_features([], lambda s: [], lambda s: [], 5000, ['Noun', 'Verb'], seed=3, vocab=vocab)
+    assert len(fd1) == 5000 and list(fd1) == list(fd2) and np.array_equal(c1, c2)
+    assert sorted(fd1.values()) == list(range(5000))
+    assert {f[0] for f in fd1} >= {0, 2, 3, 4, 6, 7, 8}
+    # without a vocabulary the dictionary stops where the lattice chains run dry
+    fd3, _ = synth.make_features([], lambda s: [], lambda s: [], 5000, ['Noun', 'Verb'], seed=3)
+    assert len(fd3) < 5000

@@ -34,7 +34,8 @@ extern "C" {
 #define LT_ERR_INVALID   1   /* bad argument / malformed table description            */
 #define LT_ERR_CUDA      2   /* a CUDA runtime call failed (message has the details)   */
 #define LT_ERR_CAPACITY  3   /* caller-provided output buffer too small                */
-#define LT_ERR_COLLISION 4   /* two distinct table keys share a 128-bit hash           */
+#define LT_ERR_COLLISION 4   /* two distinct table keys share a 128-bit hash, or a key
+                                hashes to the reserved fingerprint 0 (2^-64 per key)    */
 
 /* per-sentence status (the reference's error behaviour, tagger.py:73-78) */
 #define LT_SENT_OK        0

@@ -205,6 +205,10 @@ int  lt_tag_batch_device(lt_batch* batch, const uint16_t* d_text, const int32_t*
                          int32_t n_sent, int64_t n_units, int32_t max_sent_units, int32_t beam_size,
                          void* stream);
 
+/* sentence_lookup_as_begin_index (dictionary/lookup.py:344-369) over a batch in HOST memory:
+ * copies `text` / `sent_off` to the device and builds the lattices; fetch with lt_lattice_fetch. */
+int  lt_lattice_host(lt_batch* batch, const uint16_t* text, const int32_t* sent_off, int32_t n_sent);
+
 /* Results of the last lt_lattice / lt_beam on this batch (these synchronise the stream). */
 int  lt_lattice_size(lt_batch* batch, int64_t* n_edges);
 /* edges sorted by (sentence, e, b, reference order); end_off[sent_off[s] + e - 1 .. + e] bracket

@@ -79,6 +79,7 @@ SYMBOLS = {
     'lt_batch_destroy': (None, [_p]),
     'lt_tag_batch_host': (ctypes.c_int, [_p, _p, _p, ctypes.c_int32, ctypes.c_int32, _p, _p, ctypes.c_int64, _p, _p]),
     'lt_lattice': (ctypes.c_int, [_p, _p, _p, ctypes.c_int32, ctypes.c_int64, ctypes.c_int32, _p]),
+    'lt_lattice_host': (ctypes.c_int, [_p, _p, _p, ctypes.c_int32]),
     'lt_beam': (ctypes.c_int, [_p, ctypes.c_int32, _p]),
     'lt_tag_batch_device': (ctypes.c_int, [_p, _p, _p, ctypes.c_int32, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, _p]),
     'lt_lattice_size': (ctypes.c_int, [_p, ctypes.POINTER(ctypes.c_int64)]),

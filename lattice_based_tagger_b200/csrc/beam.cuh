@@ -405,7 +405,7 @@ __device__ __forceinline__ void prep_edge(const DevTables& T, const SentView& v,
 template <int MODE, int KT, int UC, int PROG>
 __global__ void __launch_bounds__(kBeamMaxWarps * 32, LT_BEAM_MINB) beam_kernel(const __grid_constant__ DevTables T, const __grid_constant__ BeamArgs A) {
     constexpr int KR = (MODE == 0) ? 2 : 1;      // kept entries per lane
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    LT_DYN_SMEM(smem_raw);
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;

@@ -109,6 +109,13 @@ __device__ __forceinline__ int small_div(int q, int d, float inv) {
     return q < (1 << 22) ? __float2int_rz(((float)q + 0.5f) * inv) : q / d;
 }
 
+// A shared-memory word as ONE lane reads it between two warp barriers: warp-uniform by construction, whatever
+// the lanes that leave the second barrier first go on to write.
+__device__ __forceinline__ uint32_t warp_read(const uint32_t* p) {
+    __syncwarp();
+    return __shfl_sync(kFull, *p, 0);
+}
+
 __device__ __forceinline__ bool is_py_space(uint32_t c) {
     // str.split() separators in the BMP
     return (c >= 0x09 && c <= 0x0D) || (c >= 0x1C && c <= 0x20) || c == 0x85 || c == 0xA0 || c == 0x1680 ||
@@ -491,7 +498,7 @@ __device__ LT_FLUSH_ATTR void flush_staged(const LatticeArgs& A, int lane, uint3
 template <int UC, int HCT>
 __global__ void __launch_bounds__(kLatMaxWarps * 32, LT_LAT_MINB) lattice_kernel(const __grid_constant__ DevTables T,
                                                                 const __grid_constant__ LatticeArgs A) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    LT_DYN_SMEM(smem_raw);
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int units = UC ? UC : A.units;
@@ -630,8 +637,9 @@ __global__ void __launch_bounds__(kLatMaxWarps * 32, LT_LAT_MINB) lattice_kernel
                         if (!special)
                             ncand_try += lemma_item(T, v, E, b, e, p, edge_proto(b, e, (uint32_t)(e - b), b == o), task);
                     }
-                    __syncwarp();
-                    if (*rqn > (uint32_t)(kRuleQueue - 128)) drain_rules<UC, HCT>(T, base, units, HC, DM, lane);     // a pass queues at most 4 per lane
+                    // (read by one lane between two barriers: a lane that ran ahead into the next pass must not be able
+                    // to change what the others see here)
+                    if (warp_read(rqn) > (uint32_t)(kRuleQueue - 128)) drain_rules<UC, HCT>(T, base, units, HC, DM, lane);     // a pass queues at most 4 per lane
                 }
                 drain_rules<UC, HCT>(T, base, units, HC, DM, lane);
                 // ---- a split survives only when both sides found something (lookup.py:205-209) ----
@@ -703,8 +711,7 @@ __global__ void __launch_bounds__(kLatMaxWarps * 32, LT_LAT_MINB) lattice_kernel
                                 ncand_try += lemma_item(T, v, E, b, e, p, rec, 0u);
                             }
                         }
-                        __syncwarp();
-                        if (*rqn > (uint32_t)(kRuleQueue - 128)) drain_rules<UC, HCT>(T, base, units, HC, DM, lane);
+                        if (warp_read(rqn) > (uint32_t)(kRuleQueue - 128)) drain_rules<UC, HCT>(T, base, units, HC, DM, lane);
                     }
                     drain_rules<UC, HCT>(T, base, units, HC, DM, lane);
                     nstaged = *nh;

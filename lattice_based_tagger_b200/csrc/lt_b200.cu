@@ -3,7 +3,7 @@
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -shared
 //        -Xcompiler -fPIC  (see __graft_entry__.build()).  -fmad=false keeps every fp64
 // multiply and add of the score arithmetic separately rounded, as in the reference's Python.
-#include <cuda_runtime.h>
+#include "cuda_compat.cuh"
 
 #include <algorithm>
 #include <cstdarg>
@@ -453,16 +453,16 @@ extern "C" void lt_batch_destroy(lt_batch* b) {
 
 static int scan_u32(lt_batch* b, const uint32_t* in, uint32_t* out, int64_t n, cudaStream_t st) {
     if (n <= kScanSmallMax) {
-        scan_small<<<1, kScanSmallThreads, 0, st>>>(in, out, n);
+        LT_LAUNCH(scan_small, 1, kScanSmallThreads, 0, st, in, out, n);
         CU(cudaGetLastError());
         return LT_OK;
     }
     const int64_t tiles = (n + kScanTile - 1) / kScanTile;
     if (int rc = ensure(b->scan_tmp, (size_t)tiles * 4)) return rc;
     uint32_t* sums = static_cast<uint32_t*>(b->scan_tmp.p);
-    scan_tile_sums<<<(unsigned)tiles, kScanThreads, 0, st>>>(in, n, sums);
-    scan_sums<<<1, kScanThreads, 0, st>>>(sums, tiles);
-    scan_apply<<<(unsigned)tiles, kScanThreads, 0, st>>>(in, out, n, sums);
+    LT_LAUNCH(scan_tile_sums, (unsigned)tiles, kScanThreads, 0, st, in, n, sums);
+    LT_LAUNCH(scan_sums, 1, kScanThreads, 0, st, sums, tiles);
+    LT_LAUNCH(scan_apply, (unsigned)tiles, kScanThreads, 0, st, in, out, n, sums);
     CU(cudaGetLastError());
     return LT_OK;
 }
@@ -534,7 +534,7 @@ static int launch_lattice(lt_batch* b, cudaStream_t st) {
         if (int rc = ensure(b->order, (size_t)n_sent * 4)) return rc;
         order = static_cast<uint32_t*>(b->order.p);
     }
-    batch_prologue<<<1, 1024, 0, st>>>(b->d_sent_off, n_sent, order, ctl, kCtlWords,
+    LT_LAUNCH(batch_prologue, 1, 1024, 0, st, b->d_sent_off, n_sent, order, ctl, kCtlWords,
                                        static_cast<unsigned long long*>(b->counters.p), 8);
     CU(cudaGetLastError());
     A.order = order;
@@ -563,7 +563,7 @@ static int launch_lattice(lt_batch* b, cudaStream_t st) {
         A.retry_count = ctl + kCtlRetryCount;
     }
     if (b->timed) CU(cudaEventRecord(b->ev[0], st));
-    if (n_sent > 0) lattice_kernel<<<grid, warps * 32, smem, st>>>(t->dev, A);
+    if (n_sent > 0) LT_LAUNCH(lattice_kernel, grid, warps * 32, smem, st, t->dev, A);
     CU(cudaGetLastError());
     if (b->use_retry && n_sent > 0) {
         // retry pass: the few sentences with an eojeol beyond `hcap` hits, with a staging area of their own size
@@ -584,7 +584,7 @@ static int launch_lattice(lt_batch* b, cudaStream_t st) {
         R.retry_pass = 1;
         int r_per_sm = 1;
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r_per_sm, retry_kernel, r_warps * 32, r_smem));
-        retry_kernel<<<(unsigned)(t->sm_count * std::max(1, r_per_sm)), r_warps * 32, r_smem, st>>>(t->dev, R);
+        LT_LAUNCH(retry_kernel, (unsigned)(t->sm_count * std::max(1, r_per_sm)), r_warps * 32, r_smem, st, t->dev, R);
         CU(cudaGetLastError());
     }
     if (b->timed) CU(cudaEventRecord(b->ev[1], st));
@@ -688,12 +688,12 @@ static int launch_beam(lt_batch* b, cudaStream_t st) {
     // queue cursor and counters of this stage are zero after the batch prologue; a second search of the
     // same lattice resets them (path_len needs no clearing: the kernel writes every entry)
     if (!b->beam_state_clean) {
-        beam_reset<<<1, 32, 0, st>>>(ctl + kCtlBeamQueue, static_cast<unsigned long long*>(b->counters.p) + 3, 4);
+        LT_LAUNCH(beam_reset, 1, 32, 0, st, ctl + kCtlBeamQueue, static_cast<unsigned long long*>(b->counters.p) + 3, 4);
         CU(cudaGetLastError());
     }
     b->beam_state_clean = false;
     if (b->timed) CU(cudaEventRecord(b->ev[5], st));
-    if (n_sent > 0) kernel<<<grid, warps * 32, smem, st>>>(t->dev, A);
+    if (n_sent > 0) LT_LAUNCH(kernel, grid, warps * 32, smem, st, t->dev, A);
     CU(cudaGetLastError());
     if (b->timed) CU(cudaEventRecord(b->ev[6], st));
     if (int rc = scan_u32(b, reinterpret_cast<const uint32_t*>(b->path_len.p), static_cast<uint32_t*>(b->path_off.p),
@@ -701,7 +701,7 @@ static int launch_beam(lt_batch* b, cudaStream_t st) {
         return rc;
     if (n_sent > 0) {
         const unsigned pgrid = (unsigned)std::min<int64_t>(((int64_t)n_sent + 7) / 8, (int64_t)t->sm_count * 8);
-        pack_paths<<<pgrid, 256, 0, st>>>(static_cast<const lt_edge*>(b->path_tmp.p), b->d_sent_off,
+        LT_LAUNCH(pack_paths, pgrid, 256, 0, st, static_cast<const lt_edge*>(b->path_tmp.p), b->d_sent_off,
                                           static_cast<const uint32_t*>(b->path_off.p), n_sent,
                                           static_cast<lt_edge*>(b->path_out.p));
         CU(cudaGetLastError());
@@ -903,6 +903,27 @@ extern "C" int lt_tag_batch_host(lt_batch* b, const uint16_t* text, const int32_
         CU(cudaEventSynchronize(b->ev[9]));
     }
     return LT_OK;
+}
+
+// sentence_lookup_as_begin_index for a batch in HOST memory: copies the text in and builds the lattices
+// (results with lt_lattice_size / lt_lattice_fetch)
+extern "C" int lt_lattice_host(lt_batch* b, const uint16_t* text, const int32_t* sent_off, int32_t n_sent) {
+    if (!b || !sent_off || n_sent < 0) return fail(LT_ERR_INVALID, "bad argument");
+    CU(cudaSetDevice(b->tables->device));
+    cudaStream_t st = b->own_stream;
+    const int64_t n_units = sent_off[n_sent];
+    int32_t max_units = 0;
+    for (int32_t i = 0; i < n_sent; ++i) {
+        const int32_t len = sent_off[i + 1] - sent_off[i];
+        if (len < 0) return fail(LT_ERR_INVALID, "sent_off is not monotone at %d", i);
+        max_units = std::max(max_units, len);
+    }
+    if (int rc = ensure(b->text, (size_t)std::max<int64_t>(1, n_units) * 2)) return rc;
+    if (int rc = ensure(b->sent_off, (size_t)(n_sent + 1) * 4)) return rc;
+    if (n_units) CU(cudaMemcpyAsync(b->text.p, text, (size_t)n_units * 2, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(b->sent_off.p, sent_off, (size_t)(n_sent + 1) * 4, cudaMemcpyHostToDevice, st));
+    return lt_lattice(b, static_cast<const uint16_t*>(b->text.p), static_cast<const int32_t*>(b->sent_off.p), n_sent, n_units,
+                      max_units, st);
 }
 
 extern "C" int lt_batch_counters(lt_batch* b, lt_counters* out) {

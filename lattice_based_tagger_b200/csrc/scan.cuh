@@ -1,7 +1,7 @@
 // scan.cuh — device exclusive scan of 32-bit counts (CSR offsets of the lattice, path offsets)
 // and the kernel that packs the per-sentence best paths into one contiguous output array.
 #pragma once
-#include <cuda_runtime.h>
+#include "cuda_compat.cuh"
 #include <stdint.h>
 
 #include "../../include/lt_b200.h"

@@ -9,7 +9,7 @@
 //          with presence masks — staged into shared memory by the beam kernel
 //   pows   base^n pairs for composing polynomial hashes
 #pragma once
-#include <cuda_runtime.h>
+#include "cuda_compat.cuh"
 #include <stdint.h>
 
 #include "../../include/lt_b200.h"
@@ -94,7 +94,7 @@ struct DevTables {
     H2 seeds[LT_MAX_FUNCS][10];    // feature_seed(template 0..8, f); [9] = the scorer's preference kind
 };
 
-#if defined(__CUDACC__)
+#if defined(LT_DEVICE_CODE)
 
 __device__ __forceinline__ uint4 ldg16(const void* p) {
     return __ldg(reinterpret_cast<const uint4*>(p));

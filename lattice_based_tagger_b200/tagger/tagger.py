@@ -197,19 +197,11 @@ class Tagger:
         observes); `bindex` is `[]` for a sentence without any dictionary edge
         (`lookup.py:362-363`).
         """
-        import torch
         sents = list(sents)
         text, offsets = pack_sentences(sents)
         n = len(sents)
         n_units = int(offsets[-1])
-        dev = torch.device('cuda', self.device)
-        d_text = torch.from_numpy(text.view(np.int16).copy()).to(dev)
-        d_off = torch.from_numpy(offsets.copy()).to(dev)
-        max_units = int(np.diff(offsets).max()) if n else 0
-        stream = torch.cuda.current_stream(dev)
-        _native.check(self._lib.lt_lattice(self._batch, ctypes.c_void_p(d_text.data_ptr()),
-                                           ctypes.c_void_p(d_off.data_ptr()), n, n_units, max_units,
-                                           ctypes.c_void_p(stream.cuda_stream)))
+        _native.check(self._lib.lt_lattice_host(self._batch, _native.ptr(text), _native.ptr(offsets), n))
         n_edges = ctypes.c_int64()
         _native.check(self._lib.lt_lattice_size(self._batch, ctypes.byref(n_edges)))
         edges = np.zeros(max(1, n_edges.value), dtype=_native.EDGE_DTYPE)

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define LT_ABI_VERSION 1
+#define LT_ABI_VERSION 2
 
 /* return codes */
 #define LT_OK            0
@@ -43,6 +43,23 @@ extern "C" {
                                 raises IndexError (lookup.py:362-363 + beam.py:33)              */
 #define LT_SENT_BAD_SPACE 2  /* whitespace other than U+0020: `str.split()` and
                                 `str.replace(' ','')` disagree in the reference; rejected       */
+#define LT_SENT_TOO_LONG  3  /* more code units than lt_tables_max_sentence_units(): skipped, the
+                                rest of the batch is tagged                                     */
+#define LT_SENT_UNSUPPORTED_CHAR 4  /* set by host bindings for text that has no UTF-16 BMP form
+                                (the library itself never sees such a sentence)                 */
+
+/* eojeol lookup that builds the lattice (dictionary/lookup.py), lt_batch_set_lookup():
+ *   MORPHEME  MorphemeLookup  (lookup.py:99-132, :212-279) — what Tagger.tag always uses (tagger.py:60)
+ *   LR        LRLookup(prefer_exact_match=True)   (lookup.py:75-85, :171-210)
+ *   LR_ALL    LRLookup(prefer_exact_match=False)
+ *   WORD      WordLookup(prefer_exact_match=True) (lookup.py:87-97, :134-169)
+ *   WORD_ALL  WordLookup(prefer_exact_match=False)                                             */
+#define LT_LOOKUP_MORPHEME 0
+#define LT_LOOKUP_LR       1
+#define LT_LOOKUP_LR_ALL   2
+#define LT_LOOKUP_WORD     3
+#define LT_LOOKUP_WORD_ALL 4
+#define LT_LOOKUP_EXACT    5  /* MorphemeDictionary.lookup of the whole eojeol alone (dictionary.py:304-312) */
 
 #define LT_WINDOW   8        /* beam_search max_len, beam/beam.py:5                              */
 #define LT_MAX_BEAM 64
@@ -62,6 +79,9 @@ enum { LT_TAG_NOUN = 0, LT_TAG_PRONOUN, LT_TAG_NUMBER, LT_TAG_JOSA, LT_TAG_ADJEC
 #define LT_EDGE_LEMMA  0x04  /* two-morpheme word from the lemmatizer (dictionary.py:311-312)    */
 #define LT_EDGE_SKIP2  0x08  /* lemma: the eomi continues at word[split+2:] (2/3-syllable keys,
                                 lemmatizer.py:109) instead of word[split+1:]                     */
+
+#define LT_EDGE_EXPLICIT 0x10 /* imported lattice (lt_lattice_import): word / morph0 / morph1 are the
+                                strings 3*rule, 3*rule+1, 3*rule+2 given with the import           */
 
 /* One lattice edge = the reference's `Word` (dictionary/dictionary.py:169) in 16 bytes.
  * word  = chars[b:e]
@@ -167,6 +187,22 @@ typedef struct lt_timings {
     float ms_h2d, ms_lattice, ms_reserved0, ms_reserved1, ms_beam, ms_pack, ms_d2h, ms_total;
 } lt_timings;
 
+/* State of a batch workspace: sticky buffer capacities, how often a batch had to be rerun with
+ * larger buffers, kernels launched so far, launch shapes of the last batch. */
+typedef struct lt_info {
+    int64_t launches;            /* kernels launched by this workspace so far (cumulative)            */
+    int64_t edge_cap;            /* lattice edge buffer capacity (records)                             */
+    int64_t n_edges;             /* dictionary edges of the last batch                                 */
+    int32_t reruns;              /* grow-and-rerun rounds so far (cumulative)                          */
+    int32_t hcap, retry_hcap;    /* lattice staging capacity per warp: main pass, retry pass (0 = off) */
+    int32_t retried;             /* sentences of the last batch that went through the retry pass       */
+    int32_t unit_limit;          /* = lt_tables_max_sentence_units()                                   */
+    int32_t lattice_warps, lattice_ctas_per_sm, lattice_smem;
+    int32_t beam_warps, beam_ctas_per_sm, beam_smem, beam_trail_smem;
+    int32_t sm_count;
+    int32_t reserved[3];
+} lt_info;
+
 typedef struct lt_tables lt_tables;   /* immutable device tables; shareable between batches */
 typedef struct lt_batch  lt_batch;    /* device workspace + stream state of one in-flight batch */
 
@@ -177,9 +213,15 @@ int  lt_tables_create(const lt_tables_desc* desc, int device, lt_tables** out);
 void lt_tables_destroy(lt_tables* tables);
 /* bytes of device memory held by the tables */
 int64_t lt_tables_device_bytes(const lt_tables* tables);
+/* Longest sentence (UTF-16 code units, spaces included) the kernels can hold with these tables; it
+ * shrinks with the longest dictionary string (at most 4088).  Longer sentences of a batch get
+ * LT_SENT_TOO_LONG, the others are tagged. */
+int32_t lt_tables_max_sentence_units(const lt_tables* tables);
 
 int  lt_batch_create(lt_tables* tables, lt_batch** out);
 void lt_batch_destroy(lt_batch* batch);
+/* which eojeol lookup the following lt_lattice* calls enumerate (LT_LOOKUP_*, default MORPHEME) */
+int  lt_batch_set_lookup(lt_batch* batch, int32_t mode);
 
 /* Tagger.tag over a batch in HOST memory: copies `text` / `sent_off` to the device, builds the
  * lattices, runs the beam search, copies the best paths back.
@@ -209,6 +251,30 @@ int  lt_tag_batch_device(lt_batch* batch, const uint16_t* d_text, const int32_t*
  * copies `text` / `sent_off` to the device and builds the lattices; fetch with lt_lattice_fetch. */
 int  lt_lattice_host(lt_batch* batch, const uint16_t* text, const int32_t* sent_off, int32_t n_sent);
 
+/* A lattice built by the CALLER (beam_search's `bindex` argument, beam/beam.py:5): sentences in host
+ * memory plus their edges in the layout lt_lattice_fetch returns — sorted by (sentence, end, begin,
+ * order within the span), end_off[sent_off[s] + e - 1 .. + e] bracketing the edges of sentence s that end
+ * at syllable e.  Edges flagged LT_EDGE_EXPLICIT name their strings instead of deriving them from the
+ * text: edge.rule = i, and strings 3i, 3i+1, 3i+2 of (str_chars, str_off) are its word, morph0 and
+ * morph1 (empty when there is none).  lt_beam / lt_beam_kbest then search it.                    */
+int  lt_lattice_import(lt_batch* batch, const uint16_t* text, const int32_t* sent_off, int32_t n_sent,
+                       const lt_edge* edges, const int64_t* end_off,
+                       const uint16_t* str_chars, const int64_t* str_off, int64_t n_strings);
+
+/* beam_search keeping ALL survivors of the last position (its return value, beam/beam.py:59-61),
+ * not only matures[0]: lt_beam_kbest instead of lt_beam, results with lt_kbest_fetch (the best path
+ * stays available through lt_paths_fetch as well).  lt_tag_batch_host_kbest = text from host memory
+ * + lt_lattice + lt_beam_kbest. */
+int  lt_beam_kbest(lt_batch* batch, int32_t beam_size, void* stream);
+int  lt_tag_batch_host_kbest(lt_batch* batch, const uint16_t* text, const int32_t* sent_off,
+                             int32_t n_sent, int32_t beam_size);
+int  lt_kbest_size(lt_batch* batch, int64_t* n_words);
+/* n_best[s] survivors of sentence s (<= beam, 0 when status[s] != LT_SENT_OK), best first in the
+ * reference's order; survivor r of sentence s is path_edges[path_off[s*beam+r] : path_off[s*beam+r+1]]
+ * with score scores[s*beam+r]; path_off has n_sent*beam + 1 entries, scores n_sent*beam.          */
+int  lt_kbest_fetch(lt_batch* batch, int32_t* n_best, int32_t* path_off, lt_edge* path_edges,
+                    int64_t path_cap, double* scores, int32_t* status);
+
 /* Results of the last lt_lattice / lt_beam on this batch (these synchronise the stream). */
 int  lt_lattice_size(lt_batch* batch, int64_t* n_edges);
 /* edges sorted by (sentence, e, b, reference order); end_off[sent_off[s] + e - 1 .. + e] bracket
@@ -218,6 +284,10 @@ int  lt_paths_size(lt_batch* batch, int64_t* n_words);
 int  lt_paths_fetch(lt_batch* batch, int32_t* path_off, lt_edge* path_edges, int64_t path_cap,
                     double* scores, int32_t* status);
 
+/* per-sentence status / syllable count of the last lattice (either pointer may be NULL) */
+int  lt_lattice_status(lt_batch* batch, int32_t* status, int32_t* sent_len);
+
+int  lt_batch_info(lt_batch* batch, lt_info* out);
 int  lt_batch_counters(lt_batch* batch, lt_counters* out);
 int  lt_batch_timings(lt_batch* batch, lt_timings* out);
 

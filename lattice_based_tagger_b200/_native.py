@@ -13,12 +13,14 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'liblt_b200.so')
 
-LT_ABI_VERSION = 1
+LT_ABI_VERSION = 2
 LT_OK = 0
-LT_SENT_OK, LT_SENT_NO_EDGES, LT_SENT_BAD_SPACE = 0, 1, 2
+LT_SENT_OK, LT_SENT_NO_EDGES, LT_SENT_BAD_SPACE, LT_SENT_TOO_LONG, LT_SENT_UNSUPPORTED_CHAR = 0, 1, 2, 3, 4
 LT_NO_TAG = 0xFF
 LT_NO_RULE = 0xFFFFFFFF
-LT_EDGE_IS_L, LT_EDGE_UNK, LT_EDGE_LEMMA, LT_EDGE_SKIP2 = 1, 2, 4, 8
+LT_EDGE_IS_L, LT_EDGE_UNK, LT_EDGE_LEMMA, LT_EDGE_SKIP2, LT_EDGE_EXPLICIT = 1, 2, 4, 8, 16
+(LT_LOOKUP_MORPHEME, LT_LOOKUP_LR, LT_LOOKUP_LR_ALL, LT_LOOKUP_WORD, LT_LOOKUP_WORD_ALL,
+ LT_LOOKUP_EXACT) = range(6)
 LT_FUNC_REG, LT_FUNC_MPREF, LT_FUNC_WPREF, LT_FUNC_TRIGRAM = 1, 2, 3, 4
 LT_MAX_BEAM = 64
 LT_MAX_FUNCS = 8
@@ -68,6 +70,17 @@ class lt_timings(ctypes.Structure):
         return {name: float(getattr(self, name)) for name, _ in self._fields_}
 
 
+class lt_info(ctypes.Structure):
+    _fields_ = ([('launches', ctypes.c_int64), ('edge_cap', ctypes.c_int64), ('n_edges', ctypes.c_int64)] +
+                [(name, ctypes.c_int32) for name in (
+                    'reruns', 'hcap', 'retry_hcap', 'retried', 'unit_limit', 'lattice_warps', 'lattice_ctas_per_sm',
+                    'lattice_smem', 'beam_warps', 'beam_ctas_per_sm', 'beam_smem', 'beam_trail_smem', 'sm_count')] +
+                [('reserved', ctypes.c_int32 * 3)])
+
+    def as_dict(self):
+        return {name: int(getattr(self, name)) for name, _ in self._fields_ if name != 'reserved'}
+
+
 #: every symbol include/lt_b200.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     'lt_last_error': (ctypes.c_char_p, []),
@@ -75,8 +88,17 @@ SYMBOLS = {
     'lt_tables_create': (ctypes.c_int, [ctypes.POINTER(lt_tables_desc), ctypes.c_int, ctypes.POINTER(_p)]),
     'lt_tables_destroy': (None, [_p]),
     'lt_tables_device_bytes': (ctypes.c_int64, [_p]),
+    'lt_tables_max_sentence_units': (ctypes.c_int32, [_p]),
     'lt_batch_create': (ctypes.c_int, [_p, ctypes.POINTER(_p)]),
     'lt_batch_destroy': (None, [_p]),
+    'lt_batch_set_lookup': (ctypes.c_int, [_p, ctypes.c_int32]),
+    'lt_lattice_import': (ctypes.c_int, [_p, _p, _p, ctypes.c_int32, _p, _p, _p, _p, ctypes.c_int64]),
+    'lt_beam_kbest': (ctypes.c_int, [_p, ctypes.c_int32, _p]),
+    'lt_tag_batch_host_kbest': (ctypes.c_int, [_p, _p, _p, ctypes.c_int32, ctypes.c_int32]),
+    'lt_kbest_size': (ctypes.c_int, [_p, ctypes.POINTER(ctypes.c_int64)]),
+    'lt_kbest_fetch': (ctypes.c_int, [_p, _p, _p, _p, ctypes.c_int64, _p, _p]),
+    'lt_lattice_status': (ctypes.c_int, [_p, _p, _p]),
+    'lt_batch_info': (ctypes.c_int, [_p, ctypes.POINTER(lt_info)]),
     'lt_tag_batch_host': (ctypes.c_int, [_p, _p, _p, ctypes.c_int32, ctypes.c_int32, _p, _p, ctypes.c_int64, _p, _p]),
     'lt_lattice': (ctypes.c_int, [_p, _p, _p, ctypes.c_int32, ctypes.c_int64, ctypes.c_int32, _p]),
     'lt_lattice_host': (ctypes.c_int, [_p, _p, _p, ctypes.c_int32]),

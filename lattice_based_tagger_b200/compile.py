@@ -21,6 +21,7 @@ from .tagset import Adjective, Adverb, Determiner, Exclamation, Noun, Number, Ve
 from .tagset import BUILTIN_TAGS, MAX_TAGS
 
 DEFAULT_STANDALONES = (Noun, Adverb, Exclamation, Determiner, Number)   # dictionary/lookup.py:104-105
+OTHER_TAG = '\x00other'         # device id for tags of an imported lattice that the tables have never seen
 
 
 class UnsupportedScoreFunction(ValueError):
@@ -77,7 +78,7 @@ class CompiledTables:
     """Owns the `lt_tables` handle plus the host-side lists needed to turn packed results back
     into `Word`s (tag names, flattened rules)."""
 
-    def __init__(self, dictionary, score_funcs, device=0, k3_first=None):
+    def __init__(self, dictionary, score_funcs, device=0, k3_first=None, extra_tags=()):
         if not hasattr(dictionary, 'rules'):
             raise ValueError('dictionary must be MorphemeDictionary')         # lookup.py:101-102
         self._lib = _native.load()
@@ -88,10 +89,13 @@ class CompiledTables:
         tag_to_morphs = dictionary.tag_to_morphs
         self.tag_names = list(BUILTIN_TAGS)
         tag_ids = {t: i for i, t in enumerate(self.tag_names)}
-        for tag in tag_to_morphs:
+        # (`extra_tags`: tags of caller-built lattices — beam_search's `bindex` — that no dictionary lists;
+        # OTHER_TAG stands for any further tag: no feature or preference can name it)
+        for tag in list(tag_to_morphs) + list(extra_tags):
             if tag not in tag_ids:
                 tag_ids[tag] = len(self.tag_names)
                 self.tag_names.append(tag)
+        self.other_tag_id = tag_ids.get(OTHER_TAG)
         if len(self.tag_names) > MAX_TAGS:
             raise ValueError('at most %d distinct tags are supported, dictionary has %d'
                              % (MAX_TAGS, len(self.tag_names)))
@@ -259,11 +263,17 @@ class CompiledTables:
                     'there is no CPU fallback' % kind)
 
         units, offsets = _encode_units(strings.strings)
-        a_func = np.asarray(feat_func, dtype=np.uint8)
-        a_tmpl = np.asarray(feat_tmpl, dtype=np.uint8)
-        a_s = np.asarray(feat_s, dtype=np.int32).reshape(-1, 3)
-        a_a = np.asarray(feat_a, dtype=np.int32).reshape(-1, 2)
-        a_w = np.asarray(feat_w, dtype=np.float64)
+
+        def joined(parts, dtype, width=None):
+            if not parts:
+                return np.zeros((0, width) if width else 0, dtype=dtype)
+            return np.concatenate(parts).astype(dtype, copy=False)
+        a_func = joined(feat_func, np.uint8)
+        a_tmpl = joined(feat_tmpl, np.uint8)
+        a_s = joined(feat_s, np.int32, 3).reshape(-1, 3)
+        a_a = joined(feat_a, np.int32, 2).reshape(-1, 2)
+        a_w = joined(feat_w, np.float64)
+        n_feat = int(a_func.size)
         p_func = np.asarray(pref_func, dtype=np.uint8)
         p_tag = np.asarray(pref_tag, dtype=np.uint8)
         p_s = np.asarray(pref_s, dtype=np.int32)
@@ -279,7 +289,7 @@ class CompiledTables:
         desc.n_fstr = len(strings.strings)
         desc.fstr_chars = _native.ptr(units)
         desc.fstr_off = _native.ptr(offsets)
-        desc.n_feat = len(feat_func)
+        desc.n_feat = n_feat
         desc.feat_func = _native.ptr(a_func)
         desc.feat_template = _native.ptr(a_tmpl)
         desc.feat_s = _native.ptr(a_s)
@@ -291,59 +301,76 @@ class CompiledTables:
         desc.pref_s = _native.ptr(p_s)
         desc.pref_value = _native.ptr(p_v)
 
+    # (template, tuple length) -> kinds of the components after the template id:
+    #   's' string (word / morpheme), 't' tag name, 'n' small integer, 'l' is_l flag
+    _TEMPLATES = {(0, 4): 'sst', (1, 3): 'st', (2, 4): 'tst', (3, 3): 'tt', (4, 2): 'n', (5, 4): 'stl',
+                  (6, 2): 'n', (7, 4): 'sss', (8, 3): 'ss'}
+    # where each component goes in (feat_s[0..2], feat_a[0..1]) — include/lt_b200.h, lt_tables_desc
+    _SLOTS = {0: ('s0', 's1', 'a0'), 1: ('s0', 'a0'), 2: ('a0', 's0', 'a1'), 3: ('a0', 'a1'), 4: ('a0',),
+              5: ('s0', 'a0', 'a1'), 6: ('a0',), 7: ('s0', 's1', 's2'), 8: ('s0', 's1')}
+
     def _pack_feature_dic(self, f, feature_dic, coef, strings, feat_func, feat_tmpl, feat_s, feat_a, feat_w):
         """Feature tuples (features/feature.py:94-121) -> (template, string ids, integers).
 
         A key that cannot equal any tuple the templates generate (wrong arity or types, a tag no
         word can carry) is dropped: `_filter` (feature.py:28-29) would never select it either.
+        Works column-wise per template, so that a 10 M-entry dictionary packs in seconds: the keys
+        of one template are transposed once and each component column is mapped as a whole.
         """
         tag_ids = self.tag_ids
-
-        def s_id(x):
-            return strings.add(x) if isinstance(x, str) and _is_bmp(x) else None
-
-        def t_id(x):
-            return tag_ids.get(x) if isinstance(x, str) else None
-
+        groups = {}
         for key, idx in feature_dic.items():
-            if not isinstance(key, tuple) or not key:
+            if type(key) is not tuple or not key:
                 continue
-            tmpl = _as_index(key[0])
-            n = len(key)
-            s = [-1, -1, -1]
-            a = [0, 0]
-            ok = False
-            if tmpl == 0 and n == 4:
-                s[0], s[1], a[0] = s_id(key[1]), s_id(key[2]), t_id(key[3])
-                ok = None not in (s[0], s[1], a[0])
-            elif tmpl == 1 and n == 3:
-                s[0], a[0] = s_id(key[1]), t_id(key[2])
-                ok = None not in (s[0], a[0])
-            elif tmpl == 2 and n == 4:
-                a[0], s[0], a[1] = t_id(key[1]), s_id(key[2]), t_id(key[3])
-                ok = None not in (a[0], s[0], a[1])
-            elif tmpl == 3 and n == 3:
-                a[0], a[1] = t_id(key[1]), t_id(key[2])
-                ok = None not in (a[0], a[1])
-            elif tmpl in (4, 6) and n == 2:
-                a[0] = _as_index(key[1])
-                ok = a[0] is not None and 0 <= a[0] < (1 << 24)
-            elif tmpl == 5 and n == 4:
-                s[0], a[0], a[1] = s_id(key[1]), t_id(key[2]), _as_index(key[3])
-                ok = None not in (s[0], a[0], a[1]) and a[1] in (0, 1)
-            elif tmpl == 7 and n == 4:
-                s[0], s[1], s[2] = s_id(key[1]), s_id(key[2]), s_id(key[3])
-                ok = None not in s
-            elif tmpl == 8 and n == 3:
-                s[0], s[1] = s_id(key[1]), s_id(key[2])
-                ok = None not in (s[0], s[1])
-            if not ok:
-                continue
-            feat_func.append(f)
-            feat_tmpl.append(tmpl)
-            feat_s.append(s)
-            feat_a.append(a)
-            feat_w.append(float(coef[idx]))
+            tmpl = key[0]
+            if type(tmpl) is not int:
+                tmpl = _as_index(tmpl)
+            slot = (tmpl, len(key))
+            group = groups.get(slot)
+            if group is None:
+                if slot not in self._TEMPLATES:
+                    continue
+                group = groups[slot] = ([], [])
+            group[0].append(key)
+            group[1].append(idx)
+
+        def string_ids(column):
+            ids = strings.ids
+            out = np.empty(len(column), dtype=np.int64)
+            for pos, x in enumerate(column):
+                i = ids.get(x)
+                if i is None:
+                    i = strings.add(x) if type(x) is str and _is_bmp(x) else -1
+                out[pos] = i
+            return out
+
+        for (tmpl, _), (keys, idxs) in groups.items():
+            kinds = self._TEMPLATES[(tmpl, len(keys[0]))]
+            columns = list(zip(*keys))[1:]
+            n = len(keys)
+            cols = {'s0': np.full(n, -1, np.int64), 's1': np.full(n, -1, np.int64), 's2': np.full(n, -1, np.int64),
+                    'a0': np.zeros(n, np.int64), 'a1': np.zeros(n, np.int64)}
+            ok = np.ones(n, dtype=bool)
+            for kind, where, column in zip(kinds, self._SLOTS[tmpl], columns):
+                if kind == 's':
+                    vals = string_ids(column)
+                    ok &= vals >= 0
+                elif kind == 't':
+                    vals = np.fromiter((tag_ids.get(x, -1) if type(x) is str else -1 for x in column), dtype=np.int64, count=n)
+                    ok &= vals >= 0
+                else:
+                    vals = np.fromiter((-1 if v is None else v for v in map(_as_index, column)), dtype=np.int64, count=n)
+                    ok &= (vals >= 0) & (vals < (1 << 24))
+                    if kind == 'l':
+                        ok &= vals <= 1
+                cols[where] = vals
+            keep = np.nonzero(ok)[0]
+            weights = np.asarray(coef, dtype=np.float64)[np.asarray(idxs, dtype=np.int64)[keep]]
+            feat_func.append(np.full(len(keep), f, dtype=np.uint8))
+            feat_tmpl.append(np.full(len(keep), tmpl, dtype=np.uint8))
+            feat_s.append(np.stack([cols['s0'][keep], cols['s1'][keep], cols['s2'][keep]], axis=1).astype(np.int32))
+            feat_a.append(np.stack([np.where(ok, cols['a0'], 0)[keep], np.where(ok, cols['a1'], 0)[keep]], axis=1).astype(np.int32))
+            feat_w.append(weights)
 
     def device_bytes(self):
         return int(self._lib.lt_tables_device_bytes(self.handle))

@@ -74,6 +74,13 @@ struct BeamArgs {
     unsigned int* queue;
     const uint32_t* order;      // queue position -> sentence index (longest first), or nullptr
     int32_t trail_smem;         // back-pointers in shared memory (4 B) instead of `trail` (8 B)
+    const H2* imp;              // imported lattices: 3 hashes (word, morph0, morph1) per LT_EDGE_EXPLICIT edge
+    // all survivors of the last position (beam_search's return value, beam.py:59-61) instead of matures[0] only:
+    int32_t kbest;              // 1: also write every survivor's path
+    lt_edge* kb_tmp;            // [n_units * beam] path r of sentence s, reversed, at sent_off[s] * beam + r * (raw length)
+    int32_t* kb_len;            // [n_sent * beam] words of survivor r (0 beyond the survivors)
+    double* kb_scores;          // [n_sent * beam]
+    int32_t* kb_count;          // [n_sent] survivors (1 for an empty sentence: [BOS, EOS])
 };
 
 // Prepared edges (shared memory, struct of arrays).  Slots [0, kEdgeRing): dictionary edges at
@@ -190,6 +197,14 @@ __device__ __forceinline__ void unknown_edge(int b, int e, EdgeView& k) {
 }
 
 __device__ __noinline__ void edge_hashes(const DevTables& T, const SentView& v, EdgeView& k, bool need_m1) {
+    if (k.flags & LT_EDGE_EXPLICIT) {
+        // imported lattice (lt_lattice_import): the strings of this word were hashed on the host
+        const H2* h = v.imp + 3 * (size_t)k.rule;
+        k.wk = h[0];
+        k.mk = h[1];
+        k.m1 = h[2];
+        return;
+    }
     k.wk = sub_hash(T, v, k.b, k.e);
     k.mk = k.wk;
     k.m1 = H2{0, 0};
@@ -492,7 +507,7 @@ __global__ void __launch_bounds__(kBeamMaxWarps * 32, LT_BEAM_MINB) beam_kernel(
         __syncwarp();
         for (int i = lane; i < L; i += 32) spos[i] = __ldg(A.pos + s0 + i);
         beam_prefix_hashes(ch, L, lane, ha, hb);
-        SentView v{ch, ha, hb, nullptr};
+        SentView v{ch, ha, hb, nullptr, A.imp};
 
         if (L == 0 && lane == 0) { A.path_len[s] = 0; A.scores[s] = 0.0; }
 
@@ -951,51 +966,70 @@ __global__ void __launch_bounds__(kBeamMaxWarps * 32, LT_BEAM_MINB) beam_kernel(
             __syncwarp();
         }
 
-        // ---- best path: matures[0] (tagger.py:78) ----
+        // ---- best path: matures[0] (tagger.py:78); with A.kbest every survivor (beam.py:59-61) ----
         // lane 0 follows the back-pointers (a dependent chain) and lists (end, edge reference); then the
         // lanes fetch the edge records side by side
+        if (A.kbest) {
+            const int nsurv = (L > 0) ? (int)s_nbeam[L % kRing] : 1;
+            if (lane == 0) A.kb_count[s] = (st == LT_SENT_OK) ? nsurv : 0;
+            for (int r = lane; r < K; r += 32) {
+                A.kb_len[(size_t)s * K + r] = 0;
+                A.kb_scores[(size_t)s * K + r] = 0.0;
+            }
+            __syncwarp();
+        }
         if (L > 0) {
             uint64_t* s_path = ha;              // the prefix hashes are no longer needed
-            int W = 0;
-            if (lane == 0) {
-                A.scores[s] = e_score[(L % kRing) * K + 0];
-                int e = L, r = 0;
-                while (e > 0) {
-                    uint32_t eref, span;
-                    if (trail_smem) {
-                        const uint32_t t = s_trail[(e - 1) * K + r];
-                        span = (uint32_t)LT_WINDOW - (t >> 27);
-                        const uint32_t bidx = t & kPayUnk;
-                        eref = (bidx == kPayUnk) ? kTrailUnk : spos[e - 1].x + bidx;
-                        r = (int)((t >> 20) & 0x7Fu);
-                    } else {
-                        const uint64_t t = A.trail[(size_t)(s0 + e - 1) * K + r];
-                        eref = (uint32_t)t;
-                        span = (uint32_t)((t >> 32) & 0xFFu);
-                        r = (int)((t >> 40) & 0xFFu);
+            const int nout = A.kbest ? (int)s_nbeam[L % kRing] : 1;
+            for (int r0 = 0; r0 < nout; ++r0) {
+                int W = 0;
+                if (lane == 0) {
+                    const double final_score = e_score[(L % kRing) * K + r0];
+                    if (r0 == 0) A.scores[s] = final_score;
+                    if (A.kbest) A.kb_scores[(size_t)s * K + r0] = final_score;
+                    int e = L, r = r0;
+                    while (e > 0) {
+                        uint32_t eref, span;
+                        if (trail_smem) {
+                            const uint32_t t = s_trail[(e - 1) * K + r];
+                            span = (uint32_t)LT_WINDOW - (t >> 27);
+                            const uint32_t bidx = t & kPayUnk;
+                            eref = (bidx == kPayUnk) ? kTrailUnk : spos[e - 1].x + bidx;
+                            r = (int)((t >> 20) & 0x7Fu);
+                        } else {
+                            const uint64_t t = A.trail[(size_t)(s0 + e - 1) * K + r];
+                            eref = (uint32_t)t;
+                            span = (uint32_t)((t >> 32) & 0xFFu);
+                            r = (int)((t >> 40) & 0xFFu);
+                        }
+                        s_path[W] = (uint64_t)eref | ((uint64_t)e << 32) | ((uint64_t)span << 48);
+                        ++W;
+                        e -= (int)span;
                     }
-                    s_path[W] = (uint64_t)eref | ((uint64_t)e << 32) | ((uint64_t)span << 48);
-                    ++W;
-                    e -= (int)span;
+                    if (r0 == 0) {
+                        A.path_len[s] = W;
+                        s_acc[3] += (uint32_t)W;
+                    }
+                    if (A.kbest) A.kb_len[(size_t)s * K + r0] = W;
                 }
-                A.path_len[s] = W;
-                s_acc[3] += (uint32_t)W;
-            }
-            W = __shfl_sync(kFull, W, 0);
-            __syncwarp();
-            for (int w = lane; w < W; w += 32) {
-                const uint64_t t = s_path[w];
-                const uint32_t eref = (uint32_t)t;
-                lt_edge ed;
-                if (eref == kTrailUnk) {
-                    const uint32_t e = (uint32_t)(t >> 32) & 0xFFFFu, span = (uint32_t)(t >> 48);
-                    ed.b = (uint16_t)(e - span); ed.e = (uint16_t)e; ed.len = (uint16_t)span;
-                    ed.tag0 = LT_TAG_UNK; ed.tag1 = LT_NO_TAG; ed.rule = LT_NO_RULE; ed.split = 0;
-                    ed.flags = LT_EDGE_UNK; ed.reserved = 0;
-                } else {
-                    ed = A.edges[eref];
+                W = __shfl_sync(kFull, W, 0);
+                __syncwarp();
+                for (int w = lane; w < W; w += 32) {
+                    const uint64_t t = s_path[w];
+                    const uint32_t eref = (uint32_t)t;
+                    lt_edge ed;
+                    if (eref == kTrailUnk) {
+                        const uint32_t e = (uint32_t)(t >> 32) & 0xFFFFu, span = (uint32_t)(t >> 48);
+                        ed.b = (uint16_t)(e - span); ed.e = (uint16_t)e; ed.len = (uint16_t)span;
+                        ed.tag0 = LT_TAG_UNK; ed.tag1 = LT_NO_TAG; ed.rule = LT_NO_RULE; ed.split = 0;
+                        ed.flags = LT_EDGE_UNK; ed.reserved = 0;
+                    } else {
+                        ed = A.edges[eref];
+                    }
+                    if (r0 == 0) A.path_tmp[s0 + w] = ed;
+                    if (A.kbest) A.kb_tmp[(size_t)s0 * K + (size_t)r0 * (s1 - s0) + w] = ed;
                 }
-                A.path_tmp[s0 + w] = ed;
+                __syncwarp();
             }
         }
         __syncwarp();

@@ -52,8 +52,8 @@ struct LatticeArgs {
     uint2* pos;                 // [n_units] out: (first edge, count) per (sentence, end position)
     lt_edge* edges;             // out
     uint32_t edge_cap;
-    uint32_t reserved;
-    uint32_t* cursor;           // edge allocation cursor
+    int32_t max_units;          // sentences with more raw code units are skipped with LT_SENT_TOO_LONG
+    unsigned long long* cursor; // edge allocation cursor (64 bits: the sum of all reservations cannot wrap)
     uint32_t* flags;
     int32_t* sent_len;          // [n_sent] syllables
     int32_t* sent_edges;        // [n_sent] dictionary edges
@@ -67,6 +67,7 @@ struct LatticeArgs {
     uint32_t* retry_list;
     unsigned int* retry_count;
     int32_t retry_pass;
+    int32_t mode;               // LT_LOOKUP_*: which eojeol lookup is enumerated
 };
 
 // Per-warp shared memory.  `units` = elements per sentence array (>= longest sentence + 8, a
@@ -96,6 +97,7 @@ struct SentView {
     const uint64_t* ha;
     const uint64_t* hb;
     const uint2* rref;      // rref[3 * p + (key_len - 1)] = (first rule, count | k3_first << 31)
+    const H2* imp;          // beam kernel, imported lattices: (word, morph0, morph1) hashes of LT_EDGE_EXPLICIT edges
 };
 
 __device__ __forceinline__ H2 sub_hash(const DevTables& T, const SentView& v, int b, int e) {
@@ -261,7 +263,7 @@ __device__ __forceinline__ LatticeViews lattice_views(unsigned char* base, int u
     uint32_t* rqn = nh + 1;
     uint32_t* sub = reinterpret_cast<uint32_t*>(base + lattice_fixed_smem(units, HC));
     LatticeViews W;
-    W.v = SentView{ch, ha, hb, rref};
+    W.v = SentView{ch, ha, hb, rref, nullptr};
     W.E = Enum{sub, max_str, hkey, hrec, htask, tcnt, nh, HC, rq, rqn};
     W.pstart = pstart; W.pcnt = pcnt; W.ch = ch; W.eoj = eoj; W.nend = nend; W.ha = ha; W.hb = hb; W.rref = rref;
     return W;
@@ -273,10 +275,12 @@ __device__ __forceinline__ uint32_t sub_get(const Enum& E, int x, int y) {
     return E.sub[x * E.max_str + (len - 1)];
 }
 
-// sort key: end | begin | class (0 tag hits, 1 lemma hits) | split | order within the split
-__device__ __forceinline__ uint64_t hit_key(int e, int b, uint32_t cls, uint32_t split, uint32_t k) {
-    return ((uint64_t)e << 48) | ((uint64_t)b << 32) | ((uint64_t)cls << 31) | ((uint64_t)(split & 0xFFFu) << 19) |
-           (uint64_t)(k & 0x7FFFFu);
+// sort key: end | begin | pass | class (0 tag hits, 1 lemma hits) | split | order within the split.
+// `pass` = 1 for the hits of word_lookup's substring loop, which come after the hits of its initial
+// whole-eojeol lookup (lookup.py:157-168); 0 everywhere else.  k < 2^18: at most 255 rules per key.
+__device__ __forceinline__ uint64_t hit_key(int e, int b, uint32_t cls, uint32_t split, uint32_t k, uint32_t pass = 0) {
+    return ((uint64_t)e << 48) | ((uint64_t)b << 32) | ((uint64_t)pass << 31) | ((uint64_t)cls << 30) |
+           ((uint64_t)(split & 0xFFFu) << 18) | (uint64_t)(k & 0x3FFFFu);
 }
 
 #ifndef LT_STAGE_ATTR
@@ -303,7 +307,7 @@ __device__ LT_STAGE_ATTR void stage_hit(const Enum& E, const lt_edge& rec, uint6
 // reps > 1 the same candidate recurs at candidate indices cand + rep * rep_stride.
 __device__ __forceinline__ void rule_candidate(const DevTables& T, const Enum& E, H2 stem, uint32_t stem_len, H2 eomi,
                                                uint32_t eomi_len, lt_edge proto, uint32_t split, uint32_t cand,
-                                               uint32_t reps, uint32_t rep_stride, uint32_t task) {
+                                               uint32_t reps, uint32_t rep_stride, uint32_t task, uint32_t pass) {
     if (eomi_len > (uint32_t)E.max_str || stem_len > (uint32_t)E.max_str) return;    // longer than any entry
     // both probes in flight together: the stem's is wasted when the eomi misses, but a lane never waits twice
     const uint64_t pe = dict_probe(T, eomi, eomi_len);
@@ -314,11 +318,11 @@ __device__ __forceinline__ void rule_candidate(const DevTables& T, const Enum& E
         const uint32_t k = (cand + rep * rep_stride) * 2u;
         if (ps & kLemAdj) {
             proto.tag0 = LT_TAG_ADJECTIVE;
-            stage_hit(E, proto, hit_key(proto.e, proto.b, 1, split, k), task);
+            stage_hit(E, proto, hit_key(proto.e, proto.b, 1, split, k, pass), task);
         }
         if (ps & kLemVerb) {
             proto.tag0 = LT_TAG_VERB;
-            stage_hit(E, proto, hit_key(proto.e, proto.b, 1, split, k + 1), task);
+            stage_hit(E, proto, hit_key(proto.e, proto.b, 1, split, k + 1, pass), task);
         }
     }
 }
@@ -327,15 +331,15 @@ __device__ __forceinline__ void rule_candidate(const DevTables& T, const Enum& E
 // minority of the lanes, so applying the rules inside the item loop runs the most expensive code of
 // the kernel (rule records, hash composition, two dictionary probes per rule) on a handful of lanes.
 // An item pushes one descriptor per (word, split, key); drain_rules() then gives every lane one.
-//   x = b | p << 12 | suffix code << 24 (0: p+1, 1: p+2, 2: e) | reps_is_count << 26 | is_l << 27 | skip2 << 28
+//   x = b | p << 12 | suffix code << 24 (0: p+1, 1: p+2, 2: e) | reps_is_count << 26 | is_l << 27 | skip2 << 28 | pass << 29
 //   y = e | task << 12        z = first candidate index | rule count << 19        w = first rule
 __device__ __forceinline__ void push_rules(const Enum& E, uint2 ref, int b, int p, int e, uint32_t suffix_code, bool skip2,
-                                           bool is_l, uint32_t cand0, bool reps_is_count, uint32_t task) {
+                                           bool is_l, uint32_t cand0, bool reps_is_count, uint32_t task, uint32_t pass) {
     const uint32_t count = ref.y & 0xFFFFu;
     if (count == 0) return;
     const uint32_t slot = atomicAdd(E.rqn, 1u);
     E.rq[slot] = make_uint4((uint32_t)b | ((uint32_t)p << 12) | (suffix_code << 24) | (reps_is_count ? 1u << 26 : 0u) |
-                                (is_l ? 1u << 27 : 0u) | (skip2 ? 1u << 28 : 0u),
+                                (is_l ? 1u << 27 : 0u) | (skip2 ? 1u << 28 : 0u) | (pass << 29),
                             (uint32_t)e | (task << 12), cand0 | (count << 19), ref.x);
 }
 
@@ -387,7 +391,7 @@ __device__ __noinline__ void drain_rules(const DevTables& T, unsigned char* base
             const H2 eomi = h2_concat(rec.eomi, suf, pw_suf);
             proto.rule = d.w + r;
             rule_candidate(T, E, stem, (uint32_t)(p - b) + rec.stem_len, eomi, rec.eomi_len + suf_len, proto,
-                           (uint32_t)(p - b), cand0 + r, reps, count, task);
+                           (uint32_t)(p - b), cand0 + r, reps, count, task, (d.x >> 29) & 1u);
         }
     }
     __syncwarp();
@@ -398,7 +402,7 @@ __device__ __noinline__ void drain_rules(const DevTables& T, unsigned char* base
 // Lemma candidates of the word [b, e) at split position p, in get_lemma_candidates order
 // (lemmatizer.py:90-112).  Returns the number of candidates the reference generates there.
 __device__ LT_ITEM_ATTR uint32_t lemma_item(const DevTables& T, const SentView& v, const Enum& E, int b, int e, int p,
-                                               lt_edge proto, uint32_t task) {
+                                               lt_edge proto, uint32_t task, uint32_t pass = 0) {
     uint32_t ncand = 0;
     proto.tag1 = LT_TAG_EOMI;
     proto.split = (uint16_t)(p - b);
@@ -412,11 +416,11 @@ __device__ LT_ITEM_ATTR uint32_t lemma_item(const DevTables& T, const SentView& 
             proto.flags = base_flags | LT_EDGE_LEMMA;
             if (ps & kSubAdj) {
                 proto.tag0 = LT_TAG_ADJECTIVE;
-                stage_hit(E, proto, hit_key(e, b, 1, (uint32_t)(p - b), 0), task);
+                stage_hit(E, proto, hit_key(e, b, 1, (uint32_t)(p - b), 0, pass), task);
             }
             if (ps & kSubVerb) {
                 proto.tag0 = LT_TAG_VERB;
-                stage_hit(E, proto, hit_key(e, b, 1, (uint32_t)(p - b), 1), task);
+                stage_hit(E, proto, hit_key(e, b, 1, (uint32_t)(p - b), 1, pass), task);
             }
         }
     }
@@ -428,7 +432,7 @@ __device__ LT_ITEM_ATTR uint32_t lemma_item(const DevTables& T, const SentView& 
     const bool is_l = base_flags != 0;
     // one-syllable key: the whole rule list once per rule of the key (lemmatizer.py:100-102)
     if (c1) {
-        push_rules(E, r1, b, p, e, 0u, false, is_l, 1u, true, task);
+        push_rules(E, r1, b, p, e, 0u, false, is_l, 1u, true, task, pass);
         ncand += c1 * c1;
     }
     // {word[i:i+2], word[i:i+3]} in set order; the eomi continues at word[i+2:] for both
@@ -436,15 +440,15 @@ __device__ LT_ITEM_ATTR uint32_t lemma_item(const DevTables& T, const SentView& 
     if (p == e - 1) {
         // both slices are the last syllable itself: its rules once more, empty suffix
         if (c1) {
-            push_rules(E, r1, b, p, e, 2u, true, is_l, after1, false, task);
+            push_rules(E, r1, b, p, e, 2u, true, is_l, after1, false, task, pass);
             ncand += c1;
         }
     } else {
         const bool k3_first = (r3.y >> 31) != 0;
         const uint2 first = k3_first ? r3 : r2;
         const uint2 second = k3_first ? r2 : r3;
-        push_rules(E, first, b, p, e, 1u, true, is_l, after1, false, task);
-        push_rules(E, second, b, p, e, 1u, true, is_l, after1 + (first.y & 0xFFFFu), false, task);
+        push_rules(E, first, b, p, e, 1u, true, is_l, after1, false, task, pass);
+        push_rules(E, second, b, p, e, 1u, true, is_l, after1 + (first.y & 0xFFFFu), false, task, pass);
         ncand += c2 + c3;
     }
     return ncand;
@@ -469,10 +473,11 @@ __device__ LT_FLUSH_ATTR void flush_staged(const LatticeArgs& A, int lane, uint3
                                           const uint32_t* htask, const lt_edge* hrec, uint32_t* pcnt, uint32_t* pstart,
                                           uint32_t* nh) {
     if (alive > 0) {
-        uint32_t gbase = 0;
-        if (lane == 0) gbase = atomicAdd(A.cursor, alive);
-        gbase = __shfl_sync(kFull, gbase, 0);
-        const bool fits = (gbase + alive <= A.edge_cap) && (gbase + alive >= gbase);
+        unsigned long long gbase64 = 0;
+        if (lane == 0) gbase64 = atomicAdd(A.cursor, (unsigned long long)alive);
+        gbase64 = __shfl_sync(kFull, gbase64, 0);
+        const bool fits = gbase64 + alive <= (unsigned long long)A.edge_cap;
+        const uint32_t gbase = (uint32_t)gbase64;      // exact whenever it is used (edge_cap < 2^32)
         if (!fits && lane == 0) atomicOr(A.flags + kFlagEdgeOverflow, 1u);
         #pragma unroll 1
         for (uint32_t i = lane; i < slots; i += 32) {
@@ -536,6 +541,18 @@ __global__ void __launch_bounds__(kLatMaxWarps * 32, LT_LAT_MINB) lattice_kernel
             if (A.order) s = __ldg(A.order + s);
         }
         const int s0 = __ldg(A.sent_off + s), s1 = __ldg(A.sent_off + s + 1);
+        if (s1 - s0 > A.max_units) {
+            // longer than the per-warp arrays hold: the sentence gets a status of its own, the batch goes on
+            #pragma unroll 1
+            for (int p = lane; p < s1 - s0; p += 32) A.pos[s0 + p] = make_uint2(0u, 0u);
+            if (lane == 0) {
+                A.sent_len[s] = 0;
+                A.sent_edges[s] = 0;
+                A.status[s] = LT_SENT_TOO_LONG;
+            }
+            __syncwarp();
+            continue;
+        }
         int n_eoj;
         bool bad;
         const int L = stage_sentence(A.text, s0, s1, lane, ch, eoj, ha, hb, n_eoj, bad);
@@ -587,6 +604,8 @@ __global__ void __launch_bounds__(kLatMaxWarps * 32, LT_LAT_MINB) lattice_kernel
             alive = 0;
         };
 
+        const int mode = A.mode;
+        const bool word_mode = mode >= LT_LOOKUP_WORD;
         for (int w = 0; w < n_eoj && !overflow; ++w) {
             const int o = eoj[w];
             const int n = eoj[w + 1] - o;
@@ -598,9 +617,11 @@ __global__ void __launch_bounds__(kLatMaxWarps * 32, LT_LAT_MINB) lattice_kernel
                 __syncwarp();
                 uint32_t ncand_try = 0;
                 const float inv_n = 1.0f / (float)n;
-                for (int q0 = 0; q0 < n * n; q0 += 32) {
+                // (word_lookup starts with the whole-eojeol lookup alone: the items of task 0, lookup.py:157)
+                const int n_items1 = word_mode ? n : n * n;
+                for (int q0 = 0; q0 < n_items1; q0 += 32) {
                     const int q = q0 + lane;
-                    if (q < n * n) {
+                    if (q < n_items1) {
                         const int i = small_div(q, n, inv_n), r = q - i * n;
                         const int p = o + r;
                         // task: i == 0 whole; r < i: left_i = [o, o+i); else right_i = [o+i, oe)
@@ -647,10 +668,12 @@ __global__ void __launch_bounds__(kLatMaxWarps * 32, LT_LAT_MINB) lattice_kernel
                 bool too_many = nstaged > (uint32_t)HC;
                 uint32_t alive_here = 0;
                 if (!too_many) {
+                    // LRLookup(prefer_exact_match=True) returns the whole-eojeol analyses alone when there are any (lookup.py:192-193)
+                    const bool exact_only = (mode == LT_LOOKUP_LR) && (tcnt[0] > 0);
                     for (uint32_t h = slots + lane; h < nstaged; h += 32) {
                         const uint32_t task = htask[h];
                         bool ok = true;
-                        if (task >= 2) ok = (tcnt[task] > 0) && (tcnt[task ^ 1u] > 0);
+                        if (task >= 2) ok = (tcnt[task] > 0) && (tcnt[task ^ 1u] > 0) && !exact_only;
                         if (!ok) hkey[h] = ~0ull;
                         alive_here += ok ? 1u : 0u;
                     }
@@ -658,36 +681,61 @@ __global__ void __launch_bounds__(kLatMaxWarps * 32, LT_LAT_MINB) lattice_kernel
                     for (int d = 16; d; d >>= 1) alive_here += __shfl_xor_sync(kFull, alive_here, d);
                 }
                 uint32_t nsub_try = (uint32_t)(2 * n - 1);
-                if (!too_many && alive_here == 0 && n >= 2) {
-                    // ---------------- stage 2: sub-word scan, begins from 1 (lookup.py:259-277) ----------------
+                // second stage of the lookup:
+                //   MorphemeLookup: sub-word scan when the first stage found nothing, begins from 1 (lookup.py:259-277)
+                //   WordLookup: every substring's full lookup, begins from 0 (lookup.py:161-168) — when the whole
+                //               eojeol is unknown, or always without prefer_exact_match (the whole-eojeol hits stay)
+                //   LRLookup: none
+                const bool scan = !too_many && mode != LT_LOOKUP_EXACT &&
+                                  (word_mode ? (mode == LT_LOOKUP_WORD_ALL || alive_here == 0)
+                                                          : (mode == LT_LOOKUP_MORPHEME && alive_here == 0 && n >= 2));
+                if (scan) {
                     __syncwarp();
-                    if (lane == 0) *nh = slots;          // forget the dead stage-1 hits
-                    const int M = (T.max_len > 0) ? T.max_len : n;
+                    const uint32_t pass = word_mode ? 1u : 0u;
+                    if (lane == 0 && !word_mode) *nh = slots;          // forget the dead stage-1 hits
+                    const int M = word_mode ? n : ((T.max_len > 0) ? T.max_len : n);
+                    const int bl0 = word_mode ? 0 : 1;
                     // which positions end a stand-alone Noun found by this scan
-                    #pragma unroll 1
-                    for (int el = 1 + lane; el <= n; el += 32) {
-                        bool any_noun = false;
-                        int b_lo = el - M; if (b_lo < 1) b_lo = 1;
+                    if (!word_mode) {
                         #pragma unroll 1
-                        for (int bl = b_lo; bl < el; ++bl) any_noun |= ((sub_get(E, o + bl, o + el) >> LT_TAG_NOUN) & 1u) != 0;
-                        nend[o + el] = any_noun ? 1 : 0;
+                        for (int el = 1 + lane; el <= n; el += 32) {
+                            bool any_noun = false;
+                            int b_lo = el - M; if (b_lo < 1) b_lo = 1;
+                            #pragma unroll 1
+                            for (int bl = b_lo; bl < el; ++bl) any_noun |= ((sub_get(E, o + bl, o + el) >> LT_TAG_NOUN) & 1u) != 0;
+                            nend[o + el] = any_noun ? 1 : 0;
+                        }
                     }
                     if (lane == 0) tcnt[0] = 0;
                     __syncwarp();
                     const int tri = M * (M + 1) / 2;
-                    const int items = (n - 1) * tri;
+                    const int items = (n - bl0) * tri;
                     const float inv_tri = 1.0f / (float)tri;
                     for (int q0 = 0; q0 < items; q0 += 32) {
                         const int q = q0 + lane;
                         if (q < items) {
-                            const int bl = 1 + small_div(q, tri, inv_tri);
-                            int t = q - (bl - 1) * tri;
-                            int span = 1;
-                            while (t >= span) { t -= span; ++span; }       // t = split offset inside the span
+                            const int blq = small_div(q, tri, inv_tri);
+                            const int bl = bl0 + blq;
+                            int t = q - blq * tri;
+                            // t -> (span, split offset inside the span): span (span - 1) / 2 <= t < span (span + 1) / 2
+                            int span = (int)((1.0f + sqrtf(8.0f * (float)t + 1.0f)) * 0.5f);
+                            while (span * (span - 1) / 2 > t) --span;
+                            while (span * (span + 1) / 2 <= t) ++span;
+                            t -= span * (span - 1) / 2;
                             if (bl + span <= n) {
                                 const int b = o + bl, e = b + span, p = b + t;
-                                lt_edge rec = edge_proto(b, e, (uint32_t)span, false);
-                                if (t == 0) {
+                                lt_edge rec = edge_proto(b, e, (uint32_t)span, word_mode && bl == 0);
+                                if (t == 0 && word_mode) {
+                                    // MorphemeDictionary.lookup of the substring: one hit per tag in dictionary order
+                                    uint32_t mask = sub_get(E, b, e) & kSubTagMask & T.order_mask;
+                                    #pragma unroll 1
+                                    while (mask) {
+                                        const uint32_t tg = (uint32_t)__ffs(mask) - 1u;
+                                        mask &= mask - 1u;
+                                        rec.tag0 = (uint8_t)tg;
+                                        stage_hit(E, rec, hit_key(e, b, 0, 0, (uint32_t)T.tag_pos[tg], pass), 0u);
+                                    }
+                                } else if (t == 0) {
                                     const uint32_t m = sub_get(E, b, e);
                                     // stand-alone tags in list order (lookup.py:104-105), then Josa after a Noun
                                     constexpr uint32_t standalone = (1u << LT_TAG_NOUN) | (1u << LT_TAG_ADVERB) | (1u << LT_TAG_EXCLAMATION) |
@@ -708,7 +756,7 @@ __global__ void __launch_bounds__(kLatMaxWarps * 32, LT_LAT_MINB) lattice_kernel
                                         stage_hit(E, rec, hit_key(e, b, 0, 0, 5u), 0u);
                                     }
                                 }
-                                ncand_try += lemma_item(T, v, E, b, e, p, rec, 0u);
+                                ncand_try += lemma_item(T, v, E, b, e, p, rec, 0u, pass);
                             }
                         }
                         if (warp_read(rqn) > (uint32_t)(kRuleQueue - 128)) drain_rules<UC, HCT>(T, base, units, HC, DM, lane);

@@ -50,12 +50,30 @@ extern "C" int lt_abi_version(void) { return LT_ABI_VERSION; }
 // ------------------------------------------------------------------------------------------------
 // tables
 // ------------------------------------------------------------------------------------------------
+// Every entry point runs on the tables' device and puts the caller's current device back on return.
+struct DeviceGuard {
+    int prev = -1, dev = -1;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int device) : dev(device) {
+        err = cudaGetDevice(&prev);
+        if (err == cudaSuccess && prev != dev) err = cudaSetDevice(dev);
+    }
+    ~DeviceGuard() {
+        if (prev >= 0 && prev != dev) cudaSetDevice(prev);
+    }
+};
+#define ON_DEVICE(device)                                                                         \
+    DeviceGuard _guard(device);                                                                   \
+    if (_guard.err != cudaSuccess) return fail(LT_ERR_CUDA, "cudaSetDevice(%d) failed: %s", (int)(device), cudaGetErrorString(_guard.err))
+
 struct lt_tables {
     int device = 0;
     DevTables dev{};
     std::vector<void*> allocations;
     int64_t bytes = 0;
     int sm_count = 0;
+    // kernels whose dynamic shared-memory limit was already raised on this device (function, bytes)
+    std::vector<std::pair<const void*, size_t>> smem_limits;
 };
 
 static H2 hash_units(const uint16_t* p, int64_t n) {
@@ -134,7 +152,7 @@ static int upload(lt_tables* t, const std::vector<T>& host, const T** out) {
 
 extern "C" void lt_tables_destroy(lt_tables* t) {
     if (!t) return;
-    cudaSetDevice(t->device);
+    DeviceGuard guard(t->device);
     for (void* p : t->allocations) cudaFree(p);
     delete t;
 }
@@ -352,7 +370,7 @@ static int build_tables(const lt_tables_desc* d, lt_tables* t) {
 extern "C" int lt_tables_create(const lt_tables_desc* desc, int device, lt_tables** out) {
     if (!desc || !out) return fail(LT_ERR_INVALID, "null argument");
     *out = nullptr;
-    CU(cudaSetDevice(device));
+    ON_DEVICE(device);
     lt_tables* t = new lt_tables();
     t->device = device;
     cudaDeviceProp prop;
@@ -373,8 +391,27 @@ struct DevBuf {
     size_t cap = 0;
 };
 
-// control words on the device: work-queue cursors, edge cursor, overflow flags
-enum { kCtlLatticeQueue = 0, kCtlBeamQueue = 1, kCtlCursor = 2, kCtlRetryCount = 3, kCtlFlags = 4, kCtlRetryQueue = 6, kCtlWords = 8 };
+// control words on the device: work-queue cursors, the 64-bit edge cursor, overflow flags, retry list length
+enum { kCtlLatticeQueue = 0, kCtlBeamQueue = 1, kCtlCursor = 2 /* 2 words */, kCtlFlags = 4 /* 2 words */, kCtlRetryQueue = 6,
+       kCtlRetryCount = 7, kCtlWords = 8 };
+
+static const size_t kSmemBudget = 200 * 1024;
+
+// Launch shapes are decided once per (array size, capacity) and kept: kernel instantiation, CTA shape,
+// shared memory, resident CTAs per SM.  Nothing of this is recomputed (or asked of the driver) per batch.
+struct LatticePlan {
+    int units = 0, hcap = 0;                  // key
+    void (*fn)(const DevTables, const LatticeArgs) = nullptr;
+    int warps = 0, per_sm = 1;
+    size_t smem = 0, warp_smem = 0;
+};
+struct BeamPlan {
+    int units = 0, beam = 0;                  // key
+    void (*fn)(const DevTables, const BeamArgs) = nullptr;
+    int warps = 0, per_sm = 1;
+    size_t smem = 0, warp_smem = 0;
+    bool trail_smem = false;
+};
 
 struct lt_batch {
     lt_tables* tables = nullptr;
@@ -384,6 +421,9 @@ struct lt_batch {
     DevBuf text, sent_off, pos, scan_tmp;
     DevBuf sent_len, sent_edges, status, path_len, path_off, scores;
     DevBuf edges, trail, path_tmp, path_out, counters, ctl, order, retry;
+    DevBuf kb_tmp, kb_out, kb_len, kb_off, kb_scores, kb_count;      // all survivors (lt_beam_kbest)
+    DevBuf imp;                    // string hashes of an imported lattice (lt_lattice_import)
+    bool imported = false;
     const uint16_t* d_text = nullptr;
     const int32_t* d_sent_off = nullptr;
     int32_t n_sent = 0;
@@ -391,18 +431,28 @@ struct lt_batch {
     int32_t max_sent_units = 0;
     int32_t lcap = 0;
     int32_t beam = 0;
+    int32_t lookup_mode = LT_LOOKUP_MORPHEME;
     int32_t hcap = 128;            // lattice staging capacity per warp of the main pass
     bool use_retry = false;        // a batch outgrew `hcap`: such sentences go to a retry pass from now on (sticky)
     int32_t retry_hcap = 0;        // staging capacity of the retry pass (grows on overflow, sticky)
     bool sort_by_length = true;    // persistent warps pull the longest sentences first (LT_SORT_BY_LENGTH=0 disables)
     uint32_t edge_cap = 0;         // edge buffer capacity (grows on overflow, sticky)
     bool edge_cap_fixed = false;   // LT_EDGE_CAP given: start there instead of the size guess (tests)
+    bool debug = false;            // LT_DEBUG: print launch shapes
+    bool trail_smem_ok = true;     // LT_TRAIL_SMEM=0 keeps the back-pointers in HBM
     int64_t n_edges = 0;
-    bool have_lattice = false, have_paths = false, resolved = false;
+    bool have_lattice = false, have_paths = false, have_kbest = false, resolved = false;
     bool beam_state_clean = false;   // beam queue cursor / counters still zero from the batch prologue
     cudaEvent_t ev[10]{};
     bool timed = false;
-    int reruns = 0;
+    int reruns = 0;                // grow-and-rerun rounds so far (cumulative)
+    int64_t launches = 0;          // kernels launched so far (cumulative)
+    int64_t words_hint = -1;       // path records of the previous batch: the speculative part of the result copy
+    uint32_t last_retried = 0;
+    std::vector<LatticePlan> lattice_plans;
+    std::vector<BeamPlan> beam_plans;
+    const LatticePlan* last_lattice_plan = nullptr;
+    const BeamPlan* last_beam_plan = nullptr;
 };
 
 static int ensure(DevBuf& b, size_t bytes) {
@@ -422,27 +472,51 @@ static int ensure(DevBuf& b, size_t bytes) {
     return LT_OK;
 }
 
+// Longest sentence (raw UTF-16 code units, spaces included) both kernels can hold in shared memory with
+// these tables: the lattice kernel's per-warp arrays grow with the longest dictionary string (substring
+// table), the beam kernel's with the beam size.  Longer sentences get LT_SENT_TOO_LONG.
+static int32_t unit_limit(const lt_tables* t) {
+    const int max_str = std::max(1, t->dev.max_str);
+    const size_t dense_bytes = ((size_t)t->dev.n_tri * dense_block_bytes(t->dev.n_tags) + 15) & ~(size_t)15;
+    int32_t lo = 8, hi = 4088;
+    auto fits = [&](int32_t lcap) {
+        return lattice_warp_smem(lcap + 8, kLatDefaultHcap, max_str) <= kSmemBudget &&
+               dense_bytes + beam_warp_smem(lcap + 8, LT_MAX_BEAM, t->dev.n_funcs, false) <= kSmemBudget;
+    };
+    if (fits(hi)) return hi;
+    while (hi - lo > 8) {
+        const int32_t mid = ((lo + hi) / 2) & ~7;
+        if (fits(mid)) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+extern "C" int32_t lt_tables_max_sentence_units(const lt_tables* t) { return t ? unit_limit(t) : 0; }
+
 extern "C" int lt_batch_create(lt_tables* tables, lt_batch** out) {
     if (!tables || !out) return fail(LT_ERR_INVALID, "null argument");
-    CU(cudaSetDevice(tables->device));
+    ON_DEVICE(tables->device);
     lt_batch* b = new lt_batch();
     b->tables = tables;
     CU(cudaStreamCreateWithFlags(&b->own_stream, cudaStreamNonBlocking));
     for (auto& e : b->ev) CU(cudaEventCreate(&e));
-    // debugging / test knobs: tiny initial capacities exercise the grow-and-rerun path
+    // debugging / test knobs, read once here: tiny initial capacities exercise the grow-and-rerun path
     if (const char* env = getenv("LT_HIT_CAP")) b->hcap = std::max(8, atoi(env));
     if (const char* env = getenv("LT_SORT_BY_LENGTH")) b->sort_by_length = atoi(env) != 0;
     if (const char* env = getenv("LT_EDGE_CAP")) { b->edge_cap = (uint32_t)std::max(16, atoi(env)); b->edge_cap_fixed = true; }
+    if (const char* env = getenv("LT_TRAIL_SMEM")) b->trail_smem_ok = atoi(env) != 0;
+    b->debug = getenv("LT_DEBUG") != nullptr;
     *out = b;
     return LT_OK;
 }
 
 extern "C" void lt_batch_destroy(lt_batch* b) {
     if (!b) return;
-    cudaSetDevice(b->tables->device);
+    DeviceGuard guard(b->tables->device);
     DevBuf* bufs[] = {&b->text, &b->sent_off, &b->pos, &b->scan_tmp, &b->sent_len, &b->sent_edges, &b->status,
                       &b->path_len, &b->path_off, &b->scores, &b->edges, &b->trail, &b->path_tmp, &b->path_out,
-                      &b->counters, &b->ctl, &b->order, &b->retry};
+                      &b->counters, &b->ctl, &b->order, &b->retry, &b->kb_tmp, &b->kb_out, &b->kb_len, &b->kb_off,
+                      &b->kb_scores, &b->kb_count, &b->imp};
     for (DevBuf* x : bufs)
         if (x->p) cudaFree(x->p);
     for (auto& e : b->ev)
@@ -451,10 +525,18 @@ extern "C" void lt_batch_destroy(lt_batch* b) {
     delete b;
 }
 
+extern "C" int lt_batch_set_lookup(lt_batch* b, int32_t mode) {
+    if (!b) return fail(LT_ERR_INVALID, "null argument");
+    if (mode < LT_LOOKUP_MORPHEME || mode > LT_LOOKUP_EXACT) return fail(LT_ERR_INVALID, "unknown lookup mode %d", mode);
+    b->lookup_mode = mode;
+    return LT_OK;
+}
+
 static int scan_u32(lt_batch* b, const uint32_t* in, uint32_t* out, int64_t n, cudaStream_t st) {
     if (n <= kScanSmallMax) {
         LT_LAUNCH(scan_small, 1, kScanSmallThreads, 0, st, in, out, n);
         CU(cudaGetLastError());
+        b->launches += 1;
         return LT_OK;
     }
     const int64_t tiles = (n + kScanTile - 1) / kScanTile;
@@ -464,148 +546,82 @@ static int scan_u32(lt_batch* b, const uint32_t* in, uint32_t* out, int64_t n, c
     LT_LAUNCH(scan_sums, 1, kScanThreads, 0, st, sums, tiles);
     LT_LAUNCH(scan_apply, (unsigned)tiles, kScanThreads, 0, st, in, out, n, sums);
     CU(cudaGetLastError());
+    b->launches += 3;
     return LT_OK;
 }
 
-static const size_t kSmemBudget = 200 * 1024;
+// raise a kernel's dynamic shared-memory limit once per device (and again only when more is needed)
+template <typename Fn>
+static int smem_limit(lt_tables* t, Fn fn, size_t bytes) {
+    const void* key = reinterpret_cast<const void*>(fn);
+    for (auto& kv : t->smem_limits)
+        if (kv.first == key) {
+            if (kv.second >= bytes) return LT_OK;
+            CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+            kv.second = bytes;
+            return LT_OK;
+        }
+    CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    t->smem_limits.emplace_back(key, bytes);
+    return LT_OK;
+}
 
-// ---- launches ----------------------------------------------------------------------------------
-static int launch_lattice(lt_batch* b, cudaStream_t st) {
+// ---- launch plans --------------------------------------------------------------------------------
+static int lattice_plan(lt_batch* b, int lcap, int hcap, bool retry_pass, const LatticePlan** out) {
     lt_tables* t = b->tables;
-    const int n_sent = b->n_sent;
-    const int64_t n_units = b->n_units;
-    const int lcap = b->lcap;
     const int max_str = std::max(1, t->dev.max_str);
-    int hcap = b->hcap;
     if (hcap & 1) ++hcap;                               // keeps the arrays behind the staging area 8-byte aligned
     // common sentence-array sizes (with the default staging capacity) have their own instantiation
-    const int uclass = (hcap == kLatDefaultHcap || hcap == 2 * kLatDefaultHcap) ? lattice_units_class(lcap) : 0;
+    const int uclass = (!retry_pass && (hcap == kLatDefaultHcap || hcap == 2 * kLatDefaultHcap)) ? lattice_units_class(lcap) : 0;
     const int units = uclass ? uclass : lcap + 8;
-    size_t warp_smem = lattice_warp_smem(units, hcap, max_str);
-    // CTA shape: the warps per CTA (1..8) that keep the most warps resident on an SM (128 registers per
-    // thread allow 16); ties go to 4-warp CTAs
-    int warps = 0, best_res = 0;
-    for (int w : {kLatWarps, 8, 6, 5, 3, 2, 1}) {
-        const size_t cta = warp_smem * w;
-        if (cta > kSmemBudget) continue;
-        const int res = w * (int)std::min<size_t>(16 / w, (size_t)228 * 1024 / (cta + 1024));
-        if (res > best_res) { best_res = res; warps = w; }
+    for (const LatticePlan& p : b->lattice_plans)
+        if (p.units == units && p.hcap == hcap && (p.fn == lt::lattice_kernel<0, 0>) == (uclass == 0)) { *out = &p; return LT_OK; }
+    LatticePlan P;
+    P.units = units;
+    P.hcap = hcap;
+    P.warp_smem = lattice_warp_smem(units, hcap, max_str);
+    if (retry_pass) {
+        if (P.warp_smem > kSmemBudget)
+            return fail(LT_ERR_CAPACITY, "one eojeol yields more than %d lattice candidates; the staging buffer cannot grow further", hcap / 2);
+        P.warps = (int)std::max<size_t>(1, std::min<size_t>(2, kSmemBudget / P.warp_smem));
+    } else {
+        // CTA shape: the warps per CTA (1..8) that keep the most warps resident on an SM (128 registers per
+        // thread allow 16); ties go to 4-warp CTAs
+        int best_res = 0;
+        for (int w : {kLatWarps, 8, 6, 5, 3, 2, 1}) {
+            const size_t cta = P.warp_smem * w;
+            if (cta > kSmemBudget) continue;
+            const int res = w * (int)std::min<size_t>(16 / w, (size_t)228 * 1024 / (cta + 1024));
+            if (res > best_res) { best_res = res; P.warps = w; }
+        }
+        if (P.warps < 1)
+            return fail(LT_ERR_INVALID, "a sentence of %d code units (dictionary strings up to %d) does not fit the lattice "
+                                        "kernel's shared memory", lcap, max_str);
     }
-    if (warps < 1)
-        return fail(LT_ERR_INVALID, "a sentence of %d code units (dictionary strings up to %d) does not fit the lattice "
-                                    "kernel's shared memory", b->max_sent_units, max_str);
-
-    const size_t nu = (size_t)n_units + 1;
-    if (int rc = ensure(b->pos, nu * sizeof(uint2))) return rc;
-    if (int rc = ensure(b->sent_len, (size_t)std::max(1, n_sent) * 4)) return rc;
-    if (int rc = ensure(b->sent_edges, (size_t)std::max(1, n_sent) * 4)) return rc;
-    if (int rc = ensure(b->status, (size_t)std::max(1, n_sent) * 4)) return rc;
-    if (int rc = ensure(b->counters, 8 * sizeof(unsigned long long))) return rc;
-    if (int rc = ensure(b->ctl, kCtlWords * sizeof(unsigned int))) return rc;
-    if (!b->edge_cap_fixed) {
-        const uint64_t guess = (uint64_t)n_units * 3 + 4096;
-        if (b->edge_cap < guess) b->edge_cap = (uint32_t)std::min<uint64_t>(guess, 0xFFFFFFF0ull);
-    }
-    if (int rc = ensure(b->edges, (size_t)b->edge_cap * sizeof(lt_edge))) return rc;
-
-
-    LatticeArgs A{};
-    A.text = b->d_text;
-    A.sent_off = b->d_sent_off;
-    A.n_sent = n_sent;
-    A.units = units;
-    A.hcap = hcap;
-    A.max_str = max_str;
-    A.pos = static_cast<uint2*>(b->pos.p);
-    A.edges = static_cast<lt_edge*>(b->edges.p);
-    A.edge_cap = b->edge_cap;
-    unsigned int* ctl = static_cast<unsigned int*>(b->ctl.p);
-    A.cursor = ctl + kCtlCursor;
-    A.flags = ctl + kCtlFlags;
-    A.sent_len = static_cast<int32_t*>(b->sent_len.p);
-    A.sent_edges = static_cast<int32_t*>(b->sent_edges.p);
-    A.status = static_cast<int32_t*>(b->status.p);
-    A.counters = static_cast<unsigned long long*>(b->counters.p);
-    A.queue = ctl + kCtlLatticeQueue;
-    A.order = nullptr;
-    // prologue: control words and counters zeroed, work order (longest sentences first)
-    uint32_t* order = nullptr;
-    if (b->sort_by_length && n_sent > 1) {
-        if (int rc = ensure(b->order, (size_t)n_sent * 4)) return rc;
-        order = static_cast<uint32_t*>(b->order.p);
-    }
-    LT_LAUNCH(batch_prologue, 1, 1024, 0, st, b->d_sent_off, n_sent, order, ctl, kCtlWords,
-                                       static_cast<unsigned long long*>(b->counters.p), 8);
-    CU(cudaGetLastError());
-    A.order = order;
-    b->beam_state_clean = true;
-
-    const size_t smem = warp_smem * warps;
-    void (*lattice_kernel)(const DevTables, const LatticeArgs) =
-        (uclass == 64 && hcap == kLatDefaultHcap) ? lt::lattice_kernel<64, kLatDefaultHcap>
-        : (uclass == 128 && hcap == kLatDefaultHcap) ? lt::lattice_kernel<128, kLatDefaultHcap>
-        : (uclass == 64 && hcap == 2 * kLatDefaultHcap) ? lt::lattice_kernel<64, 2 * kLatDefaultHcap>
-        : (uclass == 128 && hcap == 2 * kLatDefaultHcap) ? lt::lattice_kernel<128, 2 * kLatDefaultHcap>
-        : lt::lattice_kernel<0, 0>;
-    CU(cudaFuncSetAttribute(lattice_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 1;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lattice_kernel, warps * 32, smem));
-    per_sm = std::max(1, per_sm);
-    const int64_t want_blocks = ((int64_t)n_sent + warps - 1) / warps;
-    const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(want_blocks, (int64_t)t->sm_count * per_sm));
-
-    if (getenv("LT_DEBUG"))
-        fprintf(stderr, "[lt] lattice kernel: units %d hcap %d max_str %d, %zu B/warp, %d warps/CTA, %zu B/CTA, %d CTAs/SM\n", units, hcap,
-                max_str, warp_smem, warps, smem, per_sm);
-    if (b->use_retry) {
-        if (int rc = ensure(b->retry, (size_t)std::max(1, n_sent) * 4)) return rc;
-        A.retry_list = static_cast<uint32_t*>(b->retry.p);
-        A.retry_count = ctl + kCtlRetryCount;
-    }
-    if (b->timed) CU(cudaEventRecord(b->ev[0], st));
-    if (n_sent > 0) LT_LAUNCH(lattice_kernel, grid, warps * 32, smem, st, t->dev, A);
-    CU(cudaGetLastError());
-    if (b->use_retry && n_sent > 0) {
-        // retry pass: the few sentences with an eojeol beyond `hcap` hits, with a staging area of their own size
-        int rh = b->retry_hcap;
-        if (rh & 1) ++rh;
-        const int r_units = lcap + 8;
-        const size_t r_warp = lattice_warp_smem(r_units, rh, max_str);
-        if (r_warp > kSmemBudget)
-            return fail(LT_ERR_CAPACITY, "one eojeol yields more than %d lattice candidates; the staging buffer cannot grow further", rh / 2);
-        const int r_warps = (int)std::max<size_t>(1, std::min<size_t>(2, kSmemBudget / r_warp));
-        const size_t r_smem = r_warp * r_warps;
-        void (*retry_kernel)(const DevTables, const LatticeArgs) = lt::lattice_kernel<0, 0>;
-        CU(cudaFuncSetAttribute(retry_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(r_smem, smem)));
-        LatticeArgs R = A;
-        R.units = r_units;
-        R.hcap = rh;
-        R.queue = ctl + kCtlRetryQueue;
-        R.retry_pass = 1;
-        int r_per_sm = 1;
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r_per_sm, retry_kernel, r_warps * 32, r_smem));
-        LT_LAUNCH(retry_kernel, (unsigned)(t->sm_count * std::max(1, r_per_sm)), r_warps * 32, r_smem, st, t->dev, R);
-        CU(cudaGetLastError());
-    }
-    if (b->timed) CU(cudaEventRecord(b->ev[1], st));
-    b->have_lattice = true;
-    b->have_paths = false;
-    b->resolved = false;
+    P.smem = P.warp_smem * P.warps;
+    P.fn = (uclass == 64 && hcap == kLatDefaultHcap) ? lt::lattice_kernel<64, kLatDefaultHcap>
+         : (uclass == 128 && hcap == kLatDefaultHcap) ? lt::lattice_kernel<128, kLatDefaultHcap>
+         : (uclass == 64 && hcap == 2 * kLatDefaultHcap) ? lt::lattice_kernel<64, 2 * kLatDefaultHcap>
+         : (uclass == 128 && hcap == 2 * kLatDefaultHcap) ? lt::lattice_kernel<128, 2 * kLatDefaultHcap>
+         : lt::lattice_kernel<0, 0>;
+    if (int rc = smem_limit(t, P.fn, P.smem)) return rc;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&P.per_sm, P.fn, P.warps * 32, P.smem));
+    P.per_sm = std::max(1, P.per_sm);
+    if (b->debug)
+        fprintf(stderr, "[lt] lattice kernel%s: units %d hcap %d max_str %d, %zu B/warp, %d warps/CTA, %zu B/CTA, %d CTAs/SM\n",
+                retry_pass ? " (retry pass)" : "", units, hcap, max_str, P.warp_smem, P.warps, P.smem, P.per_sm);
+    b->lattice_plans.push_back(P);
+    *out = &b->lattice_plans.back();
     return LT_OK;
 }
 
-static int launch_beam(lt_batch* b, cudaStream_t st) {
+static int beam_plan(lt_batch* b, int lcap, int beam_size, const BeamPlan** out) {
     lt_tables* t = b->tables;
-    const int beam_size = b->beam;
-    const int n_sent = b->n_sent;
-    const size_t nu = (size_t)b->n_units + 1;
-
-    if (int rc = ensure(b->path_tmp, nu * sizeof(lt_edge))) return rc;
-    if (int rc = ensure(b->path_out, nu * sizeof(lt_edge))) return rc;
-    if (int rc = ensure(b->path_len, (size_t)(n_sent + 1) * 4)) return rc;
-    if (int rc = ensure(b->path_off, (size_t)(n_sent + 1) * 4)) return rc;
-    if (int rc = ensure(b->scores, (size_t)std::max(1, n_sent) * 8)) return rc;
-
+    // sentence arrays: common sizes are template parameters of the kernel (for beams 5 and 10)
+    const int uclass = (beam_size == 5 || beam_size == 10) ? beam_units_class(lcap) : 0;
+    const int units = uclass ? uclass : lcap + 8;
+    for (const BeamPlan& p : b->beam_plans)
+        if (p.units == units && p.beam == beam_size) { *out = &p; return LT_OK; }
     const size_t dense_bytes = ((size_t)t->dev.n_tri * dense_block_bytes(t->dev.n_tags) + 15) & ~(size_t)15;
     // CTA shape: the warps per CTA (1..8) that keep the most warps resident on an SM under the kernel's
     // 128 registers per thread (16 warps) and the per-warp shared memory; ties go to 4-warp CTAs
@@ -622,32 +638,171 @@ static int launch_beam(lt_batch* b, cudaStream_t st) {
         }
         return best;
     };
-    // sentence arrays: common sizes are template parameters of the kernel (for beams 5 and 10)
-    int units = b->lcap + 8;
-    const int uclass = (beam_size == 5 || beam_size == 10) ? beam_units_class(b->lcap) : 0;
-    if (uclass) units = uclass;
     // back-pointers live in shared memory when that does not lower the residency
     const size_t smem_hbm_trail = beam_warp_smem(units, beam_size, t->dev.n_funcs, false);
     const size_t smem_own_trail = beam_warp_smem(units, beam_size, t->dev.n_funcs, true);
     const int w_hbm = best_warps(smem_hbm_trail), w_own = best_warps(smem_own_trail);
     if (w_hbm == 0)
-        return fail(LT_ERR_INVALID, "sentence length %d with beam %d does not fit the beam kernel's shared memory", b->lcap, beam_size);
-    bool trail_smem = w_own > 0 && resident_warps(smem_own_trail, w_own) >= resident_warps(smem_hbm_trail, w_hbm);
-    if (const char* env = getenv("LT_TRAIL_SMEM")) trail_smem = trail_smem && atoi(env) != 0;
-    if (!trail_smem)
+        return fail(LT_ERR_INVALID, "sentence length %d with beam %d does not fit the beam kernel's shared memory", lcap, beam_size);
+    BeamPlan P;
+    P.units = units;
+    P.beam = beam_size;
+    P.trail_smem = b->trail_smem_ok && w_own > 0 && resident_warps(smem_own_trail, w_own) >= resident_warps(smem_hbm_trail, w_hbm);
+    P.warp_smem = P.trail_smem ? smem_own_trail : smem_hbm_trail;
+    P.warps = P.trail_smem ? w_own : w_hbm;
+    P.smem = dense_bytes + P.warp_smem * P.warps;
+    // common beam sizes, sentence-array sizes and the (RegularizationScore, SimpleTrigramFeatureScore)
+    // score program get their own instantiation (compile-time array offsets, unrolled scorer loop)
+    const bool reg_tri = t->dev.n_funcs == 2 && t->dev.funcs[0].kind == LT_FUNC_REG && t->dev.funcs[1].kind == LT_FUNC_TRIGRAM;
+    if (beam_size == 5 && uclass == 64) P.fn = reg_tri ? beam_kernel<2, 5, 64, 1> : beam_kernel<2, 5, 64, 0>;
+    else if (beam_size == 5 && uclass == 128) P.fn = reg_tri ? beam_kernel<2, 5, 128, 1> : beam_kernel<2, 5, 128, 0>;
+    else if (beam_size == 5) P.fn = reg_tri ? beam_kernel<2, 5, 0, 1> : beam_kernel<2, 5, 0, 0>;
+    else if (beam_size == 10 && uclass == 64) P.fn = reg_tri ? beam_kernel<2, 10, 64, 1> : beam_kernel<2, 10, 64, 0>;
+    else if (beam_size == 10 && uclass == 128) P.fn = reg_tri ? beam_kernel<2, 10, 128, 1> : beam_kernel<2, 10, 128, 0>;
+    else if (beam_size == 10) P.fn = reg_tri ? beam_kernel<2, 10, 0, 1> : beam_kernel<2, 10, 0, 0>;
+    else if (beam_size <= kRankMaxBeam) P.fn = reg_tri ? beam_kernel<2, 0, 0, 1> : beam_kernel<2, 0, 0, 0>;
+    else if (beam_size == 32) P.fn = reg_tri ? beam_kernel<1, 32, 0, 1> : beam_kernel<1, 32, 0, 0>;
+    else if (beam_size <= 32) P.fn = reg_tri ? beam_kernel<1, 0, 0, 1> : beam_kernel<1, 0, 0, 0>;
+    else P.fn = reg_tri ? beam_kernel<0, 0, 0, 1> : beam_kernel<0, 0, 0, 0>;
+    if (int rc = smem_limit(t, P.fn, P.smem)) return rc;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&P.per_sm, P.fn, P.warps * 32, P.smem));
+    P.per_sm = std::max(1, P.per_sm);
+    if (b->debug)
+        fprintf(stderr, "[lt] beam kernel: beam %d units %d, %zu B/warp, %d warps/CTA, %zu B/CTA, %d CTAs/SM, trail in %s\n", beam_size,
+                units, P.warp_smem, P.warps, P.smem, P.per_sm, P.trail_smem ? "shared memory" : "HBM");
+    b->beam_plans.push_back(P);
+    *out = &b->beam_plans.back();
+    return LT_OK;
+}
+
+// ---- launches ----------------------------------------------------------------------------------
+static int launch_lattice(lt_batch* b, cudaStream_t st) {
+    lt_tables* t = b->tables;
+    const int n_sent = b->n_sent;
+    const int64_t n_units = b->n_units;
+    const int lcap = b->lcap;
+    const LatticePlan* P = nullptr;
+    if (int rc = lattice_plan(b, lcap, b->hcap, false, &P)) return rc;
+    b->last_lattice_plan = P;
+
+    const size_t nu = (size_t)n_units + 1;
+    if (int rc = ensure(b->pos, nu * sizeof(uint2))) return rc;
+    if (int rc = ensure(b->sent_len, (size_t)std::max(1, n_sent) * 4)) return rc;
+    if (int rc = ensure(b->sent_edges, (size_t)std::max(1, n_sent) * 4)) return rc;
+    if (int rc = ensure(b->status, (size_t)std::max(1, n_sent) * 4)) return rc;
+    if (int rc = ensure(b->counters, 8 * sizeof(unsigned long long))) return rc;
+    if (int rc = ensure(b->ctl, kCtlWords * sizeof(unsigned int))) return rc;
+    if (!b->edge_cap_fixed) {
+        const uint64_t guess = (uint64_t)n_units * 3 + 4096;
+        if (b->edge_cap < guess) b->edge_cap = (uint32_t)std::min<uint64_t>(guess, 0xFFFFFFF0ull);
+    }
+    if (int rc = ensure(b->edges, (size_t)b->edge_cap * sizeof(lt_edge))) return rc;
+
+    LatticeArgs A{};
+    A.text = b->d_text;
+    A.sent_off = b->d_sent_off;
+    A.n_sent = n_sent;
+    A.units = P->units;
+    A.hcap = P->hcap;
+    A.max_str = std::max(1, t->dev.max_str);
+    A.pos = static_cast<uint2*>(b->pos.p);
+    A.edges = static_cast<lt_edge*>(b->edges.p);
+    A.edge_cap = b->edge_cap;
+    A.max_units = lcap;
+    A.mode = b->lookup_mode;
+    unsigned int* ctl = static_cast<unsigned int*>(b->ctl.p);
+    A.cursor = reinterpret_cast<unsigned long long*>(ctl + kCtlCursor);
+    A.flags = ctl + kCtlFlags;
+    A.sent_len = static_cast<int32_t*>(b->sent_len.p);
+    A.sent_edges = static_cast<int32_t*>(b->sent_edges.p);
+    A.status = static_cast<int32_t*>(b->status.p);
+    A.counters = static_cast<unsigned long long*>(b->counters.p);
+    A.queue = ctl + kCtlLatticeQueue;
+    A.order = nullptr;
+    // prologue: control words and counters zeroed, work order (longest sentences first)
+    uint32_t* order = nullptr;
+    if (b->sort_by_length && n_sent > 1) {
+        if (int rc = ensure(b->order, (size_t)n_sent * 4)) return rc;
+        order = static_cast<uint32_t*>(b->order.p);
+    }
+    LT_LAUNCH(batch_prologue, 1, 1024, 0, st, b->d_sent_off, n_sent, order, ctl, kCtlWords,
+              static_cast<unsigned long long*>(b->counters.p), 8);
+    CU(cudaGetLastError());
+    b->launches += 1;
+    A.order = order;
+    b->beam_state_clean = true;
+
+    const int64_t want_blocks = ((int64_t)n_sent + P->warps - 1) / P->warps;
+    const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(want_blocks, (int64_t)t->sm_count * P->per_sm));
+    if (b->use_retry) {
+        if (int rc = ensure(b->retry, (size_t)std::max(1, n_sent) * 4)) return rc;
+        A.retry_list = static_cast<uint32_t*>(b->retry.p);
+        A.retry_count = ctl + kCtlRetryCount;
+    }
+    if (b->timed) CU(cudaEventRecord(b->ev[0], st));
+    if (n_sent > 0) {
+        LT_LAUNCH(P->fn, grid, P->warps * 32, P->smem, st, t->dev, A);
+        b->launches += 1;
+    }
+    CU(cudaGetLastError());
+    if (b->use_retry && n_sent > 0) {
+        // retry pass: the few sentences with an eojeol beyond `hcap` hits, with a staging area of their own size
+        const LatticePlan* Rp = nullptr;
+        if (int rc = lattice_plan(b, lcap, b->retry_hcap, true, &Rp)) return rc;
+        LatticeArgs R = A;
+        R.units = Rp->units;
+        R.hcap = Rp->hcap;
+        R.queue = ctl + kCtlRetryQueue;
+        R.retry_pass = 1;
+        LT_LAUNCH(Rp->fn, (unsigned)(t->sm_count * Rp->per_sm), Rp->warps * 32, Rp->smem, st, t->dev, R);
+        CU(cudaGetLastError());
+        b->launches += 1;
+    }
+    if (b->timed) CU(cudaEventRecord(b->ev[1], st));
+    b->have_lattice = true;
+    b->have_paths = false;
+    b->have_kbest = false;
+    b->resolved = false;
+    return LT_OK;
+}
+
+static int launch_beam(lt_batch* b, cudaStream_t st, bool kbest) {
+    lt_tables* t = b->tables;
+    const int beam_size = b->beam;
+    const int n_sent = b->n_sent;
+    const size_t nu = (size_t)b->n_units + 1;
+
+    if (int rc = ensure(b->path_tmp, nu * sizeof(lt_edge))) return rc;
+    if (int rc = ensure(b->path_out, nu * sizeof(lt_edge))) return rc;
+    if (int rc = ensure(b->path_len, (size_t)(n_sent + 1) * 4)) return rc;
+    if (int rc = ensure(b->path_off, (size_t)(n_sent + 1) * 4)) return rc;
+    if (int rc = ensure(b->scores, (size_t)std::max(1, n_sent) * 8)) return rc;
+    const size_t nk = (size_t)n_sent * beam_size;
+    if (kbest) {
+        if (nk + 1 > 0x7FFFFFFFull || nu * beam_size > 0x7FFFFFFFull)
+            return fail(LT_ERR_CAPACITY, "k-best output of %d sentences x beam %d is too large for one batch; split it", n_sent, beam_size);
+        if (int rc = ensure(b->kb_tmp, nu * beam_size * sizeof(lt_edge))) return rc;
+        if (int rc = ensure(b->kb_out, nu * beam_size * sizeof(lt_edge))) return rc;
+        if (int rc = ensure(b->kb_len, (nk + 1) * 4)) return rc;
+        if (int rc = ensure(b->kb_off, (nk + 1) * 4)) return rc;
+        if (int rc = ensure(b->kb_scores, std::max<size_t>(1, nk) * 8)) return rc;
+        if (int rc = ensure(b->kb_count, (size_t)std::max(1, n_sent) * 4)) return rc;
+    }
+
+    const BeamPlan* P = nullptr;
+    if (int rc = beam_plan(b, b->lcap, beam_size, &P)) return rc;
+    b->last_beam_plan = P;
+    if (!P->trail_smem)
         if (int rc = ensure(b->trail, nu * (size_t)beam_size * 8)) return rc;
-    const size_t group_smem = trail_smem ? smem_own_trail : smem_hbm_trail;
-    const int warps = trail_smem ? w_own : w_hbm;
-    const size_t smem = dense_bytes + group_smem * warps;
 
     unsigned int* ctl = static_cast<unsigned int*>(b->ctl.p);
     BeamArgs A{};
     A.text = b->d_text;
     A.sent_off = b->d_sent_off;
     A.n_sent = n_sent;
-    A.units = units;
+    A.units = P->units;
     A.beam = beam_size;
-    A.warps = warps;
+    A.warps = P->warps;
     A.pos = static_cast<const uint2*>(b->pos.p);
     A.edges = static_cast<const lt_edge*>(b->edges.p);
     A.status = static_cast<const int32_t*>(b->status.p);
@@ -659,41 +814,30 @@ static int launch_beam(lt_batch* b, cudaStream_t st) {
     A.counters = static_cast<unsigned long long*>(b->counters.p);
     A.queue = ctl + kCtlBeamQueue;
     A.order = (b->sort_by_length && n_sent > 1) ? static_cast<const uint32_t*>(b->order.p) : nullptr;
-    A.trail_smem = trail_smem ? 1 : 0;
+    A.trail_smem = P->trail_smem ? 1 : 0;
+    A.imp = b->imported ? static_cast<const H2*>(b->imp.p) : nullptr;
+    A.kbest = kbest ? 1 : 0;
+    A.kb_tmp = static_cast<lt_edge*>(b->kb_tmp.p);
+    A.kb_len = static_cast<int32_t*>(b->kb_len.p);
+    A.kb_scores = static_cast<double*>(b->kb_scores.p);
+    A.kb_count = static_cast<int32_t*>(b->kb_count.p);
 
-    // common beam sizes, sentence-array sizes and the (RegularizationScore, SimpleTrigramFeatureScore)
-    // score program get their own instantiation (compile-time array offsets, unrolled scorer loop)
-    const bool reg_tri = t->dev.n_funcs == 2 && t->dev.funcs[0].kind == LT_FUNC_REG && t->dev.funcs[1].kind == LT_FUNC_TRIGRAM;
-    void (*kernel)(const DevTables, const BeamArgs);
-    if (beam_size == 5 && uclass == 64) kernel = reg_tri ? beam_kernel<2, 5, 64, 1> : beam_kernel<2, 5, 64, 0>;
-    else if (beam_size == 5 && uclass == 128) kernel = reg_tri ? beam_kernel<2, 5, 128, 1> : beam_kernel<2, 5, 128, 0>;
-    else if (beam_size == 5) kernel = reg_tri ? beam_kernel<2, 5, 0, 1> : beam_kernel<2, 5, 0, 0>;
-    else if (beam_size == 10 && uclass == 64) kernel = reg_tri ? beam_kernel<2, 10, 64, 1> : beam_kernel<2, 10, 64, 0>;
-    else if (beam_size == 10 && uclass == 128) kernel = reg_tri ? beam_kernel<2, 10, 128, 1> : beam_kernel<2, 10, 128, 0>;
-    else if (beam_size == 10) kernel = reg_tri ? beam_kernel<2, 10, 0, 1> : beam_kernel<2, 10, 0, 0>;
-    else if (beam_size <= kRankMaxBeam) kernel = reg_tri ? beam_kernel<2, 0, 0, 1> : beam_kernel<2, 0, 0, 0>;
-    else if (beam_size == 32) kernel = reg_tri ? beam_kernel<1, 32, 0, 1> : beam_kernel<1, 32, 0, 0>;
-    else if (beam_size <= 32) kernel = reg_tri ? beam_kernel<1, 0, 0, 1> : beam_kernel<1, 0, 0, 0>;
-    else kernel = reg_tri ? beam_kernel<0, 0, 0, 1> : beam_kernel<0, 0, 0, 0>;
-    CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 1;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, warps * 32, smem));
-    per_sm = std::max(1, per_sm);
-    const int64_t want_blocks = ((int64_t)n_sent + warps - 1) / warps;
-    const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(want_blocks, (int64_t)t->sm_count * per_sm));
-    if (getenv("LT_DEBUG"))
-        fprintf(stderr, "[lt] beam kernel: beam %d units %d, %zu B/warp, %d warps/CTA, %zu B/CTA, %d CTAs/SM, trail in %s\n", beam_size,
-                units, group_smem, warps, smem, per_sm, trail_smem ? "shared memory" : "HBM");
+    const int64_t want_blocks = ((int64_t)n_sent + P->warps - 1) / P->warps;
+    const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(want_blocks, (int64_t)t->sm_count * P->per_sm));
 
     // queue cursor and counters of this stage are zero after the batch prologue; a second search of the
     // same lattice resets them (path_len needs no clearing: the kernel writes every entry)
     if (!b->beam_state_clean) {
         LT_LAUNCH(beam_reset, 1, 32, 0, st, ctl + kCtlBeamQueue, static_cast<unsigned long long*>(b->counters.p) + 3, 4);
         CU(cudaGetLastError());
+        b->launches += 1;
     }
     b->beam_state_clean = false;
     if (b->timed) CU(cudaEventRecord(b->ev[5], st));
-    if (n_sent > 0) LT_LAUNCH(kernel, grid, warps * 32, smem, st, t->dev, A);
+    if (n_sent > 0) {
+        LT_LAUNCH(P->fn, grid, P->warps * 32, P->smem, st, t->dev, A);
+        b->launches += 1;
+    }
     CU(cudaGetLastError());
     if (b->timed) CU(cudaEventRecord(b->ev[6], st));
     if (int rc = scan_u32(b, reinterpret_cast<const uint32_t*>(b->path_len.p), static_cast<uint32_t*>(b->path_off.p),
@@ -702,12 +846,26 @@ static int launch_beam(lt_batch* b, cudaStream_t st) {
     if (n_sent > 0) {
         const unsigned pgrid = (unsigned)std::min<int64_t>(((int64_t)n_sent + 7) / 8, (int64_t)t->sm_count * 8);
         LT_LAUNCH(pack_paths, pgrid, 256, 0, st, static_cast<const lt_edge*>(b->path_tmp.p), b->d_sent_off,
-                                          static_cast<const uint32_t*>(b->path_off.p), n_sent,
-                                          static_cast<lt_edge*>(b->path_out.p));
+                  static_cast<const uint32_t*>(b->path_off.p), n_sent, static_cast<lt_edge*>(b->path_out.p));
         CU(cudaGetLastError());
+        b->launches += 1;
+    }
+    if (kbest) {
+        // (kb_len[n_sent * beam] is the scan's sentinel entry; the kernel cannot know it is the last one)
+        CU(cudaMemsetAsync(static_cast<int32_t*>(b->kb_len.p) + nk, 0, 4, st));
+        if (int rc = scan_u32(b, reinterpret_cast<const uint32_t*>(b->kb_len.p), static_cast<uint32_t*>(b->kb_off.p), (int64_t)nk + 1, st))
+            return rc;
+        if (n_sent > 0) {
+            const unsigned pgrid = (unsigned)std::min<int64_t>(((int64_t)nk + 7) / 8, (int64_t)t->sm_count * 8);
+            LT_LAUNCH(pack_paths_k, pgrid, 256, 0, st, static_cast<const lt_edge*>(b->kb_tmp.p), b->d_sent_off,
+                      static_cast<const uint32_t*>(b->kb_off.p), n_sent, beam_size, static_cast<lt_edge*>(b->kb_out.p));
+            CU(cudaGetLastError());
+            b->launches += 1;
+        }
     }
     if (b->timed) CU(cudaEventRecord(b->ev[7], st));
     b->have_paths = true;
+    b->have_kbest = kbest;
     b->resolved = false;
     return LT_OK;
 }
@@ -715,12 +873,51 @@ static int launch_beam(lt_batch* b, cudaStream_t st) {
 // The retry pass is meant for outliers: when more than 1 / 32 of a batch's sentences needed it, the main
 // pass's staging area doubles for the batches to come (as long as the retry pass's is larger).
 static void adapt_staging(lt_batch* b, unsigned int retried) {
+    b->last_retried = retried;
     if (!b->use_retry || b->n_sent < 64) return;
     if ((uint64_t)retried * 32 > (uint64_t)b->n_sent && b->hcap * 2 < b->retry_hcap) b->hcap *= 2;
 }
 
-// Wait for the batch and, if the lattice outgrew a buffer (edge array or per-warp staging), enlarge
-// it and run the stages again — still on the device; capacities are sticky for later batches.
+static uint64_t cursor_of(const unsigned int* ctl) { return (uint64_t)ctl[kCtlCursor] | ((uint64_t)ctl[kCtlCursor + 1] << 32); }
+
+// The control words say whether the lattice outgrew a buffer (edge array or per-warp staging); if so,
+// enlarge it and run the stages again — still on the device; capacities are sticky for later batches.
+// Returns 1 when a rerun was launched, 0 when the batch is complete, < 0 (negated code) on failure.
+static int check_and_rerun(lt_batch* b, const unsigned int* ctl, cudaStream_t st) {
+    const bool edge_over = ctl[kCtlFlags + kFlagEdgeOverflow] != 0;
+    const bool stage_over = ctl[kCtlFlags + kFlagStageOverflow] != 0;
+    if (!edge_over && !stage_over) {
+        b->n_edges = (int64_t)cursor_of(ctl);
+        b->resolved = true;
+        adapt_staging(b, ctl[kCtlRetryCount]);
+        return 0;
+    }
+    if (edge_over) {
+        const uint64_t cur = cursor_of(ctl);
+        const uint64_t need = cur + cur / 4 + 4096;
+        if (need > 0xFFFFFFF0ull) return -fail(LT_ERR_CAPACITY, "the batch produces more than 2^32 lattice edges; split it");
+        b->edge_cap = (uint32_t)need;
+    }
+    if (stage_over) {
+        // first time: switch the two-pass scheme on (the main pass keeps its small staging area and its
+        // residency); afterwards the retry pass's staging area doubles
+        const int max_str = std::max(1, b->tables->dev.max_str);
+        const int next = b->use_retry ? b->retry_hcap * 2 : std::max(512, b->hcap * 4);
+        if (lattice_warp_smem(b->lcap + 8, next, max_str) > kSmemBudget)
+            return -fail(LT_ERR_CAPACITY, "one eojeol yields more than %d lattice candidates; the staging buffer cannot grow further",
+                         b->use_retry ? b->retry_hcap : b->hcap);
+        b->use_retry = true;
+        b->retry_hcap = next;
+    }
+    ++b->reruns;
+    const bool want_paths = b->have_paths, want_kbest = b->have_kbest;
+    if (int rc = launch_lattice(b, st)) return -rc;
+    if (want_paths)
+        if (int rc = launch_beam(b, st, want_kbest)) return -rc;
+    return 1;
+}
+
+// Wait for the batch and settle its buffers (see check_and_rerun).
 static int resolve(lt_batch* b) {
     if (!b->have_lattice || b->resolved) return LT_OK;
     cudaStream_t st = b->last_stream;
@@ -728,43 +925,18 @@ static int resolve(lt_batch* b) {
         unsigned int ctl[kCtlWords];
         CU(cudaMemcpyAsync(ctl, b->ctl.p, sizeof ctl, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
-        const bool edge_over = ctl[kCtlFlags + kFlagEdgeOverflow] != 0;
-        const bool stage_over = ctl[kCtlFlags + kFlagStageOverflow] != 0;
-        if (!edge_over && !stage_over) {
-            b->n_edges = ctl[kCtlCursor];
-            b->resolved = true;
-            adapt_staging(b, ctl[kCtlRetryCount]);
-            return LT_OK;
-        }
-        if (edge_over) {
-            const uint64_t need = (uint64_t)ctl[kCtlCursor] + ctl[kCtlCursor] / 4 + 4096;
-            if (need > 0xFFFFFFF0ull) return fail(LT_ERR_CAPACITY, "the batch produces more than 2^32 lattice edges; split it");
-            b->edge_cap = (uint32_t)need;
-        }
-        if (stage_over) {
-            // first time: switch the two-pass scheme on (the main pass keeps its small staging area and its
-            // residency); afterwards the retry pass's staging area doubles
-            const int max_str = std::max(1, b->tables->dev.max_str);
-            const int next = b->use_retry ? b->retry_hcap * 2 : std::max(512, b->hcap * 4);
-            if (lattice_warp_smem(b->lcap + 8, next, max_str) > kSmemBudget)
-                return fail(LT_ERR_CAPACITY, "one eojeol yields more than %d lattice candidates; the staging buffer cannot grow further",
-                            b->use_retry ? b->retry_hcap : b->hcap);
-            b->use_retry = true;
-            b->retry_hcap = next;
-        }
-        ++b->reruns;
-        const bool want_paths = b->have_paths;
-        if (int rc = launch_lattice(b, st)) return rc;
-        if (want_paths)
-            if (int rc = launch_beam(b, st)) return rc;
+        const int r = check_and_rerun(b, ctl, st);
+        if (r < 0) return -r;
+        if (r == 0) return LT_OK;
     }
     return fail(LT_ERR_CAPACITY, "lattice buffers did not converge");
 }
 
 extern "C" int lt_lattice(lt_batch* b, const uint16_t* d_text, const int32_t* d_sent_off, int32_t n_sent,
                           int64_t n_units, int32_t max_sent_units, void* stream) {
-    if (!b || n_sent < 0 || n_units < 0) return fail(LT_ERR_INVALID, "bad argument");
-    CU(cudaSetDevice(b->tables->device));
+    if (!b || n_sent < 0 || n_units < 0 || max_sent_units < 0) return fail(LT_ERR_INVALID, "bad argument");
+    if (n_sent > 0 && (!d_text || !d_sent_off)) return fail(LT_ERR_INVALID, "null input pointer");
+    ON_DEVICE(b->tables->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     b->last_stream = st;
     b->d_text = d_text;
@@ -772,22 +944,28 @@ extern "C" int lt_lattice(lt_batch* b, const uint16_t* d_text, const int32_t* d_
     b->n_sent = n_sent;
     b->n_units = n_units;
     b->max_sent_units = max_sent_units;
-    b->have_lattice = b->have_paths = false;
+    b->have_lattice = b->have_paths = b->have_kbest = false;
+    b->imported = false;
     b->beam = 0;
-    b->lcap = std::max(8, (max_sent_units + 7) & ~7);
-    if (b->lcap > 4088) return fail(LT_ERR_INVALID, "a sentence has %d code units; at most 4088 are supported", max_sent_units);
+    // the per-warp arrays are sized for the longest sentence the caller reports, capped at what fits shared
+    // memory; the kernels skip any sentence beyond that size (LT_SENT_TOO_LONG) instead of trusting the number
+    const int32_t limit = unit_limit(b->tables);
+    b->lcap = std::max(8, (std::min(max_sent_units, limit) + 7) & ~7);
     return launch_lattice(b, st);
 }
 
-extern "C" int lt_beam(lt_batch* b, int32_t beam_size, void* stream) {
+static int beam_entry(lt_batch* b, int32_t beam_size, void* stream, bool kbest) {
     if (!b || !b->have_lattice) return fail(LT_ERR_INVALID, "lt_beam needs a lattice: call lt_lattice first");
     if (beam_size < 1 || beam_size > LT_MAX_BEAM) return fail(LT_ERR_INVALID, "beam_size must be in 1..%d", LT_MAX_BEAM);
-    CU(cudaSetDevice(b->tables->device));
+    ON_DEVICE(b->tables->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     b->last_stream = st;
     b->beam = beam_size;
-    return launch_beam(b, st);
+    return launch_beam(b, st, kbest);
 }
+
+extern "C" int lt_beam(lt_batch* b, int32_t beam_size, void* stream) { return beam_entry(b, beam_size, stream, false); }
+extern "C" int lt_beam_kbest(lt_batch* b, int32_t beam_size, void* stream) { return beam_entry(b, beam_size, stream, true); }
 
 extern "C" int lt_tag_batch_device(lt_batch* b, const uint16_t* d_text, const int32_t* d_sent_off, int32_t n_sent,
                                    int64_t n_units, int32_t max_sent_units, int32_t beam_size, void* stream) {
@@ -797,7 +975,7 @@ extern "C" int lt_tag_batch_device(lt_batch* b, const uint16_t* d_text, const in
 
 extern "C" int lt_lattice_size(lt_batch* b, int64_t* n_edges) {
     if (!b || !b->have_lattice || !n_edges) return fail(LT_ERR_INVALID, "no lattice");
-    CU(cudaSetDevice(b->tables->device));
+    ON_DEVICE(b->tables->device);
     if (int rc = resolve(b)) return rc;
     *n_edges = b->n_edges;
     return LT_OK;
@@ -805,9 +983,10 @@ extern "C" int lt_lattice_size(lt_batch* b, int64_t* n_edges) {
 
 extern "C" int lt_lattice_fetch(lt_batch* b, lt_edge* edges, int64_t edge_cap, int64_t* end_off) {
     if (!b || !b->have_lattice) return fail(LT_ERR_INVALID, "no lattice");
-    CU(cudaSetDevice(b->tables->device));
+    ON_DEVICE(b->tables->device);
     if (int rc = resolve(b)) return rc;
     if (edge_cap < b->n_edges) return fail(LT_ERR_CAPACITY, "edge buffer holds %lld, need %lld", (long long)edge_cap, (long long)b->n_edges);
+    if (b->n_edges > 0 && !edges) return fail(LT_ERR_INVALID, "null output pointer");
     // the device keeps each sentence's edges wherever its reservation landed; hand them out in
     // sentence order (CSR by end position)
     std::vector<lt_edge> raw((size_t)b->n_edges);
@@ -818,16 +997,26 @@ extern "C" int lt_lattice_fetch(lt_batch* b, lt_edge* edges, int64_t edge_cap, i
     for (int64_t i = 0; i < b->n_units; ++i) {
         if (end_off) end_off[i] = out;
         const uint2 pc = pos[i];
-        if ((int64_t)pc.x + pc.y > b->n_edges) return fail(LT_ERR_INVALID, "corrupt lattice index");
+        if ((int64_t)pc.x + pc.y > b->n_edges || out + pc.y > b->n_edges) return fail(LT_ERR_INVALID, "corrupt lattice index");
         for (uint32_t k = 0; k < pc.y; ++k) edges[out++] = raw[pc.x + k];
     }
     if (end_off) end_off[b->n_units] = out;
     return LT_OK;
 }
 
+extern "C" int lt_lattice_status(lt_batch* b, int32_t* status, int32_t* sent_len) {
+    if (!b || !b->have_lattice) return fail(LT_ERR_INVALID, "no lattice");
+    ON_DEVICE(b->tables->device);
+    if (int rc = resolve(b)) return rc;
+    if (b->n_sent == 0) return LT_OK;
+    if (status) CU(cudaMemcpy(status, b->status.p, (size_t)b->n_sent * 4, cudaMemcpyDeviceToHost));
+    if (sent_len) CU(cudaMemcpy(sent_len, b->sent_len.p, (size_t)b->n_sent * 4, cudaMemcpyDeviceToHost));
+    return LT_OK;
+}
+
 extern "C" int lt_paths_size(lt_batch* b, int64_t* n_words) {
     if (!b || !b->have_paths || !n_words) return fail(LT_ERR_INVALID, "no paths");
-    CU(cudaSetDevice(b->tables->device));
+    ON_DEVICE(b->tables->device);
     if (int rc = resolve(b)) return rc;
     uint32_t total = 0;
     CU(cudaMemcpyAsync(&total, static_cast<uint32_t*>(b->path_off.p) + b->n_sent, 4, cudaMemcpyDeviceToHost, b->last_stream));
@@ -836,63 +1025,126 @@ extern "C" int lt_paths_size(lt_batch* b, int64_t* n_words) {
     return LT_OK;
 }
 
+// Results to the host in (normally) ONE round trip: the control words (overflow flags), the small
+// per-sentence arrays and a speculative prefix of the path records — as many as the previous batch
+// produced plus a margin — travel together; only when the batch holds more records than that (or
+// needed a rerun) does a second copy follow.
 static int fetch_paths(lt_batch* b, int32_t* path_off, lt_edge* path_edges, int64_t path_cap, double* scores,
                        int32_t* status, cudaStream_t st) {
     const int n = b->n_sent;
+    if (!path_off || (n > 0 && (!scores || !status))) return fail(LT_ERR_INVALID, "null output pointer");
     if (n == 0) {
-        if (path_off) path_off[0] = 0;
+        path_off[0] = 0;
         return LT_OK;
     }
-    // one round trip: control words (overflow flags) travel with the small per-sentence arrays
     unsigned int ctl[kCtlWords];
+    int64_t copied = 0;
     for (int round = 0; round < 12; ++round) {
+        int64_t guess = b->words_hint < 0 ? b->n_units / 2 + 64 : b->words_hint + b->words_hint / 8 + 64;
+        guess = std::min<int64_t>(std::min<int64_t>(guess, path_cap), b->n_units);
+        if (!path_edges) guess = 0;
         CU(cudaMemcpyAsync(ctl, b->ctl.p, sizeof ctl, cudaMemcpyDeviceToHost, st));
         CU(cudaMemcpyAsync(path_off, b->path_off.p, (size_t)(n + 1) * 4, cudaMemcpyDeviceToHost, st));
         CU(cudaMemcpyAsync(scores, b->scores.p, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
         CU(cudaMemcpyAsync(status, b->status.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+        if (guess > 0) CU(cudaMemcpyAsync(path_edges, b->path_out.p, (size_t)guess * sizeof(lt_edge), cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
-        if (ctl[kCtlFlags + kFlagEdgeOverflow] == 0 && ctl[kCtlFlags + kFlagStageOverflow] == 0) {
-            b->n_edges = ctl[kCtlCursor];
-            b->resolved = true;
-            adapt_staging(b, ctl[kCtlRetryCount]);
-            break;
-        }
-        b->resolved = false;
-        if (int rc = resolve(b)) return rc;      // grows the buffers and reruns both stages
+        copied = guess;
+        const int r = check_and_rerun(b, ctl, st);
+        if (r < 0) return -r;
+        if (r == 0) break;
+        if (round == 11) return fail(LT_ERR_CAPACITY, "lattice buffers did not converge");
     }
     const int64_t total = path_off[n];
+    b->words_hint = total;
     if (total > path_cap) return fail(LT_ERR_CAPACITY, "path buffer holds %lld records, need %lld", (long long)path_cap, (long long)total);
-    if (total) CU(cudaMemcpyAsync(path_edges, b->path_out.p, (size_t)total * sizeof(lt_edge), cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
+    if (total > 0 && !path_edges) return fail(LT_ERR_INVALID, "null output pointer");
+    if (total > copied) {
+        CU(cudaMemcpyAsync(path_edges + copied, static_cast<const lt_edge*>(b->path_out.p) + copied, (size_t)(total - copied) * sizeof(lt_edge),
+                           cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
     return LT_OK;
 }
 
 extern "C" int lt_paths_fetch(lt_batch* b, int32_t* path_off, lt_edge* path_edges, int64_t path_cap, double* scores,
                               int32_t* status) {
     if (!b || !b->have_paths) return fail(LT_ERR_INVALID, "no paths");
-    CU(cudaSetDevice(b->tables->device));
+    ON_DEVICE(b->tables->device);
     return fetch_paths(b, path_off, path_edges, path_cap, scores, status, b->last_stream);
 }
 
-extern "C" int lt_tag_batch_host(lt_batch* b, const uint16_t* text, const int32_t* sent_off, int32_t n_sent,
-                                 int32_t beam_size, int32_t* path_off, lt_edge* path_edges, int64_t path_cap,
-                                 double* scores, int32_t* status) {
-    if (!b || !sent_off || n_sent < 0) return fail(LT_ERR_INVALID, "bad argument");
-    CU(cudaSetDevice(b->tables->device));
-    cudaStream_t st = b->own_stream;
+// All survivors of the last lt_beam_kbest (beam_search's return value, beam/beam.py:59-61).
+extern "C" int lt_kbest_size(lt_batch* b, int64_t* n_words) {
+    if (!b || !b->have_kbest || !n_words) return fail(LT_ERR_INVALID, "no k-best paths: call lt_beam_kbest first");
+    ON_DEVICE(b->tables->device);
+    if (int rc = resolve(b)) return rc;
+    uint32_t total = 0;
+    CU(cudaMemcpyAsync(&total, static_cast<uint32_t*>(b->kb_off.p) + (size_t)b->n_sent * b->beam, 4, cudaMemcpyDeviceToHost, b->last_stream));
+    CU(cudaStreamSynchronize(b->last_stream));
+    *n_words = total;
+    return LT_OK;
+}
+
+extern "C" int lt_kbest_fetch(lt_batch* b, int32_t* n_best, int32_t* path_off, lt_edge* path_edges, int64_t path_cap,
+                              double* scores, int32_t* status) {
+    if (!b || !b->have_kbest) return fail(LT_ERR_INVALID, "no k-best paths: call lt_beam_kbest first");
+    if (!path_off) return fail(LT_ERR_INVALID, "null output pointer");
+    ON_DEVICE(b->tables->device);
+    if (int rc = resolve(b)) return rc;
+    const size_t n = (size_t)b->n_sent, nk = n * (size_t)b->beam;
+    cudaStream_t st = b->last_stream;
+    if (n == 0) {
+        path_off[0] = 0;
+        return LT_OK;
+    }
+    if (!n_best || !scores || !status) return fail(LT_ERR_INVALID, "null output pointer");
+    CU(cudaMemcpyAsync(path_off, b->kb_off.p, (nk + 1) * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(n_best, b->kb_count.p, n * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(scores, b->kb_scores.p, nk * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(status, b->status.p, n * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    const int64_t total = path_off[nk];
+    if (total > path_cap) return fail(LT_ERR_CAPACITY, "path buffer holds %lld records, need %lld", (long long)path_cap, (long long)total);
+    if (total > 0 && !path_edges) return fail(LT_ERR_INVALID, "null output pointer");
+    if (total) CU(cudaMemcpyAsync(path_edges, b->kb_out.p, (size_t)total * sizeof(lt_edge), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return LT_OK;
+}
+
+// host text -> device buffers of the batch
+static int upload_text(lt_batch* b, const uint16_t* text, const int32_t* sent_off, int32_t n_sent, cudaStream_t st,
+                       int64_t* n_units_out, int32_t* max_units_out) {
+    if (!sent_off || n_sent < 0) return fail(LT_ERR_INVALID, "bad argument");
     const int64_t n_units = sent_off[n_sent];
+    if (n_units > 0 && !text) return fail(LT_ERR_INVALID, "null text pointer");
     int32_t max_units = 0;
     for (int32_t i = 0; i < n_sent; ++i) {
         const int32_t len = sent_off[i + 1] - sent_off[i];
         if (len < 0) return fail(LT_ERR_INVALID, "sent_off is not monotone at %d", i);
         max_units = std::max(max_units, len);
     }
+    if (sent_off[0] != 0) return fail(LT_ERR_INVALID, "sent_off[0] must be 0");
     if (int rc = ensure(b->text, (size_t)std::max<int64_t>(1, n_units) * 2)) return rc;
     if (int rc = ensure(b->sent_off, (size_t)(n_sent + 1) * 4)) return rc;
-    const bool timed = b->timed;
-    if (timed) CU(cudaEventRecord(b->ev[8], st));
     if (n_units) CU(cudaMemcpyAsync(b->text.p, text, (size_t)n_units * 2, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(b->sent_off.p, sent_off, (size_t)(n_sent + 1) * 4, cudaMemcpyHostToDevice, st));
+    *n_units_out = n_units;
+    *max_units_out = max_units;
+    return LT_OK;
+}
+
+extern "C" int lt_tag_batch_host(lt_batch* b, const uint16_t* text, const int32_t* sent_off, int32_t n_sent,
+                                 int32_t beam_size, int32_t* path_off, lt_edge* path_edges, int64_t path_cap,
+                                 double* scores, int32_t* status) {
+    if (!b) return fail(LT_ERR_INVALID, "bad argument");
+    ON_DEVICE(b->tables->device);
+    cudaStream_t st = b->own_stream;
+    const bool timed = b->timed;
+    if (timed) CU(cudaEventRecord(b->ev[8], st));
+    int64_t n_units = 0;
+    int32_t max_units = 0;
+    if (int rc = upload_text(b, text, sent_off, n_sent, st, &n_units, &max_units)) return rc;
     if (int rc = lt_lattice(b, static_cast<const uint16_t*>(b->text.p), static_cast<const int32_t*>(b->sent_off.p), n_sent,
                             n_units, max_units, st))
         return rc;
@@ -905,30 +1157,147 @@ extern "C" int lt_tag_batch_host(lt_batch* b, const uint16_t* text, const int32_
     return LT_OK;
 }
 
+// beam_search over a batch in HOST memory, all survivors kept on the device for lt_kbest_fetch
+extern "C" int lt_tag_batch_host_kbest(lt_batch* b, const uint16_t* text, const int32_t* sent_off, int32_t n_sent,
+                                       int32_t beam_size) {
+    if (!b) return fail(LT_ERR_INVALID, "bad argument");
+    ON_DEVICE(b->tables->device);
+    cudaStream_t st = b->own_stream;
+    int64_t n_units = 0;
+    int32_t max_units = 0;
+    if (int rc = upload_text(b, text, sent_off, n_sent, st, &n_units, &max_units)) return rc;
+    if (int rc = lt_lattice(b, static_cast<const uint16_t*>(b->text.p), static_cast<const int32_t*>(b->sent_off.p), n_sent,
+                            n_units, max_units, st))
+        return rc;
+    return lt_beam_kbest(b, beam_size, st);
+}
+
 // sentence_lookup_as_begin_index for a batch in HOST memory: copies the text in and builds the lattices
 // (results with lt_lattice_size / lt_lattice_fetch)
 extern "C" int lt_lattice_host(lt_batch* b, const uint16_t* text, const int32_t* sent_off, int32_t n_sent) {
-    if (!b || !sent_off || n_sent < 0) return fail(LT_ERR_INVALID, "bad argument");
-    CU(cudaSetDevice(b->tables->device));
+    if (!b) return fail(LT_ERR_INVALID, "bad argument");
+    ON_DEVICE(b->tables->device);
     cudaStream_t st = b->own_stream;
-    const int64_t n_units = sent_off[n_sent];
+    int64_t n_units = 0;
     int32_t max_units = 0;
-    for (int32_t i = 0; i < n_sent; ++i) {
-        const int32_t len = sent_off[i + 1] - sent_off[i];
-        if (len < 0) return fail(LT_ERR_INVALID, "sent_off is not monotone at %d", i);
-        max_units = std::max(max_units, len);
-    }
-    if (int rc = ensure(b->text, (size_t)std::max<int64_t>(1, n_units) * 2)) return rc;
-    if (int rc = ensure(b->sent_off, (size_t)(n_sent + 1) * 4)) return rc;
-    if (n_units) CU(cudaMemcpyAsync(b->text.p, text, (size_t)n_units * 2, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(b->sent_off.p, sent_off, (size_t)(n_sent + 1) * 4, cudaMemcpyHostToDevice, st));
+    if (int rc = upload_text(b, text, sent_off, n_sent, st, &n_units, &max_units)) return rc;
     return lt_lattice(b, static_cast<const uint16_t*>(b->text.p), static_cast<const int32_t*>(b->sent_off.p), n_sent, n_units,
                       max_units, st);
 }
 
+// beam_search's `bindex` argument: a lattice built by the caller (see include/lt_b200.h)
+extern "C" int lt_lattice_import(lt_batch* b, const uint16_t* text, const int32_t* sent_off, int32_t n_sent,
+                                 const lt_edge* edges, const int64_t* end_off, const uint16_t* str_chars,
+                                 const int64_t* str_off, int64_t n_strings) {
+    if (!b || !end_off || n_strings < 0) return fail(LT_ERR_INVALID, "bad argument");
+    ON_DEVICE(b->tables->device);
+    cudaStream_t st = b->own_stream;
+    int64_t n_units = 0;
+    int32_t max_units = 0;
+    if (int rc = upload_text(b, text, sent_off, n_sent, st, &n_units, &max_units)) return rc;
+    const int64_t n_edges = end_off[n_units];
+    if (n_edges < 0 || n_edges > 0xFFFFFFF0ll) return fail(LT_ERR_INVALID, "edge count out of range");
+    if (n_edges > 0 && !edges) return fail(LT_ERR_INVALID, "null edge pointer");
+    if (n_strings % 3 != 0 || (n_strings > 0 && (!str_chars || !str_off))) return fail(LT_ERR_INVALID, "strings come in (word, morph0, morph1) triples");
+    const int32_t limit = unit_limit(b->tables);
+    b->last_stream = st;
+    b->d_text = static_cast<const uint16_t*>(b->text.p);
+    b->d_sent_off = static_cast<const int32_t*>(b->sent_off.p);
+    b->n_sent = n_sent;
+    b->n_units = n_units;
+    b->max_sent_units = max_units;
+    b->beam = 0;
+    b->lcap = std::max(8, (std::min(max_units, limit) + 7) & ~7);
+    b->have_lattice = b->have_paths = b->have_kbest = false;
+
+    // CSR rows, per-sentence status and syllable counts, validated on the host
+    std::vector<uint2> pos((size_t)n_units + 1, make_uint2(0u, 0u));
+    std::vector<int32_t> status((size_t)std::max(1, n_sent), LT_SENT_OK), slen((size_t)std::max(1, n_sent), 0), sedges((size_t)std::max(1, n_sent), 0);
+    const int n_tags = b->tables->dev.n_tags;
+    for (int32_t s = 0; s < n_sent; ++s) {
+        const int32_t s0 = sent_off[s], s1 = sent_off[s + 1];
+        int32_t L = 0;
+        bool bad = false;
+        for (int32_t i = s0; i < s1; ++i) {
+            const uint32_t c = text[i];
+            if (c == 0x20u) continue;
+            ++L;
+            bad |= (c >= 0x09 && c <= 0x0D) || (c >= 0x1C && c <= 0x1F) || c == 0x85 || c == 0xA0 || c == 0x1680 ||
+                   (c >= 0x2000 && c <= 0x200A) || c == 0x2028 || c == 0x2029 || c == 0x202F || c == 0x205F || c == 0x3000;
+        }
+        slen[s] = L;
+        int64_t total = 0;
+        for (int32_t p = 0; p < s1 - s0; ++p) {
+            const int64_t lo = end_off[s0 + p], hi = end_off[s0 + p + 1];
+            if (lo > hi || hi > n_edges) return fail(LT_ERR_INVALID, "end_off is not monotone at unit %d", s0 + p);
+            if (hi > lo && p >= L) return fail(LT_ERR_INVALID, "sentence %d has edges ending beyond its %d syllables", s, L);
+            pos[(size_t)s0 + p] = make_uint2((uint32_t)lo, (uint32_t)(hi - lo));
+            uint32_t prev_b = 0;
+            for (int64_t k = lo; k < hi; ++k) {
+                const lt_edge& ed = edges[k];
+                if (ed.e != p + 1 || ed.b >= ed.e) return fail(LT_ERR_INVALID, "edge %lld: span [%d, %d) does not end at syllable %d", (long long)k, ed.b, ed.e, p + 1);
+                if (k > lo && ed.b < prev_b) return fail(LT_ERR_INVALID, "edge %lld: edges of one end position must be sorted by begin", (long long)k);
+                prev_b = ed.b;
+                if (ed.tag0 >= n_tags || (ed.tag1 != LT_NO_TAG && ed.tag1 >= n_tags)) return fail(LT_ERR_INVALID, "edge %lld: tag id out of range", (long long)k);
+                if (ed.flags & LT_EDGE_EXPLICIT) {
+                    if ((int64_t)ed.rule * 3 + 2 >= n_strings) return fail(LT_ERR_INVALID, "edge %lld: string index out of range", (long long)k);
+                } else if ((ed.flags & LT_EDGE_LEMMA) && ed.rule != LT_NO_RULE) {
+                    return fail(LT_ERR_INVALID, "edge %lld: imported lemma edges name their morphemes (LT_EDGE_EXPLICIT)", (long long)k);
+                }
+            }
+            total += hi - lo;
+        }
+        sedges[s] = (int32_t)std::min<int64_t>(total, 0x7FFFFFFF);
+        if (s1 - s0 > b->lcap) status[s] = LT_SENT_TOO_LONG;
+        else if (bad) status[s] = LT_SENT_BAD_SPACE;
+        else if (L > 0 && total == 0) status[s] = LT_SENT_NO_EDGES;
+    }
+    std::vector<H2> hashes((size_t)n_strings);
+    for (int64_t i = 0; i < n_strings; ++i) {
+        if (str_off[i + 1] < str_off[i]) return fail(LT_ERR_INVALID, "str_off is not monotone at %lld", (long long)i);
+        hashes[i] = hash_units(str_chars + str_off[i], str_off[i + 1] - str_off[i]);
+    }
+
+    const size_t nu = (size_t)n_units + 1;
+    if (int rc = ensure(b->pos, nu * sizeof(uint2))) return rc;
+    if (int rc = ensure(b->sent_len, (size_t)std::max(1, n_sent) * 4)) return rc;
+    if (int rc = ensure(b->sent_edges, (size_t)std::max(1, n_sent) * 4)) return rc;
+    if (int rc = ensure(b->status, (size_t)std::max(1, n_sent) * 4)) return rc;
+    if (int rc = ensure(b->counters, 8 * sizeof(unsigned long long))) return rc;
+    if (int rc = ensure(b->ctl, kCtlWords * sizeof(unsigned int))) return rc;
+    if (b->edge_cap < (uint64_t)n_edges + 16) b->edge_cap = (uint32_t)(n_edges + 16);
+    if (int rc = ensure(b->edges, (size_t)b->edge_cap * sizeof(lt_edge))) return rc;
+    if (int rc = ensure(b->imp, std::max<size_t>(1, hashes.size()) * sizeof(H2))) return rc;
+    CU(cudaMemcpyAsync(b->pos.p, pos.data(), nu * sizeof(uint2), cudaMemcpyHostToDevice, st));
+    if (n_edges) CU(cudaMemcpyAsync(b->edges.p, edges, (size_t)n_edges * sizeof(lt_edge), cudaMemcpyHostToDevice, st));
+    if (n_sent) {
+        CU(cudaMemcpyAsync(b->status.p, status.data(), (size_t)n_sent * 4, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(b->sent_len.p, slen.data(), (size_t)n_sent * 4, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(b->sent_edges.p, sedges.data(), (size_t)n_sent * 4, cudaMemcpyHostToDevice, st));
+    }
+    if (!hashes.empty()) CU(cudaMemcpyAsync(b->imp.p, hashes.data(), hashes.size() * sizeof(H2), cudaMemcpyHostToDevice, st));
+    // control words / counters zeroed and the work order computed, exactly as before a device-built lattice
+    uint32_t* order = nullptr;
+    if (b->sort_by_length && n_sent > 1) {
+        if (int rc = ensure(b->order, (size_t)n_sent * 4)) return rc;
+        order = static_cast<uint32_t*>(b->order.p);
+    }
+    LT_LAUNCH(batch_prologue, 1, 1024, 0, st, b->d_sent_off, n_sent, order, static_cast<unsigned int*>(b->ctl.p), kCtlWords,
+              static_cast<unsigned long long*>(b->counters.p), 8);
+    CU(cudaGetLastError());
+    b->launches += 1;
+    CU(cudaStreamSynchronize(st));          // the staging vectors above go out of scope
+    b->beam_state_clean = true;
+    b->have_lattice = true;
+    b->imported = true;
+    b->resolved = true;
+    b->n_edges = n_edges;
+    return LT_OK;
+}
+
 extern "C" int lt_batch_counters(lt_batch* b, lt_counters* out) {
     if (!b || !out) return fail(LT_ERR_INVALID, "null argument");
-    CU(cudaSetDevice(b->tables->device));
+    ON_DEVICE(b->tables->device);
     unsigned long long c[8] = {0};
     if (b->counters.p && b->have_lattice) {
         if (int rc = resolve(b)) return rc;
@@ -939,10 +1308,40 @@ extern "C" int lt_batch_counters(lt_batch* b, lt_counters* out) {
     return LT_OK;
 }
 
+// State of the workspace: buffer capacities, rerun and launch counts, the launch shapes of the last batch.
+extern "C" int lt_batch_info(lt_batch* b, lt_info* out) {
+    if (!b || !out) return fail(LT_ERR_INVALID, "null argument");
+    ON_DEVICE(b->tables->device);
+    memset(out, 0, sizeof *out);
+    if (b->have_lattice)
+        if (int rc = resolve(b)) return rc;
+    out->launches = b->launches;
+    out->reruns = b->reruns;
+    out->hcap = b->hcap;
+    out->retry_hcap = b->use_retry ? b->retry_hcap : 0;
+    out->retried = (int32_t)b->last_retried;
+    out->edge_cap = (int64_t)b->edge_cap;
+    out->n_edges = b->n_edges;
+    out->unit_limit = unit_limit(b->tables);
+    if (const LatticePlan* p = b->last_lattice_plan) {
+        out->lattice_warps = p->warps;
+        out->lattice_ctas_per_sm = p->per_sm;
+        out->lattice_smem = (int32_t)p->smem;
+    }
+    if (const BeamPlan* p = b->last_beam_plan) {
+        out->beam_warps = p->warps;
+        out->beam_ctas_per_sm = p->per_sm;
+        out->beam_smem = (int32_t)p->smem;
+        out->beam_trail_smem = p->trail_smem ? 1 : 0;
+    }
+    out->sm_count = b->tables->sm_count;
+    return LT_OK;
+}
+
 // timings: enabled by the first call (so that un-timed batches record no events)
 extern "C" int lt_batch_timings(lt_batch* b, lt_timings* out) {
     if (!b || !out) return fail(LT_ERR_INVALID, "null argument");
-    CU(cudaSetDevice(b->tables->device));
+    ON_DEVICE(b->tables->device);
     memset(out, 0, sizeof *out);
     if (!b->timed) {
         b->timed = true;      // subsequent batches are timed

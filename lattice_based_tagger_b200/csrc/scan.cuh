@@ -199,4 +199,22 @@ __global__ void pack_paths(const lt_edge* __restrict__ tmp, const int32_t* __res
     }
 }
 
+// all survivors (k-best): path r of sentence s sits reversed at tmp[sent_off[s] * K + r * raw_len(s)]
+__global__ void pack_paths_k(const lt_edge* __restrict__ tmp, const int32_t* __restrict__ sent_off,
+                             const uint32_t* __restrict__ path_off, int32_t n_sent, int32_t K, lt_edge* __restrict__ out) {
+    const int warps_per_block = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int64_t total = (int64_t)n_sent * K;
+    for (int64_t i = blockIdx.x * warps_per_block + (threadIdx.x >> 5); i < total; i += (int64_t)gridDim.x * warps_per_block) {
+        const int s = (int)(i / K), r = (int)(i - (int64_t)s * K);
+        const uint32_t o0 = path_off[i], o1 = path_off[i + 1];
+        const int W = (int)(o1 - o0);
+        if (W == 0) continue;
+        const int s0 = sent_off[s], raw = sent_off[s + 1] - s0;
+        const uint4* src = reinterpret_cast<const uint4*>(tmp + (size_t)s0 * K + (size_t)r * raw);
+        uint4* dst = reinterpret_cast<uint4*>(out + o0);
+        for (int w = lane; w < W; w += 32) dst[w] = src[W - 1 - w];
+    }
+}
+
 }  // namespace lt

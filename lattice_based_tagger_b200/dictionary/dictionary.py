@@ -66,6 +66,13 @@ class WordDictionary:
                 raise ValueError('{} tag does not exist in dictionary'.format(tag))
             self.tag_to_morphs[tag] = set()
         self.tag_to_morphs[tag].update(morphs)
+        self._invalidate()
+
+    def _invalidate(self):
+        # device tables built for lookup() / lemmatize() describe the dictionary as it was
+        lookup = self.__dict__.pop('_exact_lookup', None)
+        if lookup is not None:
+            lookup._release()
 
     def remove_words(self, morphs, tag):
         if isinstance(morphs, str):
@@ -77,6 +84,7 @@ class WordDictionary:
         # `eomis` of a MorphemeDictionary keep pointing at the old object, and the table
         # compiler reads them separately for exactly that reason.
         self.tag_to_morphs[tag] = {m for m in self.tag_to_morphs[tag] if m not in drop}
+        self._invalidate()
 
 
 class MorphemeDictionary(WordDictionary):
@@ -92,6 +100,27 @@ class MorphemeDictionary(WordDictionary):
         self.verbs = tag_to_morph.get(Verb, {})
         self.adjectives = tag_to_morph.get(Adjective, {})
         self.eomis = tag_to_morph.get(Eomi, {})
+
+    def _exact(self):
+        lookup = self.__dict__.get('_exact_lookup')
+        if lookup is None:
+            from .lookup import ExactLookup
+            lookup = self.__dict__['_exact_lookup'] = ExactLookup(self)
+        return lookup
+
+    def lookup(self, word, b=0, is_l=False):
+        """One `Word` per tag that lists `word` (dictionary order), then its lemmatised analyses
+        (reference `dictionary.py:304-312`) — looked up on the device (`LT_LOOKUP_EXACT`)."""
+        if not word:
+            return []
+        return [w._replace(b=w.b + b, e=w.e + b, is_l=is_l) for w in self._exact().lookup(word)]
+
+    def lemmatize(self, word):
+        """[((stem, tag), (eomi, 'Eomi')), ...] (reference `dictionary.py:314-315`), from the device."""
+        if not word:
+            return []
+        from .lemmatizer import analyses_of
+        return analyses_of(self._exact().lookup(word))
 
 
 def load_dictionary(directory):

@@ -31,6 +31,26 @@ def shard_bounds(lengths, world_size):
     return bounds
 
 
+def partition_by_work(lengths, world_size):
+    """Index arrays, one per rank, of (nearly) equal estimated work AND equal sentence count.
+
+    A sentence's decode work grows with its length (transitions ~ length x (8 k + k E / L), SURVEY §8e;
+    beam and lattice density are common to the batch).  Sentences are sorted by length and dealt to the
+    ranks in snake order (0 1 .. n-1 n-1 .. 1 0 ...), which balances total length and the length mix;
+    each rank's indices are returned in ascending order, so that its slice of the text is read front to
+    back.  Unlike `shard_bounds` the parts are not contiguous: results are put back with the index arrays.
+    """
+    lengths = np.asarray(lengths, dtype=np.int64)
+    n = lengths.size
+    if world_size <= 1:
+        return [np.arange(n, dtype=np.int64)]
+    order = np.argsort(-lengths, kind='stable')
+    pos = np.arange(n, dtype=np.int64)
+    lap, col = divmod(pos, world_size)
+    owner = np.where(lap % 2 == 0, col, world_size - 1 - col)
+    return [np.sort(order[owner == r]) for r in range(world_size)]
+
+
 def my_shard(sents, rank, world_size):
     """(start, stop) of this rank's slice of `sents`."""
     bounds = shard_bounds([len(s) for s in sents], world_size)

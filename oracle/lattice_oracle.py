@@ -201,18 +201,115 @@ def eojeol_lookup(eojeol, view, offset, counters=None):
     return edges
 
 
-def sentence_edges(sent, view, counters=None):
+def lr_lookup(eojeol, view, offset, prefer_exact_match=True):
+    """LRLookup.lookup -> lr_lookup — dictionary/lookup.py:75-85, :171-210: the whole eojeol's
+    analyses (alone, with prefer_exact_match, when there are any), then every left/right split
+    whose two sides are both known, the Noun + Josa split with its `len = n` quirk (Q4)."""
+    n = len(eojeol)
+    edges = full_lookup(eojeol, view, offset, True)
+    if prefer_exact_match and edges:
+        return edges
+    for i in range(1, n):
+        left, right = eojeol[:i], eojeol[i:]
+        if view.check(left, NOUN) and view.check(right, JOSA):
+            edges.append((left, left, None, NOUN, None, n, offset, offset + i, True))
+            edges.append((right, right, None, JOSA, None, n, offset + i, offset + n, False))
+            continue
+        lset = full_lookup(left, view, offset, True)
+        rset = full_lookup(right, view, offset + i, False)
+        if lset and rset:
+            edges += lset
+            edges += rset
+    return edges
+
+
+def word_lookup(eojeol, view, offset, prefer_exact_match=True):
+    """WordLookup.lookup -> word_lookup — dictionary/lookup.py:87-97, :134-169: the whole eojeol's
+    analyses (alone, with prefer_exact_match, when there are any), then the full lookup of EVERY
+    substring, the whole eojeol included once more (so its analyses appear twice without
+    prefer_exact_match); `is_l` marks substrings that start the eojeol."""
+    n = len(eojeol)
+    edges = full_lookup(eojeol, view, offset, True)
+    if prefer_exact_match and edges:
+        return edges
+    for b in range(n):
+        for e in range(b + 1, n + 1):
+            edges += full_lookup(eojeol[b:e], view, offset + b, b == 0)
+    return edges
+
+
+def flatten_edges(edges):
+    """flatten_words — dictionary/dictionary.py:114-167: a two-morpheme word becomes two
+    one-morpheme words meeting at min(e, b + len(morph0)); a leading jamo of the second morpheme
+    does not count as a syllable of its `len`."""
+    out = []
+    for w in edges:
+        if w[TAG1] is None:
+            out.append(w)
+            continue
+        len0, len1 = len(w[MORPH0]), len(w[MORPH1])
+        m = min(w[E], w[B] + len0)
+        if 'ㄱ' <= w[MORPH1][0] <= 'ㅎ':
+            len1 -= 1
+        out.append((w[MORPH0], w[MORPH0], None, w[TAG0], None, len0, w[B], m, w[IS_L]))
+        out.append((w[MORPH1], w[MORPH1], None, w[TAG1], None, len1, m, w[E], False))
+    return out
+
+
+#: lookup modes: name -> eojeol lookup (eojeol, view, offset, counters) of the reference's EojeolLookup classes
+LOOKUPS = {
+    'morpheme': lambda eojeol, view, offset, counters=None: eojeol_lookup(eojeol, view, offset, counters),
+    'lr': lambda eojeol, view, offset, counters=None: lr_lookup(eojeol, view, offset, True),
+    'lr_all': lambda eojeol, view, offset, counters=None: lr_lookup(eojeol, view, offset, False),
+    'word': lambda eojeol, view, offset, counters=None: word_lookup(eojeol, view, offset, True),
+    'word_all': lambda eojeol, view, offset, counters=None: word_lookup(eojeol, view, offset, False),
+}
+
+
+def sentence_edges(sent, view, counters=None, lookup='morpheme', flatten=False):
     """Dictionary edges of a sentence in the order `sentence_lookup` produces them, without the
     BOS/EOS sentinels — dictionary/lookup.py:51-62.  Eojeols are `sent.split()`; offsets count
-    syllables of the preceding eojeols."""
+    syllables of the preceding eojeols.  `lookup` names the EojeolLookup class (LOOKUPS)."""
+    fn = LOOKUPS[lookup]
     edges = []
     offset = 0
     for eojeol in sent.split():
-        edges += eojeol_lookup(eojeol, view, offset, counters)
+        found = fn(eojeol, view, offset, counters)
+        edges += flatten_edges(found) if flatten else found
         offset += len(eojeol)
     if counters is not None:
         counters.E += len(edges)
     return edges
+
+
+def lattice_graph(sent, edges):
+    """sentence_lookup_as_graph — dictionary/lookup.py:281-342: (nodes, links) with nodes =
+    [BOS] + edges + [EOS] and links [from, to, 0] between a word and the words that begin at the
+    closest non-empty begin index at or after its end.  IndexError without any edge, as there
+    (`bindex` is `[]`, :362-363, and :326 indexes it)."""
+    n = len(sent.replace(' ', ''))
+    bos = (BOS, BOS, None, BOS, None, 0, 0, 0, False)
+    eos = (EOS, EOS, None, EOS, None, 0, n, n, False)
+    bindex = begin_index(sent, edges)
+
+    def closest(begin):
+        for i in range(begin, n):
+            if bindex[i]:
+                return i
+        return -1
+
+    links = [[bos, word, 0] for word in bindex[closest(0)]]
+    for bucket in bindex:
+        for src in bucket:
+            nxt = closest(src[E])
+            if nxt == -1:
+                links.append([src, eos, 0])
+            else:
+                for dst in bindex[nxt]:
+                    if src[LEN] == 0 and dst[LEN] == 0:
+                        continue
+                    links.append([src, dst, 0])
+    return [bos] + list(edges) + [eos], links
 
 
 def begin_index(sent, edges):
@@ -379,18 +476,19 @@ def beam_search(bindex, chars, program, beam_size=5, counters=None):
 class OracleTagger:
     """`Tagger(dictionary, score_funcs=...)` / `.tag(sent, beam_size)` — tagger/tagger.py:47-78."""
 
-    def __init__(self, dictionary, score_funcs, k3_first=None):
+    def __init__(self, dictionary, score_funcs, k3_first=None, lookup='morpheme'):
         self.view = DictView(dictionary, k3_first)
-        self.program = ScoreProgram(score_funcs)
+        self.program = ScoreProgram(score_funcs) if score_funcs is not None else None
+        self.lookup = lookup       # the reference's Tagger always uses MorphemeLookup (tagger.py:60)
 
-    def lattice(self, sent, counters=None):
-        return sentence_edges(sent, self.view, counters)
+    def lattice(self, sent, counters=None, flatten=False):
+        return sentence_edges(sent, self.view, counters, self.lookup, flatten)
 
     def survivors(self, sent, beam_size=5, counters=None):
         chars = sent.replace(' ', '')
         if counters is not None:
             counters.L += len(chars)
-        edges = sentence_edges(sent, self.view, counters)
+        edges = sentence_edges(sent, self.view, counters, self.lookup)
         return beam_search(begin_index(sent, edges), chars, self.program, beam_size, counters)
 
     def tag(self, sent, beam_size=5, counters=None):

@@ -1,0 +1,95 @@
+"""The CUDA kernel SOURCES, compiled for the host against the SIMT emulator (tests/simt), checked
+against the oracle on the CPU — test infrastructure: it exercises the kernels' logic (enumeration
+order, tie-breaking, fp64 association, overflow / retry paths, lookup modes, k-best, imported
+lattices) where no GPU exists, and the emulator aborts on warp-divergent collectives.  The product
+never loads this build; the `-m gpu` tests run the same checks through `liblt_b200.so`.
+"""
+
+import pytest
+
+import lattice_based_tagger_b200 as pkg
+from oracle import lattice_oracle as lo
+from tests import _cases, _checks, _emu, _golden
+
+
+@pytest.fixture(autouse=True)
+def emulated():
+    with _emu.emulated():
+        yield
+
+
+@pytest.mark.parametrize('seed', [2001, 2016])
+def test_random_cases(seed):
+    case = _checks.make_case(seed, n_sent=10, max_sent_len=40)
+    dictionary, funcs = _cases.build_objects(case, pkg)
+    tagger = pkg.Tagger(dictionary, score_funcs=funcs)
+    oracle = lo.OracleTagger(dictionary, funcs)
+    _checks.check_against_oracle(tagger, oracle, case['sentences'], (1, 5, 10, 33), counters=True)
+
+
+def test_golden_demo_fixture():
+    payload = _golden.load('demo_morph')
+    case = payload['case']
+    dictionary, funcs = _cases.build_objects(case, pkg)
+    tagger = pkg.Tagger(dictionary, score_funcs=funcs, k3_first=payload['k3_first'])
+    sents = case['sentences']
+    for sent, entry, (words, bindex) in zip(sents, payload['expected'], tagger.lattice_batch(sents)):
+        assert [tuple(w) for w in words[1:-1]] == _checks.lattice_key([_golden.edge(w) for w in entry['lattice']]), sent
+    for k in (1, 3, 5, 32):
+        got = tagger.tag_batch_kbest(sents, beam_size=k, errors='none')
+        for sent, entry, seqs in zip(sents, payload['expected'], got):
+            want = _golden.expected_survivors(entry, k)
+            if want is None:
+                assert seqs is None, sent
+                continue
+            assert len(seqs) == len(want)
+            for seq, (words, score, num_unk) in zip(seqs, want):       # every survivor the reference returned
+                assert [tuple(w) for w in seq.sequences] == words and seq.score == score and seq.num_unk == num_unk
+
+
+def test_kbest_survivors():
+    case = _checks.make_case(3001, n_sent=10, max_sent_len=24)
+    dictionary, funcs = _cases.build_objects(case, pkg)
+    tagger = pkg.Tagger(dictionary, score_funcs=funcs)
+    _checks.check_kbest(tagger, lo.OracleTagger(dictionary, funcs), case['sentences'], (1, 3, 5, 12, 40))
+
+
+def test_lookup_modes_and_flatten():
+    _checks.check_lookup_modes(_checks.make_case(3002, n_sent=8, max_sent_len=14))
+
+
+def test_host_level_api():
+    _checks.check_host_api(_checks.make_case(3003, n_sent=10, max_sent_len=20))
+
+
+def test_overflow_rerun_and_retry_pass(monkeypatch):
+    case = _checks.make_case(2001, n_sent=18, prefs=False, max_sent_len=60)
+    dictionary, funcs = _cases.build_objects(case, pkg)
+    oracle = lo.OracleTagger(dictionary, funcs)
+    monkeypatch.setenv('LT_HIT_CAP', '8')
+    monkeypatch.setenv('LT_EDGE_CAP', '16')
+    tagger = pkg.Tagger(dictionary, score_funcs=funcs)
+    _checks.check_against_oracle(tagger, oracle, case['sentences'], (5,))
+    info = tagger.info()
+    assert info['reruns'] > 0 and info['retry_hcap'] > 0
+
+
+def test_per_sentence_statuses():
+    """One bad sentence does not fail its batch: too long for the kernels' shared memory, characters
+    outside the BMP, foreign whitespace, no dictionary word — each gets its own status."""
+    dictionary = pkg.dictionary.DemoMorphemeDictionary()
+    funcs = pkg.beam.BeamScoreFunctions(pkg.beam.RegularizationScore())
+    tagger = pkg.Tagger(dictionary, score_funcs=funcs)
+    limit = tagger.info()['unit_limit']
+    assert 1000 <= limit <= 4088
+    sents = ['노래 입니다', '노래 ' * (limit // 3 + 2), '노래 \U0001F600', '노래\t입니다', '가나다라', '']
+    got = tagger.tag_batch(sents, errors='none')
+    assert [s is not None for s in got] == [True, False, False, False, False, True]
+    assert got[0].score == lo.OracleTagger(dictionary, funcs).tag(sents[0]).score
+    assert list(got.status) == [0, 3, 4, 2, 1, 0]
+    for i, exc in ((1, ValueError), (2, ValueError), (3, ValueError), (4, IndexError)):
+        with pytest.raises(exc):
+            tagger.tag(sents[i])
+    assert [w is None for w in tagger.eojeol_lookup.lookup_batch(sents, errors='none')] == [False, True, True, True, False, False]
+    long_ok = '노래 ' * ((limit - 8) // 3)
+    assert tagger.tag(long_ok).score == lo.OracleTagger(dictionary, funcs).tag(long_ok).score

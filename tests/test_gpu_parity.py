@@ -4,7 +4,7 @@ import pytest
 
 import lattice_based_tagger_b200 as pkg
 from oracle import lattice_oracle as lo
-from tests import _cases, _golden
+from tests import _cases, _checks, _golden
 
 pytestmark = pytest.mark.gpu
 
@@ -312,3 +312,142 @@ def test_retry_pass_and_adaptive_staging(monkeypatch):
     tagger = pkg.Tagger(dictionary, score_funcs=funcs)
     for _ in range(4):                       # capacities are sticky per tagger: 8 -> 16 -> 32 ...
         _check_against_oracle(tagger, oracle, sents, (5,))
+
+
+# ---- round 2: all survivors, lookup modes, host-level API, per-sentence statuses, larger configurations ----
+
+@pytest.mark.parametrize('name', ['demo_morph', 'random_1003', 'random_1011'])
+def test_golden_all_survivors(name):
+    """`beam_search` returns every survivor (beam.py:59-61): the fixtures hold all of them for k = 5
+    (demo_morph: for every recorded k), as the reference returned them."""
+    payload = _golden.load(name)
+    case = payload['case']
+    dictionary, funcs = _cases.build_objects(case, pkg)
+    tagger = pkg.Tagger(dictionary, score_funcs=funcs, k3_first=payload['k3_first'])
+    sents = case['sentences']
+    for k in sorted({int(k) for entry in payload['expected'] for k in entry['beams']}):
+        got = tagger.tag_batch_kbest(sents, beam_size=k, errors='none')
+        for sent, entry, seqs in zip(sents, payload['expected'], got):
+            want = _golden.expected_survivors(entry, k)
+            if want is None:
+                assert seqs is None, sent
+                continue
+            if len(want) == 1 and k > 1:
+                seqs = seqs[:1]                  # the fixture kept matures[0] only for this k
+            assert len(seqs) == len(want), (sent, k)
+            for seq, (words, score, num_unk) in zip(seqs, want):
+                assert [tuple(w) for w in seq.sequences] == words and seq.score == score and seq.num_unk == num_unk
+
+
+@pytest.mark.parametrize('seed', [3001, 3011, 3012])
+def test_kbest_against_oracle(seed):
+    case = _checks.make_case(seed, n_sent=24, max_sent_len=50)
+    dictionary, funcs = _cases.build_objects(case, pkg)
+    tagger = pkg.Tagger(dictionary, score_funcs=funcs)
+    _checks.check_kbest(tagger, lo.OracleTagger(dictionary, funcs), case['sentences'], (1, 3, 5, 10, 12, 32, 40, 64))
+
+
+@pytest.mark.parametrize('seed', [3002, 3021, 3022, 3023])
+def test_lookup_modes_and_flatten(seed):
+    _checks.check_lookup_modes(_checks.make_case(seed, n_sent=16, max_sent_len=30), beams=(1, 5, 33))
+
+
+@pytest.mark.parametrize('seed', [3003, 3031])
+def test_host_level_api(seed):
+    _checks.check_host_api(_checks.make_case(seed, n_sent=16, max_sent_len=30))
+
+
+def test_reference_docstring_examples():
+    """The reference's docstring examples that still reproduce against its own code."""
+    d = pkg.dictionary.DemoMorphemeDictionary()
+    assert pkg.dictionary.analyze_morphology('파랬다', {}, {'파랗'}, {'았다'}, {'랬': (('랗', '았'),)}) == [
+        (('파랗', 'Adjective'), ('았다', 'Eomi'))]                                        # lemmatizer.py:34-40
+    assert d.lemmatize('있다') == [(('있', 'Adjective'), ('다', 'Eomi')), (('이', 'Adjective'), ('ㅆ다', 'Eomi'))]   # dictionary.py:283-291
+    assert [str(w) for w in d.lookup('있다', b=3)] == ['Word(있다, 있/Adjective + 다/Eomi, len=2, b=3, e=5)',
+                                                       'Word(있다, 이/Adjective + ㅆ다/Eomi, len=2, b=3, e=5)']
+    assert [str(w) for w in d.lookup('아이오아이', 5)] == ['Word(아이오아이, 아이오아이/Noun, len=5, b=5, e=10)']
+    lr = pkg.dictionary.LRLookup(d)
+    assert [str(w) for w in lr('아이오아이', 2)] == ['Word(아이오아이, 아이오아이/Noun, len=5, b=2, e=7, L)']     # lookup.py:176-185
+    lr_all = pkg.dictionary.LRLookup(d, prefer_exact_match=False)
+    assert sorted(str(w) for w in lr_all('아이오아이')) == sorted([
+        'Word(아이오아이, 아이오아이/Noun, len=5, b=0, e=5, L)', 'Word(아이오, 아이오/Noun, len=3, b=0, e=3, L)',
+        'Word(아이, 아이/Noun, len=2, b=3, e=5)'])
+    # lr_lookup's Noun + Josa special case: both words carry len = n (SURVEY App. A Q4)
+    assert [(w.word, w.tag0, w.len) for w in lr_all('아이오아이의')] == [('아이오아이', 'Noun', 6), ('의', 'Josa', 6)]
+
+
+def test_per_sentence_statuses():
+    """One bad sentence does not fail its batch: too long for the kernels' shared memory,
+    characters outside the BMP, foreign whitespace, no dictionary word — each gets its own status."""
+    dictionary = pkg.dictionary.DemoMorphemeDictionary()
+    funcs = pkg.beam.BeamScoreFunctions(pkg.beam.RegularizationScore())
+    tagger = pkg.Tagger(dictionary, score_funcs=funcs)
+    oracle = lo.OracleTagger(dictionary, funcs)
+    limit = tagger.info()['unit_limit']
+    assert 1000 <= limit <= 4088
+    sents = ['노래 입니다', '노래 ' * (limit // 3 + 2), '노래 \U0001F600', '노래\t입니다', '가나다라', '']
+    got = tagger.tag_batch(sents, errors='none')
+    assert [s is not None for s in got] == [True, False, False, False, False, True]
+    assert got[0].score == oracle.tag(sents[0]).score
+    assert list(got.status) == [0, 3, 4, 2, 1, 0]
+    long_ok = '노래 ' * ((limit - 8) // 3)
+    want = oracle.tag(long_ok)
+    seq = tagger.tag(long_ok)
+    assert [tuple(w) for w in seq.sequences] == want.words and seq.score == want.score
+
+
+def test_tag_debug_trace(capsys):
+    dictionary = pkg.dictionary.DemoMorphemeDictionary()
+    funcs = pkg.beam.BeamScoreFunctions(pkg.beam.RegularizationScore(unknown_penalty=-.1, known_preference=0.5))
+    tagger = pkg.Tagger(dictionary, score_funcs=funcs)
+    oracle = lo.OracleTagger(dictionary, funcs)
+    sent = '노래 입니다'
+    best = tagger.tag(sent, beam_size=3, debug=True)
+    out = capsys.readouterr().out
+    assert out.count('End point = ') == 5 and best.score == oracle.tag(sent, 3).score
+    # the survivors printed for the last position are the search result itself
+    assert str(round(best.score, 6)) in out or repr(best.score) in out
+
+
+_CONFIG_SAMPLES = {'c3': (600, (10,)), 'c4': (24, (32,)), 'c5': (400, (1, 8, 10, 64))}
+
+
+@pytest.mark.parametrize('name', ['c3', 'c4', 'c5'])
+def test_config_samples(name):
+    """BASELINE configs[2-4] at their full dictionary sizes (1 M / 100 k entries; C5's feature table is cut to
+    2 M weights here — the 10 M table is built by bench.py), sentence samples against the oracle."""
+    from lattice_based_tagger_b200 import synth
+    n_sent, beams = _CONFIG_SAMPLES[name]
+    cfg = dict(synth.CONFIGS[name])
+    cfg['n_feat'] = min(cfg['n_feat'], 2_000_000)
+    cfg, dictionary, sents = synth.build_workload(cfg, n_sent=max(n_sent, 256))
+    reg = pkg.beam.BeamScoreFunctions(pkg.beam.RegularizationScore())
+    reg_tagger = pkg.Tagger(dictionary, score_funcs=reg)
+    vocab = None
+    if cfg['n_feat'] > 1_000_000:
+        vocab = [(m, t) for t, ms in dictionary.tag_to_morphs.items() for m in sorted(ms)]
+    feature_dic, coef = synth.make_features(
+        sents[:256], lambda s: reg_tagger.tag_batch(s, cfg['beam'], errors='none'), reg_tagger.lattice_batch,
+        cfg['n_feat'], list(dictionary.tag_to_morphs), seed=3, vocab=vocab)
+    reg_tagger.close()
+    funcs = pkg.beam.BeamScoreFunctions(
+        pkg.beam.RegularizationScore(),
+        pkg.beam.SimpleTrigramFeatureScore(pkg.features.SimpleTrigramEncoder(feature_dic), coef))
+    tagger = pkg.Tagger(dictionary, score_funcs=funcs)
+    oracle = lo.OracleTagger(dictionary, funcs)
+    sample = sents[:n_sent]
+    for k in beams:
+        got = tagger.tag_batch(sample, beam_size=k, errors='none')
+        for sent, seq in zip(sample, got):
+            try:
+                want = oracle.tag(sent, k)
+            except IndexError:
+                assert seq is None
+                continue
+            assert [tuple(w) for w in seq.sequences] == want.words, (name, k, sent)
+            assert seq.score == want.score
+    # the lattice itself on a part of the sample, and a batch large enough to go through the adaptive staging
+    for sent, (words, bindex) in zip(sample[:50], tagger.lattice_batch(sample[:50])):
+        assert [tuple(w) for w in words[1:-1]] == _checks.lattice_key(oracle.lattice(sent)), sent
+    info = tagger.info()
+    assert info['reruns'] >= 0 and info['launches'] > 0

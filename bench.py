@@ -426,6 +426,13 @@ def time_workload(W, B, steps, warmup, dev, barrier, flush):
     barrier()
     out['host_ms_per_step'] = 1e3 * host_s / steps
     out['n_words'] = int(B.h_poff.numpy()[:4 * (B.n + 1)].view(np.int32)[B.n])
+    # digest of everything the last end-to-end step returned: equal digests = bit-identical results (used to
+    # compare kernel variants with a build that was checked against the CPU arm)
+    import hashlib
+    digest = hashlib.sha1()
+    for part in B.results():
+        digest.update(np.ascontiguousarray(part).view(np.uint8).tobytes())
+    out['results_sha1'] = digest.hexdigest()
     return out
 
 
@@ -645,6 +652,7 @@ def run_gpu(args):
             'gpu_launches': int(round(R['launches_per_step'] * args.steps)),
             'stage_ms_per_step': R['stage'],
             'reruns_in_timed_region': R['reruns_in_timed_region'],
+            'results_sha1': R['results_sha1'],
             'ms_per_step_by_rank': rank_ms,
             'counters_per_step': counters,
             'roofline': roofline_of(args.config, counters, R['stage'], peak, peak_kind),
@@ -689,7 +697,7 @@ def other_config(name, args, dev, local_rank, barrier, flush, peak, peak_kind):
         'edges_per_sec': c['E'] / (R['ms_per_step'] * 1e-3), 'transitions_per_sec': c['T'] / (R['ms_per_step'] * 1e-3),
         'e2e': {'value': B.n / (R['host_ms_per_step'] * 1e-3), 'unit': UNIT, 'ms_per_step': R['host_ms_per_step']},
         'stage_ms_per_step': R['stage'], 'reruns_in_timed_region': R['reruns_in_timed_region'],
-        'counters_per_step': c, 'roofline': roofline_of(name, c, R['stage'], peak, peak_kind),
+        'results_sha1': R['results_sha1'], 'counters_per_step': c, 'roofline': roofline_of(name, c, R['stage'], peak, peak_kind),
         'launch': {k: R['info'][k] for k in ('hcap', 'retry_hcap', 'retried', 'lattice_warps', 'lattice_ctas_per_sm', 'beam_warps',
                                               'beam_ctas_per_sm', 'beam_trail_smem')},
         'tables_device_bytes': W.tagger._tables.device_bytes(), 'build_seconds': build_s,

@@ -324,6 +324,9 @@ __device__ __forceinline__ double unsortable(uint64_t key) {
 #ifndef LT_BEAM_MINB
 #define LT_BEAM_MINB 2
 #endif
+#ifndef LT_TOPK_ROUNDS
+#define LT_TOPK_ROUNDS 1       // 1: positions whose candidates fit one chunk select by K rounds of warp arg-max
+#endif
 #ifndef LT_PROBE_SPLIT
 #define LT_PROBE_SPLIT 1       // 1: generic kernels issue the loads of templates 7 and 8 after templates 0..2 are consumed
 #endif
@@ -417,7 +420,9 @@ __device__ __forceinline__ void prep_edge(const DevTables& T, const SentView& v,
 // constants, which is what keeps the kernel's address arithmetic out of registers); 0 = A.beam / A.units.
 // PROG: 1 = the score program is exactly (RegularizationScore, SimpleTrigramFeatureScore) — the
 // scorer loop of a candidate unrolls, the template seeds become immediates; 0 = read it from T.
-template <int MODE, int KT, int UC, int PROG>
+// KB: 1 = every survivor of the last position is written out as well (lt_beam_kbest); 0 compiles that out of
+// the instantiations the throughput path runs.
+template <int MODE, int KT, int UC, int PROG, int KB = 0>
 __global__ void __launch_bounds__(kBeamMaxWarps * 32, LT_BEAM_MINB) beam_kernel(const __grid_constant__ DevTables T, const __grid_constant__ BeamArgs A) {
     constexpr int KR = (MODE == 0) ? 2 : 1;      // kept entries per lane
     LT_DYN_SMEM(smem_raw);
@@ -660,7 +665,8 @@ __global__ void __launch_bounds__(kBeamMaxWarps * 32, LT_BEAM_MINB) beam_kernel(
                     if (unk_edge) {
                         prank = (j < jmax) ? (uint32_t)s_nonunk[pbase + rem] : rem;
                     } else {
-                        prank = (cj == 1u) ? rem : rem / cj;
+                        // (exact through a float reciprocal for the small numbers that occur, see small_div)
+                        prank = (cj == 1u) ? rem : (uint32_t)small_div((int)rem, (int)cj, 1.0f / (float)cj);
                         eidx = rem - prank * cj;
                     }
                     const int pslot = pbase + (int)prank;
@@ -773,6 +779,42 @@ __global__ void __launch_bounds__(kBeamMaxWarps * 32, LT_BEAM_MINB) beam_kernel(
                 {
                     const uint32_t chunk_F = __reduce_add_sync(kFull, cand_F);
                     if (lane == 0) { s_acc[0] += chunk_T; s_acc[1] += chunk_F; }
+                }
+                if constexpr (MODE == 2 && LT_TOPK_ROUNDS) {
+                    if (N <= 32u) {
+                        // ---- the position's candidates fit one chunk (the common case at small beams): K rounds of
+                        // warp arg-max.  A round costs two reductions (high word; low word among the lanes that hold
+                        // the maximum high word — skipped when that lane is alone) and one vote; ties go to the lower
+                        // lane = the earlier candidate (beam.py:85 is a stable sort).  Round r's winner lands in lane r.
+                        uint32_t hi = (uint32_t)(ckey >> 32), lo = (uint32_t)ckey;
+                        uint64_t wkey = 0;
+                        uint32_t wpay = 0;
+                        const uint32_t rounds = chunk_T < (uint32_t)K ? chunk_T : (uint32_t)K;
+                        for (uint32_t round = 0; round < rounds; ++round) {
+                            const uint32_t mhi = __reduce_max_sync(kFull, hi);
+                            unsigned wm = __ballot_sync(kFull, hi == mhi && (hi | lo) != 0u);
+                            uint32_t mlo = lo;
+                            if (wm & (wm - 1u)) {
+                                mlo = __reduce_max_sync(kFull, hi == mhi ? lo : 0u);
+                                wm = __ballot_sync(kFull, hi == mhi && lo == mlo);
+                            }
+                            const int src = __ffs(wm) - 1;
+                            mlo = __shfl_sync(kFull, mlo, src);
+                            const uint32_t pay = __shfl_sync(kFull, cpay, src);
+                            if (lane == (int)round) { wkey = ((uint64_t)mhi << 32) | mlo; wpay = pay; }
+                            if (lane == src) { hi = 0u; lo = 0u; }
+                        }
+                        keep_key[0] = wkey;
+                        keep_pay[0] = wpay;
+                        nk = rounds;
+                        continue;
+                    }
+                    // a later chunk contributes nothing unless one of its candidates beats the K-th kept entry (kept
+                    // entries are earlier candidates: they win ties)
+                    if (nk == (uint32_t)K) {
+                        const uint64_t thr = __shfl_sync(kFull, keep_key[0], K - 1);
+                        if (__ballot_sync(kFull, ckey > thr) == 0u) continue;
+                    }
                 }
                 if constexpr (MODE == 2) {
                     // ---- top-K by rank counting: an entry's rank = number of pool entries that beat it ----
@@ -969,7 +1011,7 @@ __global__ void __launch_bounds__(kBeamMaxWarps * 32, LT_BEAM_MINB) beam_kernel(
         // ---- best path: matures[0] (tagger.py:78); with A.kbest every survivor (beam.py:59-61) ----
         // lane 0 follows the back-pointers (a dependent chain) and lists (end, edge reference); then the
         // lanes fetch the edge records side by side
-        if (A.kbest) {
+        if constexpr (KB != 0) {
             const int nsurv = (L > 0) ? (int)s_nbeam[L % kRing] : 1;
             if (lane == 0) A.kb_count[s] = (st == LT_SENT_OK) ? nsurv : 0;
             for (int r = lane; r < K; r += 32) {
@@ -980,13 +1022,13 @@ __global__ void __launch_bounds__(kBeamMaxWarps * 32, LT_BEAM_MINB) beam_kernel(
         }
         if (L > 0) {
             uint64_t* s_path = ha;              // the prefix hashes are no longer needed
-            const int nout = A.kbest ? (int)s_nbeam[L % kRing] : 1;
+            const int nout = (KB != 0) ? (int)s_nbeam[L % kRing] : 1;
             for (int r0 = 0; r0 < nout; ++r0) {
                 int W = 0;
                 if (lane == 0) {
                     const double final_score = e_score[(L % kRing) * K + r0];
                     if (r0 == 0) A.scores[s] = final_score;
-                    if (A.kbest) A.kb_scores[(size_t)s * K + r0] = final_score;
+                    if constexpr (KB != 0) A.kb_scores[(size_t)s * K + r0] = final_score;
                     int e = L, r = r0;
                     while (e > 0) {
                         uint32_t eref, span;
@@ -1010,7 +1052,7 @@ __global__ void __launch_bounds__(kBeamMaxWarps * 32, LT_BEAM_MINB) beam_kernel(
                         A.path_len[s] = W;
                         s_acc[3] += (uint32_t)W;
                     }
-                    if (A.kbest) A.kb_len[(size_t)s * K + r0] = W;
+                    if constexpr (KB != 0) A.kb_len[(size_t)s * K + r0] = W;
                 }
                 W = __shfl_sync(kFull, W, 0);
                 __syncwarp();
@@ -1027,7 +1069,7 @@ __global__ void __launch_bounds__(kBeamMaxWarps * 32, LT_BEAM_MINB) beam_kernel(
                         ed = A.edges[eref];
                     }
                     if (r0 == 0) A.path_tmp[s0 + w] = ed;
-                    if (A.kbest) A.kb_tmp[(size_t)s0 * K + (size_t)r0 * (s1 - s0) + w] = ed;
+                    if constexpr (KB != 0) A.kb_tmp[(size_t)s0 * K + (size_t)r0 * (s1 - s0) + w] = ed;
                 }
                 __syncwarp();
             }

@@ -500,7 +500,9 @@ __device__ LT_FLUSH_ATTR void flush_staged(const LatticeArgs& A, int lane, uint3
 #define LT_LAT_MINB 2
 #endif
 // UC / HCT: sentence-array size and staging capacity when known at compile time (0 = A.units / A.hcap)
-template <int UC, int HCT>
+// LM: 0 = MorphemeLookup only (what Tagger.tag uses; the other lookups compile out of the throughput path),
+//     1 = the lookup named by A.mode.
+template <int UC, int HCT, int LM = 0>
 __global__ void __launch_bounds__(kLatMaxWarps * 32, LT_LAT_MINB) lattice_kernel(const __grid_constant__ DevTables T,
                                                                 const __grid_constant__ LatticeArgs A) {
     LT_DYN_SMEM(smem_raw);
@@ -604,8 +606,8 @@ __global__ void __launch_bounds__(kLatMaxWarps * 32, LT_LAT_MINB) lattice_kernel
             alive = 0;
         };
 
-        const int mode = A.mode;
-        const bool word_mode = mode >= LT_LOOKUP_WORD;
+        const int mode = LM ? A.mode : LT_LOOKUP_MORPHEME;
+        const bool word_mode = LM && mode >= LT_LOOKUP_WORD;
         for (int w = 0; w < n_eoj && !overflow; ++w) {
             const int o = eoj[w];
             const int n = eoj[w + 1] - o;

@@ -401,12 +401,14 @@ static const size_t kSmemBudget = 200 * 1024;
 // shared memory, resident CTAs per SM.  Nothing of this is recomputed (or asked of the driver) per batch.
 struct LatticePlan {
     int units = 0, hcap = 0;                  // key
+    bool generic = false, any_lookup = false;
     void (*fn)(const DevTables, const LatticeArgs) = nullptr;
     int warps = 0, per_sm = 1;
     size_t smem = 0, warp_smem = 0;
 };
 struct BeamPlan {
     int units = 0, beam = 0;                  // key
+    bool kbest = false;
     void (*fn)(const DevTables, const BeamArgs) = nullptr;
     int warps = 0, per_sm = 1;
     size_t smem = 0, warp_smem = 0;
@@ -572,13 +574,16 @@ static int lattice_plan(lt_batch* b, int lcap, int hcap, bool retry_pass, const 
     const int max_str = std::max(1, t->dev.max_str);
     if (hcap & 1) ++hcap;                               // keeps the arrays behind the staging area 8-byte aligned
     // common sentence-array sizes (with the default staging capacity) have their own instantiation
-    const int uclass = (!retry_pass && (hcap == kLatDefaultHcap || hcap == 2 * kLatDefaultHcap)) ? lattice_units_class(lcap) : 0;
+    const bool any_lookup = b->lookup_mode != LT_LOOKUP_MORPHEME;      // the other lookups run in the generic instantiation
+    const int uclass = (!any_lookup && !retry_pass && (hcap == kLatDefaultHcap || hcap == 2 * kLatDefaultHcap)) ? lattice_units_class(lcap) : 0;
     const int units = uclass ? uclass : lcap + 8;
     for (const LatticePlan& p : b->lattice_plans)
-        if (p.units == units && p.hcap == hcap && (p.fn == lt::lattice_kernel<0, 0>) == (uclass == 0)) { *out = &p; return LT_OK; }
+        if (p.units == units && p.hcap == hcap && p.generic == (uclass == 0) && p.any_lookup == any_lookup) { *out = &p; return LT_OK; }
     LatticePlan P;
     P.units = units;
     P.hcap = hcap;
+    P.generic = uclass == 0;
+    P.any_lookup = any_lookup;
     P.warp_smem = lattice_warp_smem(units, hcap, max_str);
     if (retry_pass) {
         if (P.warp_smem > kSmemBudget)
@@ -603,7 +608,7 @@ static int lattice_plan(lt_batch* b, int lcap, int hcap, bool retry_pass, const 
          : (uclass == 128 && hcap == kLatDefaultHcap) ? lt::lattice_kernel<128, kLatDefaultHcap>
          : (uclass == 64 && hcap == 2 * kLatDefaultHcap) ? lt::lattice_kernel<64, 2 * kLatDefaultHcap>
          : (uclass == 128 && hcap == 2 * kLatDefaultHcap) ? lt::lattice_kernel<128, 2 * kLatDefaultHcap>
-         : lt::lattice_kernel<0, 0>;
+         : any_lookup ? lt::lattice_kernel<0, 0, 1> : lt::lattice_kernel<0, 0, 0>;
     if (int rc = smem_limit(t, P.fn, P.smem)) return rc;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&P.per_sm, P.fn, P.warps * 32, P.smem));
     P.per_sm = std::max(1, P.per_sm);
@@ -615,13 +620,14 @@ static int lattice_plan(lt_batch* b, int lcap, int hcap, bool retry_pass, const 
     return LT_OK;
 }
 
-static int beam_plan(lt_batch* b, int lcap, int beam_size, const BeamPlan** out) {
+static int beam_plan(lt_batch* b, int lcap, int beam_size, bool kbest, const BeamPlan** out) {
     lt_tables* t = b->tables;
-    // sentence arrays: common sizes are template parameters of the kernel (for beams 5 and 10)
-    const int uclass = (beam_size == 5 || beam_size == 10) ? beam_units_class(lcap) : 0;
+    // sentence arrays: common sizes are template parameters of the kernel (for beams 5 and 10); the all-survivors
+    // variant (lt_beam_kbest) exists in the generic instantiations only
+    const int uclass = (!kbest && (beam_size == 5 || beam_size == 10)) ? beam_units_class(lcap) : 0;
     const int units = uclass ? uclass : lcap + 8;
     for (const BeamPlan& p : b->beam_plans)
-        if (p.units == units && p.beam == beam_size) { *out = &p; return LT_OK; }
+        if (p.units == units && p.beam == beam_size && p.kbest == kbest) { *out = &p; return LT_OK; }
     const size_t dense_bytes = ((size_t)t->dev.n_tri * dense_block_bytes(t->dev.n_tags) + 15) & ~(size_t)15;
     // CTA shape: the warps per CTA (1..8) that keep the most warps resident on an SM under the kernel's
     // 128 registers per thread (16 warps) and the per-warp shared memory; ties go to 4-warp CTAs
@@ -647,6 +653,7 @@ static int beam_plan(lt_batch* b, int lcap, int beam_size, const BeamPlan** out)
     BeamPlan P;
     P.units = units;
     P.beam = beam_size;
+    P.kbest = kbest;
     P.trail_smem = b->trail_smem_ok && w_own > 0 && resident_warps(smem_own_trail, w_own) >= resident_warps(smem_hbm_trail, w_hbm);
     P.warp_smem = P.trail_smem ? smem_own_trail : smem_hbm_trail;
     P.warps = P.trail_smem ? w_own : w_hbm;
@@ -654,7 +661,8 @@ static int beam_plan(lt_batch* b, int lcap, int beam_size, const BeamPlan** out)
     // common beam sizes, sentence-array sizes and the (RegularizationScore, SimpleTrigramFeatureScore)
     // score program get their own instantiation (compile-time array offsets, unrolled scorer loop)
     const bool reg_tri = t->dev.n_funcs == 2 && t->dev.funcs[0].kind == LT_FUNC_REG && t->dev.funcs[1].kind == LT_FUNC_TRIGRAM;
-    if (beam_size == 5 && uclass == 64) P.fn = reg_tri ? beam_kernel<2, 5, 64, 1> : beam_kernel<2, 5, 64, 0>;
+    if (kbest) P.fn = beam_size <= kRankMaxBeam ? beam_kernel<2, 0, 0, 0, 1> : (beam_size <= 32 ? beam_kernel<1, 0, 0, 0, 1> : beam_kernel<0, 0, 0, 0, 1>);
+    else if (beam_size == 5 && uclass == 64) P.fn = reg_tri ? beam_kernel<2, 5, 64, 1> : beam_kernel<2, 5, 64, 0>;
     else if (beam_size == 5 && uclass == 128) P.fn = reg_tri ? beam_kernel<2, 5, 128, 1> : beam_kernel<2, 5, 128, 0>;
     else if (beam_size == 5) P.fn = reg_tri ? beam_kernel<2, 5, 0, 1> : beam_kernel<2, 5, 0, 0>;
     else if (beam_size == 10 && uclass == 64) P.fn = reg_tri ? beam_kernel<2, 10, 64, 1> : beam_kernel<2, 10, 64, 0>;
@@ -790,7 +798,7 @@ static int launch_beam(lt_batch* b, cudaStream_t st, bool kbest) {
     }
 
     const BeamPlan* P = nullptr;
-    if (int rc = beam_plan(b, b->lcap, beam_size, &P)) return rc;
+    if (int rc = beam_plan(b, b->lcap, beam_size, kbest, &P)) return rc;
     b->last_beam_plan = P;
     if (!P->trail_smem)
         if (int rc = ensure(b->trail, nu * (size_t)beam_size * 8)) return rc;

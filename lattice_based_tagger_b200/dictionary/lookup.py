@@ -10,8 +10,9 @@ One call looks one eojeol up; `lookup_batch` / `sentence_lookup_batch` are the c
 built for.
 
 Order of the returned words: the device emits edges grouped by (end, begin), each group in the
-reference's order — the only order `beam_search` can observe.  `sentence_lookup`
-returns them in that order, not in the reference's enumeration order across groups.
+reference's order — the only order `beam_search` can observe.  `lookup_batch`
+returns that order; `sentence_lookup*` and `lookup()` put the groups back into the reference's
+enumeration order (`enumeration_order`, a permutation that follows from the spans alone).
 """
 
 from .. import _native
@@ -73,15 +74,23 @@ class EojeolLookup:
         """Words of one eojeol, `b` / `e` shifted by `offset`."""
         if ' ' in eojeol:
             raise ValueError('an eojeol holds no space')
-        words = self.lookup_batch([eojeol])[0]
+        words = self.lookup_batch([eojeol], reference_order=True)[0]
         if offset:
             words = [w._replace(b=w.b + offset, e=w.e + offset) for w in words]
         return words
 
     # -- batched -----------------------------------------------------------------------------------
-    def lookup_batch(self, sents, errors='raise'):
-        """Dictionary words of every sentence (eojeols separated by spaces), without BOS / EOS."""
-        found = self._ensure().lattice_words(list(sents), errors)
+    def lookup_batch(self, sents, errors='raise', reference_order=None):
+        """Dictionary words of every sentence (eojeols separated by spaces), without BOS / EOS.
+
+        The device returns them grouped by (end, begin); `reference_order=True` puts them back into the
+        order the reference's lookup enumerates them in (whole eojeol, then its splits / substrings).
+        `flatten=True` needs that order — the split words land in other (begin, end) groups, and their
+        order inside a group is the enumeration order — and therefore implies it."""
+        sents = list(sents)
+        found = self._ensure().lattice_words(sents, errors)
+        if reference_order or (reference_order is None and self.flatten):
+            found = [None if words is None else enumeration_order(sent, words, self.mode) for sent, words in zip(sents, found)]
         if self.flatten:
             found = [None if words is None else flatten_words(words) for words in found]
         return found
@@ -143,6 +152,51 @@ class ExactLookup(EojeolLookup):
     mode = _native.LT_LOOKUP_EXACT
 
 
+def enumeration_order(sent, words, mode):
+    """Device order (end, begin, order inside the span) -> the reference's enumeration order.
+
+    Inside one (begin, end) span both orders agree; across spans the reference's order follows from
+    the span alone.  Per eojeol [o, oe): `lr_lookup` / the first stage of `morpheme_lookup` list the
+    whole eojeol, then for i = 1.. the left part [o, o+i) followed by the right part [o+i, oe)
+    (`lookup.py:191-209`); the sub-word scan and `word_lookup`'s loop go by begin, then end
+    (`lookup.py:259-277`, `:161-168`).  A first-stage result always holds a word that starts the
+    eojeol, a scan result never does (it begins at 1), which tells the two apart; `word_lookup`'s
+    initial whole-eojeol analyses come first and — without prefer_exact_match — once more inside the loop.
+    """
+    if not words:
+        return words
+    bounds = []
+    o = 0
+    for eojeol in sent.split():
+        bounds.append((o, o + len(eojeol)))
+        o += len(eojeol)
+    by_eojeol = {bound: [] for bound in bounds}
+    starts = [b for b, _ in bounds]
+    import bisect
+    for w in words:
+        by_eojeol[bounds[bisect.bisect_right(starts, w.b) - 1]].append(w)
+    word_mode = mode in (_native.LT_LOOKUP_WORD, _native.LT_LOOKUP_WORD_ALL)
+    out = []
+    for (o, oe) in bounds:
+        group = by_eojeol[(o, oe)]
+        if not group:
+            continue
+        if word_mode:
+            whole = [w for w in group if w.b == o and w.e == oe]
+            rest = [w for w in group if not (w.b == o and w.e == oe)]
+            if mode == _native.LT_LOOKUP_WORD_ALL:
+                first, again = whole[:len(whole) // 2], whole[len(whole) // 2:]
+            else:
+                first, again = (whole, []) if not rest else ([], whole)
+            out += first
+            out += sorted(rest + again, key=lambda w: (w.b, w.e))
+        elif any(w.b == o for w in group):
+            out += sorted(group, key=lambda w: 0 if (w.b == o and w.e == oe) else (2 * (w.e - o) - 1 if w.b == o else 2 * (w.b - o)))
+        else:
+            out += sorted(group, key=lambda w: (w.b, w.e))
+    return out
+
+
 def begin_index(n, words):
     """`bindex` of `sentence_lookup_as_begin_index` (`lookup.py:357-369`)."""
     if not words:
@@ -159,13 +213,13 @@ def _with_sentinels(sent, words):
 
 
 def sentence_lookup(sent, eojeol_lookup):
-    """[BOS] + dictionary words + [EOS] (reference `lookup.py:7-62`)."""
-    return _with_sentinels(sent, eojeol_lookup.lookup_batch([sent])[0])
+    """[BOS] + dictionary words + [EOS], in the reference's order (reference `lookup.py:7-62`)."""
+    return _with_sentinels(sent, eojeol_lookup.lookup_batch([sent], reference_order=True)[0])
 
 
 def sentence_lookup_batch(sents, eojeol_lookup):
     sents = list(sents)
-    return [_with_sentinels(s, w) for s, w in zip(sents, eojeol_lookup.lookup_batch(sents))]
+    return [_with_sentinels(s, w) for s, w in zip(sents, eojeol_lookup.lookup_batch(sents, reference_order=True))]
 
 
 def sentence_lookup_as_begin_index(sent, eojeol_lookup):

@@ -1,9 +1,11 @@
 """Sentence sharding across GPUs (host side).
 
 The decode path shards by independent sentences: every rank holds the full (read-only)
-tables and tags a contiguous, length-balanced slice of the batch; there is no collective on the data
-path.  The only exchange is the final gather of the per-sentence results on the host, for which
-`gather_results` uses `torch.distributed.all_gather_object` (NCCL or gloo process groups alike).
+tables and tags its part of the batch; there is no collective on the data path.  The only exchange
+is the final gather of the results: `tag_sharded_packed` moves the PACKED results (numpy arrays: path
+lengths, 16-byte word records, scores, statuses) as tensors over the process group — NCCL or gloo —
+and puts them back into input order on rank 0; `gather_results` / `tag_sharded` do the same for
+lists of Python objects with `all_gather_object` (convenient, slow for large batches).
 """
 
 import numpy as np
@@ -80,3 +82,73 @@ def gather_results(local, world_size):
     for p in parts:
         out.extend(p)
     return out
+
+
+def tag_sharded_packed(tagger, sents, beam_size, rank, world_size, device=None, parts=None):
+    """One batch over `world_size` ranks: every rank tags the sentences `partition_by_work` deals it
+    (`tagger.tag_batch_packed`, i.e. `lt_tag_batch_host`), the packed results are gathered on rank 0
+    as tensors and returned there in INPUT order as (path_off, path_edges, scores, status) — the
+    tuple `Tagger.tag_batch_packed` returns for the whole batch on one GPU; other ranks get None.
+
+    `device`: where the exchanged tensors live (a CUDA device for NCCL groups, None = CPU for gloo).
+    """
+    import torch
+    import torch.distributed as dist
+    from . import _native
+    n = len(sents)
+    if parts is None:
+        parts = partition_by_work([len(s) for s in sents], world_size)
+    mine = parts[rank]
+    path_off, edges, scores, status = tagger.tag_batch_packed([sents[i] for i in mine], beam_size)
+    plen = np.diff(path_off).astype(np.int32)
+    if world_size <= 1:
+        return path_off, edges, scores, status
+
+    def tensor(arr, dtype):
+        t = torch.from_numpy(np.ascontiguousarray(arr)).to(dtype)
+        return t if device is None else t.to(device)
+
+    counts = tensor(np.array([plen.size, edges.size], dtype=np.int64), torch.int64)
+    all_counts = [torch.zeros_like(counts) for _ in range(world_size)]
+    dist.all_gather(all_counts, counts)
+    sizes = [(int(c[0]), int(c[1])) for c in all_counts]
+    max_s = max(1, max(a for a, _ in sizes))
+    max_e = max(1, max(b for _, b in sizes))
+
+    def padded(arr, size, dtype):
+        buf = torch.zeros(size, dtype=dtype, device=counts.device)
+        if arr.size:
+            buf[:arr.size] = tensor(arr, dtype)
+        return buf
+
+    raw_edges = np.ascontiguousarray(edges).view(np.uint8).reshape(-1, 16).view(np.int64).reshape(-1)
+    send = [padded(plen, max_s, torch.int32), padded(status.astype(np.int32), max_s, torch.int32),
+            padded(scores, max_s, torch.float64), padded(raw_edges, 2 * max_e, torch.int64)]
+    got = []
+    for buf in send:
+        dst = [torch.empty_like(buf) for _ in range(world_size)] if rank == 0 else None
+        dist.gather(buf, dst, 0)
+        got.append(dst)
+    if rank != 0:
+        return None
+    plen_all = np.zeros(n, dtype=np.int32)
+    status_all = np.zeros(n, dtype=np.int32)
+    scores_all = np.zeros(n, dtype=np.float64)
+    pieces = []
+    for r in range(world_size):
+        ns, ne = sizes[r]
+        plen_all[parts[r]] = got[0][r][:ns].cpu().numpy()
+        status_all[parts[r]] = got[1][r][:ns].cpu().numpy()
+        scores_all[parts[r]] = got[2][r][:ns].cpu().numpy()
+        pieces.append(got[3][r][:2 * ne].cpu().numpy().view(np.uint8).reshape(-1, 16).view(_native.EDGE_DTYPE).reshape(-1))
+    # inverse permutation of the word records: those of sentence i go to path_off[i]
+    out_off = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(plen_all, out=out_off[1:])
+    out_edges = np.empty(int(out_off[-1]), dtype=_native.EDGE_DTYPE)
+    for r in range(world_size):
+        idx = parts[r]
+        src_off = np.zeros(idx.size + 1, dtype=np.int64)
+        np.cumsum(plen_all[idx], out=src_off[1:])
+        dst = np.repeat(out_off[idx] - src_off[:-1], plen_all[idx]) + np.arange(int(src_off[-1]), dtype=np.int64)
+        out_edges[dst] = pieces[r]
+    return out_off.astype(np.int32), out_edges, scores_all, status_all

@@ -80,10 +80,13 @@ def check_lookup_modes(case, beams=(1, 4)):
             lookup = make(dictionary, flatten)
             tagger = pkg.Tagger(dictionary, lookup=lookup, score_funcs=funcs)
             for sent, words in zip(sents, lookup.lookup_batch(sents)):
-                want = lattice_key(oracle.lattice(sent))
-                if flatten:
-                    want = lo.flatten_edges(want)
+                # flatten=False: device order (end, begin); flatten=True: the reference's own order
+                want = oracle.lattice(sent, flatten=True) if flatten else lattice_key(oracle.lattice(sent))
                 assert [tuple(w) for w in words] == want, (name, flatten, sent)
+            for sent in sents[:6]:
+                # sentence_lookup: the reference's enumeration order, word for word
+                got = pkg.dictionary.sentence_lookup(sent, lookup)[1:-1]
+                assert [tuple(w) for w in got] == oracle.lattice(sent, flatten=flatten), (name, flatten, sent)
             for k in beams:
                 got = tagger.tag_batch_kbest(sents, beam_size=k, errors='none')
                 for sent, seqs in zip(sents, got):
@@ -122,7 +125,7 @@ def check_host_api(case):
     for sent in sents[:8]:
         edges = lo.sentence_edges(sent, view, lookup='lr_all')
         words, bindex = pkg.dictionary.sentence_lookup_as_begin_index(sent, lookup)
-        assert [tuple(w) for w in words[1:-1]] == lattice_key(edges)
+        assert [tuple(w) for w in words[1:-1]] == edges
         chars = sent.replace(' ', '')
         try:
             want = lo.beam_search(lo.begin_index(sent, edges), chars, program, 3)
@@ -138,6 +141,6 @@ def check_host_api(case):
             assert [tuple(w) for w in seq.sequences] == hyp.words, sent
             assert seq.score == hyp.score
         nodes, links = pkg.dictionary.sentence_lookup_as_graph(sent, lookup)
-        want_nodes, want_links = lo.lattice_graph(sent, lattice_key(edges))
+        want_nodes, want_links = lo.lattice_graph(sent, edges)
         assert [tuple(w) for w in nodes] == want_nodes
         assert [[tuple(a), tuple(b), w] for a, b, w in links] == want_links

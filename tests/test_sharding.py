@@ -66,3 +66,62 @@ def test_two_ranks_gather_in_order(tmp_path):
     mp.spawn(_worker, args=(world, _free_port(), 77, str(tmp_path)), nprocs=world, join=True)
     for rank in range(world):
         assert (tmp_path / ('rank%d' % rank)).read_text() == 'ok'
+
+
+def test_partition_by_work_balances_and_covers():
+    rng = np.random.default_rng(1)
+    lengths = rng.integers(0, 120, size=1003)
+    for world in (1, 2, 4, 8):
+        parts = sharding.partition_by_work(lengths, world)
+        assert len(parts) == world
+        assert sorted(np.concatenate(parts).tolist()) == list(range(1003))
+        counts = [len(p) for p in parts]
+        assert max(counts) - min(counts) <= 1
+        work = [int(lengths[p].sum()) for p in parts]
+        assert max(work) - min(work) <= 120 * 2
+        assert all((np.diff(p) > 0).all() for p in parts if len(p) > 1)
+
+
+def _packed_worker(rank, world, port, seed, out_dir):
+    """`tag_sharded_packed` over gloo: the packed results of two ranks gathered as tensors and put back
+    into input order must equal one rank tagging everything.  The tagger is the package's own, running
+    the kernel sources through the SIMT emulator (tests/_emu.py)."""
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from tests import _checks, _emu
+    with _emu.emulated():
+        case = _checks.make_case(seed, n_sent=20, max_sent_len=30)
+        dictionary, funcs = _cases.build_objects(case, pkg)
+        tagger = pkg.Tagger(dictionary, score_funcs=funcs)
+        sents = case['sentences']
+        merged = sharding.tag_sharded_packed(tagger, sents, 5, rank, world)
+        ok = True
+        if rank == 0:
+            whole = tagger.tag_batch_packed(sents, 5)
+            ok = all(np.array_equal(a, b) for a, b in zip(merged, whole))
+            oracle = lo.OracleTagger(dictionary, funcs)
+            seqs = tagger.unpack(sents, merged, errors='none')
+            for sent, seq in zip(sents, seqs):
+                try:
+                    want = oracle.tag(sent, 5)
+                except IndexError:
+                    ok = ok and seq is None
+                    continue
+                ok = ok and [tuple(w) for w in seq.sequences] == want.words and seq.score == want.score
+        else:
+            ok = merged is None
+        tagger.close()
+    with open(os.path.join(out_dir, 'rank%d' % rank), 'w') as f:
+        f.write('ok' if ok else 'mismatch')
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_ranks_packed_gather(tmp_path):
+    from tests import _emu
+    _emu.emu_lib()          # built once here, not by two processes at the same time
+    world = 2
+    mp.spawn(_packed_worker, args=(world, _free_port(), 91, str(tmp_path)), nprocs=world, join=True)
+    for rank in range(world):
+        assert (tmp_path / ('rank%d' % rank)).read_text() == 'ok'

@@ -114,9 +114,18 @@ __host__ __device__ inline size_t beam_ring_bytes(int beam) {
     return (((size_t)kRing * beam * (8 + 48 + 4 + 1)) + 15) & ~(size_t)15;
 }
 __host__ __device__ inline size_t beam_sentence_bytes(int units) { return (size_t)units * (8 + 8 + 8 + 2); }
-__host__ __device__ inline size_t beam_warp_smem(int units, int beam, int n_funcs, bool trail_smem) {
-    const size_t nf = (size_t)(n_funcs > 0 ? n_funcs : 1);
-    const size_t bytes = kBeamFixedBytes + beam_ring_bytes(beam) + beam_sentence_bytes(units) + (size_t)kCacheSlots * 16 * nf +
+#ifndef LT_BEAM_KVAL2
+#define LT_BEAM_KVAL2 1        // 1: the (Regularization, Trigram) program caches only the template-4 / 5 weights per edge
+#endif
+// doubles of edge-only score values per cache slot: two per scorer; the (RegularizationScore,
+// SimpleTrigramFeatureScore) program keeps only the template-4 / template-5 weights (the regulariser is a
+// function of tag and length, recomputed per candidate: 1.5 KB of shared memory per warp is worth more)
+__host__ __device__ inline int beam_kval_doubles(int n_funcs, bool reg_tri) {
+    if (reg_tri) return LT_BEAM_KVAL2 ? 2 : 4;
+    return 2 * (n_funcs > 0 ? n_funcs : 1);
+}
+__host__ __device__ inline size_t beam_warp_smem(int units, int beam, int kval_doubles, bool trail_smem) {
+    const size_t bytes = kBeamFixedBytes + beam_ring_bytes(beam) + beam_sentence_bytes(units) + (size_t)kCacheSlots * 8 * (size_t)kval_doubles +
                          (trail_smem ? (size_t)units * beam * 4 : 0);
     return (bytes + 15) & ~(size_t)15;
 }
@@ -196,8 +205,11 @@ __device__ __forceinline__ void unknown_edge(int b, int e, EdgeView& k) {
     k.split = 0; k.flags = LT_EDGE_UNK;
 }
 
+// IMP: the batch may hold an imported lattice (lt_lattice_import) — only the all-survivors kernels (KB = 1)
+// are launched on one, so the throughput instantiations compile the test out.
+template <int IMP>
 __device__ __noinline__ void edge_hashes(const DevTables& T, const SentView& v, EdgeView& k, bool need_m1) {
-    if (k.flags & LT_EDGE_EXPLICIT) {
+    if (IMP != 0 && (k.flags & LT_EDGE_EXPLICIT)) {
         // imported lattice (lt_lattice_import): the strings of this word were hashed on the host
         const H2* h = v.imp + 3 * (size_t)k.rule;
         k.wk = h[0];
@@ -325,11 +337,24 @@ __device__ __forceinline__ double unsortable(uint64_t key) {
 #define LT_BEAM_MINB 2
 #endif
 #ifndef LT_TOPK_ROUNDS
-#define LT_TOPK_ROUNDS 1       // 1: positions whose candidates fit one chunk select by K rounds of warp arg-max
+#define LT_TOPK_ROUNDS 0       // 1: positions whose candidates fit one chunk select by K rounds of warp arg-max (measured: no
+                               // faster than rank counting — the kernel waits on dependent latency, not on issue slots)
+#endif
+#ifndef LT_FLOAT_DIV
+#define LT_FLOAT_DIV 0
 #endif
 #ifndef LT_PROBE_SPLIT
 #define LT_PROBE_SPLIT 1       // 1: generic kernels issue the loads of templates 7 and 8 after templates 0..2 are consumed
 #endif
+#ifndef LT_BEAM_HOT_MINB
+#define LT_BEAM_HOT_MINB 4     // resident 4-warp CTAs per SM the small-beam throughput instantiations are compiled for
+#endif
+// Launch bounds per instantiation: the throughput instantiations of beams 5 / 10 on 64- or 128-element sentence
+// arrays always run as 4-warp CTAs and may be compiled for more of them per SM (fewer registers); everything
+// else keeps CTAs of up to 8 warps at 128 registers.
+constexpr bool beam_is_hot(int KT, int UC, int PROG, int KB) { return KT != 0 && UC != 0 && PROG == 1 && KB == 0; }
+constexpr int beam_max_threads(int KT, int UC, int PROG, int KB) { return beam_is_hot(KT, UC, PROG, KB) ? 128 : 256; }
+constexpr int beam_min_blocks(int KT, int UC, int PROG, int KB) { return beam_is_hot(KT, UC, PROG, KB) ? LT_BEAM_HOT_MINB : LT_BEAM_MINB; }
 constexpr int kBeamWarps = 4;                 // preferred warps per CTA of the beam kernel
 constexpr int kBeamMaxWarps = 8;              // largest CTA (128 registers per thread either way: 8 warps x 2 CTAs = 4 warps x 4 CTAs)
 
@@ -378,10 +403,10 @@ __device__ __forceinline__ void beam_prefix_hashes(const uint16_t* ch, int L, in
 }
 
 // Edge prep: hash products and the edge-only part of the score program into cache slot `slot`.
-template <int PROG>
+template <int PROG, int IMP>
 __device__ __forceinline__ void prep_edge(const DevTables& T, const SentView& v, const unsigned char* dense_smem,
                                           EdgeView& k, bool need_m1, int nf, int kvs, const EdgeCache& C, uint32_t slot) {
-    edge_hashes(T, v, k, need_m1);
+    edge_hashes<IMP>(T, v, k, need_m1);
     const H2 e0 = h2_mul(k.wk, kM0a, kM0b), g0 = h2_mul(k.mk, kM0a, kM0b);
     uint32_t present = 0;
     if (PROG == 1) {
@@ -390,12 +415,23 @@ __device__ __forceinline__ void prep_edge(const DevTables& T, const SentView& v,
         double reg, unused, w4, w5;
         const uint32_t tri = edge_score_body(T, dense_smem, k, e0, g0, 1, LT_FUNC_TRIGRAM, feature_seed(4u, 1u), feature_seed(5u, 1u),
                                              H2{0, 0}, w4, w5);
+#if !LT_BEAM_KVAL2
         edge_score_body(T, dense_smem, k, e0, g0, 0, LT_FUNC_REG, H2{0, 0}, H2{0, 0}, H2{0, 0}, reg, unused);
+#else
+        reg = 0.0; unused = 0.0;
+#endif
+        (void)unused;
         present = tri << 2;
+#if LT_BEAM_KVAL2
+        (void)reg;
+        C.kval[slot * 2 + 0] = w4;
+        C.kval[slot * 2 + 1] = w5;
+#else
         C.kval[slot * 4 + 0] = reg;
         C.kval[slot * 4 + 1] = 0.0;
         C.kval[slot * 4 + 2] = w4;
         C.kval[slot * 4 + 3] = w5;
+#endif
     } else {
         #pragma unroll 1
         for (int f = 0; f < nf; ++f) {
@@ -423,7 +459,7 @@ __device__ __forceinline__ void prep_edge(const DevTables& T, const SentView& v,
 // KB: 1 = every survivor of the last position is written out as well (lt_beam_kbest); 0 compiles that out of
 // the instantiations the throughput path runs.
 template <int MODE, int KT, int UC, int PROG, int KB = 0>
-__global__ void __launch_bounds__(kBeamMaxWarps * 32, LT_BEAM_MINB) beam_kernel(const __grid_constant__ DevTables T, const __grid_constant__ BeamArgs A) {
+__global__ void __launch_bounds__(beam_max_threads(KT, UC, PROG, KB), beam_min_blocks(KT, UC, PROG, KB)) beam_kernel(const __grid_constant__ DevTables T, const __grid_constant__ BeamArgs A) {
     constexpr int KR = (MODE == 0) ? 2 : 1;      // kept entries per lane
     LT_DYN_SMEM(smem_raw);
     const int lane = threadIdx.x & 31;
@@ -450,7 +486,8 @@ __global__ void __launch_bounds__(kBeamMaxWarps * 32, LT_BEAM_MINB) beam_kernel(
     const bool trail_smem = A.trail_smem != 0;
     const int units = UC ? UC : A.units;
     const int RK = kRing * K;
-    unsigned char* wbase = smem_raw + dense_bytes + (size_t)warp * beam_warp_smem(units, K, T.n_funcs, trail_smem);
+    const int kvs = beam_kval_doubles(T.n_funcs, PROG == 1);   // kval stride
+    unsigned char* wbase = smem_raw + dense_bytes + (size_t)warp * beam_warp_smem(units, K, kvs, trail_smem);
     // fixed part
     EdgeCache C;
     C.e0 = reinterpret_cast<H2*>(wbase);
@@ -479,7 +516,6 @@ __global__ void __launch_bounds__(kBeamMaxWarps * 32, LT_BEAM_MINB) beam_kernel(
     uint2* spos = reinterpret_cast<uint2*>(hb + units);
     uint16_t* ch = reinterpret_cast<uint16_t*>(spos + units);
     C.kval = reinterpret_cast<double*>(ch + units);
-    const int kvs = PROG == 1 ? 4 : 2 * (T.n_funcs > 0 ? T.n_funcs : 1);   // kval stride
     uint32_t* s_trail = reinterpret_cast<uint32_t*>(C.kval + kCacheSlots * kvs);   // [units * K] when trail_smem
 
     if (lane < 4) s_acc[lane] = 0;
@@ -512,7 +548,7 @@ __global__ void __launch_bounds__(kBeamMaxWarps * 32, LT_BEAM_MINB) beam_kernel(
         __syncwarp();
         for (int i = lane; i < L; i += 32) spos[i] = __ldg(A.pos + s0 + i);
         beam_prefix_hashes(ch, L, lane, ha, hb);
-        SentView v{ch, ha, hb, nullptr, A.imp};
+        SentView v{ch, ha, hb, nullptr, KB ? A.imp : nullptr};
 
         if (L == 0 && lane == 0) { A.path_len[s] = 0; A.scores[s] = 0.0; }
 
@@ -564,7 +600,7 @@ __global__ void __launch_bounds__(kBeamMaxWarps * 32, LT_BEAM_MINB) beam_kernel(
                         const uint32_t gi = start + lane;
                         EdgeView k;
                         unpack_edge(ldg16(A.edges + gi), k);
-                        prep_edge<PROG>(T, v, dense_smem, k, need_m1, nf, kvs, C, gi & (kEdgeRing - 1));
+                        prep_edge<PROG, KB>(T, v, dense_smem, k, need_m1, nf, kvs, C, gi & (kEdgeRing - 1));
                     }
                     ring_hi = start + n;
                     if (ring_hi - ring_lo > (uint32_t)kEdgeRing) ring_lo = ring_hi - kEdgeRing;
@@ -578,7 +614,7 @@ __global__ void __launch_bounds__(kBeamMaxWarps * 32, LT_BEAM_MINB) beam_kernel(
                 if (pe <= L && j <= pe) {
                     EdgeView k;
                     unknown_edge(pe - j, pe, k);
-                    prep_edge<PROG>(T, v, dense_smem, k, need_m1, nf, kvs, C, (uint32_t)(kEdgeRing + lane));
+                    prep_edge<PROG, KB>(T, v, dense_smem, k, need_m1, nf, kvs, C, (uint32_t)(kEdgeRing + lane));
                 }
                 __syncwarp();
             }
@@ -665,8 +701,12 @@ __global__ void __launch_bounds__(kBeamMaxWarps * 32, LT_BEAM_MINB) beam_kernel(
                     if (unk_edge) {
                         prank = (j < jmax) ? (uint32_t)s_nonunk[pbase + rem] : rem;
                     } else {
+#if LT_FLOAT_DIV
                         // (exact through a float reciprocal for the small numbers that occur, see small_div)
                         prank = (cj == 1u) ? rem : (uint32_t)small_div((int)rem, (int)cj, 1.0f / (float)cj);
+#else
+                        prank = (cj == 1u) ? rem : rem / cj;
+#endif
                         eidx = rem - prank * cj;
                     }
                     const int pslot = pbase + (int)prank;
@@ -681,7 +721,7 @@ __global__ void __launch_bounds__(kBeamMaxWarps * 32, LT_BEAM_MINB) beam_kernel(
                     if (uncached) {
                         // bucket larger than the cached part: prepare this edge on the fly
                         unpack_edge(ldg16(A.edges + es + bidx), kfly);
-                        edge_hashes(T, v, kfly, need_m1);
+                        edge_hashes<KB>(T, v, kfly, need_m1);
                         e0 = h2_mul(kfly.wk, kM0a, kM0b);
                         g0 = h2_mul(kfly.mk, kM0a, kM0b);
                         emeta = kfly.tag0 | (kfly.len << 8) | (kfly.flags << 24);
@@ -709,6 +749,19 @@ __global__ void __launch_bounds__(kBeamMaxWarps * 32, LT_BEAM_MINB) beam_kernel(
                             epresent |= edge_score(T, dense_smem, kfly, e0, g0, f, uv, uv5) << (2 * f);
                             val = uv;
                             val5 = uv5;
+                        } else if (PROG == 1 && LT_BEAM_KVAL2) {
+                            if (f == 0) {
+                                // RegularizationScore.score (score_funcs.py:65-73) from the cached tag / length
+                                const uint32_t elen = (emeta >> 8) & 0xFFFFu;
+                                const lt_func& fn = T.funcs[0];
+                                val = (tk == LT_TAG_UNK) ? __dmul_rn(fn.p[0], __dadd_rn((double)elen, 0.1)) : __dmul_rn(fn.p[1], (double)elen);
+                                val = __dadd_rn(0.0, val);
+                                if (elen == 1u && tk == LT_TAG_NOUN) val = __dadd_rn(val, fn.p[2]);
+                                val5 = 0.0;
+                            } else {
+                                val = C.kval[slot * 2 + 0];
+                                val5 = C.kval[slot * 2 + 1];
+                            }
                         } else {
                             val = C.kval[slot * kvs + 2 * f];
                             val5 = C.kval[slot * kvs + 2 * f + 1];
@@ -976,7 +1029,7 @@ __global__ void __launch_bounds__(kBeamMaxWarps * 32, LT_BEAM_MINB) beam_kernel(
                     } else {
                         EdgeView k;
                         unpack_edge(ldg16(A.edges + eref), k);
-                        edge_hashes(T, v, k, false);
+                        edge_hashes<KB>(T, v, k, false);
                         tag0 = k.tag0;
                         len = k.len;
                         wk1 = h2_mul(k.wk, kM1a, kM1b);

@@ -35,7 +35,11 @@ namespace lt {
 
 constexpr int kLatWarps = 4;                 // preferred warps per CTA of the lattice kernel
 constexpr int kLatMaxWarps = 8;              // largest CTA (128 registers per thread either way)
-constexpr int kRuleQueue = 256;              // rule-work descriptors per warp (drained when more than half full)
+#ifndef LT_RULE_QUEUE
+#define LT_RULE_QUEUE 256
+#endif
+constexpr int kRuleQueue = LT_RULE_QUEUE;    // rule-work descriptors per warp; a pass queues at most 3 per lane (96)
+constexpr int kRuleDrainAt = kRuleQueue - 96;   // drained between two passes once more than this many wait
 constexpr unsigned kFull = 0xFFFFFFFFu;
 
 // flags[] written by the lattice kernel, read by the beam kernel and the host
@@ -299,7 +303,7 @@ __device__ LT_STAGE_ATTR void stage_hit(const Enum& E, const lt_edge& rec, uint6
         E.hkey[slot] = key;
         E.htask[slot] = task;
     }
-    atomicAdd(&E.tcnt[task], 1u);
+    E.tcnt[task] = 1u;              // (only ever tested against zero)
 }
 
 // One (stem, eomi) lemma candidate whose strings are COMPOSED (a rule applied): the eomi must be a
@@ -468,6 +472,96 @@ __device__ __forceinline__ lt_edge edge_proto(int b, int e, uint32_t len, bool i
     return p;
 }
 
+#ifndef LT_LAT_COMPACT
+#define LT_LAT_COMPACT 1       // 1: an enumeration pass stages its hits / rule descriptors by warp compaction (emit_pass)
+#endif
+
+// One pass of an enumeration loop = 32 items, one per lane.  All lanes first decide what their item
+// produces — single-morpheme hits (`tagbits`), the plain-split analyses and the conjugation keys that
+// start at the split position (lemmatizer.py:90-112) — then the hits and the rule descriptors of
+// the whole pass are written side by side at offsets from ONE warp scan: no atomics, and the warp
+// stays converged (staging hit by hit under `if (found)` ran the staging code on 3-5 lanes at a time).
+//   tagbits   bit t: emit the single-morpheme word with tag t (Word.len = tag_len, is_l = tag_is_l)
+//   order4    position of tag t in the emission order of its span, 4 bits per tag id — or ~0: the
+//             dictionary's tag order (T.tag_pos, get_tags, dictionary.py:238-242)
+//   lemmas    also run the lemmatizer part for (word [b, e), split p)
+// Returns the number of lemma candidates the reference generates for the item.
+__device__ __forceinline__ uint32_t emit_pass(const DevTables& T, const SentView& v, const Enum& E, int lane, bool valid,
+                                              int b, int e, int p, uint32_t task, bool is_l, uint32_t tagbits,
+                                              uint32_t tag_len, bool tag_is_l, uint64_t order4, bool lemmas, uint32_t pass) {
+    uint32_t ncand = 0;
+    uint32_t hits = valid ? tagbits : 0u;
+    uint2 r1 = make_uint2(0u, 0u), rf = r1, rs = r1;
+    const bool last = (p == e - 1);
+    if (valid && lemmas) {
+        // plain split (not at the last syllable): both strings are sentence substrings -> table
+        if (!last) {
+            ncand = 1;
+            if (sub_get(E, p + 1, e) & kSubEomi) {
+                const uint32_t ps = sub_get(E, b, p + 1);
+                hits |= ((ps & kSubAdj) ? 1u << 29 : 0u) | ((ps & kSubVerb) ? 1u << 30 : 0u);
+            }
+        }
+        r1 = v.rref[3 * p + 0];
+        const uint2 r2 = (p + 2 <= e) ? v.rref[3 * p + 1] : make_uint2(0u, 0u);
+        const uint2 r3 = (p + 3 <= e) ? v.rref[3 * p + 2] : make_uint2(0u, 0u);
+        // {word[i:i+2], word[i:i+3]} in set order; at the last syllable both slices are that syllable itself:
+        // its rules once more, with an empty suffix
+        const bool k3_first = (r3.y >> 31) != 0;
+        rf = last ? r1 : (k3_first ? r3 : r2);
+        rs = last ? make_uint2(0u, 0u) : (k3_first ? r2 : r3);
+    }
+    const uint32_t c1 = r1.y & 0xFFFFu, cf = rf.y & 0xFFFFu, cs = rs.y & 0xFFFFu;
+    // one-syllable key: the whole rule list once per rule of the key (lemmatizer.py:100-102)
+    const uint32_t after1 = 1u + c1 * c1;
+    ncand += c1 * c1 + cf + cs;
+    const uint32_t nh_mine = (uint32_t)__popc(hits);
+    const uint32_t np_mine = (c1 ? 1u : 0u) + (cf ? 1u : 0u) + (cs ? 1u : 0u);
+    uint32_t incl = nh_mine | (np_mine << 16);
+    #pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(kFull, incl, d);
+        if (lane >= d) incl += t;
+    }
+    const uint32_t total = __shfl_sync(kFull, incl, 31);
+    const uint32_t cur_h = *E.nh, cur_q = *E.rqn;
+    __syncwarp();                                   // every lane has read the counters
+    if (lane == 31) {
+        *E.nh = cur_h + (total & 0xFFFFu);
+        *E.rqn = cur_q + (total >> 16);
+    }
+    uint32_t slot = cur_h + (incl & 0xFFFFu) - nh_mine;
+    if (hits) E.tcnt[task] = 1u;                    // (only ever tested against zero)
+    #pragma unroll 1
+    while (hits) {
+        const uint32_t t = (uint32_t)__ffs(hits) - 1u;
+        hits &= hits - 1u;
+        if (slot < (uint32_t)E.hcap) {
+            const bool lemma = t >= 29u;
+            const uint32_t tag0 = lemma ? (t == 29u ? (uint32_t)LT_TAG_ADJECTIVE : (uint32_t)LT_TAG_VERB) : t;
+            const uint32_t len = lemma ? (uint32_t)(e - b) : tag_len;
+            const uint32_t flags = lemma ? ((is_l ? LT_EDGE_IS_L : 0u) | LT_EDGE_LEMMA) : (tag_is_l ? LT_EDGE_IS_L : 0u);
+            const uint32_t split = lemma ? (uint32_t)(p - b) : 0u;
+            const uint32_t k = lemma ? t - 29u
+                                     : (order4 == ~0ull ? (uint32_t)T.tag_pos[t] : (uint32_t)((order4 >> (4u * (t & 15u))) & 0xFu));
+            reinterpret_cast<uint4*>(E.hrec)[slot] =
+                make_uint4((uint32_t)b | ((uint32_t)e << 16), len | (tag0 << 16) | ((lemma ? (uint32_t)LT_TAG_EOMI : (uint32_t)LT_NO_TAG) << 24),
+                           LT_NO_RULE, split | (flags << 16));
+            E.hkey[slot] = hit_key(e, b, lemma ? 1u : 0u, split, k, pass);
+            E.htask[slot] = task;
+        }
+        ++slot;
+    }
+    uint32_t qs = cur_q + (incl >> 16) - np_mine;
+    const uint32_t common = (uint32_t)b | ((uint32_t)p << 12) | (is_l ? 1u << 27 : 0u) | (pass << 29);
+    const uint32_t ytask = (uint32_t)e | (task << 12);
+    if (c1) E.rq[qs++] = make_uint4(common | (0u << 24) | (1u << 26), ytask, 1u | (c1 << 19), r1.x);
+    if (cf) E.rq[qs++] = make_uint4(common | ((last ? 2u : 1u) << 24) | (1u << 28), ytask, after1 | (cf << 19), rf.x);
+    if (cs) E.rq[qs++] = make_uint4(common | (1u << 24) | (1u << 28), ytask, (after1 + cf) | (cs << 19), rs.x);
+    __syncwarp();
+    return ncand;
+}
+
 // Write the staged survivors to HBM at (reservation + rank); CSR bookkeeping in shared memory.
 __device__ LT_FLUSH_ATTR void flush_staged(const LatticeArgs& A, int lane, uint32_t slots, uint32_t alive,
                                           const uint32_t* htask, const lt_edge* hrec, uint32_t* pcnt, uint32_t* pstart,
@@ -499,11 +593,19 @@ __device__ LT_FLUSH_ATTR void flush_staged(const LatticeArgs& A, int lane, uint3
 #ifndef LT_LAT_MINB
 #define LT_LAT_MINB 2
 #endif
+#ifndef LT_LAT_HOT_MINB
+#define LT_LAT_HOT_MINB 4      // resident 4-warp CTAs per SM the instantiations with compile-time array sizes are compiled for
+#endif
+// Launch bounds per instantiation (as for the beam kernel): the instantiations with compile-time sizes always run
+// as 4-warp CTAs; the generic one keeps CTAs of up to 8 warps at 128 registers.
+constexpr bool lattice_is_hot(int UC, int HCT, int LM) { return UC != 0 && HCT != 0 && LM == 0; }
+constexpr int lattice_max_threads(int UC, int HCT, int LM) { return lattice_is_hot(UC, HCT, LM) ? 128 : kLatMaxWarps * 32; }
+constexpr int lattice_min_blocks(int UC, int HCT, int LM) { return lattice_is_hot(UC, HCT, LM) ? LT_LAT_HOT_MINB : LT_LAT_MINB; }
 // UC / HCT: sentence-array size and staging capacity when known at compile time (0 = A.units / A.hcap)
 // LM: 0 = MorphemeLookup only (what Tagger.tag uses; the other lookups compile out of the throughput path),
 //     1 = the lookup named by A.mode.
 template <int UC, int HCT, int LM = 0>
-__global__ void __launch_bounds__(kLatMaxWarps * 32, LT_LAT_MINB) lattice_kernel(const __grid_constant__ DevTables T,
+__global__ void __launch_bounds__(lattice_max_threads(UC, HCT, LM), lattice_min_blocks(UC, HCT, LM)) lattice_kernel(const __grid_constant__ DevTables T,
                                                                 const __grid_constant__ LatticeArgs A) {
     LT_DYN_SMEM(smem_raw);
     const int lane = threadIdx.x & 31;
@@ -623,6 +725,27 @@ __global__ void __launch_bounds__(kLatMaxWarps * 32, LT_LAT_MINB) lattice_kernel
                 const int n_items1 = word_mode ? n : n * n;
                 for (int q0 = 0; q0 < n_items1; q0 += 32) {
                     const int q = q0 + lane;
+#if LT_LAT_COMPACT
+                    {
+                        const bool valid = q < n_items1;
+                        const int qq = valid ? q : 0;
+                        const int i = small_div(qq, n, inv_n), r = qq - i * n;
+                        const int p = o + r;
+                        // task: i == 0 whole; r < i: left_i = [o, o+i); else right_i = [o+i, oe)
+                        const bool left = (i > 0) && (r < i);
+                        const int b = (i > 0 && !left) ? o + i : o;
+                        const int e = left ? o + i : oe;
+                        const uint32_t task = (i == 0) ? 0u : (left ? 2u * i : 2u * i + 1u);
+                        // Noun + Josa special case: both edges carry len = n and nothing else is looked up (lookup.py:200-203)
+                        const bool special = (i > 0) && ((sub_get(E, o, o + i) >> LT_TAG_NOUN) & 1u) && ((sub_get(E, o + i, oe) >> LT_TAG_JOSA) & 1u);
+                        // the task's first item also reports its tag hits: one per tag of the string, in the dictionary's
+                        // tag order (get_tags, dictionary.py:238-242)
+                        uint32_t tagbits = 0;
+                        if (p == b) tagbits = special ? (left ? 1u << LT_TAG_NOUN : 1u << LT_TAG_JOSA) : (sub_get(E, b, e) & kSubTagMask & T.order_mask);
+                        ncand_try += emit_pass(T, v, E, lane, valid, b, e, p, task, b == o, tagbits, special ? (uint32_t)n : (uint32_t)(e - b),
+                                               special ? left : (b == o), special ? 0ull : ~0ull, !special, 0u);
+                    }
+#else
                     if (q < n_items1) {
                         const int i = small_div(q, n, inv_n), r = q - i * n;
                         const int p = o + r;
@@ -660,9 +783,10 @@ __global__ void __launch_bounds__(kLatMaxWarps * 32, LT_LAT_MINB) lattice_kernel
                         if (!special)
                             ncand_try += lemma_item(T, v, E, b, e, p, edge_proto(b, e, (uint32_t)(e - b), b == o), task);
                     }
+#endif
                     // (read by one lane between two barriers: a lane that ran ahead into the next pass must not be able
                     // to change what the others see here)
-                    if (warp_read(rqn) > (uint32_t)(kRuleQueue - 128)) drain_rules<UC, HCT>(T, base, units, HC, DM, lane);     // a pass queues at most 4 per lane
+                    if (warp_read(rqn) > (uint32_t)kRuleDrainAt) drain_rules<UC, HCT>(T, base, units, HC, DM, lane);     // a pass queues at most 3 per lane
                 }
                 drain_rules<UC, HCT>(T, base, units, HC, DM, lane);
                 // ---- a split survives only when both sides found something (lookup.py:205-209) ----
@@ -713,8 +837,41 @@ __global__ void __launch_bounds__(kLatMaxWarps * 32, LT_LAT_MINB) lattice_kernel
                     const int tri = M * (M + 1) / 2;
                     const int items = (n - bl0) * tri;
                     const float inv_tri = 1.0f / (float)tri;
+                    // stand-alone tags in list order (lookup.py:104-105), then Josa after a Noun
+                    constexpr uint32_t standalone_tags = (1u << LT_TAG_NOUN) | (1u << LT_TAG_ADVERB) | (1u << LT_TAG_EXCLAMATION) |
+                                                         (1u << LT_TAG_DETERMINER) | (1u << LT_TAG_NUMBER);
+                    constexpr uint64_t standalone_order = (0ull << (4 * LT_TAG_NOUN)) | (1ull << (4 * LT_TAG_ADVERB)) |
+                                                          (2ull << (4 * LT_TAG_EXCLAMATION)) | (3ull << (4 * LT_TAG_DETERMINER)) |
+                                                          (4ull << (4 * LT_TAG_NUMBER)) | (5ull << (4 * LT_TAG_JOSA));
                     for (int q0 = 0; q0 < items; q0 += 32) {
                         const int q = q0 + lane;
+#if LT_LAT_COMPACT
+                        {
+                            const bool in_range = q < items;
+                            const int qq = in_range ? q : 0;
+                            const int blq = small_div(qq, tri, inv_tri);
+                            const int bl = bl0 + blq;
+                            int t = qq - blq * tri;
+                            // t -> (span, split offset inside the span): span (span - 1) / 2 <= t < span (span + 1) / 2
+                            int span = (int)((1.0f + sqrtf(8.0f * (float)t + 1.0f)) * 0.5f);
+                            span -= (span * (span - 1) / 2 > t) ? 1 : 0;
+                            span += (span * (span + 1) / 2 <= t) ? 1 : 0;
+                            t -= span * (span - 1) / 2;
+                            const bool valid = in_range && (bl + span <= n);
+                            const int b = o + bl, e = valid ? b + span : b + 1, p = valid ? b + t : b;
+                            uint32_t tagbits = 0;
+                            if (valid && t == 0) {
+                                const uint32_t m = sub_get(E, b, e);
+                                // WordLookup: MorphemeDictionary.lookup of the substring, one hit per tag in dictionary order;
+                                // MorphemeLookup: the stand-alone tags, and Josa right after a Noun found by this scan
+                                tagbits = word_mode ? (m & kSubTagMask & T.order_mask)
+                                                    : ((m & standalone_tags) | ((nend[b] && ((m >> LT_TAG_JOSA) & 1u)) ? 1u << LT_TAG_JOSA : 0u));
+                            }
+                            const bool first = word_mode && bl == 0;
+                            ncand_try += emit_pass(T, v, E, lane, valid, b, e, p, 0u, first, tagbits, (uint32_t)span, first,
+                                                   word_mode ? ~0ull : standalone_order, true, pass);
+                        }
+#else
                         if (q < items) {
                             const int blq = small_div(q, tri, inv_tri);
                             const int bl = bl0 + blq;
@@ -761,7 +918,8 @@ __global__ void __launch_bounds__(kLatMaxWarps * 32, LT_LAT_MINB) lattice_kernel
                                 ncand_try += lemma_item(T, v, E, b, e, p, rec, 0u, pass);
                             }
                         }
-                        if (warp_read(rqn) > (uint32_t)(kRuleQueue - 128)) drain_rules<UC, HCT>(T, base, units, HC, DM, lane);
+#endif
+                        if (warp_read(rqn) > (uint32_t)kRuleDrainAt) drain_rules<UC, HCT>(T, base, units, HC, DM, lane);
                     }
                     drain_rules<UC, HCT>(T, base, units, HC, DM, lane);
                     nstaged = *nh;

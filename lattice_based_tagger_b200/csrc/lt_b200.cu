@@ -483,7 +483,7 @@ static int32_t unit_limit(const lt_tables* t) {
     int32_t lo = 8, hi = 4088;
     auto fits = [&](int32_t lcap) {
         return lattice_warp_smem(lcap + 8, kLatDefaultHcap, max_str) <= kSmemBudget &&
-               dense_bytes + beam_warp_smem(lcap + 8, LT_MAX_BEAM, t->dev.n_funcs, false) <= kSmemBudget;
+               dense_bytes + beam_warp_smem(lcap + 8, LT_MAX_BEAM, beam_kval_doubles(t->dev.n_funcs, false), false) <= kSmemBudget;
     };
     if (fits(hi)) return hi;
     while (hi - lo > 8) {
@@ -591,12 +591,14 @@ static int lattice_plan(lt_batch* b, int lcap, int hcap, bool retry_pass, const 
         P.warps = (int)std::max<size_t>(1, std::min<size_t>(2, kSmemBudget / P.warp_smem));
     } else {
         // CTA shape: the warps per CTA (1..8) that keep the most warps resident on an SM (128 registers per
-        // thread allow 16); ties go to 4-warp CTAs
+        // thread allow 16); ties go to 4-warp CTAs.  The instantiations with compile-time sizes run as 4-warp CTAs only.
         int best_res = 0;
+        const int reg_warps = uclass ? 4 * LT_LAT_HOT_MINB : 16;
         for (int w : {kLatWarps, 8, 6, 5, 3, 2, 1}) {
+            if (uclass && w != kLatWarps) continue;
             const size_t cta = P.warp_smem * w;
             if (cta > kSmemBudget) continue;
-            const int res = w * (int)std::min<size_t>(16 / w, (size_t)228 * 1024 / (cta + 1024));
+            const int res = w * (int)std::min<size_t>(reg_warps / w, (size_t)228 * 1024 / (cta + 1024));
             if (res > best_res) { best_res = res; P.warps = w; }
         }
         if (P.warps < 1)
@@ -629,24 +631,31 @@ static int beam_plan(lt_batch* b, int lcap, int beam_size, bool kbest, const Bea
     for (const BeamPlan& p : b->beam_plans)
         if (p.units == units && p.beam == beam_size && p.kbest == kbest) { *out = &p; return LT_OK; }
     const size_t dense_bytes = ((size_t)t->dev.n_tri * dense_block_bytes(t->dev.n_tags) + 15) & ~(size_t)15;
+    const bool reg_tri = t->dev.n_funcs == 2 && t->dev.funcs[0].kind == LT_FUNC_REG && t->dev.funcs[1].kind == LT_FUNC_TRIGRAM;
+    const bool prog1 = reg_tri && !kbest;                      // the instantiation specialised for that score program
+    const bool hot = prog1 && uclass != 0;                     // ... and for the sentence-array size: 4-warp CTAs only
+    const int kvd = beam_kval_doubles(t->dev.n_funcs, prog1);
     // CTA shape: the warps per CTA (1..8) that keep the most warps resident on an SM under the kernel's
     // 128 registers per thread (16 warps) and the per-warp shared memory; ties go to 4-warp CTAs
+    // (registers: 16 warps per SM at 128 registers; the hot instantiations are compiled for LT_BEAM_HOT_MINB CTAs of 4)
     auto resident_warps = [&](size_t warp_smem, int w) -> int {
         const size_t cta = dense_bytes + warp_smem * w;
         if (cta > kSmemBudget) return 0;
-        return w * (int)std::min<size_t>(16 / w, (size_t)228 * 1024 / (cta + 1024));
+        const int reg_warps = hot ? 4 * LT_BEAM_HOT_MINB : 16;
+        return w * (int)std::min<size_t>(reg_warps / w, (size_t)228 * 1024 / (cta + 1024));
     };
     auto best_warps = [&](size_t warp_smem) -> int {
         int best = 0, best_res = 0;
         for (int w : {kBeamWarps, 8, 6, 5, 3, 2, 1}) {
+            if (hot && w != kBeamWarps) continue;
             const int r = resident_warps(warp_smem, w);
             if (r > best_res) { best_res = r; best = w; }
         }
         return best;
     };
     // back-pointers live in shared memory when that does not lower the residency
-    const size_t smem_hbm_trail = beam_warp_smem(units, beam_size, t->dev.n_funcs, false);
-    const size_t smem_own_trail = beam_warp_smem(units, beam_size, t->dev.n_funcs, true);
+    const size_t smem_hbm_trail = beam_warp_smem(units, beam_size, kvd, false);
+    const size_t smem_own_trail = beam_warp_smem(units, beam_size, kvd, true);
     const int w_hbm = best_warps(smem_hbm_trail), w_own = best_warps(smem_own_trail);
     if (w_hbm == 0)
         return fail(LT_ERR_INVALID, "sentence length %d with beam %d does not fit the beam kernel's shared memory", lcap, beam_size);
@@ -660,7 +669,6 @@ static int beam_plan(lt_batch* b, int lcap, int beam_size, bool kbest, const Bea
     P.smem = dense_bytes + P.warp_smem * P.warps;
     // common beam sizes, sentence-array sizes and the (RegularizationScore, SimpleTrigramFeatureScore)
     // score program get their own instantiation (compile-time array offsets, unrolled scorer loop)
-    const bool reg_tri = t->dev.n_funcs == 2 && t->dev.funcs[0].kind == LT_FUNC_REG && t->dev.funcs[1].kind == LT_FUNC_TRIGRAM;
     if (kbest) P.fn = beam_size <= kRankMaxBeam ? beam_kernel<2, 0, 0, 0, 1> : (beam_size <= 32 ? beam_kernel<1, 0, 0, 0, 1> : beam_kernel<0, 0, 0, 0, 1>);
     else if (beam_size == 5 && uclass == 64) P.fn = reg_tri ? beam_kernel<2, 5, 64, 1> : beam_kernel<2, 5, 64, 0>;
     else if (beam_size == 5 && uclass == 128) P.fn = reg_tri ? beam_kernel<2, 5, 128, 1> : beam_kernel<2, 5, 128, 0>;
@@ -776,6 +784,8 @@ static int launch_lattice(lt_batch* b, cudaStream_t st) {
 
 static int launch_beam(lt_batch* b, cudaStream_t st, bool kbest) {
     lt_tables* t = b->tables;
+    // (an imported lattice names its strings: only the all-survivors instantiations read those, see edge_hashes)
+    kbest = kbest || b->imported;
     const int beam_size = b->beam;
     const int n_sent = b->n_sent;
     const size_t nu = (size_t)b->n_units + 1;

@@ -115,7 +115,9 @@ __host__ __device__ inline size_t beam_ring_bytes(int beam) {
 }
 __host__ __device__ inline size_t beam_sentence_bytes(int units) { return (size_t)units * (8 + 8 + 8 + 2); }
 #ifndef LT_BEAM_KVAL2
-#define LT_BEAM_KVAL2 1        // 1: the (Regularization, Trigram) program caches only the template-4 / 5 weights per edge
+#define LT_BEAM_KVAL2 0        // 1: the (Regularization, Trigram) program caches only the template-4 / 5 weights per edge
+                               // (measured r2d: 1.5 KB less shared memory per warp buys no residency at 128 registers, and
+                               // recomputing the regulariser per candidate costs 1 %)
 #endif
 // doubles of edge-only score values per cache slot: two per scorer; the (RegularizationScore,
 // SimpleTrigramFeatureScore) program keeps only the template-4 / template-5 weights (the regulariser is a
@@ -336,6 +338,7 @@ __device__ __forceinline__ double unsortable(uint64_t key) {
 #ifndef LT_BEAM_MINB
 #define LT_BEAM_MINB 2
 #endif
+constexpr int kBeamMaxWarpsC = 8;
 #ifndef LT_TOPK_ROUNDS
 #define LT_TOPK_ROUNDS 0       // 1: positions whose candidates fit one chunk select by K rounds of warp arg-max (measured: no
                                // faster than rank counting — the kernel waits on dependent latency, not on issue slots)
@@ -346,17 +349,13 @@ __device__ __forceinline__ double unsortable(uint64_t key) {
 #ifndef LT_PROBE_SPLIT
 #define LT_PROBE_SPLIT 1       // 1: generic kernels issue the loads of templates 7 and 8 after templates 0..2 are consumed
 #endif
-#ifndef LT_BEAM_HOT_MINB
-#define LT_BEAM_HOT_MINB 4     // resident 4-warp CTAs per SM the small-beam throughput instantiations are compiled for
-#endif
-// Launch bounds per instantiation: the throughput instantiations of beams 5 / 10 on 64- or 128-element sentence
-// arrays always run as 4-warp CTAs and may be compiled for more of them per SM (fewer registers); everything
-// else keeps CTAs of up to 8 warps at 128 registers.
-constexpr bool beam_is_hot(int KT, int UC, int PROG, int KB) { return KT != 0 && UC != 0 && PROG == 1 && KB == 0; }
-constexpr int beam_max_threads(int KT, int UC, int PROG, int KB) { return beam_is_hot(KT, UC, PROG, KB) ? 128 : 256; }
-constexpr int beam_min_blocks(int KT, int UC, int PROG, int KB) { return beam_is_hot(KT, UC, PROG, KB) ? LT_BEAM_HOT_MINB : LT_BEAM_MINB; }
+// (launch bounds: 128 registers per thread for every instantiation.  Compiling the small-beam instantiations for
+// 5 resident 4-warp CTAs — 96 registers, with the shared-memory diet that makes room for the fifth — spills ~120
+// bytes per thread and runs 16 % slower than 4 CTAs at 128 registers: profiles/README.md, r2d.)
+constexpr int beam_max_threads(int, int, int, int) { return kBeamMaxWarpsC * 32; }
+constexpr int beam_min_blocks(int, int, int, int) { return LT_BEAM_MINB; }
 constexpr int kBeamWarps = 4;                 // preferred warps per CTA of the beam kernel
-constexpr int kBeamMaxWarps = 8;              // largest CTA (128 registers per thread either way: 8 warps x 2 CTAs = 4 warps x 4 CTAs)
+constexpr int kBeamMaxWarps = kBeamMaxWarpsC;              // largest CTA (128 registers per thread either way: 8 warps x 2 CTAs = 4 warps x 4 CTAs)
 
 // Prefix hashes of the staged syllables by warp scan: H[0] = 0, H[i+1] = H[i] * B + (c_i + 1).
 __device__ __forceinline__ void beam_prefix_hashes(const uint16_t* ch, int L, int lane, uint64_t* ha, uint64_t* hb) {

@@ -31,6 +31,12 @@
 #pragma once
 #include "tables.cuh"
 
+#ifndef LT_LAT_FLATRULES
+#define LT_LAT_FLATRULES 0     // 1: the rule queue holds one entry per RULE (not per key): a drain applies them all side by side
+                               // (measured r2f: slower, 0.251 vs 0.208 ms on C2 — every entry recomputes the prefix / suffix hashes its
+                               // key's rules share, and that outweighs the shorter dependent chain)
+#endif
+
 namespace lt {
 
 constexpr int kLatWarps = 4;                 // preferred warps per CTA of the lattice kernel
@@ -385,6 +391,21 @@ __device__ __noinline__ void drain_rules(const DevTables& T, unsigned char* base
         }
         const H2 pre = (p > b) ? sub_hash(T, v, b, p) : H2{0, 0};
         const H2 pw_suf = pow_at(T, suf_len);
+#if LT_LAT_FLATRULES
+        {
+            // one RULE per descriptor (emit_pass queues them that way): every lane applies exactly one rule, so a
+            // drain costs the same two dependent table round trips whatever the keys' rule counts are
+            const RuleRec rec = rule_load(T, d.w);
+            // no dictionary string is longer than max_str: most candidates die here, before any hashing
+            if (rec.eomi_len + suf_len > (uint32_t)E.max_str || (uint32_t)(p - b) + rec.stem_len > (uint32_t)E.max_str) continue;
+            const H2 stem = h2_concat(pre, rec.stem, pow_at(T, rec.stem_len));
+            const H2 eomi = h2_concat(rec.eomi, suf, pw_suf);
+            proto.rule = d.w;
+            rule_candidate(T, E, stem, (uint32_t)(p - b) + rec.stem_len, eomi, rec.eomi_len + suf_len, proto,
+                           (uint32_t)(p - b), cand0, reps, count, task, (d.x >> 29) & 1u);
+            continue;
+        }
+#endif
         RuleRec next = rule_load(T, d.w);
         for (uint32_t r = 0; r < count; ++r) {
             const RuleRec rec = next;
@@ -486,7 +507,9 @@ __device__ __forceinline__ lt_edge edge_proto(int b, int e, uint32_t len, bool i
 //             dictionary's tag order (T.tag_pos, get_tags, dictionary.py:238-242)
 //   lemmas    also run the lemmatizer part for (word [b, e), split p)
 // Returns the number of lemma candidates the reference generates for the item.
-__device__ __forceinline__ uint32_t emit_pass(const DevTables& T, const SentView& v, const Enum& E, int lane, bool valid,
+template <int UC, int HCT>
+__device__ __forceinline__ uint32_t emit_pass(const DevTables& T, const SentView& v, const Enum& E, unsigned char* base, int units_rt,
+                                              int lane, bool valid,
                                               int b, int e, int p, uint32_t task, bool is_l, uint32_t tagbits,
                                               uint32_t tag_len, bool tag_is_l, uint64_t order4, bool lemmas, uint32_t pass) {
     uint32_t ncand = 0;
@@ -516,7 +539,11 @@ __device__ __forceinline__ uint32_t emit_pass(const DevTables& T, const SentView
     const uint32_t after1 = 1u + c1 * c1;
     ncand += c1 * c1 + cf + cs;
     const uint32_t nh_mine = (uint32_t)__popc(hits);
+#if LT_LAT_FLATRULES
+    const uint32_t np_mine = c1 + cf + cs;          // one queue entry per RULE (<= 3 x 255 per lane)
+#else
     const uint32_t np_mine = (c1 ? 1u : 0u) + (cf ? 1u : 0u) + (cs ? 1u : 0u);
+#endif
     uint32_t incl = nh_mine | (np_mine << 16);
     #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -524,12 +551,28 @@ __device__ __forceinline__ uint32_t emit_pass(const DevTables& T, const SentView
         if (lane >= d) incl += t;
     }
     const uint32_t total = __shfl_sync(kFull, incl, 31);
+#if LT_LAT_FLATRULES
+    const uint32_t total_p = total >> 16;
+    uint32_t cur_q = *E.rqn;
+    if (cur_q + total_p > (uint32_t)kRuleQueue && cur_q > 0u) {
+        // the pass's rules do not fit behind what is queued: apply the queued ones first (warp-uniform)
+        drain_rules<UC, HCT>(T, base, units_rt, E.hcap, E.max_str, lane);
+        cur_q = 0u;
+    }
+    const uint32_t cur_h = *E.nh;
+    __syncwarp();                                   // every lane has read the counters
+    if (lane == 31) {
+        *E.nh = cur_h + (total & 0xFFFFu);
+        if (total_p <= (uint32_t)kRuleQueue) *E.rqn = cur_q + total_p;
+    }
+#else
     const uint32_t cur_h = *E.nh, cur_q = *E.rqn;
     __syncwarp();                                   // every lane has read the counters
     if (lane == 31) {
         *E.nh = cur_h + (total & 0xFFFFu);
         *E.rqn = cur_q + (total >> 16);
     }
+#endif
     uint32_t slot = cur_h + (incl & 0xFFFFu) - nh_mine;
     if (hits) E.tcnt[task] = 1u;                    // (only ever tested against zero)
     #pragma unroll 1
@@ -552,12 +595,40 @@ __device__ __forceinline__ uint32_t emit_pass(const DevTables& T, const SentView
         }
         ++slot;
     }
-    uint32_t qs = cur_q + (incl >> 16) - np_mine;
     const uint32_t common = (uint32_t)b | ((uint32_t)p << 12) | (is_l ? 1u << 27 : 0u) | (pass << 29);
     const uint32_t ytask = (uint32_t)e | (task << 12);
+#if LT_LAT_FLATRULES
+    {
+        // entries of this pass are numbered [0, total_p) in lane order; normally they all fit behind the queue's
+        // contents, else (rule lists of hundreds) they go through the queue one window at a time
+        const uint32_t first = (incl >> 16) - np_mine;
+        uint32_t w0 = 0;
+        do {
+            const uint32_t room = total_p <= (uint32_t)kRuleQueue ? total_p : (uint32_t)kRuleQueue;
+            uint32_t idx = first;
+            #pragma unroll 1
+            for (int k = 0; k < 3; ++k) {
+                const uint32_t cnt = k == 0 ? c1 : (k == 1 ? cf : cs);
+                const uint32_t ref = k == 0 ? r1.x : (k == 1 ? rf.x : rs.x);
+                const uint32_t cand0 = k == 0 ? 1u : (k == 1 ? after1 : after1 + cf);
+                const uint32_t x = common | (k == 0 ? (1u << 26) : (((k == 1 && last) ? 2u : 1u) << 24) | (1u << 28));
+                #pragma unroll 1
+                for (uint32_t r = 0; r < cnt; ++r, ++idx)
+                    if (idx >= w0 && idx < w0 + room) E.rq[cur_q + idx - w0] = make_uint4(x, ytask, (cand0 + r) | (cnt << 19), ref + r);
+            }
+            if (total_p <= (uint32_t)kRuleQueue) break;
+            __syncwarp();
+            if (lane == 31) *E.rqn = (total_p - w0 < room) ? total_p - w0 : room;
+            drain_rules<UC, HCT>(T, base, units_rt, E.hcap, E.max_str, lane);
+            w0 += room;
+        } while (w0 < total_p);
+    }
+#else
+    uint32_t qs = cur_q + (incl >> 16) - np_mine;
     if (c1) E.rq[qs++] = make_uint4(common | (0u << 24) | (1u << 26), ytask, 1u | (c1 << 19), r1.x);
     if (cf) E.rq[qs++] = make_uint4(common | ((last ? 2u : 1u) << 24) | (1u << 28), ytask, after1 | (cf << 19), rf.x);
     if (cs) E.rq[qs++] = make_uint4(common | (1u << 24) | (1u << 28), ytask, (after1 + cf) | (cs << 19), rs.x);
+#endif
     __syncwarp();
     return ncand;
 }
@@ -593,14 +664,8 @@ __device__ LT_FLUSH_ATTR void flush_staged(const LatticeArgs& A, int lane, uint3
 #ifndef LT_LAT_MINB
 #define LT_LAT_MINB 2
 #endif
-#ifndef LT_LAT_HOT_MINB
-#define LT_LAT_HOT_MINB 4      // resident 4-warp CTAs per SM the instantiations with compile-time array sizes are compiled for
-#endif
-// Launch bounds per instantiation (as for the beam kernel): the instantiations with compile-time sizes always run
-// as 4-warp CTAs; the generic one keeps CTAs of up to 8 warps at 128 registers.
-constexpr bool lattice_is_hot(int UC, int HCT, int LM) { return UC != 0 && HCT != 0 && LM == 0; }
-constexpr int lattice_max_threads(int UC, int HCT, int LM) { return lattice_is_hot(UC, HCT, LM) ? 128 : kLatMaxWarps * 32; }
-constexpr int lattice_min_blocks(int UC, int HCT, int LM) { return lattice_is_hot(UC, HCT, LM) ? LT_LAT_HOT_MINB : LT_LAT_MINB; }
+constexpr int lattice_max_threads(int, int, int) { return kLatMaxWarps * 32; }      // (register caps for more resident CTAs
+constexpr int lattice_min_blocks(int, int, int) { return LT_LAT_MINB; }              // spill and lose: profiles/README.md, r2d)
 // UC / HCT: sentence-array size and staging capacity when known at compile time (0 = A.units / A.hcap)
 // LM: 0 = MorphemeLookup only (what Tagger.tag uses; the other lookups compile out of the throughput path),
 //     1 = the lookup named by A.mode.
@@ -742,7 +807,7 @@ __global__ void __launch_bounds__(lattice_max_threads(UC, HCT, LM), lattice_min_
                         // tag order (get_tags, dictionary.py:238-242)
                         uint32_t tagbits = 0;
                         if (p == b) tagbits = special ? (left ? 1u << LT_TAG_NOUN : 1u << LT_TAG_JOSA) : (sub_get(E, b, e) & kSubTagMask & T.order_mask);
-                        ncand_try += emit_pass(T, v, E, lane, valid, b, e, p, task, b == o, tagbits, special ? (uint32_t)n : (uint32_t)(e - b),
+                        ncand_try += emit_pass<UC, HCT>(T, v, E, base, units, lane, valid, b, e, p, task, b == o, tagbits, special ? (uint32_t)n : (uint32_t)(e - b),
                                                special ? left : (b == o), special ? 0ull : ~0ull, !special, 0u);
                     }
 #else
@@ -868,7 +933,7 @@ __global__ void __launch_bounds__(lattice_max_threads(UC, HCT, LM), lattice_min_
                                                     : ((m & standalone_tags) | ((nend[b] && ((m >> LT_TAG_JOSA) & 1u)) ? 1u << LT_TAG_JOSA : 0u));
                             }
                             const bool first = word_mode && bl == 0;
-                            ncand_try += emit_pass(T, v, E, lane, valid, b, e, p, 0u, first, tagbits, (uint32_t)span, first,
+                            ncand_try += emit_pass<UC, HCT>(T, v, E, base, units, lane, valid, b, e, p, 0u, first, tagbits, (uint32_t)span, first,
                                                    word_mode ? ~0ull : standalone_order, true, pass);
                         }
 #else

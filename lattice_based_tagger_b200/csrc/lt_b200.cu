@@ -74,6 +74,9 @@ struct lt_tables {
     int sm_count = 0;
     // kernels whose dynamic shared-memory limit was already raised on this device (function, bytes)
     std::vector<std::pair<const void*, size_t>> smem_limits;
+    // feature table extent and the device's L2 persistence limits (LT_L2_PERSIST, see launch_beam)
+    size_t feat_bytes = 0;
+    int l2_bytes = 0, l2_persist_max = 0, l2_window_max = 0;
 };
 
 static H2 hash_units(const uint16_t* p, int64_t n) {
@@ -359,6 +362,7 @@ static int build_tables(const lt_tables_desc* d, lt_tables* t) {
         }
         D.feat_mask = table.size() - 1;
         if (int rc = upload(t, table, &D.feat)) return rc;
+        t->feat_bytes = table.size() * sizeof(FeatSlot);
     }
     if (int rc = upload(t, dense, &D.dense)) return rc;
 
@@ -377,6 +381,11 @@ extern "C" int lt_tables_create(const lt_tables_desc* desc, int device, lt_table
     cudaError_t e = cudaGetDeviceProperties(&prop, device);
     if (e != cudaSuccess) { delete t; return fail(LT_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e)); }
     t->sm_count = prop.multiProcessorCount;
+#if !defined(LT_SIMT_EMU)
+    t->l2_bytes = prop.l2CacheSize;
+    t->l2_persist_max = prop.persistingL2CacheMaxSize;
+    t->l2_window_max = prop.accessPolicyMaxWindowSize;
+#endif
     int rc = build_tables(desc, t);
     if (rc != LT_OK) { lt_tables_destroy(t); return rc; }
     *out = t;
@@ -442,6 +451,7 @@ struct lt_batch {
     bool edge_cap_fixed = false;   // LT_EDGE_CAP given: start there instead of the size guess (tests)
     bool debug = false;            // LT_DEBUG: print launch shapes
     bool trail_smem_ok = true;     // LT_TRAIL_SMEM=0 keeps the back-pointers in HBM
+    int l2_persist_pct = 0;        // LT_L2_PERSIST=<percent of L2>: persisting access-policy window over the feature table
     int64_t n_edges = 0;
     bool have_lattice = false, have_paths = false, have_kbest = false, resolved = false;
     bool beam_state_clean = false;   // beam queue cursor / counters still zero from the batch prologue
@@ -507,6 +517,7 @@ extern "C" int lt_batch_create(lt_tables* tables, lt_batch** out) {
     if (const char* env = getenv("LT_SORT_BY_LENGTH")) b->sort_by_length = atoi(env) != 0;
     if (const char* env = getenv("LT_EDGE_CAP")) { b->edge_cap = (uint32_t)std::max(16, atoi(env)); b->edge_cap_fixed = true; }
     if (const char* env = getenv("LT_TRAIL_SMEM")) b->trail_smem_ok = atoi(env) != 0;
+    if (const char* env = getenv("LT_L2_PERSIST")) b->l2_persist_pct = std::min(100, std::max(0, atoi(env)));
     b->debug = getenv("LT_DEBUG") != nullptr;
     *out = b;
     return LT_OK;
@@ -591,11 +602,10 @@ static int lattice_plan(lt_batch* b, int lcap, int hcap, bool retry_pass, const 
         P.warps = (int)std::max<size_t>(1, std::min<size_t>(2, kSmemBudget / P.warp_smem));
     } else {
         // CTA shape: the warps per CTA (1..8) that keep the most warps resident on an SM (128 registers per
-        // thread allow 16); ties go to 4-warp CTAs.  The instantiations with compile-time sizes run as 4-warp CTAs only.
+        // thread allow 16); ties go to 4-warp CTAs
         int best_res = 0;
-        const int reg_warps = uclass ? 4 * LT_LAT_HOT_MINB : 16;
+        const int reg_warps = 16;
         for (int w : {kLatWarps, 8, 6, 5, 3, 2, 1}) {
-            if (uclass && w != kLatWarps) continue;
             const size_t cta = P.warp_smem * w;
             if (cta > kSmemBudget) continue;
             const int res = w * (int)std::min<size_t>(reg_warps / w, (size_t)228 * 1024 / (cta + 1024));
@@ -633,21 +643,17 @@ static int beam_plan(lt_batch* b, int lcap, int beam_size, bool kbest, const Bea
     const size_t dense_bytes = ((size_t)t->dev.n_tri * dense_block_bytes(t->dev.n_tags) + 15) & ~(size_t)15;
     const bool reg_tri = t->dev.n_funcs == 2 && t->dev.funcs[0].kind == LT_FUNC_REG && t->dev.funcs[1].kind == LT_FUNC_TRIGRAM;
     const bool prog1 = reg_tri && !kbest;                      // the instantiation specialised for that score program
-    const bool hot = prog1 && uclass != 0;                     // ... and for the sentence-array size: 4-warp CTAs only
     const int kvd = beam_kval_doubles(t->dev.n_funcs, prog1);
     // CTA shape: the warps per CTA (1..8) that keep the most warps resident on an SM under the kernel's
     // 128 registers per thread (16 warps) and the per-warp shared memory; ties go to 4-warp CTAs
-    // (registers: 16 warps per SM at 128 registers; the hot instantiations are compiled for LT_BEAM_HOT_MINB CTAs of 4)
     auto resident_warps = [&](size_t warp_smem, int w) -> int {
         const size_t cta = dense_bytes + warp_smem * w;
         if (cta > kSmemBudget) return 0;
-        const int reg_warps = hot ? 4 * LT_BEAM_HOT_MINB : 16;
-        return w * (int)std::min<size_t>(reg_warps / w, (size_t)228 * 1024 / (cta + 1024));
+        return w * (int)std::min<size_t>(16 / w, (size_t)228 * 1024 / (cta + 1024));
     };
     auto best_warps = [&](size_t warp_smem) -> int {
         int best = 0, best_res = 0;
         for (int w : {kBeamWarps, 8, 6, 5, 3, 2, 1}) {
-            if (hot && w != kBeamWarps) continue;
             const int r = resident_warps(warp_smem, w);
             if (r > best_res) { best_res = r; best = w; }
         }
@@ -851,6 +857,27 @@ static int launch_beam(lt_batch* b, cudaStream_t st, bool kbest) {
         b->launches += 1;
     }
     b->beam_state_clean = false;
+#if !defined(LT_SIMT_EMU)
+    // Experiment (LT_L2_PERSIST, off by default; profiles/README.md has the measurement): a persisting L2 access-policy
+    // window over the feature table while the beam kernel runs.  The table is a hash table — its hot slots are
+    // scattered — so the window covers as much of it as the device allows and asks for the fraction that fits
+    // the persisting carve-out to stay resident.
+    bool windowed = false;
+    if (b->l2_persist_pct > 0 && t->feat_bytes > 0 && t->l2_persist_max > 0) {
+        const size_t carve = std::min<size_t>((size_t)t->l2_persist_max, (size_t)t->l2_bytes * (size_t)b->l2_persist_pct / 100);
+        CU(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve));
+        cudaStreamAttrValue attr{};
+        attr.accessPolicyWindow.base_ptr = const_cast<FeatSlot*>(t->dev.feat);
+        attr.accessPolicyWindow.num_bytes = std::min<size_t>(t->feat_bytes, (size_t)t->l2_window_max);
+        attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)carve / (double)attr.accessPolicyWindow.num_bytes);
+        attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        CU(cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr));
+        windowed = true;
+        if (b->debug) fprintf(stderr, "[lt] L2 persisting window: %zu B of the %zu B feature table, carve-out %zu B, hit ratio %.3f\n",
+                              (size_t)attr.accessPolicyWindow.num_bytes, t->feat_bytes, carve, attr.accessPolicyWindow.hitRatio);
+    }
+#endif
     if (b->timed) CU(cudaEventRecord(b->ev[5], st));
     if (n_sent > 0) {
         LT_LAUNCH(P->fn, grid, P->warps * 32, P->smem, st, t->dev, A);
@@ -858,6 +885,13 @@ static int launch_beam(lt_batch* b, cudaStream_t st, bool kbest) {
     }
     CU(cudaGetLastError());
     if (b->timed) CU(cudaEventRecord(b->ev[6], st));
+#if !defined(LT_SIMT_EMU)
+    if (windowed) {
+        cudaStreamAttrValue attr{};
+        attr.accessPolicyWindow.num_bytes = 0;
+        CU(cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr));
+    }
+#endif
     if (int rc = scan_u32(b, reinterpret_cast<const uint32_t*>(b->path_len.p), static_cast<uint32_t*>(b->path_off.p),
                           (int64_t)n_sent + 1, st))
         return rc;

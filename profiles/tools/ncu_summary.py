@@ -1,11 +1,12 @@
 #!/usr/bin/env python
 """Selected counters of the lattice / beam kernels from an `ncu --set full` report, as JSON.
 
-usage: ncu_summary.py <report.ncu-rep> <out.json> [traffic.json]
+usage: ncu_summary.py <report.ncu-rep> <out.json> [traffic.json <config>]
 
 Takes the LAST captured launch of each kernel (earlier launches of a bench run belong to table
-set-up).  With a third argument it also rewrites the DRAM bytes per launch that bench.py reports as
-`roofline.traffic`.
+set-up).  With the last two arguments it also records, under the key <config> of traffic.json, the
+DRAM bytes per launch that bench.py reports as `roofline.traffic` for that configuration
+(configurations without a capture report null).
 """
 import csv
 import io
@@ -55,10 +56,17 @@ def main():
                            to_bytes(d['dram__bytes_write.sum'], unit_of['dram__bytes_write.sum']))
     with open(out, 'w') as f:
         json.dump(summary, f, indent=1)
-    if len(sys.argv) > 3:
-        traffic['_source'] = '%s: dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, config c2' % out
-        with open(sys.argv[3], 'w') as f:
-            json.dump(traffic, f, indent=1)
+    if len(sys.argv) > 4:
+        path, config = sys.argv[3], sys.argv[4]
+        try:
+            with open(path) as f:
+                table = json.load(f)
+        except Exception:
+            table = {}
+        traffic['_source'] = '%s: dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full' % out
+        table[config] = traffic
+        with open(path, 'w') as f:
+            json.dump(table, f, indent=1)
     print(json.dumps(summary, indent=1))
 
 

@@ -771,7 +771,7 @@ def strong_scaling(args, W_headline, dev, rank, world, local_rank, flush):
     else:
         d_text = torch.empty(n_text, dtype=torch.int16, device=dev)
         d_off = torch.empty(n_off, dtype=torch.int32, device=dev)
-    dist.broadcast(d_text, 0)
+    dist.broadcast(d_text.view(torch.uint8), 0)          # (NCCL has no 16-bit integer type: the code units travel as bytes)
     dist.broadcast(d_off, 0)
     text = d_text.cpu().numpy().view(np.uint16)
     offsets = d_off.cpu().numpy()
@@ -779,9 +779,12 @@ def strong_scaling(args, W_headline, dev, rank, world, local_rank, flush):
     n = offsets.size - 1
     lengths = np.diff(offsets).astype(np.int64)
 
-    # partition: sentences sorted by estimated work (transitions ~ length x (8 k + k E / L), SURVEY §8e: the batch's
-    # beam and lattice density are common factors, so length orders them), dealt round-robin in blocks
-    parts = sharding.partition_by_work(lengths, world)
+    # partition by estimated work (transitions ~ length x (8 k + k E / L), SURVEY §8e: the batch's beam and lattice
+    # density are common factors): CONTIGUOUS slices of equal total length, so that the gathered results are a plain
+    # concatenation in input order (sharding.partition_by_work deals sorted sentences instead; it balances the
+    # length mix too but needs an inverse permutation of every word record at the gather)
+    bounds = sharding.shard_bounds(lengths, world)
+    parts = [np.arange(bounds[r], bounds[r + 1], dtype=np.int64) for r in range(world)]
     mine = parts[rank]
     lib, batch = W.tagger._lib, W.tagger._batch
 
@@ -848,28 +851,18 @@ def strong_scaling(args, W_headline, dev, rank, world, local_rank, flush):
             got.append(dst)
         if rank != 0:
             return None
-        plen_all = np.zeros(n, dtype=np.int32)
-        status_all = np.zeros(n, dtype=np.int32)
-        scores_all = np.zeros(n, dtype=np.float64)
-        pieces = []
-        for r in range(world):
-            ns, ne = int(all_counts[r][0]), int(all_counts[r][1])
-            plen_all[parts[r]] = got[0][r][:ns].cpu().numpy()
-            status_all[parts[r]] = got[1][r][:ns].cpu().numpy()
-            scores_all[parts[r]] = got[2][r][:ns].cpu().numpy()
-            pieces.append(got[3][r][:ne * 2].cpu().numpy().view(np.uint8).reshape(-1, 16).view(_native.EDGE_DTYPE).reshape(-1))
-        # inverse permutation of the edge records: the records of sentence i go to path_off[i]
+        sizes = [(int(c[0]), int(c[1])) for c in all_counts]
+        # contiguous shards: the batch's results are the ranks' results one after the other
+        plen_all = np.concatenate([got[0][r][:ns].cpu().numpy() for r, (ns, _) in enumerate(sizes)])
+        status_all = np.concatenate([got[1][r][:ns].cpu().numpy() for r, (ns, _) in enumerate(sizes)])
+        scores_all = np.concatenate([got[2][r][:ns].cpu().numpy() for r, (ns, _) in enumerate(sizes)])
+        out_edges = np.concatenate([got[3][r][:ne * 2].cpu().numpy() for r, (_, ne) in enumerate(sizes)])
+        out_edges = out_edges.view(np.uint8).reshape(-1, 16).view(_native.EDGE_DTYPE).reshape(-1)
         path_off = np.zeros(n + 1, dtype=np.int64)
         np.cumsum(plen_all, out=path_off[1:])
-        out_edges = np.empty(int(path_off[-1]), dtype=_native.EDGE_DTYPE)
-        for r in range(world):
-            idx = parts[r]
-            src_off = np.zeros(idx.size + 1, dtype=np.int64)
-            np.cumsum(plen_all[idx], out=src_off[1:])
-            dst = np.repeat(path_off[idx] - src_off[:-1], plen_all[idx]) + np.arange(int(src_off[-1]), dtype=np.int64)
-            out_edges[dst] = pieces[r]
         return path_off, out_edges, scores_all, status_all
 
+    gather()                              # (first use of the collective: communicator set-up is not part of a gather)
     torch.cuda.synchronize(dev)
     dist.barrier()
     t0 = time.perf_counter()
@@ -906,6 +899,7 @@ def strong_scaling(args, W_headline, dev, rank, world, local_rank, flush):
             'speedup': t_single / (max(per_rank_ms) * 1e-3), 'speedup_with_gather': t_single / t_total,
             'efficiency': t_single / (max(per_rank_ms) * 1e-3) / world,
             'imbalance': imbalance, 'work_units_by_rank': [float(w[0]) for w in all_work],
+            'partition': 'contiguous slices of equal total length (sharding.shard_bounds)',
             'limiter': ('gather on one host' if t_gather > max(per_rank_ms) * 1e-3 * (imbalance - 1.0) * 2 and t_gather > 0.1 * t_total
                         else 'imbalance between shards' if imbalance > 1.05 else 'per-call host overhead and launch tail of smaller shards'),
             'identical_to_single_gpu': bool(identical), 'corpus_build_seconds': build_s,

@@ -940,59 +940,69 @@ __global__ void __launch_bounds__(beam_max_threads(KT, UC, PROG, KB), beam_min_b
                     }
                     if (lane >= K) { keep_key[0] = 0; keep_pay[0] = 0; }
                 } else {
-                    // ---- top-K of (kept so far) U (this chunk): K rounds of warp arg-max ----
-                    // Priority on equal keys: kept entries (earlier candidates) by rank, then chunk lanes in order.
-                    uint64_t new_key[KR];
-                    uint32_t new_pay[KR];
-                    #pragma unroll
-                    for (int r = 0; r < KR; ++r) { new_key[r] = 0; new_pay[r] = 0; }
-                    uint64_t pool_key[KR + 1];
-                    #pragma unroll
-                    for (int r = 0; r < KR; ++r) pool_key[r] = keep_key[r];
-                    pool_key[KR] = ckey;
-                    uint32_t pool_n = __popc(__ballot_sync(kFull, ckey != 0));
-                    #pragma unroll
-                    for (int r = 0; r < KR; ++r) pool_n += __popc(__ballot_sync(kFull, keep_key[r] != 0));
-                    const int rounds = (int)(pool_n < (uint32_t)K ? pool_n : (uint32_t)K);
-                    for (int round = 0; round < rounds; ++round) {
-                        // lane-local best: lower pool index wins ties
-                        uint64_t best = pool_key[0];
-                        int cls = 0;
+                    // ---- beams of 33..64: the kept list is two sorted runs of 32 (ranks 0..31 in keep[0], 32..63 in
+                    // keep[1]); a chunk is sorted by the same network as above, merged into the first run, and the 32
+                    // entries that lose there are merged into the second.  One total order everywhere: larger key first,
+                    // equal keys by payload = generation ordinal (beam.py:85 is a stable sort).
+                    auto first_of = [](uint64_t ak, uint32_t ap, uint64_t bk2, uint32_t bp2) { return (ak > bk2) || (ak == bk2 && ap < bp2); };
+                    // best-first order of a BITONIC sequence held one element per lane
+                    auto clean = [&](uint64_t& k0, uint32_t& p0) {
                         #pragma unroll
-                        for (int r = 1; r <= KR; ++r)
-                            if (pool_key[r] > best) { best = pool_key[r]; cls = r; }
-                        const uint32_t hi = (uint32_t)(best >> 32), lo = (uint32_t)best;
-                        const uint32_t mhi = __reduce_max_sync(kFull, hi);
-                        const bool c1 = (hi == mhi);
-                        const uint32_t mlo = __reduce_max_sync(kFull, c1 ? lo : 0u);
-                        const bool c2 = c1 && (lo == mlo);
-                        int win_cls = 0;
-                        unsigned wm = 0;
-                        #pragma unroll
-                        for (int r = 0; r <= KR; ++r) {
-                            const unsigned m = __ballot_sync(kFull, c2 && cls == r);
-                            if (wm == 0 && m != 0) { wm = m; win_cls = r; }
+                        for (int stride = 16; stride > 0; stride >>= 1) {
+                            const uint64_t ok = __shfl_xor_sync(kFull, k0, stride);
+                            const uint32_t op = __shfl_xor_sync(kFull, p0, stride);
+                            const bool mine_first = first_of(k0, p0, ok, op);
+                            const bool lower = (lane & stride) == 0;
+                            if (lower != mine_first) { k0 = ok; p0 = op; }
                         }
-                        const int src = __ffs(wm) - 1;                          // lane of the winner
-                        uint32_t pay_mine = cpay;
+                    };
+                    bool skip = false;
+                    if (c0 != 0 && K > 0) {
+                        // a later chunk changes nothing unless one of its candidates beats the K-th kept entry
+                        const int last = K - 1;
+                        const uint64_t thr_k = __shfl_sync(kFull, last >= 32 ? keep_key[KR - 1] : keep_key[0], last & 31);
+                        skip = thr_k != 0 && __ballot_sync(kFull, ckey > thr_k) == 0u;
+                    }
+                    if (!skip) {
+                        uint64_t bk = ckey;
+                        uint32_t bp = cpay;
+                        #pragma unroll
+                        for (int size = 2; size <= 32; size <<= 1) {
+                            #pragma unroll
+                            for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                                const uint64_t ok = __shfl_xor_sync(kFull, bk, stride);
+                                const uint32_t op = __shfl_xor_sync(kFull, bp, stride);
+                                const bool mine_first = first_of(bk, bp, ok, op);
+                                const bool lower = (lane & stride) == 0;
+                                const bool descending = (lane & size) == 0;
+                                const bool keep_mine = (lower == descending) ? mine_first : !mine_first;
+                                if (!keep_mine) { bk = ok; bp = op; }
+                            }
+                        }
+                        if (c0 == 0) {
+                            keep_key[0] = bk;
+                            keep_pay[0] = bp;
+                            #pragma unroll
+                            for (int r = 1; r < KR; ++r) { keep_key[r] = 0; keep_pay[r] = 0; }
+                        } else {
+                            // run 0 against the reversed chunk: lane-wise winners = the best 32 of both, losers = the rest
+                            // (both bitonic); the losers then meet run 1 the same way
+                            #pragma unroll
+                            for (int r = 0; r < KR; ++r) {
+                                const uint64_t rk = __shfl_sync(kFull, bk, 31 - lane);
+                                const uint32_t rp = __shfl_sync(kFull, bp, 31 - lane);
+                                const bool theirs = first_of(rk, rp, keep_key[r], keep_pay[r]);
+                                bk = theirs ? keep_key[r] : rk;          // the loser of the pair moves on
+                                bp = theirs ? keep_pay[r] : rp;
+                                if (theirs) { keep_key[r] = rk; keep_pay[r] = rp; }
+                                clean(keep_key[r], keep_pay[r]);
+                                if (r + 1 < KR) clean(bk, bp);
+                            }
+                        }
                         #pragma unroll
                         for (int r = 0; r < KR; ++r)
-                            if (win_cls == r) pay_mine = keep_pay[r];
-                        const uint32_t wpay = __shfl_sync(kFull, pay_mine, src);
-                        const uint64_t wkey = ((uint64_t)mhi << 32) | mlo;
-                        if (lane == (round & 31)) {
-                            #pragma unroll
-                            for (int r = 0; r < KR; ++r)
-                                if ((round >> 5) == r) { new_key[r] = wkey; new_pay[r] = wpay; }
-                        }
-                        if (lane == src) {
-                            #pragma unroll
-                            for (int r = 0; r <= KR; ++r)
-                                if (win_cls == r) pool_key[r] = 0;
-                        }
+                            if (r * 32 + lane >= K) { keep_key[r] = 0; keep_pay[r] = 0; }
                     }
-                    #pragma unroll
-                    for (int r = 0; r < KR; ++r) { keep_key[r] = new_key[r]; keep_pay[r] = new_pay[r]; }
                 }
             }
 

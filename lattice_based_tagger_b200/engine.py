@@ -43,7 +43,10 @@ def pack_sentences(sents, unsupported=None):
     """
     n = len(sents)
     raw = ''.join(sents).encode('utf-16-le', 'surrogatepass')
-    if len(raw) != 2 * sum(map(len, sents)):
+    lengths = np.fromiter(map(len, sents), dtype=np.int64, count=n)
+    offsets = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(lengths, out=offsets[1:])
+    if len(raw) != 2 * int(offsets[-1]):
         bad = [i for i, s in enumerate(sents) if len(s.encode('utf-16-le', 'surrogatepass')) != 2 * len(s)]
         if unsupported is None:
             raise ValueError(_STATUS_MESSAGES[_native.LT_SENT_UNSUPPORTED_CHAR] % bad[0])
@@ -52,9 +55,8 @@ def pack_sentences(sents, unsupported=None):
         for i in bad:
             sents[i] = ''
         raw = ''.join(sents).encode('utf-16-le', 'surrogatepass')
-    lengths = np.fromiter((len(s) for s in sents), dtype=np.int64, count=n)
-    offsets = np.zeros(n + 1, dtype=np.int64)
-    np.cumsum(lengths, out=offsets[1:])
+        lengths = np.fromiter(map(len, sents), dtype=np.int64, count=n)
+        np.cumsum(lengths, out=offsets[1:])
     if offsets[-1] >= 2 ** 31:
         raise ValueError('batch holds %d code units; split it (limit 2^31)' % offsets[-1])
     text = np.frombuffer(raw, dtype='<u2')

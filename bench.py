@@ -1038,12 +1038,12 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-api', action='store_true')
     ap.add_argument('--other-configs', default='c3,c4,c5',
-                    help='bounded samples of these configurations after the headline (N=1 only); "" disables')
+                    help='bounded samples of these configurations after the headline (N=1 only); "none" disables')
     ap.add_argument('--no-strong', action='store_true', help='N>1: skip the sharded-corpus (strong scaling) section')
     ap.add_argument('--strong-sentences', type=int, default=200_000)
     ap.add_argument('--strong-config', default='c3', help='configuration of the sharded corpus (BASELINE configs[2])')
     args = ap.parse_args()
-    args.other_configs = [c for c in args.other_configs.split(',') if c and c != args.config]
+    args.other_configs = [c for c in args.other_configs.split(',') if c and c != 'none' and c != args.config]
     capture_stdout()
     if args.impl == 'reference':
         run_reference(args)

@@ -218,6 +218,11 @@ int64_t lt_tables_device_bytes(const lt_tables* tables);
  * LT_SENT_TOO_LONG, the others are tagged. */
 int32_t lt_tables_max_sentence_units(const lt_tables* tables);
 
+/* New coefficients for the SAME features the tables were created with (desc->feat_* order): the trainer's
+ * epoch (trainer/train.py:44-65 changes `coefficients`, never the feature dictionary).  Weights are written
+ * in place on the device; nothing is re-hashed.  No batch may be in flight on these tables. */
+int  lt_tables_update_weights(lt_tables* tables, const double* weights, int64_t n_weights);
+
 int  lt_batch_create(lt_tables* tables, lt_batch** out);
 void lt_batch_destroy(lt_batch* batch);
 /* which eojeol lookup the following lt_lattice* calls enumerate (LT_LOOKUP_*, default MORPHEME) */

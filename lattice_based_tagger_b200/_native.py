@@ -89,6 +89,7 @@ SYMBOLS = {
     'lt_tables_destroy': (None, [_p]),
     'lt_tables_device_bytes': (ctypes.c_int64, [_p]),
     'lt_tables_max_sentence_units': (ctypes.c_int32, [_p]),
+    'lt_tables_update_weights': (ctypes.c_int, [_p, _p, ctypes.c_int64]),
     'lt_batch_create': (ctypes.c_int, [_p, ctypes.POINTER(_p)]),
     'lt_batch_destroy': (None, [_p]),
     'lt_batch_set_lookup': (ctypes.c_int, [_p, ctypes.c_int32]),

@@ -211,6 +211,8 @@ class CompiledTables:
         if len(funcs) > _native.LT_MAX_FUNCS:
             raise UnsupportedScoreFunction('at most %d score functions are supported' % _native.LT_MAX_FUNCS)
         prog = (_native.lt_func * max(1, len(funcs)))()
+        self._weight_source = []
+        self._funcs = funcs
         strings = _StringTable()
         feat_func, feat_tmpl, feat_s, feat_a, feat_w = [], [], [], [], []
         pref_func, pref_tag, pref_s, pref_v = [], [], [], []
@@ -365,12 +367,26 @@ class CompiledTables:
                         ok &= vals <= 1
                 cols[where] = vals
             keep = np.nonzero(ok)[0]
-            weights = np.asarray(coef, dtype=np.float64)[np.asarray(idxs, dtype=np.int64)[keep]]
+            source = np.asarray(idxs, dtype=np.int64)[keep]
+            self._weight_source.append((f, source))          # where each packed weight comes from (update_weights)
+            weights = np.asarray(coef, dtype=np.float64)[source]
             feat_func.append(np.full(len(keep), f, dtype=np.uint8))
             feat_tmpl.append(np.full(len(keep), tmpl, dtype=np.uint8))
             feat_s.append(np.stack([cols['s0'][keep], cols['s1'][keep], cols['s2'][keep]], axis=1).astype(np.int32))
             feat_a.append(np.stack([np.where(ok, cols['a0'], 0)[keep], np.where(ok, cols['a1'], 0)[keep]], axis=1).astype(np.int32))
             feat_w.append(weights)
+
+    def update_weights(self):
+        """Write the scorers' CURRENT `coefficients` into the device tables in place (same features, new
+        weights — the trainer's epoch).  Nothing is re-hashed: `lt_tables_update_weights`."""
+        parts = []
+        for f, source in self._weight_source:
+            coef = np.asarray(self._funcs[f].coefficients, dtype=np.float64)
+            if len(coef) != len(self._funcs[f].encoder.feature_dic):
+                raise ValueError('Encoder and coefficients have different size features')
+            parts.append(coef[source])
+        weights = np.ascontiguousarray(np.concatenate(parts)) if parts else np.zeros(0, dtype=np.float64)
+        _native.check(self._lib.lt_tables_update_weights(self.handle, _native.ptr(weights) if weights.size else None, int(weights.size)))
 
     def device_bytes(self):
         return int(self._lib.lt_tables_device_bytes(self.handle))

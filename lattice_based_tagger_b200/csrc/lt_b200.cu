@@ -22,6 +22,8 @@
 
 using namespace lt;
 
+static constexpr uint32_t kDstNone = 0xFFFFFFFFu, kDstDense = 0x80000000u;
+
 // ------------------------------------------------------------------------------------------------
 // errors
 // ------------------------------------------------------------------------------------------------
@@ -74,6 +76,12 @@ struct lt_tables {
     int sm_count = 0;
     // kernels whose dynamic shared-memory limit was already raised on this device (function, bytes)
     std::vector<std::pair<const void*, size_t>> smem_limits;
+    // where the weight of input feature i lives (lt_tables_update_weights): a slot of the hashed table, an offset into
+    // the dense blocks (kDstDense | byte offset / 8), or kDstNone for a feature no tuple can equal
+    std::vector<uint32_t> feat_dst;
+    std::vector<unsigned char> dense_host;
+    uint32_t* d_feat_dst = nullptr;
+    double* d_weights = nullptr;
     // feature table extent and the device's L2 persistence limits (LT_L2_PERSIST, see launch_beam)
     size_t feat_bytes = 0;
     int l2_bytes = 0, l2_persist_max = 0, l2_window_max = 0;
@@ -102,7 +110,7 @@ struct CuckooSlot {
     uint64_t fp, payload;
 };
 static int build_cuckoo(const std::vector<CuckooItem>& items, uint64_t min_slots, std::vector<CuckooSlot>* table,
-                        uint32_t* bits_out, const char* what) {
+                        uint32_t* bits_out, const char* what, std::vector<uint32_t>* slot_of = nullptr) {
     uint32_t bits = 4;
     while ((1ull << bits) < min_slots) ++bits;
     for (const CuckooItem& it : items)
@@ -133,8 +141,12 @@ static int build_cuckoo(const std::vector<CuckooItem>& items, uint64_t min_slots
         }
         if (!placed_all) continue;
         table->assign(slots, CuckooSlot{0, 0});
+        if (slot_of) slot_of->assign(items.size(), 0xFFFFFFFFu);
         for (uint64_t sl = 0; sl < slots; ++sl)
-            if (owner[sl] >= 0) (*table)[sl] = CuckooSlot{items[owner[sl]].fp, items[owner[sl]].payload};
+            if (owner[sl] >= 0) {
+                (*table)[sl] = CuckooSlot{items[owner[sl]].fp, items[owner[sl]].payload};
+                if (slot_of) (*slot_of)[(size_t)owner[sl]] = (uint32_t)sl;
+            }
         *bits_out = bits;
         return LT_OK;
     }
@@ -157,6 +169,8 @@ extern "C" void lt_tables_destroy(lt_tables* t) {
     if (!t) return;
     DeviceGuard guard(t->device);
     for (void* p : t->allocations) cudaFree(p);
+    if (t->d_feat_dst) cudaFree(t->d_feat_dst);
+    if (t->d_weights) cudaFree(t->d_weights);
     delete t;
 }
 
@@ -284,7 +298,9 @@ static int build_tables(const lt_tables_desc* d, lt_tables* t) {
     std::vector<unsigned char> dense(std::max<size_t>(1, (size_t)D.n_tri * blk), 0);
     struct Pending { FKey key; double w; };
     std::vector<Pending> pending;
+    std::vector<int64_t> pending_src;                    // input feature of a hashed entry (-1: a preference)
     pending.reserve((size_t)(d->n_feat + d->n_pref));
+    t->feat_dst.assign((size_t)d->n_feat, kDstNone);
     for (int64_t i = 0; i < d->n_feat; ++i) {
         const int f = d->feat_func[i];
         if (f >= d->n_funcs || D.func_dense[f] < 0) return fail(LT_ERR_INVALID, "feature %lld belongs to scorer %d which is not a trigram scorer", (long long)i, f);
@@ -303,17 +319,20 @@ static int build_tables(const lt_tables_desc* d, lt_tables* t) {
             if (a[0] < 0 || a[0] >= NT || a[1] < 0 || a[1] >= NT) return fail(LT_ERR_INVALID, "feature %lld: tag id out of range", (long long)i);
             t3[a[0] * NT + a[1]] = w;
             m3[a[0]] |= 1u << a[1];
+            t->feat_dst[i] = kDstDense | (uint32_t)(&t3[a[0] * NT + a[1]] - reinterpret_cast<double*>(dense.data()));
             continue;
         }
         if (tmpl == 4 && a[0] >= 0 && a[0] < kT4Dense) {
             t4[a[0]] = w;
             m4[a[0] >> 5] |= 1u << (a[0] & 31);
+            t->feat_dst[i] = kDstDense | (uint32_t)(&t4[a[0]] - reinterpret_cast<double*>(dense.data()));
             continue;
         }
         if (tmpl == 6) {
             if (a[0] < 0 || a[0] > 8) continue;          // min(8, len) never exceeds 8
             t6[a[0]] = w;
             m6[0] |= 1u << a[0];
+            t->feat_dst[i] = kDstDense | (uint32_t)(&t6[a[0]] - reinterpret_cast<double*>(dense.data()));
             continue;
         }
         if (tmpl < 0 || tmpl > 8) return fail(LT_ERR_INVALID, "feature %lld: template %d", (long long)i, tmpl);
@@ -333,6 +352,7 @@ static int build_tables(const lt_tables_desc* d, lt_tables* t) {
             default: break;                                  // 2, 4, 5: (wk) in slot 0
         }
         pending.push_back(Pending{feature_key((uint32_t)tmpl, (uint32_t)f, r0, r1, r2, (uint32_t)a[0], (uint32_t)a[1]), w});
+        pending_src.push_back(i);
     }
     for (int64_t i = 0; i < d->n_pref; ++i) {
         const int f = d->pref_func[i];
@@ -343,6 +363,7 @@ static int build_tables(const lt_tables_desc* d, lt_tables* t) {
         if (!str_hash(d->pref_s[i], &h0)) return fail(LT_ERR_INVALID, "preference %lld: string id out of range", (long long)i);
         pending.push_back(Pending{feature_key(kind == LT_FUNC_MPREF ? kKindMPref : kKindWPref, (uint32_t)f, h0, H2{0, 0}, H2{0, 0},
                                               d->pref_tag[i], 0), d->pref_value[i]});
+        pending_src.push_back(-1);
     }
     {
         const uint64_t n = pending.size();
@@ -353,7 +374,10 @@ static int build_tables(const lt_tables_desc* d, lt_tables* t) {
             items[i] = CuckooItem{feature_slot_hash(pending[i].key.k1), pending[i].key.k2, wbits};
         }
         std::vector<CuckooSlot> slots;
-        if (int rc = build_cuckoo(items, next_pow2(n * (n < (1u << 22) ? 4 : 2)), &slots, &D.feat_bits, "feature keys")) return rc;
+        std::vector<uint32_t> slot_of;
+        if (int rc = build_cuckoo(items, next_pow2(n * (n < (1u << 22) ? 4 : 2)), &slots, &D.feat_bits, "feature keys", &slot_of)) return rc;
+        for (uint64_t i = 0; i < n; ++i)
+            if (pending_src[i] >= 0) t->feat_dst[(size_t)pending_src[i]] = slot_of[i];
         static_assert(sizeof(CuckooSlot) == sizeof(FeatSlot), "slot layout");
         std::vector<FeatSlot> table(slots.size());
         for (size_t i = 0; i < slots.size(); ++i) {
@@ -365,6 +389,7 @@ static int build_tables(const lt_tables_desc* d, lt_tables* t) {
         t->feat_bytes = table.size() * sizeof(FeatSlot);
     }
     if (int rc = upload(t, dense, &D.dense)) return rc;
+    t->dense_host = dense;
 
     const uint16_t bos[3] = {'B', 'O', 'S'};
     D.bos = hash_units(bos, 3);
@@ -504,6 +529,37 @@ static int32_t unit_limit(const lt_tables* t) {
 }
 
 extern "C" int32_t lt_tables_max_sentence_units(const lt_tables* t) { return t ? unit_limit(t) : 0; }
+
+// New weights for the features the tables were built with (the trainer's epoch: same features, new
+// coefficients) — written in place: a scatter into the hashed table's weight fields and a rewrite of the small
+// dense blocks.  No table is rebuilt.  The caller must not have a batch in flight on these tables.
+extern "C" int lt_tables_update_weights(lt_tables* t, const double* weights, int64_t n_weights) {
+    if (!t || (n_weights > 0 && !weights)) return fail(LT_ERR_INVALID, "null argument");
+    if ((size_t)n_weights != t->feat_dst.size())
+        return fail(LT_ERR_INVALID, "the tables were built with %zu features, %lld weights given", t->feat_dst.size(), (long long)n_weights);
+    ON_DEVICE(t->device);
+    if (n_weights == 0) return LT_OK;
+    if (!t->d_feat_dst) {
+        CU(cudaMalloc(reinterpret_cast<void**>(&t->d_feat_dst), (size_t)n_weights * 4));
+        CU(cudaMalloc(reinterpret_cast<void**>(&t->d_weights), (size_t)n_weights * 8));
+        CU(cudaMemcpy(t->d_feat_dst, t->feat_dst.data(), (size_t)n_weights * 4, cudaMemcpyHostToDevice));
+    }
+    CU(cudaMemcpy(t->d_weights, weights, (size_t)n_weights * 8, cudaMemcpyHostToDevice));
+    const unsigned grid = (unsigned)std::min<int64_t>((n_weights + 255) / 256, (int64_t)t->sm_count * 16);
+    LT_LAUNCH(scatter_weights, grid, 256, 0, (cudaStream_t) nullptr, const_cast<FeatSlot*>(t->dev.feat), t->d_feat_dst, t->d_weights, n_weights);
+    CU(cudaGetLastError());
+    double* dense = reinterpret_cast<double*>(t->dense_host.data());
+    bool any_dense = false;
+    for (int64_t i = 0; i < n_weights; ++i)
+        if (t->feat_dst[(size_t)i] != kDstNone && (t->feat_dst[(size_t)i] & kDstDense)) {
+            dense[t->feat_dst[(size_t)i] & ~kDstDense] = weights[i];
+            any_dense = true;
+        }
+    if (any_dense)
+        CU(cudaMemcpy(const_cast<unsigned char*>(t->dev.dense), t->dense_host.data(), t->dense_host.size(), cudaMemcpyHostToDevice));
+    CU(cudaDeviceSynchronize());
+    return LT_OK;
+}
 
 extern "C" int lt_batch_create(lt_tables* tables, lt_batch** out) {
     if (!tables || !out) return fail(LT_ERR_INVALID, "null argument");

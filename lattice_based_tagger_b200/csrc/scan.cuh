@@ -178,6 +178,18 @@ __global__ void __launch_bounds__(1024) batch_prologue(const int32_t* __restrict
     }
 }
 
+// lt_tables_update_weights: weight i goes to the slot of the hashed feature table that holds feature i
+// (slot = 0x8000'0000 | ... marks a dense-table weight, 0xFFFF'FFFF a dropped feature: both are skipped here)
+struct WeightSlot { uint64_t fp; double w; };
+template <typename Slot>
+__global__ void scatter_weights(Slot* __restrict__ table, const uint32_t* __restrict__ dst, const double* __restrict__ w, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t d = dst[i];
+        if (d & 0x80000000u) continue;
+        table[d].w = w[i];
+    }
+}
+
 // zeroes the beam stage's queue cursor and counters when a lattice is searched a second time
 __global__ void beam_reset(unsigned int* __restrict__ queue, unsigned long long* __restrict__ counters, int n_counters) {
     if (threadIdx.x == 0) *queue = 0;

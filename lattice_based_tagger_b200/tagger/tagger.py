@@ -59,6 +59,11 @@ class Tagger:
         self.eojeol_lookup._attach(self._engine, self._engine.tables.max_len)
         self._engine.set_lookup(self.eojeol_lookup.mode)
 
+    def update_weights(self):
+        """After changing the `coefficients` of the tagger's trigram scorers (same `feature_dic`): write them
+        to the device tables in place — much cheaper than `refresh()`, which recompiles everything."""
+        self._engine.tables.update_weights()
+
     def close(self):
         if self._engine is not None:
             self._engine.close()

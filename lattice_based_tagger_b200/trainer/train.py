@@ -72,14 +72,30 @@ def train(word_morph_pairs, dictionary, encoder, score_func, regularity_func,
     return params
 
 
-def fit_parameter(word_morph_pairs, encoder, tagger, max_epochs=100, verbose=False, beam_size=5):
-    """Reference `fit_parameter()` (`train.py:44-59`); stops early once an epoch makes no mistake."""
+def fit_parameter(word_morph_pairs, encoder, tagger, max_epochs=100, verbose=False, beam_size=5, patience=5,
+                  averaged=False):
+    """Reference `fit_parameter()` (`train.py:44-59`).  Stops once an epoch makes no mistake, or when the
+    number of mistakes has not improved for `patience` epochs (a corpus with an unreachable gold path — a word the
+    dictionary cannot produce — never reaches zero); returns the best weights seen (`averaged=True`: the mean of
+    the weights of all epochs, the averaged perceptron)."""
     coef = np.zeros(len(encoder.feature_dic), dtype=np.float64)
+    best_loss, best_coef, stale = None, coef, 0
+    total = np.zeros_like(coef)
+    epochs = 0
     for epoch in range(1, max_epochs + 1):
+        decoded_with = coef
         coef, loss = train_epoch(word_morph_pairs, encoder, tagger, coef, epoch, verbose, beam_size=beam_size)
-        if loss == 0:
+        total += coef
+        epochs += 1
+        if best_loss is None or loss < best_loss:
+            best_loss, best_coef, stale = loss, decoded_with, 0       # `loss` was measured with the weights the epoch started from
+        else:
+            stale += 1
+        if loss == 0 or stale >= patience:
             break
-    return coef
+    if averaged:
+        return total / max(1, epochs)
+    return best_coef
 
 
 def _trigram_scorer(tagger):
@@ -97,8 +113,14 @@ def train_epoch(word_morph_pairs, encoder, tagger, coef, epoch, verbose, beam_si
     """
     coef = np.asarray(coef, dtype=np.float64).copy()
     scorer = _trigram_scorer(tagger)
-    scorer.set_encoder(encoder, coef)
-    tagger.refresh()                                   # weights -> device feature table
+    if scorer.encoder is encoder and scorer.coefficients is not None and len(scorer.coefficients) == len(coef) \
+            and getattr(tagger, '_trained_features', None) is encoder.feature_dic:
+        scorer.coefficients = coef
+        tagger.update_weights()                        # same features as the device tables hold: weights in place
+    else:
+        scorer.set_encoder(encoder, coef)
+        tagger.refresh()                               # first epoch: feature table compiled once
+        tagger._trained_features = encoder.feature_dic
 
     golds, sents = [], []
     for word_text, morph_text in word_morph_pairs:

@@ -8,10 +8,12 @@
 # Every ncu pass starts only after the plain run of the same command exited 0.
 cd "$(dirname "$0")/../.."
 TAG=${1:-run}
-SHORT="--steps 2 --warmup 3 --no-cpu-baseline --no-api --other-configs """
+SHORT="--steps 2 --warmup 3 --no-cpu-baseline --no-api --other-configs none"
 set -x
+if [ -z "$NCU_ONLY" ]; then
 python bench.py --steps 20 --warmup 3 > gpurun_out/bench_c2_$TAG.json 2> gpurun_out/bench_c2_$TAG.err || exit 1
 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_reference_$TAG.json 2> gpurun_out/bench_reference_$TAG.err || exit 1
+fi
 python bench.py $SHORT > /dev/null 2>&1 || exit 1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$TAG.csv \
     python bench.py $SHORT > gpurun_out/ncu_launches_$TAG.log 2>&1

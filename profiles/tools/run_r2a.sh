@@ -9,9 +9,9 @@ tail -5 gpurun_out/pytest_$TAG.log
 ( time python bench.py --steps 20 --warmup 3 ) > gpurun_out/bench_c2_$TAG.json 2> gpurun_out/bench_c2_$TAG.err
 tail -c 600 gpurun_out/bench_c2_$TAG.err
 ( time python bench.py --impl reference --steps 3 --warmup 1 ) > gpurun_out/bench_reference_$TAG.json 2> gpurun_out/bench_reference_$TAG.err
-python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-api --other-configs "" > /dev/null 2>&1 || exit 1
+python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-api --other-configs none > /dev/null 2>&1 || exit 1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$TAG.csv \
-    python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-api --other-configs "" > gpurun_out/ncu_launches_$TAG.log 2>&1
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-api --other-configs none > gpurun_out/ncu_launches_$TAG.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:"beam_kernel|lattice_kernel" -s 10 -c 4 -f \
-    -o gpurun_out/prof_$TAG python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-api --other-configs "" > gpurun_out/ncu_full_$TAG.log 2>&1
+    -o gpurun_out/prof_$TAG python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-api --other-configs none > gpurun_out/ncu_full_$TAG.log 2>&1
 ls -la gpurun_out/*$TAG*

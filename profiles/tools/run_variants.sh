@@ -8,7 +8,7 @@ cp $LIB /tmp/liblt_default.so
 for V in lattice_based_tagger_b200/variants/*.so; do
     N=$(basename $V .so)
     cp $V $LIB
-    python bench.py --config $CONFIG --steps 20 --warmup 3 --no-cpu-baseline --no-api --other-configs "" "$@" \
+    python bench.py --config $CONFIG --steps 20 --warmup 3 --no-cpu-baseline --no-api --other-configs none "$@" \
         > gpurun_out/var_${TAG}_${CONFIG}_$N.json 2> gpurun_out/var_${TAG}_${CONFIG}_$N.err
     python - <<PY
 import json

@@ -93,3 +93,16 @@ def test_per_sentence_statuses():
     assert [w is None for w in tagger.eojeol_lookup.lookup_batch(sents, errors='none')] == [False, True, True, True, False, False]
     long_ok = '노래 ' * ((limit - 8) // 3)
     assert tagger.tag(long_ok).score == lo.OracleTagger(dictionary, funcs).tag(long_ok).score
+
+
+def test_update_weights_and_trainer():
+    import numpy as np
+    import tests.test_trainer as trainer_tests
+    trainer_tests.test_perceptron_fits_the_toy_corpus()          # the perceptron over the (emulated) decoder
+    case = _checks.make_case(3001, n_sent=8, max_sent_len=24)
+    dictionary, funcs = _cases.build_objects(case, pkg)
+    tagger = pkg.Tagger(dictionary, score_funcs=funcs)
+    tri = next(f for f in funcs.funcs if type(f).__name__ == 'SimpleTrigramFeatureScore')
+    tri.coefficients = np.random.default_rng(0).standard_normal(len(tri.coefficients))
+    tagger.update_weights()
+    _checks.check_against_oracle(tagger, lo.OracleTagger(dictionary, funcs), case['sentences'], (1, 5))

@@ -451,3 +451,19 @@ def test_config_samples(name):
         assert [tuple(w) for w in words[1:-1]] == _checks.lattice_key(oracle.lattice(sent)), sent
     info = tagger.info()
     assert info['reruns'] >= 0 and info['launches'] > 0
+
+
+def test_update_weights_in_place():
+    """`Tagger.update_weights()` (lt_tables_update_weights): new coefficients for the same features, written
+    into the device tables without a rebuild — results follow the oracle with the new weights, hashed and
+    dense (templates 3 / 4 / 6) features alike."""
+    import numpy as np
+    case = _checks.make_case(3041, n_sent=20, max_sent_len=40, prefs=True)
+    dictionary, funcs = _cases.build_objects(case, pkg)
+    tagger = pkg.Tagger(dictionary, score_funcs=funcs)
+    tri = next(f for f in funcs.funcs if type(f).__name__ == 'SimpleTrigramFeatureScore')
+    rng = np.random.default_rng(4)
+    for _ in range(2):
+        tri.coefficients = rng.standard_normal(len(tri.coefficients))
+        tagger.update_weights()
+        _checks.check_against_oracle(tagger, lo.OracleTagger(dictionary, funcs), case['sentences'], (1, 5, 33))

@@ -20,6 +20,8 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 ncu --set full --clock-control none --import-source on -k regex:"beam_kernel|lattice_kernel" -s 10 -c 4 -f \
     -o gpurun_out/prof_$TAG python bench.py $SHORT > gpurun_out/ncu_full_$TAG.log 2>&1
 python bench.py --config c3 --sentences 20000 $SHORT > /dev/null 2>&1 || exit 1
-ncu --set full --clock-control none --import-source on -k regex:"beam_kernel|lattice_kernel" -s 14 -c 4 -f \
+# (every launch of the two kernels: the warm-up of this configuration holds grow-and-rerun rounds and retry passes, the
+# steady-state launches are the longest ones — ncu_summary.py picks those)
+ncu --set full --clock-control none --import-source on -k regex:"beam_kernel|lattice_kernel" -c 80 -f \
     -o gpurun_out/prof_c3_$TAG python bench.py --config c3 --sentences 20000 $SHORT > gpurun_out/ncu_full_c3_$TAG.log 2>&1
 ls -la gpurun_out/*$TAG*

@@ -3,8 +3,8 @@
 
 usage: ncu_summary.py <report.ncu-rep> <out.json> [traffic.json <config>]
 
-Takes the LAST captured launch of each kernel (earlier launches of a bench run belong to table
-set-up).  With the last two arguments it also records, under the key <config> of traffic.json, the
+Takes the LONGEST captured launch of each kernel (a capture window also holds the retry pass of the
+lattice kernel and launches that exit early because a buffer overflowed during warm-up).  With the last two arguments it also records, under the key <config> of traffic.json, the
 DRAM bytes per launch that bench.py reports as `roofline.traffic` for that configuration
 (configurations without a capture report null).
 """
@@ -34,13 +34,20 @@ def main():
     raw = subprocess.run(['ncu', '-i', report, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units = rows[0], rows[1]
+    unit_of_name = dict(zip(hdr, units))
     last = {}
     for r in rows[2:]:
         d = dict(zip(hdr, r))
         name = d['Kernel Name']
         key = 'beam_kernel' if 'beam_kernel' in name else ('lattice_kernel' if 'lattice_kernel' in name else None)
         if key:
-            last[key] = d
+            def duration(row):
+                try:
+                    return float(row['gpu__time_duration.sum']) * {'us': 1e-3, 'ms': 1.0, 'ns': 1e-6, 's': 1e3}.get(unit_of_name.get('gpu__time_duration.sum', 'ms'), 1.0)
+                except (KeyError, ValueError):
+                    return 0.0
+            if key not in last or duration(d) > duration(last[key]):
+                last[key] = d
     unit_of = dict(zip(hdr, units))
     summary, traffic = [], {}
     for key, d in last.items():

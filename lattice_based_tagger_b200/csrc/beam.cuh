@@ -114,18 +114,8 @@ __host__ __device__ inline size_t beam_ring_bytes(int beam) {
     return (((size_t)kRing * beam * (8 + 48 + 4 + 1)) + 15) & ~(size_t)15;
 }
 __host__ __device__ inline size_t beam_sentence_bytes(int units) { return (size_t)units * (8 + 8 + 8 + 2); }
-#ifndef LT_BEAM_KVAL2
-#define LT_BEAM_KVAL2 0        // 1: the (Regularization, Trigram) program caches only the template-4 / 5 weights per edge
-                               // (measured r2d: 1.5 KB less shared memory per warp buys no residency at 128 registers, and
-                               // recomputing the regulariser per candidate costs 1 %)
-#endif
-// doubles of edge-only score values per cache slot: two per scorer; the (RegularizationScore,
-// SimpleTrigramFeatureScore) program keeps only the template-4 / template-5 weights (the regulariser is a
-// function of tag and length, recomputed per candidate: 1.5 KB of shared memory per warp is worth more)
-__host__ __device__ inline int beam_kval_doubles(int n_funcs, bool reg_tri) {
-    if (reg_tri) return LT_BEAM_KVAL2 ? 2 : 4;
-    return 2 * (n_funcs > 0 ? n_funcs : 1);
-}
+// doubles of edge-only score values per cache slot: two per scorer
+__host__ __device__ inline int beam_kval_doubles(int n_funcs, bool /*reg_tri*/) { return 2 * (n_funcs > 0 ? n_funcs : 1); }
 __host__ __device__ inline size_t beam_warp_smem(int units, int beam, int kval_doubles, bool trail_smem) {
     const size_t bytes = kBeamFixedBytes + beam_ring_bytes(beam) + beam_sentence_bytes(units) + (size_t)kCacheSlots * 8 * (size_t)kval_doubles +
                          (trail_smem ? (size_t)units * beam * 4 : 0);
@@ -338,14 +328,13 @@ __device__ __forceinline__ double unsortable(uint64_t key) {
 #ifndef LT_BEAM_MINB
 #define LT_BEAM_MINB 2
 #endif
-constexpr int kBeamMaxWarpsC = 8;
-#ifndef LT_TOPK_ROUNDS
-#define LT_TOPK_ROUNDS 0       // 1: positions whose candidates fit one chunk select by K rounds of warp arg-max (measured: no
-                               // faster than rank counting — the kernel waits on dependent latency, not on issue slots)
+#ifndef LT_BEAM_MAXW
+#define LT_BEAM_MAXW 8         // largest CTA in warps (with LT_BEAM_MINB: the register budget the kernels are compiled for)
 #endif
-#ifndef LT_FLOAT_DIV
-#define LT_FLOAT_DIV 0
+#ifndef LT_BEAM_REG_WARPS
+#define LT_BEAM_REG_WARPS 16   // warps per SM that budget allows (the host's residency estimate)
 #endif
+constexpr int kBeamMaxWarpsC = LT_BEAM_MAXW;
 #ifndef LT_PROBE_SPLIT
 #define LT_PROBE_SPLIT 1       // 1: generic kernels issue the loads of templates 7 and 8 after templates 0..2 are consumed
 #endif
@@ -356,50 +345,6 @@ constexpr int beam_max_threads(int, int, int, int) { return kBeamMaxWarpsC * 32;
 constexpr int beam_min_blocks(int, int, int, int) { return LT_BEAM_MINB; }
 constexpr int kBeamWarps = 4;                 // preferred warps per CTA of the beam kernel
 constexpr int kBeamMaxWarps = kBeamMaxWarpsC;              // largest CTA (128 registers per thread either way: 8 warps x 2 CTAs = 4 warps x 4 CTAs)
-
-// Prefix hashes of the staged syllables by warp scan: H[0] = 0, H[i+1] = H[i] * B + (c_i + 1).
-__device__ __forceinline__ void beam_prefix_hashes(const uint16_t* ch, int L, int lane, uint64_t* ha, uint64_t* hb) {
-    H2 carry{0, 0};
-    if (lane == 0) {
-        ha[0] = 0;
-        hb[0] = 0;
-    }
-    constexpr uint64_t A1 = kBaseA, A2 = A1 * A1, A4 = A2 * A2, A8 = A4 * A4, A16 = A8 * A8;
-    constexpr uint64_t B1 = kBaseB, B2 = B1 * B1, B4 = B2 * B2, B8 = B4 * B4, B16 = B8 * B8;
-    for (int base = 0; base < L; base += 32) {
-        const int i = base + lane;
-        const uint64_t v = (i < L) ? (uint64_t)ch[i] + 1u : 0u;
-        uint64_t sa = v, sb = v, ta, tb;
-        ta = __shfl_up_sync(kFull, sa, 1);  tb = __shfl_up_sync(kFull, sb, 1);
-        if (lane >= 1)  { sa += ta * A1;  sb += tb * B1; }
-        ta = __shfl_up_sync(kFull, sa, 2);  tb = __shfl_up_sync(kFull, sb, 2);
-        if (lane >= 2)  { sa += ta * A2;  sb += tb * B2; }
-        ta = __shfl_up_sync(kFull, sa, 4);  tb = __shfl_up_sync(kFull, sb, 4);
-        if (lane >= 4)  { sa += ta * A4;  sb += tb * B4; }
-        ta = __shfl_up_sync(kFull, sa, 8);  tb = __shfl_up_sync(kFull, sb, 8);
-        if (lane >= 8)  { sa += ta * A8;  sb += tb * B8; }
-        ta = __shfl_up_sync(kFull, sa, 16); tb = __shfl_up_sync(kFull, sb, 16);
-        if (lane >= 16) { sa += ta * A16; sb += tb * B16; }
-        uint64_t pa = 1, pb = 1;   // B^(lane+1)
-        {
-            uint64_t xa = A1, xb = B1;
-            const int k = lane + 1;
-            #pragma unroll
-            for (int bit = 0; bit < 6; ++bit) {
-                if (k & (1 << bit)) { pa *= xa; pb *= xb; }
-                xa *= xa; xb *= xb;
-            }
-        }
-        const uint64_t outa = carry.a * pa + sa, outb = carry.b * pb + sb;
-        if (i < L) {
-            ha[i + 1] = outa;
-            hb[i + 1] = outb;
-        }
-        carry.a = __shfl_sync(kFull, outa, 31);
-        carry.b = __shfl_sync(kFull, outb, 31);
-    }
-    __syncwarp();
-}
 
 // Edge prep: hash products and the edge-only part of the score program into cache slot `slot`.
 template <int PROG, int IMP>
@@ -414,23 +359,13 @@ __device__ __forceinline__ void prep_edge(const DevTables& T, const SentView& v,
         double reg, unused, w4, w5;
         const uint32_t tri = edge_score_body(T, dense_smem, k, e0, g0, 1, LT_FUNC_TRIGRAM, feature_seed(4u, 1u), feature_seed(5u, 1u),
                                              H2{0, 0}, w4, w5);
-#if !LT_BEAM_KVAL2
         edge_score_body(T, dense_smem, k, e0, g0, 0, LT_FUNC_REG, H2{0, 0}, H2{0, 0}, H2{0, 0}, reg, unused);
-#else
-        reg = 0.0; unused = 0.0;
-#endif
         (void)unused;
         present = tri << 2;
-#if LT_BEAM_KVAL2
-        (void)reg;
-        C.kval[slot * 2 + 0] = w4;
-        C.kval[slot * 2 + 1] = w5;
-#else
         C.kval[slot * 4 + 0] = reg;
         C.kval[slot * 4 + 1] = 0.0;
         C.kval[slot * 4 + 2] = w4;
         C.kval[slot * 4 + 3] = w5;
-#endif
     } else {
         #pragma unroll 1
         for (int f = 0; f < nf; ++f) {
@@ -546,7 +481,7 @@ __global__ void __launch_bounds__(beam_max_threads(KT, UC, PROG, KB), beam_min_b
         }
         __syncwarp();
         for (int i = lane; i < L; i += 32) spos[i] = __ldg(A.pos + s0 + i);
-        beam_prefix_hashes(ch, L, lane, ha, hb);
+        prefix_hashes_inline(ch, L, lane, ha, hb);
         SentView v{ch, ha, hb, nullptr, KB ? A.imp : nullptr};
 
         if (L == 0 && lane == 0) { A.path_len[s] = 0; A.scores[s] = 0.0; }
@@ -700,12 +635,7 @@ __global__ void __launch_bounds__(beam_max_threads(KT, UC, PROG, KB), beam_min_b
                     if (unk_edge) {
                         prank = (j < jmax) ? (uint32_t)s_nonunk[pbase + rem] : rem;
                     } else {
-#if LT_FLOAT_DIV
-                        // (exact through a float reciprocal for the small numbers that occur, see small_div)
-                        prank = (cj == 1u) ? rem : (uint32_t)small_div((int)rem, (int)cj, 1.0f / (float)cj);
-#else
                         prank = (cj == 1u) ? rem : rem / cj;
-#endif
                         eidx = rem - prank * cj;
                     }
                     const int pslot = pbase + (int)prank;
@@ -748,19 +678,6 @@ __global__ void __launch_bounds__(beam_max_threads(KT, UC, PROG, KB), beam_min_b
                             epresent |= edge_score(T, dense_smem, kfly, e0, g0, f, uv, uv5) << (2 * f);
                             val = uv;
                             val5 = uv5;
-                        } else if (PROG == 1 && LT_BEAM_KVAL2) {
-                            if (f == 0) {
-                                // RegularizationScore.score (score_funcs.py:65-73) from the cached tag / length
-                                const uint32_t elen = (emeta >> 8) & 0xFFFFu;
-                                const lt_func& fn = T.funcs[0];
-                                val = (tk == LT_TAG_UNK) ? __dmul_rn(fn.p[0], __dadd_rn((double)elen, 0.1)) : __dmul_rn(fn.p[1], (double)elen);
-                                val = __dadd_rn(0.0, val);
-                                if (elen == 1u && tk == LT_TAG_NOUN) val = __dadd_rn(val, fn.p[2]);
-                                val5 = 0.0;
-                            } else {
-                                val = C.kval[slot * 2 + 0];
-                                val5 = C.kval[slot * 2 + 1];
-                            }
                         } else {
                             val = C.kval[slot * kvs + 2 * f];
                             val5 = C.kval[slot * kvs + 2 * f + 1];
@@ -831,42 +748,6 @@ __global__ void __launch_bounds__(beam_max_threads(KT, UC, PROG, KB), beam_min_b
                 {
                     const uint32_t chunk_F = __reduce_add_sync(kFull, cand_F);
                     if (lane == 0) { s_acc[0] += chunk_T; s_acc[1] += chunk_F; }
-                }
-                if constexpr (MODE == 2 && LT_TOPK_ROUNDS) {
-                    if (N <= 32u) {
-                        // ---- the position's candidates fit one chunk (the common case at small beams): K rounds of
-                        // warp arg-max.  A round costs two reductions (high word; low word among the lanes that hold
-                        // the maximum high word — skipped when that lane is alone) and one vote; ties go to the lower
-                        // lane = the earlier candidate (beam.py:85 is a stable sort).  Round r's winner lands in lane r.
-                        uint32_t hi = (uint32_t)(ckey >> 32), lo = (uint32_t)ckey;
-                        uint64_t wkey = 0;
-                        uint32_t wpay = 0;
-                        const uint32_t rounds = chunk_T < (uint32_t)K ? chunk_T : (uint32_t)K;
-                        for (uint32_t round = 0; round < rounds; ++round) {
-                            const uint32_t mhi = __reduce_max_sync(kFull, hi);
-                            unsigned wm = __ballot_sync(kFull, hi == mhi && (hi | lo) != 0u);
-                            uint32_t mlo = lo;
-                            if (wm & (wm - 1u)) {
-                                mlo = __reduce_max_sync(kFull, hi == mhi ? lo : 0u);
-                                wm = __ballot_sync(kFull, hi == mhi && lo == mlo);
-                            }
-                            const int src = __ffs(wm) - 1;
-                            mlo = __shfl_sync(kFull, mlo, src);
-                            const uint32_t pay = __shfl_sync(kFull, cpay, src);
-                            if (lane == (int)round) { wkey = ((uint64_t)mhi << 32) | mlo; wpay = pay; }
-                            if (lane == src) { hi = 0u; lo = 0u; }
-                        }
-                        keep_key[0] = wkey;
-                        keep_pay[0] = wpay;
-                        nk = rounds;
-                        continue;
-                    }
-                    // a later chunk contributes nothing unless one of its candidates beats the K-th kept entry (kept
-                    // entries are earlier candidates: they win ties)
-                    if (nk == (uint32_t)K) {
-                        const uint64_t thr = __shfl_sync(kFull, keep_key[0], K - 1);
-                        if (__ballot_sync(kFull, ckey > thr) == 0u) continue;
-                    }
                 }
                 if constexpr (MODE == 2) {
                     // ---- top-K by rank counting: an entry's rank = number of pool entries that beat it ----

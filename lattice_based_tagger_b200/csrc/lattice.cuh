@@ -31,12 +31,6 @@
 #pragma once
 #include "tables.cuh"
 
-#ifndef LT_LAT_FLATRULES
-#define LT_LAT_FLATRULES 0     // 1: the rule queue holds one entry per RULE (not per key): a drain applies them all side by side
-                               // (measured r2f: slower, 0.251 vs 0.208 ms on C2 — every entry recomputes the prefix / suffix hashes its
-                               // key's rules share, and that outweighs the shorter dependent chain)
-#endif
-
 namespace lt {
 
 constexpr int kLatWarps = 4;                 // preferred warps per CTA of the lattice kernel
@@ -136,19 +130,18 @@ __device__ __forceinline__ bool is_py_space(uint32_t c) {
 }
 
 // Prefix hashes of the staged syllables by warp scan: H[0] = 0, H[i+1] = H[i] * B + (c_i + 1).
-__device__ __noinline__ void prefix_hashes(const uint16_t* ch, int L, int lane, uint64_t* ha, uint64_t* hb) {
+__device__ __forceinline__ void prefix_hashes_inline(const uint16_t* ch, int L, int lane, uint64_t* ha, uint64_t* hb) {
     H2 carry{0, 0};
     if (lane == 0) {
         ha[0] = 0;
         hb[0] = 0;
     }
-    constexpr uint64_t A1 = kBaseA, A2 = A1 * A1, A4 = A2 * A2, A8 = A4 * A4, A16 = A8 * A8, A32 = A16 * A16;
-    constexpr uint64_t B1 = kBaseB, B2 = B1 * B1, B4 = B2 * B2, B8 = B4 * B4, B16 = B8 * B8, B32 = B16 * B16;
+    constexpr uint64_t A1 = kBaseA, A2 = A1 * A1, A4 = A2 * A2, A8 = A4 * A4, A16 = A8 * A8;
+    constexpr uint64_t B1 = kBaseB, B2 = B1 * B1, B4 = B2 * B2, B8 = B4 * B4, B16 = B8 * B8;
     for (int base = 0; base < L; base += 32) {
-        int i = base + lane;
-        uint64_t v = (i < L) ? (uint64_t)ch[i] + 1u : 0u;
-        uint64_t sa = v, sb = v;
-        uint64_t ta, tb;
+        const int i = base + lane;
+        const uint64_t v = (i < L) ? (uint64_t)ch[i] + 1u : 0u;
+        uint64_t sa = v, sb = v, ta, tb;
         ta = __shfl_up_sync(kFull, sa, 1);  tb = __shfl_up_sync(kFull, sb, 1);
         if (lane >= 1)  { sa += ta * A1;  sb += tb * B1; }
         ta = __shfl_up_sync(kFull, sa, 2);  tb = __shfl_up_sync(kFull, sb, 2);
@@ -163,23 +156,27 @@ __device__ __noinline__ void prefix_hashes(const uint16_t* ch, int L, int lane, 
         uint64_t pa = 1, pb = 1;   // B^(lane+1)
         {
             uint64_t xa = A1, xb = B1;
-            int k = lane + 1;
+            const int k = lane + 1;
             #pragma unroll
             for (int bit = 0; bit < 6; ++bit) {
                 if (k & (1 << bit)) { pa *= xa; pb *= xb; }
                 xa *= xa; xb *= xb;
             }
         }
-        uint64_t outa = carry.a * pa + sa, outb = carry.b * pb + sb;
+        const uint64_t outa = carry.a * pa + sa, outb = carry.b * pb + sb;
         if (i < L) {
             ha[i + 1] = outa;
             hb[i + 1] = outb;
         }
         carry.a = __shfl_sync(kFull, outa, 31);
         carry.b = __shfl_sync(kFull, outb, 31);
-        (void)A32; (void)B32;
     }
     __syncwarp();
+}
+
+// (out of line in the lattice kernel, whose instruction footprint is the tighter one; the beam kernel inlines it)
+__device__ __noinline__ void prefix_hashes(const uint16_t* ch, int L, int lane, uint64_t* ha, uint64_t* hb) {
+    prefix_hashes_inline(ch, L, lane, ha, hb);
 }
 
 // Stage the sentence: compaction, eojeol starts, prefix hashes.  Returns syllable count; n_eoj and
@@ -296,9 +293,6 @@ __device__ __forceinline__ uint64_t hit_key(int e, int b, uint32_t cls, uint32_t
 #ifndef LT_STAGE_ATTR
 #define LT_STAGE_ATTR __forceinline__
 #endif
-#ifndef LT_ITEM_ATTR
-#define LT_ITEM_ATTR __forceinline__
-#endif
 #ifndef LT_FLUSH_ATTR
 #define LT_FLUSH_ATTR __noinline__
 #endif
@@ -340,19 +334,9 @@ __device__ __forceinline__ void rule_candidate(const DevTables& T, const Enum& E
 // Rule work is QUEUED, not done in place: the items of an eojeol that meet a conjugation key are a
 // minority of the lanes, so applying the rules inside the item loop runs the most expensive code of
 // the kernel (rule records, hash composition, two dictionary probes per rule) on a handful of lanes.
-// An item pushes one descriptor per (word, split, key); drain_rules() then gives every lane one.
+// emit_pass() queues one descriptor per (word, split, key); drain_rules() then gives every lane one.
 //   x = b | p << 12 | suffix code << 24 (0: p+1, 1: p+2, 2: e) | reps_is_count << 26 | is_l << 27 | skip2 << 28 | pass << 29
 //   y = e | task << 12        z = first candidate index | rule count << 19        w = first rule
-__device__ __forceinline__ void push_rules(const Enum& E, uint2 ref, int b, int p, int e, uint32_t suffix_code, bool skip2,
-                                           bool is_l, uint32_t cand0, bool reps_is_count, uint32_t task, uint32_t pass) {
-    const uint32_t count = ref.y & 0xFFFFu;
-    if (count == 0) return;
-    const uint32_t slot = atomicAdd(E.rqn, 1u);
-    E.rq[slot] = make_uint4((uint32_t)b | ((uint32_t)p << 12) | (suffix_code << 24) | (reps_is_count ? 1u << 26 : 0u) |
-                                (is_l ? 1u << 27 : 0u) | (skip2 ? 1u << 28 : 0u) | (pass << 29),
-                            (uint32_t)e | (task << 12), cand0 | (count << 19), ref.x);
-}
-
 // Rules of one key applied at split p of the word [b, e): stem = word[:p-b] + rule.stem,
 // eomi = rule.eomi + word[suffix_from - b:]  (lemmatizer.py:100-102, :107-111).  `cand0` is the
 // candidate index of the key's first rule inside this split; with reps > 1 the whole list repeats
@@ -391,21 +375,6 @@ __device__ __noinline__ void drain_rules(const DevTables& T, unsigned char* base
         }
         const H2 pre = (p > b) ? sub_hash(T, v, b, p) : H2{0, 0};
         const H2 pw_suf = pow_at(T, suf_len);
-#if LT_LAT_FLATRULES
-        {
-            // one RULE per descriptor (emit_pass queues them that way): every lane applies exactly one rule, so a
-            // drain costs the same two dependent table round trips whatever the keys' rule counts are
-            const RuleRec rec = rule_load(T, d.w);
-            // no dictionary string is longer than max_str: most candidates die here, before any hashing
-            if (rec.eomi_len + suf_len > (uint32_t)E.max_str || (uint32_t)(p - b) + rec.stem_len > (uint32_t)E.max_str) continue;
-            const H2 stem = h2_concat(pre, rec.stem, pow_at(T, rec.stem_len));
-            const H2 eomi = h2_concat(rec.eomi, suf, pw_suf);
-            proto.rule = d.w;
-            rule_candidate(T, E, stem, (uint32_t)(p - b) + rec.stem_len, eomi, rec.eomi_len + suf_len, proto,
-                           (uint32_t)(p - b), cand0, reps, count, task, (d.x >> 29) & 1u);
-            continue;
-        }
-#endif
         RuleRec next = rule_load(T, d.w);
         for (uint32_t r = 0; r < count; ++r) {
             const RuleRec rec = next;
@@ -423,79 +392,6 @@ __device__ __noinline__ void drain_rules(const DevTables& T, unsigned char* base
     if (lane == 0) *E.rqn = 0;
     __syncwarp();
 }
-
-// Lemma candidates of the word [b, e) at split position p, in get_lemma_candidates order
-// (lemmatizer.py:90-112).  Returns the number of candidates the reference generates there.
-__device__ LT_ITEM_ATTR uint32_t lemma_item(const DevTables& T, const SentView& v, const Enum& E, int b, int e, int p,
-                                               lt_edge proto, uint32_t task, uint32_t pass = 0) {
-    uint32_t ncand = 0;
-    proto.tag1 = LT_TAG_EOMI;
-    proto.split = (uint16_t)(p - b);
-    const uint8_t base_flags = proto.flags & LT_EDGE_IS_L;
-    // plain split (not at the last syllable): both strings are sentence substrings -> table
-    if (p < e - 1) {
-        ++ncand;
-        if (sub_get(E, p + 1, e) & kSubEomi) {
-            const uint32_t ps = sub_get(E, b, p + 1);
-            proto.rule = LT_NO_RULE;
-            proto.flags = base_flags | LT_EDGE_LEMMA;
-            if (ps & kSubAdj) {
-                proto.tag0 = LT_TAG_ADJECTIVE;
-                stage_hit(E, proto, hit_key(e, b, 1, (uint32_t)(p - b), 0, pass), task);
-            }
-            if (ps & kSubVerb) {
-                proto.tag0 = LT_TAG_VERB;
-                stage_hit(E, proto, hit_key(e, b, 1, (uint32_t)(p - b), 1, pass), task);
-            }
-        }
-    }
-    const uint2 r1 = v.rref[3 * p + 0];
-    const uint2 r2 = (p + 2 <= e) ? v.rref[3 * p + 1] : make_uint2(0u, 0u);
-    const uint2 r3 = (p + 3 <= e) ? v.rref[3 * p + 2] : make_uint2(0u, 0u);
-    const uint32_t c1 = r1.y & 0xFFFFu, c2 = r2.y & 0xFFFFu, c3 = r3.y & 0xFFFFu;
-    if (!(c1 | c2 | c3)) return ncand;
-    const bool is_l = base_flags != 0;
-    // one-syllable key: the whole rule list once per rule of the key (lemmatizer.py:100-102)
-    if (c1) {
-        push_rules(E, r1, b, p, e, 0u, false, is_l, 1u, true, task, pass);
-        ncand += c1 * c1;
-    }
-    // {word[i:i+2], word[i:i+3]} in set order; the eomi continues at word[i+2:] for both
-    const uint32_t after1 = 1u + c1 * c1;
-    if (p == e - 1) {
-        // both slices are the last syllable itself: its rules once more, empty suffix
-        if (c1) {
-            push_rules(E, r1, b, p, e, 2u, true, is_l, after1, false, task, pass);
-            ncand += c1;
-        }
-    } else {
-        const bool k3_first = (r3.y >> 31) != 0;
-        const uint2 first = k3_first ? r3 : r2;
-        const uint2 second = k3_first ? r2 : r3;
-        push_rules(E, first, b, p, e, 1u, true, is_l, after1, false, task, pass);
-        push_rules(E, second, b, p, e, 1u, true, is_l, after1 + (first.y & 0xFFFFu), false, task, pass);
-        ncand += c2 + c3;
-    }
-    return ncand;
-}
-
-__device__ __forceinline__ lt_edge edge_proto(int b, int e, uint32_t len, bool is_l) {
-    lt_edge p;
-    p.b = (uint16_t)b;
-    p.e = (uint16_t)e;
-    p.len = (uint16_t)len;
-    p.tag0 = 0;
-    p.tag1 = LT_NO_TAG;
-    p.rule = LT_NO_RULE;
-    p.split = 0;
-    p.flags = is_l ? LT_EDGE_IS_L : 0;
-    p.reserved = 0;
-    return p;
-}
-
-#ifndef LT_LAT_COMPACT
-#define LT_LAT_COMPACT 1       // 1: an enumeration pass stages its hits / rule descriptors by warp compaction (emit_pass)
-#endif
 
 // One pass of an enumeration loop = 32 items, one per lane.  All lanes first decide what their item
 // produces — single-morpheme hits (`tagbits`), the plain-split analyses and the conjugation keys that
@@ -539,11 +435,7 @@ __device__ __forceinline__ uint32_t emit_pass(const DevTables& T, const SentView
     const uint32_t after1 = 1u + c1 * c1;
     ncand += c1 * c1 + cf + cs;
     const uint32_t nh_mine = (uint32_t)__popc(hits);
-#if LT_LAT_FLATRULES
-    const uint32_t np_mine = c1 + cf + cs;          // one queue entry per RULE (<= 3 x 255 per lane)
-#else
     const uint32_t np_mine = (c1 ? 1u : 0u) + (cf ? 1u : 0u) + (cs ? 1u : 0u);
-#endif
     uint32_t incl = nh_mine | (np_mine << 16);
     #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -551,28 +443,12 @@ __device__ __forceinline__ uint32_t emit_pass(const DevTables& T, const SentView
         if (lane >= d) incl += t;
     }
     const uint32_t total = __shfl_sync(kFull, incl, 31);
-#if LT_LAT_FLATRULES
-    const uint32_t total_p = total >> 16;
-    uint32_t cur_q = *E.rqn;
-    if (cur_q + total_p > (uint32_t)kRuleQueue && cur_q > 0u) {
-        // the pass's rules do not fit behind what is queued: apply the queued ones first (warp-uniform)
-        drain_rules<UC, HCT>(T, base, units_rt, E.hcap, E.max_str, lane);
-        cur_q = 0u;
-    }
-    const uint32_t cur_h = *E.nh;
-    __syncwarp();                                   // every lane has read the counters
-    if (lane == 31) {
-        *E.nh = cur_h + (total & 0xFFFFu);
-        if (total_p <= (uint32_t)kRuleQueue) *E.rqn = cur_q + total_p;
-    }
-#else
     const uint32_t cur_h = *E.nh, cur_q = *E.rqn;
     __syncwarp();                                   // every lane has read the counters
     if (lane == 31) {
         *E.nh = cur_h + (total & 0xFFFFu);
         *E.rqn = cur_q + (total >> 16);
     }
-#endif
     uint32_t slot = cur_h + (incl & 0xFFFFu) - nh_mine;
     if (hits) E.tcnt[task] = 1u;                    // (only ever tested against zero)
     #pragma unroll 1
@@ -597,38 +473,10 @@ __device__ __forceinline__ uint32_t emit_pass(const DevTables& T, const SentView
     }
     const uint32_t common = (uint32_t)b | ((uint32_t)p << 12) | (is_l ? 1u << 27 : 0u) | (pass << 29);
     const uint32_t ytask = (uint32_t)e | (task << 12);
-#if LT_LAT_FLATRULES
-    {
-        // entries of this pass are numbered [0, total_p) in lane order; normally they all fit behind the queue's
-        // contents, else (rule lists of hundreds) they go through the queue one window at a time
-        const uint32_t first = (incl >> 16) - np_mine;
-        uint32_t w0 = 0;
-        do {
-            const uint32_t room = total_p <= (uint32_t)kRuleQueue ? total_p : (uint32_t)kRuleQueue;
-            uint32_t idx = first;
-            #pragma unroll 1
-            for (int k = 0; k < 3; ++k) {
-                const uint32_t cnt = k == 0 ? c1 : (k == 1 ? cf : cs);
-                const uint32_t ref = k == 0 ? r1.x : (k == 1 ? rf.x : rs.x);
-                const uint32_t cand0 = k == 0 ? 1u : (k == 1 ? after1 : after1 + cf);
-                const uint32_t x = common | (k == 0 ? (1u << 26) : (((k == 1 && last) ? 2u : 1u) << 24) | (1u << 28));
-                #pragma unroll 1
-                for (uint32_t r = 0; r < cnt; ++r, ++idx)
-                    if (idx >= w0 && idx < w0 + room) E.rq[cur_q + idx - w0] = make_uint4(x, ytask, (cand0 + r) | (cnt << 19), ref + r);
-            }
-            if (total_p <= (uint32_t)kRuleQueue) break;
-            __syncwarp();
-            if (lane == 31) *E.rqn = (total_p - w0 < room) ? total_p - w0 : room;
-            drain_rules<UC, HCT>(T, base, units_rt, E.hcap, E.max_str, lane);
-            w0 += room;
-        } while (w0 < total_p);
-    }
-#else
     uint32_t qs = cur_q + (incl >> 16) - np_mine;
     if (c1) E.rq[qs++] = make_uint4(common | (0u << 24) | (1u << 26), ytask, 1u | (c1 << 19), r1.x);
     if (cf) E.rq[qs++] = make_uint4(common | ((last ? 2u : 1u) << 24) | (1u << 28), ytask, after1 | (cf << 19), rf.x);
     if (cs) E.rq[qs++] = make_uint4(common | (1u << 24) | (1u << 28), ytask, (after1 + cf) | (cs << 19), rs.x);
-#endif
     __syncwarp();
     return ncand;
 }
@@ -790,7 +638,6 @@ __global__ void __launch_bounds__(lattice_max_threads(UC, HCT, LM), lattice_min_
                 const int n_items1 = word_mode ? n : n * n;
                 for (int q0 = 0; q0 < n_items1; q0 += 32) {
                     const int q = q0 + lane;
-#if LT_LAT_COMPACT
                     {
                         const bool valid = q < n_items1;
                         const int qq = valid ? q : 0;
@@ -810,45 +657,6 @@ __global__ void __launch_bounds__(lattice_max_threads(UC, HCT, LM), lattice_min_
                         ncand_try += emit_pass<UC, HCT>(T, v, E, base, units, lane, valid, b, e, p, task, b == o, tagbits, special ? (uint32_t)n : (uint32_t)(e - b),
                                                special ? left : (b == o), special ? 0ull : ~0ull, !special, 0u);
                     }
-#else
-                    if (q < n_items1) {
-                        const int i = small_div(q, n, inv_n), r = q - i * n;
-                        const int p = o + r;
-                        // task: i == 0 whole; r < i: left_i = [o, o+i); else right_i = [o+i, oe)
-                        const bool left = (i > 0) && (r < i);
-                        const int b = (i > 0 && !left) ? o + i : o;
-                        const int e = left ? o + i : oe;
-                        const uint32_t task = (i == 0) ? 0u : (left ? 2u * i : 2u * i + 1u);
-                        bool special = false;
-                        if (i > 0)
-                            special = ((sub_get(E, o, o + i) >> LT_TAG_NOUN) & 1u) && ((sub_get(E, o + i, oe) >> LT_TAG_JOSA) & 1u);
-                        if (p == b) {
-                            // the task's first item also reports its tag hits
-                            if (special) {
-                                // Noun + Josa special case: both edges carry len = n (lookup.py:200-203)
-                                lt_edge rec = edge_proto(b, e, (uint32_t)n, left);
-                                rec.tag0 = left ? LT_TAG_NOUN : LT_TAG_JOSA;
-                                stage_hit(E, rec, hit_key(e, b, 0, 0, 0), task);
-                            } else {
-                                // one hit per tag of the string; the sort key carries the tag's position in the
-                                // dictionary's tag order (get_tags, dictionary.py:238-242), so set bits are simply walked
-                                uint32_t mask = sub_get(E, b, e) & kSubTagMask & T.order_mask;
-                                if (mask) {
-                                    lt_edge rec = edge_proto(b, e, (uint32_t)(e - b), b == o);
-                                    #pragma unroll 1
-                                    while (mask) {
-                                        const uint32_t t = (uint32_t)__ffs(mask) - 1u;
-                                        mask &= mask - 1u;
-                                        rec.tag0 = (uint8_t)t;
-                                        stage_hit(E, rec, hit_key(e, b, 0, 0, (uint32_t)T.tag_pos[t]), task);
-                                    }
-                                }
-                            }
-                        }
-                        if (!special)
-                            ncand_try += lemma_item(T, v, E, b, e, p, edge_proto(b, e, (uint32_t)(e - b), b == o), task);
-                    }
-#endif
                     // (read by one lane between two barriers: a lane that ran ahead into the next pass must not be able
                     // to change what the others see here)
                     if (warp_read(rqn) > (uint32_t)kRuleDrainAt) drain_rules<UC, HCT>(T, base, units, HC, DM, lane);     // a pass queues at most 3 per lane
@@ -910,7 +718,6 @@ __global__ void __launch_bounds__(lattice_max_threads(UC, HCT, LM), lattice_min_
                                                           (4ull << (4 * LT_TAG_NUMBER)) | (5ull << (4 * LT_TAG_JOSA));
                     for (int q0 = 0; q0 < items; q0 += 32) {
                         const int q = q0 + lane;
-#if LT_LAT_COMPACT
                         {
                             const bool in_range = q < items;
                             const int qq = in_range ? q : 0;
@@ -936,54 +743,6 @@ __global__ void __launch_bounds__(lattice_max_threads(UC, HCT, LM), lattice_min_
                             ncand_try += emit_pass<UC, HCT>(T, v, E, base, units, lane, valid, b, e, p, 0u, first, tagbits, (uint32_t)span, first,
                                                    word_mode ? ~0ull : standalone_order, true, pass);
                         }
-#else
-                        if (q < items) {
-                            const int blq = small_div(q, tri, inv_tri);
-                            const int bl = bl0 + blq;
-                            int t = q - blq * tri;
-                            // t -> (span, split offset inside the span): span (span - 1) / 2 <= t < span (span + 1) / 2
-                            int span = (int)((1.0f + sqrtf(8.0f * (float)t + 1.0f)) * 0.5f);
-                            while (span * (span - 1) / 2 > t) --span;
-                            while (span * (span + 1) / 2 <= t) ++span;
-                            t -= span * (span - 1) / 2;
-                            if (bl + span <= n) {
-                                const int b = o + bl, e = b + span, p = b + t;
-                                lt_edge rec = edge_proto(b, e, (uint32_t)span, word_mode && bl == 0);
-                                if (t == 0 && word_mode) {
-                                    // MorphemeDictionary.lookup of the substring: one hit per tag in dictionary order
-                                    uint32_t mask = sub_get(E, b, e) & kSubTagMask & T.order_mask;
-                                    #pragma unroll 1
-                                    while (mask) {
-                                        const uint32_t tg = (uint32_t)__ffs(mask) - 1u;
-                                        mask &= mask - 1u;
-                                        rec.tag0 = (uint8_t)tg;
-                                        stage_hit(E, rec, hit_key(e, b, 0, 0, (uint32_t)T.tag_pos[tg], pass), 0u);
-                                    }
-                                } else if (t == 0) {
-                                    const uint32_t m = sub_get(E, b, e);
-                                    // stand-alone tags in list order (lookup.py:104-105), then Josa after a Noun
-                                    constexpr uint32_t standalone = (1u << LT_TAG_NOUN) | (1u << LT_TAG_ADVERB) | (1u << LT_TAG_EXCLAMATION) |
-                                                                    (1u << LT_TAG_DETERMINER) | (1u << LT_TAG_NUMBER);
-                                    constexpr uint64_t pos_of = (0ull << (4 * LT_TAG_NOUN)) | (1ull << (4 * LT_TAG_ADVERB)) |
-                                                                (2ull << (4 * LT_TAG_EXCLAMATION)) | (3ull << (4 * LT_TAG_DETERMINER)) |
-                                                                (4ull << (4 * LT_TAG_NUMBER));
-                                    uint32_t sm = m & standalone;
-                                    #pragma unroll 1
-                                    while (sm) {
-                                        const uint32_t t = (uint32_t)__ffs(sm) - 1u;
-                                        sm &= sm - 1u;
-                                        rec.tag0 = (uint8_t)t;
-                                        stage_hit(E, rec, hit_key(e, b, 0, 0, (uint32_t)((pos_of >> (4 * t)) & 0xFu)), 0u);
-                                    }
-                                    if (nend[b] && ((m >> LT_TAG_JOSA) & 1u)) {
-                                        rec.tag0 = LT_TAG_JOSA;
-                                        stage_hit(E, rec, hit_key(e, b, 0, 0, 5u), 0u);
-                                    }
-                                }
-                                ncand_try += lemma_item(T, v, E, b, e, p, rec, 0u, pass);
-                            }
-                        }
-#endif
                         if (warp_read(rqn) > (uint32_t)kRuleDrainAt) drain_rules<UC, HCT>(T, base, units, HC, DM, lane);
                     }
                     drain_rules<UC, HCT>(T, base, units, HC, DM, lane);

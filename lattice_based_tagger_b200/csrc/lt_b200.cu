@@ -705,11 +705,12 @@ static int beam_plan(lt_batch* b, int lcap, int beam_size, bool kbest, const Bea
     auto resident_warps = [&](size_t warp_smem, int w) -> int {
         const size_t cta = dense_bytes + warp_smem * w;
         if (cta > kSmemBudget) return 0;
-        return w * (int)std::min<size_t>(16 / w, (size_t)228 * 1024 / (cta + 1024));
+        return w * (int)std::min<size_t>(LT_BEAM_REG_WARPS / w, (size_t)228 * 1024 / (cta + 1024));
     };
     auto best_warps = [&](size_t warp_smem) -> int {
         int best = 0, best_res = 0;
         for (int w : {kBeamWarps, 8, 6, 5, 3, 2, 1}) {
+            if (w > kBeamMaxWarps) continue;
             const int r = resident_warps(warp_smem, w);
             if (r > best_res) { best_res = r; best = w; }
         }

@@ -295,6 +295,10 @@ int  lt_lattice_status(lt_batch* batch, int32_t* status, int32_t* sent_len);
 int  lt_batch_info(lt_batch* batch, lt_info* out);
 int  lt_batch_counters(lt_batch* batch, lt_counters* out);
 int  lt_batch_timings(lt_batch* batch, lt_timings* out);
+/* Per-stage CUDA events on / off for the batches to come (the first lt_batch_timings call switches them on).
+ * While they are recorded BETWEEN the kernels of a batch, the kernels are launched one strictly after the other;
+ * without them each kernel is a programmatic dependent launch whose prologue overlaps its predecessor's tail.   */
+int  lt_batch_set_stage_timing(lt_batch* batch, int32_t on);
 
 #ifdef __cplusplus
 }

@@ -111,6 +111,7 @@ SYMBOLS = {
     'lt_paths_fetch': (ctypes.c_int, [_p, _p, _p, ctypes.c_int64, _p, _p]),
     'lt_batch_counters': (ctypes.c_int, [_p, ctypes.POINTER(lt_counters)]),
     'lt_batch_timings': (ctypes.c_int, [_p, ctypes.POINTER(lt_timings)]),
+    'lt_batch_set_stage_timing': (ctypes.c_int, [_p, ctypes.c_int32]),
 }
 
 _lib = None

@@ -477,6 +477,9 @@ struct lt_batch {
     bool debug = false;            // LT_DEBUG: print launch shapes
     bool trail_smem_ok = true;     // LT_TRAIL_SMEM=0 keeps the back-pointers in HBM
     int l2_persist_pct = 0;        // LT_L2_PERSIST=<percent of L2>: persisting access-policy window over the feature table
+    bool pdl = false;              // LT_PDL=1: programmatic dependent launch between the kernels of a batch (never while per-stage
+                                   // events are recorded between them).  Measured r2k: 5 us per C2 step SLOWER than plain launches
+    int prologue_ctas = kPrologueMaxCtas;   // LT_PROLOGUE_CTAS: CTAs of the work-order prologue (1 = exact order)
     int64_t n_edges = 0;
     bool have_lattice = false, have_paths = false, have_kbest = false, resolved = false;
     bool beam_state_clean = false;   // beam queue cursor / counters still zero from the batch prologue
@@ -574,6 +577,8 @@ extern "C" int lt_batch_create(lt_tables* tables, lt_batch** out) {
     if (const char* env = getenv("LT_EDGE_CAP")) { b->edge_cap = (uint32_t)std::max(16, atoi(env)); b->edge_cap_fixed = true; }
     if (const char* env = getenv("LT_TRAIL_SMEM")) b->trail_smem_ok = atoi(env) != 0;
     if (const char* env = getenv("LT_L2_PERSIST")) b->l2_persist_pct = std::min(100, std::max(0, atoi(env)));
+    if (const char* env = getenv("LT_PDL")) b->pdl = atoi(env) != 0;
+    if (const char* env = getenv("LT_PROLOGUE_CTAS")) b->prologue_ctas = std::min(32, std::max(1, atoi(env)));
     b->debug = getenv("LT_DEBUG") != nullptr;
     *out = b;
     return LT_OK;
@@ -804,7 +809,7 @@ static int launch_lattice(lt_batch* b, cudaStream_t st) {
         if (int rc = ensure(b->order, (size_t)n_sent * 4)) return rc;
         order = static_cast<uint32_t*>(b->order.p);
     }
-    LT_LAUNCH(batch_prologue, 1, 1024, 0, st, b->d_sent_off, n_sent, order, ctl, kCtlWords,
+    LT_LAUNCH(batch_prologue, (unsigned)(order ? std::min(b->prologue_ctas, prologue_ctas(n_sent)) : 1), 1024, 0, st, b->d_sent_off, n_sent, order, ctl, kCtlWords,
               static_cast<unsigned long long*>(b->counters.p), 8);
     CU(cudaGetLastError());
     b->launches += 1;
@@ -820,7 +825,7 @@ static int launch_lattice(lt_batch* b, cudaStream_t st) {
     }
     if (b->timed) CU(cudaEventRecord(b->ev[0], st));
     if (n_sent > 0) {
-        LT_LAUNCH(P->fn, grid, P->warps * 32, P->smem, st, t->dev, A);
+        CU(LT_LAUNCH_PDL(b->pdl && !b->timed, P->fn, grid, P->warps * 32, P->smem, st, t->dev, A));
         b->launches += 1;
     }
     CU(cudaGetLastError());
@@ -833,7 +838,7 @@ static int launch_lattice(lt_batch* b, cudaStream_t st) {
         R.hcap = Rp->hcap;
         R.queue = ctl + kCtlRetryQueue;
         R.retry_pass = 1;
-        LT_LAUNCH(Rp->fn, (unsigned)(t->sm_count * Rp->per_sm), Rp->warps * 32, Rp->smem, st, t->dev, R);
+        CU(LT_LAUNCH_PDL(b->pdl && !b->timed, Rp->fn, (unsigned)(t->sm_count * Rp->per_sm), Rp->warps * 32, Rp->smem, st, t->dev, R));
         CU(cudaGetLastError());
         b->launches += 1;
     }
@@ -937,7 +942,7 @@ static int launch_beam(lt_batch* b, cudaStream_t st, bool kbest) {
 #endif
     if (b->timed) CU(cudaEventRecord(b->ev[5], st));
     if (n_sent > 0) {
-        LT_LAUNCH(P->fn, grid, P->warps * 32, P->smem, st, t->dev, A);
+        CU(LT_LAUNCH_PDL(b->pdl && !b->timed && !windowed, P->fn, grid, P->warps * 32, P->smem, st, t->dev, A));
         b->launches += 1;
     }
     CU(cudaGetLastError());
@@ -949,6 +954,16 @@ static int launch_beam(lt_batch* b, cudaStream_t st, bool kbest) {
         CU(cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr));
     }
 #endif
+    if (n_sent > 0 && n_sent <= kPackScanMax) {
+        // offsets and packing in one launch (scan.cuh: pack_paths_scan)
+        const int ctas = (int)std::min<int64_t>(((int64_t)n_sent + 31) / 32, (int64_t)t->sm_count);
+        const int per = (n_sent + ctas - 1) / ctas;
+        CU(LT_LAUNCH_PDL(b->pdl && !b->timed, pack_paths_scan, (unsigned)((n_sent + per - 1) / per), kPackScanThreads, 0, st,
+                         static_cast<const lt_edge*>(b->path_tmp.p), b->d_sent_off, static_cast<const int32_t*>(b->path_len.p),
+                         static_cast<uint32_t*>(b->path_off.p), n_sent, per, static_cast<lt_edge*>(b->path_out.p)));
+        CU(cudaGetLastError());
+        b->launches += 1;
+    } else {
     if (int rc = scan_u32(b, reinterpret_cast<const uint32_t*>(b->path_len.p), static_cast<uint32_t*>(b->path_off.p),
                           (int64_t)n_sent + 1, st))
         return rc;
@@ -958,6 +973,7 @@ static int launch_beam(lt_batch* b, cudaStream_t st, bool kbest) {
                   static_cast<const uint32_t*>(b->path_off.p), n_sent, static_cast<lt_edge*>(b->path_out.p));
         CU(cudaGetLastError());
         b->launches += 1;
+    }
     }
     if (kbest) {
         // (kb_len[n_sent * beam] is the scan's sentinel entry; the kernel cannot know it is the last one)
@@ -1391,7 +1407,7 @@ extern "C" int lt_lattice_import(lt_batch* b, const uint16_t* text, const int32_
         if (int rc = ensure(b->order, (size_t)n_sent * 4)) return rc;
         order = static_cast<uint32_t*>(b->order.p);
     }
-    LT_LAUNCH(batch_prologue, 1, 1024, 0, st, b->d_sent_off, n_sent, order, static_cast<unsigned int*>(b->ctl.p), kCtlWords,
+    LT_LAUNCH(batch_prologue, (unsigned)(order ? std::min(b->prologue_ctas, prologue_ctas(n_sent)) : 1), 1024, 0, st, b->d_sent_off, n_sent, order, static_cast<unsigned int*>(b->ctl.p), kCtlWords,
               static_cast<unsigned long long*>(b->counters.p), 8);
     CU(cudaGetLastError());
     b->launches += 1;
@@ -1444,6 +1460,12 @@ extern "C" int lt_batch_info(lt_batch* b, lt_info* out) {
         out->beam_trail_smem = p->trail_smem ? 1 : 0;
     }
     out->sm_count = b->tables->sm_count;
+    return LT_OK;
+}
+
+extern "C" int lt_batch_set_stage_timing(lt_batch* b, int32_t on) {
+    if (!b) return fail(LT_ERR_INVALID, "null argument");
+    b->timed = on != 0;
     return LT_OK;
 }
 

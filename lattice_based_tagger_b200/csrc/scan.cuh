@@ -42,6 +42,7 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* w
 
 // pass 1: per-tile sums
 __global__ void __launch_bounds__(kScanThreads) scan_tile_sums(const uint32_t* __restrict__ in, int64_t n, uint32_t* __restrict__ sums) {
+    lt_pdl_wait();
     __shared__ uint32_t ws[kScanThreads / 32 + 1];
     const int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
     uint32_t local = 0;
@@ -92,6 +93,7 @@ __global__ void __launch_bounds__(kScanThreads) scan_apply(const uint32_t* __res
 constexpr int kScanSmallThreads = 1024;
 constexpr int64_t kScanSmallMax = 64 * 1024;
 __global__ void __launch_bounds__(kScanSmallThreads) scan_small(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int64_t n) {
+    lt_pdl_wait();
     __shared__ uint32_t warp_sums[33];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t per = (n + kScanSmallThreads - 1) / kScanSmallThreads;
@@ -125,24 +127,39 @@ __global__ void __launch_bounds__(kScanSmallThreads) scan_small(const uint32_t* 
     }
 }
 
-// Prologue of a batch, one CTA: zeroes the control words and work counters (instead of separate
-// memsets) and computes the WORK ORDER — sentence indices sorted by raw length, longest first, so
-// that the persistent warps of the lattice / beam kernels pull the expensive sentences early and
-// the launch tail stays short.  Histogram of lengths (clamped), scan, scatter; the order inside a
-// length bucket is arbitrary (atomics) and results do not depend on it.
+// Prologue of a batch: zeroes the control words and work counters (instead of separate memsets) and
+// computes the WORK ORDER — sentence indices by raw length, longest first, so that the persistent warps
+// of the lattice / beam kernels pull the expensive sentences early and the launch tail stays short
+// (C2: 0.571 ms per step against 0.620 ms in input order).
+// The CTAs do not talk to each other: CTA g of G sorts the sentences g, g + G, g + 2G, ... (histogram of
+// clamped lengths, scan, scatter; the order inside a length bucket is arbitrary, results do not depend on
+// it) and its r-th longest goes to position r * G + g — the G sorted sequences interleaved, a permutation
+// whatever the lengths are.  One CTA = the exact order.  Measured on C2 (r2l): the exact order by one CTA
+// makes the two big kernels 5.5 us faster than 32 interleaved sequences do and costs as much in the
+// prologue itself; 4 CTAs are the best of both by a microsecond.
 constexpr int kOrderBins = 1024;
+constexpr int kPrologueMaxCtas = 4;
+__host__ __device__ inline int prologue_ctas(int n_sent) {
+    const int want = (n_sent + 2047) / 2048;
+    return want < 1 ? 1 : (want > kPrologueMaxCtas ? kPrologueMaxCtas : want);
+}
 __global__ void __launch_bounds__(1024) batch_prologue(const int32_t* __restrict__ sent_off, int32_t n_sent,
                                                        uint32_t* __restrict__ order, unsigned int* __restrict__ ctl, int n_ctl,
                                                        unsigned long long* __restrict__ counters, int n_counters) {
-    if ((int)threadIdx.x < n_ctl) ctl[threadIdx.x] = 0;
-    if ((int)threadIdx.x < n_counters) counters[threadIdx.x] = 0;
+    const int G = (int)gridDim.x, g = (int)blockIdx.x;
+    lt_pdl_trigger();
+    lt_pdl_wait();
+    if (g == 0) {
+        if ((int)threadIdx.x < n_ctl) ctl[threadIdx.x] = 0;
+        if ((int)threadIdx.x < n_counters) counters[threadIdx.x] = 0;
+    }
     if (order == nullptr) return;
     __shared__ uint32_t bins[kOrderBins];
     __shared__ uint32_t warp_sums[32];
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     bins[t] = 0;
     __syncthreads();
-    for (int s = t; s < n_sent; s += blockDim.x) {
+    for (int64_t s = (int64_t)g + (int64_t)t * G; s < n_sent; s += (int64_t)blockDim.x * G) {
         int len = sent_off[s + 1] - sent_off[s];
         len = len < 0 ? 0 : (len >= kOrderBins ? kOrderBins - 1 : len);
         atomicAdd(&bins[kOrderBins - 1 - len], 1u);          // bin 0 = longest
@@ -171,10 +188,11 @@ __global__ void __launch_bounds__(1024) batch_prologue(const int32_t* __restrict
     __syncthreads();
     bins[t] = warp_sums[warp] + incl - v;           // start of every bin
     __syncthreads();
-    for (int s = t; s < n_sent; s += blockDim.x) {
+    for (int64_t s = (int64_t)g + (int64_t)t * G; s < n_sent; s += (int64_t)blockDim.x * G) {
         int len = sent_off[s + 1] - sent_off[s];
         len = len < 0 ? 0 : (len >= kOrderBins ? kOrderBins - 1 : len);
-        order[atomicAdd(&bins[kOrderBins - 1 - len], 1u)] = (uint32_t)s;
+        const uint32_t r = atomicAdd(&bins[kOrderBins - 1 - len], 1u);
+        order[(int64_t)r * G + g] = (uint32_t)s;
     }
 }
 
@@ -199,6 +217,7 @@ __global__ void beam_reset(unsigned int* __restrict__ queue, unsigned long long*
 // best paths: reversed per-sentence scratch -> contiguous forward order
 __global__ void pack_paths(const lt_edge* __restrict__ tmp, const int32_t* __restrict__ sent_off,
                            const uint32_t* __restrict__ path_off, int32_t n_sent, lt_edge* __restrict__ out) {
+    lt_pdl_wait();
     const int warps_per_block = blockDim.x >> 5;
     const int lane = threadIdx.x & 31;
     for (int s = blockIdx.x * warps_per_block + (threadIdx.x >> 5); s < n_sent; s += gridDim.x * warps_per_block) {
@@ -208,6 +227,74 @@ __global__ void pack_paths(const lt_edge* __restrict__ tmp, const int32_t* __res
         const uint4* src = reinterpret_cast<const uint4*>(tmp + s0);
         uint4* dst = reinterpret_cast<uint4*>(out + o0);
         for (int i = lane; i < W; i += 32) dst[i] = src[W - 1 - i];
+    }
+}
+
+// Batches of up to kPackScanMax sentences: offsets AND packing in one launch.  CTA g owns the contiguous
+// sentence range [g * per, (g + 1) * per): it sums the path lengths in front of its range itself (at most
+// 256 KB of L2-resident counts, read side by side — cheaper than a scan launch of its own plus the gap
+// behind it), scans its own range, writes path_off and moves its paths.
+constexpr int kPackScanThreads = 256;
+constexpr int64_t kPackScanMax = 64 * 1024;
+__global__ void __launch_bounds__(kPackScanThreads) pack_paths_scan(const lt_edge* __restrict__ tmp, const int32_t* __restrict__ sent_off,
+                                                                    const int32_t* __restrict__ path_len, uint32_t* __restrict__ path_off,
+                                                                    int32_t n_sent, int32_t per, lt_edge* __restrict__ out) {
+    __shared__ uint32_t warp_sums[kPackScanThreads / 32 + 1];
+    __shared__ uint32_t s_off[kPackScanThreads + 1];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    lt_pdl_trigger();
+    lt_pdl_wait();          // the beam kernel's paths are complete
+    const int r0 = (int)blockIdx.x * per;
+    const int r1 = min(n_sent, r0 + per);
+    if (r0 >= n_sent) return;
+    // words in front of this CTA's range
+    uint32_t local = 0;
+    for (int i = t; i < r0; i += kPackScanThreads) local += (uint32_t)path_len[i];
+    #pragma unroll
+    for (int d = 16; d; d >>= 1) local += __shfl_xor_sync(0xFFFFFFFFu, local, d);
+    if (lane == 0) warp_sums[warp] = local;
+    __syncthreads();
+    uint32_t carry = 0;
+    #pragma unroll
+    for (int w = 0; w < kPackScanThreads / 32; ++w) carry += warp_sums[w];
+    __syncthreads();
+    for (int base = r0; base < r1; base += kPackScanThreads) {
+        const int s = base + t;
+        const uint32_t v = (s < r1) ? (uint32_t)path_len[s] : 0u;
+        uint32_t incl = v;
+        #pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+            if (lane >= d) incl += u;
+        }
+        if (lane == 31) warp_sums[warp] = incl;
+        __syncthreads();
+        uint32_t before = 0, total = 0;
+        #pragma unroll
+        for (int w = 0; w < kPackScanThreads / 32; ++w) {
+            const uint32_t x = warp_sums[w];
+            before += (w < warp) ? x : 0u;
+            total += x;
+        }
+        const uint32_t off = carry + before + incl - v;
+        s_off[t] = off;
+        if (s < r1) {
+            path_off[s] = off;
+            if (s == n_sent - 1) path_off[n_sent] = off + v;      // (the last sentence's owner alone)
+        }
+        if (t == kPackScanThreads - 1) s_off[kPackScanThreads] = carry + total;
+        __syncthreads();
+        // this tile's paths: one warp per sentence
+        const int tile_n = min(kPackScanThreads, r1 - base);
+        for (int i = warp; i < tile_n; i += kPackScanThreads / 32) {
+            const uint32_t o0 = s_off[i];
+            const int W = (int)(((i + 1 < tile_n) ? s_off[i + 1] : s_off[kPackScanThreads]) - o0);
+            const uint4* src = reinterpret_cast<const uint4*>(tmp + sent_off[base + i]);
+            uint4* dst = reinterpret_cast<uint4*>(out + o0);
+            for (int k = lane; k < W; k += 32) dst[k] = src[W - 1 - k];
+        }
+        carry += total;
+        __syncthreads();
     }
 }
 

@@ -374,6 +374,10 @@ class Engine:
         _native.check(self._lib.lt_batch_timings(self.batch, ctypes.byref(t)))
         return t.as_dict()
 
+    def set_stage_timing(self, on):
+        """Per-stage CUDA events between the kernels of a batch on / off (off: programmatic dependent launches)."""
+        _native.check(self._lib.lt_batch_set_stage_timing(self.batch, 1 if on else 0))
+
     def info(self):
         i = _native.lt_info()
         _native.check(self._lib.lt_batch_info(self.batch, ctypes.byref(i)))

@@ -207,6 +207,11 @@ class Tagger:
         """Device times of the last batch by stage (first call only switches timing on)."""
         return self._engine.timings()
 
+    def set_stage_timing(self, on):
+        """Per-stage events on / off for the batches to come; off lets the kernels of a batch overlap their
+        launch prologues with their predecessors' tails (programmatic dependent launch)."""
+        self._engine.set_stage_timing(on)
+
     def info(self):
         """Workspace state: buffer capacities, reruns, kernel launches so far, launch shapes."""
         return self._engine.info()

@@ -1,4 +1,5 @@
 // simt.cpp — fibers, scheduler and collectives of the SIMT emulator (tests only, see simt.h).
+#include <cstdlib>
 #include "simt.h"
 
 #include <deque>
@@ -169,7 +170,12 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()
     S.body = &body;
     if (S.fibers.size() < nthreads) S.fibers.resize(nthreads);
     const unsigned nwarps = (nthreads + kWarp - 1) / kWarp;
-    for (unsigned b = 0; b < grid.x; ++b) {
+    // Blocks run one after another; LT_SIMT_BLOCK_ORDER=reverse runs them last to first, so that a kernel whose
+    // result depends on which of two CTAs writes last (a race on the GPU) fails one of the two orders.
+    const char* order_env = getenv("LT_SIMT_BLOCK_ORDER");
+    const bool reverse = order_env && order_env[0] == 'r';
+    for (unsigned bi = 0; bi < grid.x; ++bi) {
+        const unsigned b = reverse ? grid.x - 1 - bi : bi;
         S.bid = uint3{b, 0, 0};
         // poison shared memory: a kernel that relies on stale contents fails the same way everywhere
         memset(S.smem, 0xA5, smem_bytes);

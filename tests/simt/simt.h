@@ -128,6 +128,7 @@ static inline void __syncwarp(unsigned mask = 0xFFFFFFFFu, SIMT_SITE) { simt::co
 static inline void __syncthreads() { simt::block_barrier(); }
 static inline unsigned __ballot_sync(unsigned mask, int pred, SIMT_SITE) { return (unsigned)simt::collective(simt::OP_BALLOT, mask, pred ? 1 : 0, 0, file_, line_); }
 static inline int __any_sync(unsigned mask, int pred, SIMT_SITE) { return __ballot_sync(mask, pred, file_, line_) != 0; }
+static inline int __all_sync(unsigned mask, int pred, SIMT_SITE) { return __ballot_sync(mask, pred, file_, line_) == mask; }
 static inline unsigned __activemask() { return 0xFFFFFFFFu; }
 
 template <typename T>
@@ -199,7 +200,8 @@ struct cudaDeviceProp { int multiProcessorCount; char name[64]; };
 
 static inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 static inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
-static inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) { p->multiProcessorCount = 2; strcpy(p->name, "simt-emu"); return cudaSuccess; }
+// (LT_SIMT_SMS: the SM count the host code sizes its grids by — 2 unless a test asks for a wider device)
+static inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) { const char* sms_ = getenv("LT_SIMT_SMS"); p->multiProcessorCount = sms_ ? atoi(sms_) : 2; strcpy(p->name, "simt-emu"); return cudaSuccess; }
 static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 static inline const char* cudaGetErrorString(cudaError_t) { return "simt-emu error"; }
 static inline cudaError_t cudaMalloc(void** p, size_t n) { *p = aligned_alloc(256, (n + 255) & ~(size_t)255); if (*p) memset(*p, 0xCD, n); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }

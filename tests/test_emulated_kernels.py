@@ -47,6 +47,32 @@ def test_golden_demo_fixture():
                 assert [tuple(w) for w in seq.sequences] == words and seq.score == score and seq.num_unk == num_unk
 
 
+@pytest.mark.parametrize('block_order', ['forward', 'reverse'])
+def test_many_sentences_across_ctas(monkeypatch, block_order):
+    """A batch large enough for the multi-CTA kernels around the two big ones (work-order prologue, path
+    offsets + packing), with the emulator running the CTAs first-to-last and last-to-first: a result that
+    depends on which CTA writes last is a race on the GPU."""
+    monkeypatch.setenv('LT_SIMT_BLOCK_ORDER', block_order)
+    monkeypatch.setenv('LT_SIMT_SMS', '64')          # grids as wide as on the device: several CTAs per kernel
+    case = _checks.make_case(2001, n_sent=12, max_sent_len=14)
+    dictionary, funcs = _cases.build_objects(case, pkg)
+    tagger = pkg.Tagger(dictionary, score_funcs=funcs)
+    oracle = lo.OracleTagger(dictionary, funcs)
+    sents = [case['sentences'][i % 12] for i in range(4200)]
+    want = {}
+    for sent in set(sents):
+        try:
+            want[sent] = oracle.tag(sent, 5)
+        except IndexError:
+            want[sent] = None
+    got = tagger.tag_batch(sents, beam_size=5, errors='none')
+    for sent, seq in zip(sents, got):
+        if want[sent] is None:
+            assert seq is None
+        else:
+            assert [tuple(w) for w in seq.sequences] == want[sent].words and seq.score == want[sent].score
+
+
 def test_kbest_survivors():
     case = _checks.make_case(3001, n_sent=10, max_sent_len=24)
     dictionary, funcs = _cases.build_objects(case, pkg)

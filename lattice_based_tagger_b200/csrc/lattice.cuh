@@ -65,13 +65,15 @@ struct LatticeArgs {
     unsigned long long* counters;   // [0]=L [1]=P [2]=E
     unsigned int* queue;        // work-queue cursor
     const uint32_t* order;      // queue position -> sentence index (longest first), or nullptr
-    // Two-pass staging: when `retry_list` is set, a sentence whose eojeol outgrows the staging area of the
-    // main pass is appended to it instead of raising the overflow flag; the retry pass (retry_pass = 1, a
-    // small launch with a larger staging area) takes its sentences from that list.
-    uint32_t* retry_list;
+    // Two-pass staging: when `retry_list` is set, an EOJEOL that outgrows the staging area of the main pass is
+    // appended to it as (sentence, eojeol index) instead of raising the overflow flag, and the main pass goes on
+    // with the sentence's other eojeols; the retry pass (retry_pass = 1, a small launch with a larger staging
+    // area) takes its eojeols from that list and adds their edges to the sentence's lattice.
+    uint2* retry_list;
     unsigned int* retry_count;
     int32_t retry_pass;
     int32_t mode;               // LT_LOOKUP_*: which eojeol lookup is enumerated
+    int32_t sort_min;           // eojeols with at least this many staged hits are ranked by sorting (rank_staged)
 };
 
 // Per-warp shared memory.  `units` = elements per sentence array (>= longest sentence + 8, a
@@ -228,7 +230,7 @@ struct Enum {
     // staging
     uint64_t* hkey;
     lt_edge* hrec;
-    uint32_t* htask;         // task id while an eojeol is enumerated, final rank afterwards
+    uint32_t* htask;         // task id while an eojeol is enumerated; afterwards htask[r] = staging slot of the survivor with rank r
     uint32_t* tcnt;          // hits per task of the current eojeol
     uint32_t* nh;            // staged entries (shared counter)
     int hcap;
@@ -481,10 +483,10 @@ __device__ __forceinline__ uint32_t emit_pass(const DevTables& T, const SentView
     return ncand;
 }
 
-// Write the staged survivors to HBM at (reservation + rank); CSR bookkeeping in shared memory.
-__device__ LT_FLUSH_ATTR void flush_staged(const LatticeArgs& A, int lane, uint32_t slots, uint32_t alive,
-                                          const uint32_t* htask, const lt_edge* hrec, uint32_t* pcnt, uint32_t* pstart,
-                                          uint32_t* nh) {
+// Write the staged survivors to HBM in rank order (ord[r] = staging slot of the record with rank r): consecutive
+// lanes write consecutive edge records; CSR bookkeeping in shared memory.
+__device__ LT_FLUSH_ATTR void flush_staged(const LatticeArgs& A, int lane, uint32_t alive, const uint32_t* ord, const lt_edge* hrec,
+                                          uint32_t* pcnt, uint32_t* pstart, uint32_t* nh) {
     if (alive > 0) {
         unsigned long long gbase64 = 0;
         if (lane == 0) gbase64 = atomicAdd(A.cursor, (unsigned long long)alive);
@@ -493,18 +495,64 @@ __device__ LT_FLUSH_ATTR void flush_staged(const LatticeArgs& A, int lane, uint3
         const uint32_t gbase = (uint32_t)gbase64;      // exact whenever it is used (edge_cap < 2^32)
         if (!fits && lane == 0) atomicOr(A.flags + kFlagEdgeOverflow, 1u);
         #pragma unroll 1
-        for (uint32_t i = lane; i < slots; i += 32) {
-            const uint32_t rank = htask[i];
-            if (rank == 0xFFFFFFFFu) continue;
-            const lt_edge rec = hrec[i];
-            if (fits) A.edges[gbase + rank] = rec;
+        for (uint32_t r = lane; r < alive; r += 32) {
+            const lt_edge rec = hrec[ord[r]];
+            if (fits) A.edges[gbase + r] = rec;
             atomicAdd(&pcnt[rec.e - 1], 1u);
-            atomicMin(&pstart[rec.e - 1], gbase + rank);
+            atomicMin(&pstart[rec.e - 1], gbase + r);
         }
     }
     __syncwarp();
     if (lane == 0) *nh = 0;
     __syncwarp();
+}
+
+// Rank of an eojeol's survivors by sort key.  Staged entries [first, first + H) hold keys (dead ones ~0) and records;
+// afterwards ord[alive .. alive + n_alive) lists the staging slots of the survivors in key order (`ord` is the task-id
+// array, whose contents are dead once the split filter has run; ord[0, alive) belongs to earlier eojeols).
+//   small eojeols (in the kernel): every entry counts the keys below its own (H^2 / 32 shared-memory reads per lane);
+//   larger ones (here): bitonic sort of (key, slot) pairs in place, padded to P = a power of two with dead keys — taken
+//                  when the padding fits the staging area (a 1 000-hit eojeol ranks in ~14 k warp instructions instead
+//                  of ~160 k; the counting loop was 12 % of C3's main pass and most of its retry pass).
+constexpr int kSortMin = 96;                // entries from which the sort pays (LatticeArgs::sort_min; LT_SORT_MIN overrides)
+#ifndef LT_RANK_UNROLL
+#define LT_RANK_UNROLL 4
+#endif
+constexpr int kRankUnroll = LT_RANK_UNROLL;
+__device__ __noinline__ void rank_by_sort(uint64_t* hkey, uint32_t* ord, uint32_t first, uint32_t H, uint32_t P, uint32_t alive,
+                                          uint32_t n_alive, int lane) {
+    for (uint32_t i = lane; i < P; i += 32) {
+        if (i >= H) hkey[first + i] = ~0ull;
+        ord[first + i] = first + i;
+    }
+    __syncwarp();
+    uint64_t* key = hkey + first;
+    uint32_t* pay = ord + first;
+    for (uint32_t k = 2; k <= P; k <<= 1) {
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            #pragma unroll 2
+            for (uint32_t t = lane; t < P / 2; t += 32) {
+                const uint32_t i = ((t & ~(j - 1u)) << 1) | (t & (j - 1u));      // bit j clear
+                const uint32_t q = i | j;
+                const uint64_t a = key[i], b = key[q];
+                const bool ascending = (i & k) == 0;
+                if ((a > b) == ascending) {
+                    key[i] = b; key[q] = a;
+                    const uint32_t pa = pay[i], pb = pay[q];
+                    pay[i] = pb; pay[q] = pa;
+                }
+            }
+            __syncwarp();
+        }
+    }
+    // survivors first, in key order: their slots move down to ord[alive ..) (never above where they were read)
+    for (uint32_t base = 0; base < n_alive; base += 32) {
+        const uint32_t r = base + lane;
+        const uint32_t src = (r < n_alive) ? pay[r] : 0u;
+        __syncwarp();
+        if (r < n_alive) ord[alive + r] = src;
+        __syncwarp();
+    }
 }
 
 // ---- the kernel -----------------------------------------------------------------------------------
@@ -552,9 +600,13 @@ __global__ void __launch_bounds__(lattice_max_threads(UC, HCT, LM), lattice_min_
         unsigned int s = 0;
         if (lane == 0) s = atomicAdd(A.queue, 1u);
         s = __shfl_sync(kFull, s, 0);
+        int w_first = 0, w_count = 0x7FFFFFFF;       // eojeols of the sentence this warp enumerates
         if (A.retry_pass) {
             if (s >= *A.retry_count) break;
-            s = A.retry_list[s];
+            const uint2 item = A.retry_list[s];
+            s = item.x;
+            w_first = (int)item.y;
+            w_count = 1;
         } else {
             if (s >= (unsigned)A.n_sent) break;
             if (A.order) s = __ldg(A.order + s);
@@ -618,14 +670,15 @@ __global__ void __launch_bounds__(lattice_max_threads(UC, HCT, LM), lattice_min_
         bool overflow = false;
 
         auto flush = [&]() {
-            flush_staged(A, lane, slots, alive, htask, hrec, pcnt, pstart, nh);
+            flush_staged(A, lane, alive, htask, hrec, pcnt, pstart, nh);
             slots = 0;
             alive = 0;
         };
 
         const int mode = LM ? A.mode : LT_LOOKUP_MORPHEME;
         const bool word_mode = LM && mode >= LT_LOOKUP_WORD;
-        for (int w = 0; w < n_eoj && !overflow; ++w) {
+        const int w_end = (w_count < n_eoj - w_first) ? w_first + w_count : n_eoj;
+        for (int w = w_first; w < w_end && !overflow; ++w) {
             const int o = eoj[w];
             const int n = eoj[w + 1] - o;
             const int oe = o + n;
@@ -763,6 +816,12 @@ __global__ void __launch_bounds__(lattice_max_threads(UC, HCT, LM), lattice_min_
                     if (lane == 0) *nh = slots;
                     __syncwarp();
                     if (attempt == 0 && slots > 0) { flush(); continue; }
+                    if (!A.retry_pass && A.retry_list != nullptr) {
+                        // this eojeol alone goes to the retry pass; the sentence's other eojeols are done here
+                        if (lane == 0) A.retry_list[atomicAdd(A.retry_count, 1u)] = make_uint2(s, (uint32_t)w);
+                        __syncwarp();
+                        break;
+                    }
                     overflow = true;
                     break;
                 }
@@ -770,15 +829,27 @@ __global__ void __launch_bounds__(lattice_max_threads(UC, HCT, LM), lattice_min_
                 if (lane == 0) nsub += nsub_try;
                 // ---- final position of every survivor: rank of its key among the eojeol's survivors ----
                 __syncwarp();
-                for (uint32_t h = slots + lane; h < nstaged; h += 32) {
-                    const uint64_t key = hkey[h];
-                    uint32_t rank = 0xFFFFFFFFu;
-                    if (key != ~0ull) {
-                        rank = alive;
-                        #pragma unroll 1
-                        for (uint32_t g = slots; g < nstaged; ++g) rank += (hkey[g] < key) ? 1u : 0u;
+                {
+                    const uint32_t H = nstaged - slots;
+                    uint32_t P = 0;                      // padded size when the eojeol is ranked by sorting
+                    if (H >= (uint32_t)A.sort_min) {
+                        P = 32;
+                        while (P < H) P <<= 1;
+                        if (slots + P > (uint32_t)HC) P = 0;
                     }
-                    htask[h] = rank;
+                    if (P) {
+                        rank_by_sort(hkey, htask, slots, H, P, alive, alive_here, lane);
+                    } else {
+                        for (uint32_t h = slots + lane; h < nstaged; h += 32) {
+                            const uint64_t key = hkey[h];
+                            if (key != ~0ull) {
+                                uint32_t rank = alive;
+                                #pragma unroll kRankUnroll
+                                for (uint32_t g = slots; g < nstaged; ++g) rank += (hkey[g] < key) ? 1u : 0u;
+                                htask[rank] = h;        // (task ids are dead by now: a rank slot may be any entry of this eojeol)
+                            }
+                        }
+                    }
                 }
                 slots = nstaged;
                 alive += alive_here;
@@ -788,24 +859,38 @@ __global__ void __launch_bounds__(lattice_max_threads(UC, HCT, LM), lattice_min_
             }
         }
         if (overflow) {
-            if (!A.retry_pass && A.retry_list != nullptr) {
-                // the retry pass redoes this sentence from scratch (edges already flushed stay unreferenced)
-                if (lane == 0) A.retry_list[atomicAdd(A.retry_count, 1u)] = s;
-                __syncwarp();
-                continue;
-            }
             if (lane == 0) atomicOr(A.flags + kFlagStageOverflow, 1u);
         } else {
             flush();
         }
         __syncwarp();
+        #pragma unroll
+        for (int d = 16; d; d >>= 1) ncand += __shfl_xor_sync(kFull, ncand, d);
+        if (A.retry_pass) {
+            // one eojeol of a sentence the main pass has otherwise finished: its positions, its edges, its share of
+            // the work counters; a sentence that had no edge without it gets its status back
+            const int o = (w_first < n_eoj) ? eoj[w_first] : 0, oe = (w_first < n_eoj) ? eoj[w_first + 1] : 0;
+            #pragma unroll 1
+            for (int p = o + lane; p < oe; p += 32) {
+                const uint32_t c = pcnt[p];
+                A.pos[s0 + p] = make_uint2(c ? pstart[p] : 0u, c);
+            }
+            if (lane == 0) {
+                if (sent_total > 0) {
+                    atomicAdd(A.sent_edges + s, (int32_t)sent_total);
+                    atomicCAS(A.status + s, (int32_t)LT_SENT_NO_EDGES, (int32_t)LT_SENT_OK);
+                }
+                acc_P += (unsigned long long)nsub + 2ull * ncand;
+                acc_E += sent_total;
+            }
+            __syncwarp();
+            continue;
+        }
         #pragma unroll 1
         for (int p = lane; p < s1 - s0; p += 32) {
             const uint32_t c = pcnt[p];
             A.pos[s0 + p] = make_uint2(c ? pstart[p] : 0u, c);
         }
-        #pragma unroll
-        for (int d = 16; d; d >>= 1) ncand += __shfl_xor_sync(kFull, ncand, d);
         if (lane == 0) {
             A.sent_len[s] = L;
             A.sent_edges[s] = (int32_t)sent_total;

@@ -479,6 +479,7 @@ struct lt_batch {
     int l2_persist_pct = 0;        // LT_L2_PERSIST=<percent of L2>: persisting access-policy window over the feature table
     bool pdl = false;              // LT_PDL=1: programmatic dependent launch between the kernels of a batch (never while per-stage
                                    // events are recorded between them).  Measured r2k: 5 us per C2 step SLOWER than plain launches
+    int sort_min = kSortMin;       // LT_SORT_MIN: staged hits per eojeol from which the lattice kernel ranks by sorting (tests: 1)
     int prologue_ctas = kPrologueMaxCtas;   // LT_PROLOGUE_CTAS: CTAs of the work-order prologue (1 = exact order)
     int64_t n_edges = 0;
     bool have_lattice = false, have_paths = false, have_kbest = false, resolved = false;
@@ -578,6 +579,7 @@ extern "C" int lt_batch_create(lt_tables* tables, lt_batch** out) {
     if (const char* env = getenv("LT_TRAIL_SMEM")) b->trail_smem_ok = atoi(env) != 0;
     if (const char* env = getenv("LT_L2_PERSIST")) b->l2_persist_pct = std::min(100, std::max(0, atoi(env)));
     if (const char* env = getenv("LT_PDL")) b->pdl = atoi(env) != 0;
+    if (const char* env = getenv("LT_SORT_MIN")) b->sort_min = std::max(1, atoi(env));
     if (const char* env = getenv("LT_PROLOGUE_CTAS")) b->prologue_ctas = std::min(32, std::max(1, atoi(env)));
     b->debug = getenv("LT_DEBUG") != nullptr;
     *out = b;
@@ -794,6 +796,7 @@ static int launch_lattice(lt_batch* b, cudaStream_t st) {
     A.edge_cap = b->edge_cap;
     A.max_units = lcap;
     A.mode = b->lookup_mode;
+    A.sort_min = b->sort_min;
     unsigned int* ctl = static_cast<unsigned int*>(b->ctl.p);
     A.cursor = reinterpret_cast<unsigned long long*>(ctl + kCtlCursor);
     A.flags = ctl + kCtlFlags;
@@ -819,8 +822,9 @@ static int launch_lattice(lt_batch* b, cudaStream_t st) {
     const int64_t want_blocks = ((int64_t)n_sent + P->warps - 1) / P->warps;
     const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(want_blocks, (int64_t)t->sm_count * P->per_sm));
     if (b->use_retry) {
-        if (int rc = ensure(b->retry, (size_t)std::max(1, n_sent) * 4)) return rc;
-        A.retry_list = static_cast<uint32_t*>(b->retry.p);
+        // (sentence, eojeol) pairs: an eojeol takes at least one code unit and a separator
+        if (int rc = ensure(b->retry, ((size_t)n_units / 2 + (size_t)n_sent + 16) * sizeof(uint2))) return rc;
+        A.retry_list = static_cast<uint2*>(b->retry.p);
         A.retry_count = ctl + kCtlRetryCount;
     }
     if (b->timed) CU(cudaEventRecord(b->ev[0], st));

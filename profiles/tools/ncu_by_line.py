@@ -17,8 +17,9 @@ import tempfile
 
 
 def sass_rows(report, kernel):
-    out = subprocess.run(['ncu', '-i', report, '--page', 'source', '--csv', '-k', 'regex:' + kernel],
-                         capture_output=True, text=True).stdout
+    # `kernel`: a regex on the kernel name, or `id:N` = the N-th profiled launch of the report
+    sel = ['--kernel-id', ':::' + kernel[3:]] if kernel.startswith('id:') else ['-k', 'regex:' + kernel]
+    out = subprocess.run(['ncu', '-i', report, '--page', 'source', '--csv'] + sel, capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     blocks = []
     cur = None

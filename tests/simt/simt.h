@@ -186,6 +186,7 @@ template <typename T, typename U> static inline T atomicAdd(T* p, U v) { T old =
 template <typename T, typename U> static inline T atomicMin(T* p, U v) { T old = *p; if ((T)v < old) *p = (T)v; return old; }
 template <typename T, typename U> static inline T atomicMax(T* p, U v) { T old = *p; if ((T)v > old) *p = (T)v; return old; }
 template <typename T, typename U> static inline T atomicOr(T* p, U v) { T old = *p; *p = (T)(old | (T)v); return old; }
+template <typename T, typename U, typename V> static inline T atomicCAS(T* p, U cmp, V v) { T old = *p; if (old == (T)cmp) *p = (T)v; return old; }
 template <typename T, typename U> static inline T atomicExch(T* p, U v) { T old = *p; *p = (T)v; return old; }
 
 // ---- host runtime stubs ---------------------------------------------------------------------------

@@ -73,6 +73,21 @@ def test_many_sentences_across_ctas(monkeypatch, block_order):
             assert [tuple(w) for w in seq.sequences] == want[sent].words and seq.score == want[sent].score
 
 
+@pytest.mark.parametrize('hit_cap', [None, '32'])
+def test_rank_by_sorting(monkeypatch, hit_cap):
+    """The lattice kernel ranks the hits of large eojeols with an in-place sort instead of the counting loop;
+    LT_SORT_MIN=1 sends every eojeol through it (with a small staging area: next to flushes, retries and the
+    fallback for eojeols whose padding does not fit)."""
+    monkeypatch.setenv('LT_SORT_MIN', '1')
+    if hit_cap:
+        monkeypatch.setenv('LT_HIT_CAP', hit_cap)
+    case = _checks.make_case(2016, n_sent=14, max_sent_len=48)
+    dictionary, funcs = _cases.build_objects(case, pkg)
+    tagger = pkg.Tagger(dictionary, score_funcs=funcs)
+    oracle = lo.OracleTagger(dictionary, funcs)
+    _checks.check_against_oracle(tagger, oracle, case['sentences'], (5,), counters=True)
+
+
 def test_kbest_survivors():
     case = _checks.make_case(3001, n_sent=10, max_sent_len=24)
     dictionary, funcs = _cases.build_objects(case, pkg)

@@ -314,6 +314,20 @@ def test_retry_pass_and_adaptive_staging(monkeypatch):
         _check_against_oracle(tagger, oracle, sents, (5,))
 
 
+@pytest.mark.parametrize('hit_cap', [None, '32'])
+def test_rank_by_sorting(monkeypatch, hit_cap):
+    """Large eojeols are ranked by an in-place sort (lattice.cuh: rank_staged); LT_SORT_MIN=1 sends every eojeol
+    through it: same lattices (edge order included), same paths, same scores."""
+    case = _cases.random_case(778, n_sent=90, features=True, max_sent_len=50)
+    _cases.add_features(case, _cases.observed_features(case, lo, seed=2), 2)
+    dictionary, funcs = _cases.build_objects(case, pkg)
+    monkeypatch.setenv('LT_SORT_MIN', '1')
+    if hit_cap:
+        monkeypatch.setenv('LT_HIT_CAP', hit_cap)
+    tagger = pkg.Tagger(dictionary, score_funcs=funcs)
+    _check_against_oracle(tagger, lo.OracleTagger(dictionary, funcs), list(case['sentences']), (5,))
+
+
 # ---- round 2: all survivors, lookup modes, host-level API, per-sentence statuses, larger configurations ----
 
 @pytest.mark.parametrize('name', ['demo_morph', 'random_1003', 'random_1011'])

@@ -565,7 +565,8 @@ constexpr int lattice_min_blocks(int, int, int) { return LT_LAT_MINB; }         
 // UC / HCT: sentence-array size and staging capacity when known at compile time (0 = A.units / A.hcap)
 // LM: 0 = MorphemeLookup only (what Tagger.tag uses; the other lookups compile out of the throughput path),
 //     1 = the lookup named by A.mode.
-template <int UC, int HCT, int LM = 0>
+// RP: 1 = the retry pass (one eojeol per work item); the main-pass instantiations carry none of its code.
+template <int UC, int HCT, int LM = 0, int RP = 0>
 __global__ void __launch_bounds__(lattice_max_threads(UC, HCT, LM), lattice_min_blocks(UC, HCT, LM)) lattice_kernel(const __grid_constant__ DevTables T,
                                                                 const __grid_constant__ LatticeArgs A) {
     LT_DYN_SMEM(smem_raw);
@@ -601,7 +602,7 @@ __global__ void __launch_bounds__(lattice_max_threads(UC, HCT, LM), lattice_min_
         if (lane == 0) s = atomicAdd(A.queue, 1u);
         s = __shfl_sync(kFull, s, 0);
         int w_first = 0, w_count = 0x7FFFFFFF;       // eojeols of the sentence this warp enumerates
-        if (A.retry_pass) {
+        if (RP != 0) {
             if (s >= *A.retry_count) break;
             const uint2 item = A.retry_list[s];
             s = item.x;
@@ -816,7 +817,7 @@ __global__ void __launch_bounds__(lattice_max_threads(UC, HCT, LM), lattice_min_
                     if (lane == 0) *nh = slots;
                     __syncwarp();
                     if (attempt == 0 && slots > 0) { flush(); continue; }
-                    if (!A.retry_pass && A.retry_list != nullptr) {
+                    if (RP == 0 && A.retry_list != nullptr) {
                         // this eojeol alone goes to the retry pass; the sentence's other eojeols are done here
                         if (lane == 0) A.retry_list[atomicAdd(A.retry_count, 1u)] = make_uint2(s, (uint32_t)w);
                         __syncwarp();
@@ -866,7 +867,7 @@ __global__ void __launch_bounds__(lattice_max_threads(UC, HCT, LM), lattice_min_
         __syncwarp();
         #pragma unroll
         for (int d = 16; d; d >>= 1) ncand += __shfl_xor_sync(kFull, ncand, d);
-        if (A.retry_pass) {
+        if constexpr (RP != 0) {
             // one eojeol of a sentence the main pass has otherwise finished: its positions, its edges, its share of
             // the work counters; a sentence that had no edge without it gets its status back
             const int o = (w_first < n_eoj) ? eoj[w_first] : 0, oe = (w_first < n_eoj) ? eoj[w_first + 1] : 0;
@@ -884,25 +885,25 @@ __global__ void __launch_bounds__(lattice_max_threads(UC, HCT, LM), lattice_min_
                 acc_E += sent_total;
             }
             __syncwarp();
-            continue;
+        } else {
+            #pragma unroll 1
+            for (int p = lane; p < s1 - s0; p += 32) {
+                const uint32_t c = pcnt[p];
+                A.pos[s0 + p] = make_uint2(c ? pstart[p] : 0u, c);
+            }
+            if (lane == 0) {
+                A.sent_len[s] = L;
+                A.sent_edges[s] = (int32_t)sent_total;
+                int st = LT_SENT_OK;
+                if (bad) st = LT_SENT_BAD_SPACE;
+                else if (L > 0 && sent_total == 0) st = LT_SENT_NO_EDGES;
+                A.status[s] = st;
+                acc_L += (unsigned long long)L;
+                acc_P += (unsigned long long)nsub + 2ull * ncand;
+                acc_E += sent_total;
+            }
+            __syncwarp();
         }
-        #pragma unroll 1
-        for (int p = lane; p < s1 - s0; p += 32) {
-            const uint32_t c = pcnt[p];
-            A.pos[s0 + p] = make_uint2(c ? pstart[p] : 0u, c);
-        }
-        if (lane == 0) {
-            A.sent_len[s] = L;
-            A.sent_edges[s] = (int32_t)sent_total;
-            int st = LT_SENT_OK;
-            if (bad) st = LT_SENT_BAD_SPACE;
-            else if (L > 0 && sent_total == 0) st = LT_SENT_NO_EDGES;
-            A.status[s] = st;
-            acc_L += (unsigned long long)L;
-            acc_P += (unsigned long long)nsub + 2ull * ncand;
-            acc_E += sent_total;
-        }
-        __syncwarp();
     }
     if (lane == 0) {
         atomicAdd(A.counters + 0, acc_L);

@@ -435,7 +435,7 @@ static const size_t kSmemBudget = 200 * 1024;
 // shared memory, resident CTAs per SM.  Nothing of this is recomputed (or asked of the driver) per batch.
 struct LatticePlan {
     int units = 0, hcap = 0;                  // key
-    bool generic = false, any_lookup = false;
+    bool generic = false, any_lookup = false, retry = false;
     void (*fn)(const DevTables, const LatticeArgs) = nullptr;
     int warps = 0, per_sm = 1;
     size_t smem = 0, warp_smem = 0;
@@ -479,6 +479,8 @@ struct lt_batch {
     int l2_persist_pct = 0;        // LT_L2_PERSIST=<percent of L2>: persisting access-policy window over the feature table
     bool pdl = false;              // LT_PDL=1: programmatic dependent launch between the kernels of a batch (never while per-stage
                                    // events are recorded between them).  Measured r2k: 5 us per C2 step SLOWER than plain launches
+    int adapt_div = 32;            // LT_ADAPT_DIV: the main pass's staging area doubles when more than n_sent / this many eojeols
+                                   // needed the retry pass (0 = never; measured on C3: the default is right)
     int sort_min = kSortMin;       // LT_SORT_MIN: staged hits per eojeol from which the lattice kernel ranks by sorting (tests: 1)
     int prologue_ctas = kPrologueMaxCtas;   // LT_PROLOGUE_CTAS: CTAs of the work-order prologue (1 = exact order)
     int64_t n_edges = 0;
@@ -579,6 +581,7 @@ extern "C" int lt_batch_create(lt_tables* tables, lt_batch** out) {
     if (const char* env = getenv("LT_TRAIL_SMEM")) b->trail_smem_ok = atoi(env) != 0;
     if (const char* env = getenv("LT_L2_PERSIST")) b->l2_persist_pct = std::min(100, std::max(0, atoi(env)));
     if (const char* env = getenv("LT_PDL")) b->pdl = atoi(env) != 0;
+    if (const char* env = getenv("LT_ADAPT_DIV")) b->adapt_div = std::max(0, atoi(env));
     if (const char* env = getenv("LT_SORT_MIN")) b->sort_min = std::max(1, atoi(env));
     if (const char* env = getenv("LT_PROLOGUE_CTAS")) b->prologue_ctas = std::min(32, std::max(1, atoi(env)));
     b->debug = getenv("LT_DEBUG") != nullptr;
@@ -652,12 +655,13 @@ static int lattice_plan(lt_batch* b, int lcap, int hcap, bool retry_pass, const 
     const int uclass = (!any_lookup && !retry_pass && (hcap == kLatDefaultHcap || hcap == 2 * kLatDefaultHcap)) ? lattice_units_class(lcap) : 0;
     const int units = uclass ? uclass : lcap + 8;
     for (const LatticePlan& p : b->lattice_plans)
-        if (p.units == units && p.hcap == hcap && p.generic == (uclass == 0) && p.any_lookup == any_lookup) { *out = &p; return LT_OK; }
+        if (p.units == units && p.hcap == hcap && p.generic == (uclass == 0) && p.any_lookup == any_lookup && p.retry == retry_pass) { *out = &p; return LT_OK; }
     LatticePlan P;
     P.units = units;
     P.hcap = hcap;
     P.generic = uclass == 0;
     P.any_lookup = any_lookup;
+    P.retry = retry_pass;
     P.warp_smem = lattice_warp_smem(units, hcap, max_str);
     if (retry_pass) {
         if (P.warp_smem > kSmemBudget)
@@ -683,6 +687,7 @@ static int lattice_plan(lt_batch* b, int lcap, int hcap, bool retry_pass, const 
          : (uclass == 128 && hcap == kLatDefaultHcap) ? lt::lattice_kernel<128, kLatDefaultHcap>
          : (uclass == 64 && hcap == 2 * kLatDefaultHcap) ? lt::lattice_kernel<64, 2 * kLatDefaultHcap>
          : (uclass == 128 && hcap == 2 * kLatDefaultHcap) ? lt::lattice_kernel<128, 2 * kLatDefaultHcap>
+         : retry_pass ? (any_lookup ? lt::lattice_kernel<0, 0, 1, 1> : lt::lattice_kernel<0, 0, 0, 1>)
          : any_lookup ? lt::lattice_kernel<0, 0, 1> : lt::lattice_kernel<0, 0, 0>;
     if (int rc = smem_limit(t, P.fn, P.smem)) return rc;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&P.per_sm, P.fn, P.warps * 32, P.smem));
@@ -1004,7 +1009,7 @@ static int launch_beam(lt_batch* b, cudaStream_t st, bool kbest) {
 static void adapt_staging(lt_batch* b, unsigned int retried) {
     b->last_retried = retried;
     if (!b->use_retry || b->n_sent < 64) return;
-    if ((uint64_t)retried * 32 > (uint64_t)b->n_sent && b->hcap * 2 < b->retry_hcap) b->hcap *= 2;
+    if (b->adapt_div > 0 && (uint64_t)retried * (uint64_t)b->adapt_div > (uint64_t)b->n_sent && b->hcap * 2 < b->retry_hcap) b->hcap *= 2;
 }
 
 static uint64_t cursor_of(const unsigned int* ctl) { return (uint64_t)ctl[kCtlCursor] | ((uint64_t)ctl[kCtlCursor + 1] << 32); }

@@ -43,7 +43,11 @@ namespace lt {
 
 constexpr int kRing = LT_WINDOW + 1;
 constexpr int kEdgeRing = 64;                 // prepared dictionary edges: ring over the global edge index
-constexpr int kBucketCached = 32;             // bucket-local edge indices below this are served from the ring
+#ifndef LT_BUCKET_CACHED
+#define LT_BUCKET_CACHED 64
+#endif
+constexpr int kBucketCached = LT_BUCKET_CACHED;   // bucket-local edge indices below this are served from the ring (<= kEdgeRing)
+static_assert(kBucketCached <= kEdgeRing, "a cached bucket must fit the ring");
 constexpr int kUnkBlock = 4;                  // end positions whose unknown words are prepared together
 constexpr int kCacheSlots = kEdgeRing + kUnkBlock * LT_WINDOW;
 constexpr int kRankMaxBeam = 16;              // beams up to this size select by rank counting, larger ones by sorting network
@@ -200,7 +204,7 @@ __device__ __forceinline__ void unknown_edge(int b, int e, EdgeView& k) {
 // IMP: the batch may hold an imported lattice (lt_lattice_import) — only the all-survivors kernels (KB = 1)
 // are launched on one, so the throughput instantiations compile the test out.
 template <int IMP>
-__device__ __noinline__ void edge_hashes(const DevTables& T, const SentView& v, EdgeView& k, bool need_m1) {
+__device__ __forceinline__ void edge_hashes_inline(const DevTables& T, const SentView& v, EdgeView& k, bool need_m1) {
     if (IMP != 0 && (k.flags & LT_EDGE_EXPLICIT)) {
         // imported lattice (lt_lattice_import): the strings of this word were hashed on the host
         const H2* h = v.imp + 3 * (size_t)k.rule;
@@ -230,6 +234,11 @@ __device__ __noinline__ void edge_hashes(const DevTables& T, const SentView& v, 
             }
         }
     }
+}
+// (out of line where code size matters more than the call: the kernels' any-sentence copies)
+template <int IMP>
+__device__ __noinline__ void edge_hashes(const DevTables& T, const SentView& v, EdgeView& k, bool need_m1) {
+    edge_hashes_inline<IMP>(T, v, k, need_m1);
 }
 
 // Everything of a transition's score that depends on the edge alone, for scorer f:
@@ -295,7 +304,8 @@ __device__ __noinline__ uint32_t edge_score(const DevTables& T, const unsigned c
 
 // numpy's association from eight surviving weights on: rare, so the nine weights are
 // simply gathered again and summed by numpy_order_sum9.
-__device__ __noinline__ double trigram_sum_tree(const DevTables& T, const unsigned char* dense_blk, int NT, int f, FKey q0, FKey q1,
+// (inline: a call in the candidate loop costs more than the code, see beam_positions.inc)
+__device__ __forceinline__ double trigram_sum_tree(const DevTables& T, const unsigned char* dense_blk, int NT, int f, FKey q0, FKey q1,
                                                 FKey q2, FKey q7, FKey q8, uint32_t tj, uint32_t tk, uint32_t epresent,
                                                 double val4, double val5, bool j_unk, uint32_t ul, bool has_i, bool ctx8) {
     const DenseView D = dense_view(dense_blk, NT);
@@ -347,10 +357,11 @@ constexpr int kBeamWarps = 4;                 // preferred warps per CTA of the 
 constexpr int kBeamMaxWarps = kBeamMaxWarpsC;              // largest CTA (128 registers per thread either way: 8 warps x 2 CTAs = 4 warps x 4 CTAs)
 
 // Edge prep: hash products and the edge-only part of the score program into cache slot `slot`.
-template <int PROG, int IMP>
+template <int PROG, int IMP, bool LEAN = false>
 __device__ __forceinline__ void prep_edge(const DevTables& T, const SentView& v, const unsigned char* dense_smem,
                                           EdgeView& k, bool need_m1, int nf, int kvs, const EdgeCache& C, uint32_t slot) {
-    edge_hashes<IMP>(T, v, k, need_m1);
+    if constexpr (LEAN) edge_hashes_inline<IMP>(T, v, k, need_m1);
+    else edge_hashes<IMP>(T, v, k, need_m1);
     const H2 e0 = h2_mul(k.wk, kM0a, kM0b), g0 = h2_mul(k.mk, kM0a, kM0b);
     uint32_t present = 0;
     if (PROG == 1) {
@@ -392,7 +403,8 @@ __device__ __forceinline__ void prep_edge(const DevTables& T, const SentView& v,
 // scorer loop of a candidate unrolls, the template seeds become immediates; 0 = read it from T.
 // KB: 1 = every survivor of the last position is written out as well (lt_beam_kbest); 0 compiles that out of
 // the instantiations the throughput path runs.
-template <int MODE, int KT, int UC, int PROG, int KB = 0>
+// TS: back-pointers in shared memory (1) or HBM (0) known at compile time; -1 = A.trail_smem.
+template <int MODE, int KT, int UC, int PROG, int KB = 0, int TS = -1>
 __global__ void __launch_bounds__(beam_max_threads(KT, UC, PROG, KB), beam_min_blocks(KT, UC, PROG, KB)) beam_kernel(const __grid_constant__ DevTables T, const __grid_constant__ BeamArgs A) {
     constexpr int KR = (MODE == 0) ? 2 : 1;      // kept entries per lane
     LT_DYN_SMEM(smem_raw);
@@ -420,7 +432,9 @@ __global__ void __launch_bounds__(beam_max_threads(KT, UC, PROG, KB), beam_min_b
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) A.path_len[A.n_sent] = 0;      // the scan runs over n_sent + 1 entries
 
-    const bool trail_smem = A.trail_smem != 0;
+    const bool trail_smem = TS < 0 ? A.trail_smem != 0 : TS != 0;
+    // instantiations of the throughput path carry a second copy of the position loop without the big-bucket code
+    constexpr bool kLeanCopy = (PROG == 1 && KB == 0);
     const int units = UC ? UC : A.units;
     const int RK = kRing * K;
     const int kvs = beam_kval_doubles(T.n_funcs, PROG == 1);   // kval stride
@@ -483,7 +497,12 @@ __global__ void __launch_bounds__(beam_max_threads(KT, UC, PROG, KB), beam_min_b
             L += __popc(km);
         }
         __syncwarp();
-        for (int i = lane; i < L; i += 32) spos[i] = __ldg(A.pos + s0 + i);
+        bool big_bucket = false;
+        for (int i = lane; i < L; i += 32) {
+            const uint2 row = __ldg(A.pos + s0 + i);
+            spos[i] = row;
+            big_bucket |= row.y > (uint32_t)kBucketCached;
+        }
         prefix_hashes_inline(ch, L, lane, ha, hb);
         SentView v{ch, ha, hb, nullptr, KB ? A.imp : nullptr};
 
@@ -502,456 +521,17 @@ __global__ void __launch_bounds__(beam_max_threads(KT, UC, PROG, KB), beam_min_b
         }
         __syncwarp();
 
-        uint32_t ring_lo = 0, ring_hi = 0;      // global edge indices [ring_lo, ring_hi) are prepared
-
-        for (int e = 1; e <= L; ++e) {
-            const int slot_e = e % kRing;
-            const uint2 bucket = spos[e - 1];
-            const uint32_t es = bucket.x, ne = bucket.y;
-            const int jmax = (e < LT_WINDOW) ? e : LT_WINDOW;
-
-            // ---- 1. EDGE PREP of dictionary edges, 32 consecutive edges at a time ----
-            // Buckets of consecutive end positions are adjacent in HBM (one reservation per sentence, edges
-            // ranked by end), so one pass normally prepares the edges of many positions ahead.
-            if (ne > 0) {
-                const uint32_t need_hi = es + (ne < (uint32_t)kBucketCached ? ne : (uint32_t)kBucketCached);
-                if (es < ring_lo || es > ring_hi || need_hi > ring_hi) {
-                    uint32_t start = ring_hi;
-                    if (es < ring_lo || es > ring_hi) { start = es; ring_lo = es; }
-                    // how far beyond this bucket the sentence's edges continue without a gap
-                    const int p = e + lane;                       // 0-based index of end position e + 1 + lane
-                    const uint2 nb = (p < L) ? spos[p] : make_uint2(0u, 0u);
-                    uint32_t incl = nb.y;
-                    #pragma unroll
-                    for (int d = 1; d < 32; d <<= 1) {
-                        const uint32_t t = __shfl_up_sync(kFull, incl, d);
-                        if (lane >= d) incl += t;
-                    }
-                    const bool gap = (p >= L) || (nb.y != 0 && nb.x != es + ne + (incl - nb.y));
-                    const unsigned gaps = __ballot_sync(kFull, gap);
-                    const int run = gaps ? __ffs(gaps) - 1 : 32;     // positions ahead that continue the range
-                    const uint32_t ahead = run ? __shfl_sync(kFull, incl, run - 1) : 0u;
-                    const uint32_t avail = es + ne + ahead - start;
-                    const uint32_t n = avail < 32u ? avail : 32u;
-                    if ((uint32_t)lane < n) {
-                        const uint32_t gi = start + lane;
-                        EdgeView k;
-                        unpack_edge(ldg16(A.edges + gi), k);
-                        prep_edge<PROG, KB>(T, v, dense_smem, k, need_m1, nf, kvs, C, gi & (kEdgeRing - 1));
-                    }
-                    ring_hi = start + n;
-                    if (ring_hi - ring_lo > (uint32_t)kEdgeRing) ring_lo = ring_hi - kEdgeRing;
-                    __syncwarp();
-                }
+        // the position loop, in the copy that fits the sentence (beam_positions.inc)
+        bool lean = false;
+        if constexpr (kLeanCopy) lean = !__any_sync(kFull, big_bucket);
+        if (lean) {
+            if constexpr (kLeanCopy) {
+                constexpr bool kBig = false;
+#include "beam_positions.inc"
             }
-            // ---- the unknown words of kUnkBlock end positions at a time, lanes = (position, span) ----
-            if (((e - 1) & (kUnkBlock - 1)) == 0) {
-                const int pe = e + (lane >> 3);
-                const int j = (lane & 7) + 1;
-                if (pe <= L && j <= pe) {
-                    EdgeView k;
-                    unknown_edge(pe - j, pe, k);
-                    prep_edge<PROG, KB>(T, v, dense_smem, k, need_m1, nf, kvs, C, (uint32_t)(kEdgeRing + lane));
-                }
-                __syncwarp();
-            }
-            const uint32_t unk_base = (uint32_t)(kEdgeRing + (((e - 1) & (kUnkBlock - 1)) << 3) - 1);   // + span
-
-            // ---- 2. edges per span (bucket sorted by begin ascending = span descending) ----
-            if (lane >= 1 && lane <= LT_WINDOW) s_cnt[lane] = 0;
-            __syncwarp();
-            for (uint32_t base = 0; base < ne; base += 32) {
-                const uint32_t idx = base + lane;
-                const unsigned act = __ballot_sync(kFull, idx < ne);
-                if (idx < ne) {
-                    uint32_t span;
-                    if (idx < (uint32_t)kBucketCached) {
-                        span = C.present[(es + idx) & (kEdgeRing - 1)] >> 24;
-                    } else {
-                        const uint32_t x = __ldg(reinterpret_cast<const uint32_t*>(A.edges + es + idx));
-                        span = (x >> 16) - (x & 0xFFFFu);
-                    }
-                    const unsigned same = __match_any_sync(act, span);
-                    if (span <= (uint32_t)LT_WINDOW && (same & lt_mask) == 0) {
-                        // first lane of the span's group in this chunk (a group may continue from the previous chunk)
-                        const uint32_t old = s_cnt[span];
-                        if (old == 0) s_gstart[span] = idx;
-                        s_cnt[span] = old + __popc(same);
-                    }
-                }
-                __syncwarp();
-            }
-            // lane t < 8 owns span LT_WINDOW - t: generation order (begin ascending) is lane order
-            uint32_t span_nc = 0, span_c0 = 0;      // candidates of the lane's span, index of its first candidate
-            uint32_t N;
-            {
-                const int jj = LT_WINDOW - lane;
-                if (lane < LT_WINDOW && jj <= jmax) {
-                    const uint32_t c = s_cnt[jj];
-                    const int ps = (e - jj) % kRing;
-                    // an unknown word may follow an unknown word only from the window's first begin (beam.py:44-45):
-                    // elsewhere only the parents that do not end in an unknown word generate a candidate
-                    span_nc = c ? s_nbeam[ps] * c : ((jj < jmax) ? s_nnon[ps] : s_nbeam[ps]);
-                }
-                uint32_t incl = span_nc;
-                #pragma unroll
-                for (int d = 1; d < LT_WINDOW; d <<= 1) {
-                    const uint32_t t = __shfl_up_sync(kFull, incl, d);
-                    if (lane >= d) incl += t;
-                }
-                span_c0 = incl - span_nc;
-                N = __shfl_sync(kFull, incl, LT_WINDOW - 1);
-                const unsigned gen = __ballot_sync(kFull, span_nc > 0);
-                if (span_nc > 0) s_tlist[__popc(gen & lt_mask)] = (span_c0 << 4) | (uint32_t)jj;
-            }
-            __syncwarp();
-
-            // ---- 3 + 4. candidates in generation order, running top-K ----
-            uint64_t keep_key[KR];
-            uint32_t keep_pay[KR];
-            #pragma unroll
-            for (int r = 0; r < KR; ++r) { keep_key[r] = 0; keep_pay[r] = 0; }
-            uint32_t nk = 0;      // kept entries so far (MODE 2)
-
-            for (uint32_t c0 = 0; c0 < N; c0 += 32) {
-                const uint32_t c = c0 + lane;
-                bool valid = c < N;
-                // the span of candidate c: spans that start inside this chunk vote their first lane
-                const bool gen = span_nc > 0;
-                const unsigned starts = __reduce_or_sync(kFull, (gen && span_c0 >= c0 && span_c0 < c0 + 32u) ? (1u << (span_c0 - c0)) : 0u);
-                const uint32_t before = __popc(__ballot_sync(kFull, gen && span_c0 < c0));
-                int j = 0;
-                uint32_t rem = 0;
-                if (valid) {
-                    const uint32_t tl = s_tlist[before + __popc(starts & (0xFFFFFFFFu >> (31 - lane))) - 1];
-                    j = (int)(tl & 15u);
-                    rem = c - (tl >> 4);
-                }
-                uint64_t ckey = 0;
-                uint32_t cpay = 0;
-                uint32_t cand_F = 0;        // feature tuples this candidate generates
-                if (valid) {
-                    const uint32_t cj = s_cnt[j];
-                    const bool unk_edge = (cj == 0);
-                    const int pbase = ((e - j) % kRing) * K;
-                    uint32_t prank, eidx = 0;
-                    if (unk_edge) {
-                        prank = (j < jmax) ? (uint32_t)s_nonunk[pbase + rem] : rem;
-                    } else {
-                        prank = (cj == 1u) ? rem : rem / cj;
-                        eidx = rem - prank * cj;
-                    }
-                    const int pslot = pbase + (int)prank;
-                    const uint32_t pmeta = e_meta[pslot];
-                    const uint32_t tj = pmeta & kMetaTagMask;
-                    const uint32_t bidx = unk_edge ? 0u : s_gstart[j] + eidx;      // bucket-local edge index
-                    const uint32_t slot = unk_edge ? unk_base + (uint32_t)j : ((es + bidx) & (kEdgeRing - 1));
-                    H2 e0, g0;
-                    uint32_t emeta, epresent = 0;
-                    const bool uncached = !unk_edge && bidx >= (uint32_t)kBucketCached;
-                    EdgeView kfly;
-                    if (uncached) {
-                        // bucket larger than the cached part: prepare this edge on the fly
-                        unpack_edge(ldg16(A.edges + es + bidx), kfly);
-                        edge_hashes<KB>(T, v, kfly, need_m1);
-                        e0 = h2_mul(kfly.wk, kM0a, kM0b);
-                        g0 = h2_mul(kfly.mk, kM0a, kM0b);
-                        emeta = kfly.tag0 | (kfly.len << 8) | (kfly.flags << 24);
-                    } else {
-                        e0 = C.e0[slot];
-                        g0 = unk_edge ? e0 : C.g0[slot];
-                        emeta = C.meta[slot];
-                        epresent = C.present[slot];
-                    }
-                    const uint32_t tk = emeta & 0xFFu;
-                    // (only a dictionary that files entries under the tag 'Unknown' can still meet beam.py:44-45 here)
-                    valid = !(tj == LT_TAG_UNK && tk == LT_TAG_UNK && j < jmax);
-                    const double pscore = e_score[pslot];
-                    const H2 p1 = e_p1[pslot];
-                    const bool has_i = (pmeta & kMetaHasI) != 0;
-                    const bool j_unk = (tj == LT_TAG_UNK);
-                    const bool ctx8 = ((kCtxMask >> tk) & 1u) && (pmeta & kMetaHasCtx);
-                    double inc = 0.0;
-                    #pragma unroll (PROG == 1 ? 2 : 1)
-                    for (int f = 0; f < nf; ++f) {
-                        const int kind = PROG == 1 ? (f == 0 ? LT_FUNC_REG : LT_FUNC_TRIGRAM) : T.funcs[f].kind;
-                        double val, val5;
-                        if (uncached) {
-                            double uv, uv5;      // (by reference to a call: keep val / val5 themselves in registers)
-                            epresent |= edge_score(T, dense_smem, kfly, e0, g0, f, uv, uv5) << (2 * f);
-                            val = uv;
-                            val5 = uv5;
-                        } else {
-                            val = C.kval[slot * kvs + 2 * f];
-                            val5 = C.kval[slot * kvs + 2 * f + 1];
-                        }
-                        if (kind == LT_FUNC_TRIGRAM) {
-                            // SimpleTrigramFeatureScore.score (score_funcs.py:137-144)
-                            const unsigned char* dense_blk = dense_smem + (PROG == 1 ? 0 : (size_t)T.func_dense[f] * dense_block_bytes(NT));
-                            const H2 sd0 = PROG == 1 ? feature_seed(0u, (uint32_t)f) : T.seeds[f][0];
-                            const H2 sd1 = PROG == 1 ? feature_seed(1u, (uint32_t)f) : T.seeds[f][1];
-                            const H2 sd2 = PROG == 1 ? feature_seed(2u, (uint32_t)f) : T.seeds[f][2];
-                            const H2 sd7 = PROG == 1 ? feature_seed(7u, (uint32_t)f) : T.seeds[f][7];
-                            const H2 sd8 = PROG == 1 ? feature_seed(8u, (uint32_t)f) : T.seeds[f][8];
-                            const DenseView D = dense_view(dense_blk, NT);
-                            cand_F += valid ? 6u + (j_unk ? 1u : 0u) + (has_i ? 1u : 0u) + (ctx8 ? 1u : 0u) : 0u;
-                            const H2 pp = has_i ? e_pp[pslot] : H2{0, 0};
-                            const H2 c1v = ctx8 ? e_c1[pslot] : H2{0, 0};
-                            const uint32_t hk = feature_head32(tk, 0);
-                            const FKey q0 = feature_key_sum32(sd0, hk, h2_add(e0, p1));
-                            const FKey q1 = feature_key_sum32(sd1, hk, p1);
-                            const FKey q2 = feature_key_sum32(sd2, feature_head32(tj, tk), e0);
-                            const FKey q7 = feature_key_sum32(sd7, 0u, h2_add(e0, pp));
-                            const FKey q8 = feature_key_sum32(sd8, 0u, h2_add(g0, c1v));
-                            // all first-slot loads in flight before any is consumed
-                            const FeatProbe s0 = feat_first(T, q0);
-                            const FeatProbe s1 = feat_first(T, q1);
-                            const FeatProbe s2 = feat_first(T, q2);
-                            FeatProbe s7, s8;
-                            // generic score programs issue templates 7 / 8 after 0..2 are consumed (all five at once
-                            // spill there); the specialised kernel has the registers for a single round trip
-                            constexpr bool kSplitProbes = LT_PROBE_SPLIT && PROG != 1;
-                            if constexpr (!kSplitProbes) {
-                                if (has_i) s7 = feat_first(T, q7);
-                                if (ctx8) s8 = feat_first(T, q8);
-                            }
-                            // running left-to-right sum = numpy's order while fewer than 8 weights survive
-                            double acc = 0.0, w;
-                            int n = 0;
-                            if (feat_resolve(T, q0, s0, w)) { acc = __dadd_rn(acc, w); ++n; }
-                            if (feat_resolve(T, q1, s1, w)) { acc = __dadd_rn(acc, w); ++n; }
-                            if (feat_resolve(T, q2, s2, w)) { acc = __dadd_rn(acc, w); ++n; }
-                            if constexpr (kSplitProbes) {
-                                if (has_i) s7 = feat_first(T, q7);
-                                if (ctx8) s8 = feat_first(T, q8);
-                            }
-                            if ((D.m3[tj] >> tk) & 1u) { acc = __dadd_rn(acc, D.t3[tj * NT + tk]); ++n; }
-                            if ((epresent >> (2 * f)) & 1u) { acc = __dadd_rn(acc, val); ++n; }
-                            if ((epresent >> (2 * f + 1)) & 1u) { acc = __dadd_rn(acc, val5); ++n; }
-                            const uint32_t ul = (pmeta >> kMetaUnkLenShift) & 0xFu;
-                            if (j_unk && ((D.m6[0] >> ul) & 1u)) { acc = __dadd_rn(acc, D.t6[ul]); ++n; }
-                            if (has_i && feat_resolve(T, q7, s7, w)) { acc = __dadd_rn(acc, w); ++n; }
-                            if (ctx8 && feat_resolve(T, q8, s8, w)) { acc = __dadd_rn(acc, w); ++n; }
-                            if (n >= 8)   // numpy switches to an 8-lane tree: redo the gather and add in that order (rare)
-                                acc = trigram_sum_tree(T, dense_blk, NT, f, q0, q1, q2, q7, q8, tj, tk, epresent, val, val5, j_unk, ul,
-                                                       has_i, ctx8);
-                            val = n ? acc : 0.0;
-                        }
-                        inc = __dadd_rn(inc, val);          // score += f(...), score_funcs.py:51-53
-                    }
-                    double newscore = __dadd_rn(pscore, inc);        // Sequence.add, beam.py:115
-                    newscore = __dadd_rn(newscore, 0.0);             // -0.0 sorts as 0.0
-                    ckey = valid ? sortable(newscore) : 0ull;
-                    // payload doubles as the generation ordinal: begin ascending (= span descending), parent
-                    // rank ascending, edge order ascending (beam.py:30-48)
-                    cpay = ((uint32_t)(LT_WINDOW - j) << 27) | (prank << 20) | (unk_edge ? kPayUnk : bidx);
-                }
-                // work counters: scored transitions and generated feature tuples of this chunk
-                const uint32_t chunk_T = __popc(__ballot_sync(kFull, ckey != 0));
-                {
-                    const uint32_t chunk_F = __reduce_add_sync(kFull, cand_F);
-                    if (lane == 0) { s_acc[0] += chunk_T; s_acc[1] += chunk_F; }
-                }
-                if constexpr (MODE == 2) {
-                    // ---- top-K by rank counting: an entry's rank = number of pool entries that beat it ----
-                    // pool = kept entries (earlier candidates, they win ties) + this chunk's lanes in generation order
-                    const uint32_t nc = (N - c0 < 32u) ? (N - c0) : 32u;
-                    const uint64_t kkey = keep_key[0];
-                    s_pool[32 + lane] = ckey;
-                    if ((uint32_t)lane < nk) s_pool[lane] = kkey;
-                    __syncwarp();
-                    uint32_t gt_c = 0, gt_k = 0;
-                    if (nk == 0) {
-                        #pragma unroll 4
-                        for (uint32_t l = 0; l < nc; ++l) gt_c += (s_pool[32 + l] > ckey) ? 1u : 0u;
-                    } else {
-                        #pragma unroll 4
-                        for (uint32_t l = 0; l < nc; ++l) {
-                            const uint64_t o = s_pool[32 + l];
-                            gt_c += (o > ckey) ? 1u : 0u;
-                            gt_k += (o > kkey) ? 1u : 0u;
-                        }
-                        const uint64_t cm1 = ckey - 1;        // a kept entry with an equal key is the earlier candidate
-                        #pragma unroll 4
-                        for (uint32_t r = 0; r < nk; ++r) gt_c += (s_pool[r] > cm1) ? 1u : 0u;
-                    }
-                    // equal keys inside the chunk: the earlier lane first
-                    gt_c += __popc(__match_any_sync(kFull, ckey) & lt_mask);
-                    const uint32_t nvalid = chunk_T;
-                    if (ckey != 0 && gt_c < (uint32_t)K) { s_newkey[gt_c] = ckey; s_newpay[gt_c] = cpay; }
-                    if ((uint32_t)lane < nk && lane + gt_k < (uint32_t)K) { s_newkey[lane + gt_k] = kkey; s_newpay[lane + gt_k] = keep_pay[0]; }
-                    __syncwarp();
-                    nk = (nk + nvalid < (uint32_t)K) ? nk + nvalid : (uint32_t)K;
-                    keep_key[0] = ((uint32_t)lane < nk) ? s_newkey[lane] : 0ull;
-                    keep_pay[0] = ((uint32_t)lane < nk) ? s_newpay[lane] : 0u;
-                    __syncwarp();
-                } else if constexpr (MODE == 1) {
-                    // ---- top-K by sorting network: sort the chunk (best first), then merge with the kept list ----
-                    // order: larger key first; equal keys: smaller payload (= earlier candidate) first
-                    uint64_t bk = ckey;
-                    uint32_t bp = cpay;
-                    #pragma unroll
-                    for (int size = 2; size <= 32; size <<= 1) {
-                        #pragma unroll
-                        for (int stride = size >> 1; stride > 0; stride >>= 1) {
-                            const uint64_t ok = __shfl_xor_sync(kFull, bk, stride);
-                            const uint32_t op = __shfl_xor_sync(kFull, bp, stride);
-                            const bool mine_first = (bk > ok) || (bk == ok && bp < op);
-                            const bool lower = (lane & stride) == 0;
-                            const bool descending = (lane & size) == 0;      // this block sorts best-first
-                            const bool keep_mine = (lower == descending) ? mine_first : !mine_first;
-                            if (!keep_mine) { bk = ok; bp = op; }
-                        }
-                    }
-                    if (c0 == 0) {
-                        keep_key[0] = bk;
-                        keep_pay[0] = bp;
-                    } else {
-                        // kept list is best-first in lanes 0..31; against the reversed chunk the lane-wise
-                        // winners form a bitonic sequence holding the 32 best of the union
-                        const uint64_t rk = __shfl_sync(kFull, bk, 31 - lane);
-                        const uint32_t rp = __shfl_sync(kFull, bp, 31 - lane);
-                        // kept entries are earlier candidates: they win ties
-                        if (rk > keep_key[0]) { keep_key[0] = rk; keep_pay[0] = rp; }
-                        #pragma unroll
-                        for (int stride = 16; stride > 0; stride >>= 1) {
-                            const uint64_t ok = __shfl_xor_sync(kFull, keep_key[0], stride);
-                            const uint32_t op = __shfl_xor_sync(kFull, keep_pay[0], stride);
-                            const bool mine_first = (keep_key[0] > ok) || (keep_key[0] == ok && keep_pay[0] < op);
-                            const bool lower = (lane & stride) == 0;
-                            if (lower != mine_first) { keep_key[0] = ok; keep_pay[0] = op; }
-                        }
-                    }
-                    if (lane >= K) { keep_key[0] = 0; keep_pay[0] = 0; }
-                } else {
-                    // ---- beams of 33..64: the kept list is two sorted runs of 32 (ranks 0..31 in keep[0], 32..63 in
-                    // keep[1]); a chunk is sorted by the same network as above, merged into the first run, and the 32
-                    // entries that lose there are merged into the second.  One total order everywhere: larger key first,
-                    // equal keys by payload = generation ordinal (beam.py:85 is a stable sort).
-                    auto first_of = [](uint64_t ak, uint32_t ap, uint64_t bk2, uint32_t bp2) { return (ak > bk2) || (ak == bk2 && ap < bp2); };
-                    // best-first order of a BITONIC sequence held one element per lane
-                    auto clean = [&](uint64_t& k0, uint32_t& p0) {
-                        #pragma unroll
-                        for (int stride = 16; stride > 0; stride >>= 1) {
-                            const uint64_t ok = __shfl_xor_sync(kFull, k0, stride);
-                            const uint32_t op = __shfl_xor_sync(kFull, p0, stride);
-                            const bool mine_first = first_of(k0, p0, ok, op);
-                            const bool lower = (lane & stride) == 0;
-                            if (lower != mine_first) { k0 = ok; p0 = op; }
-                        }
-                    };
-                    bool skip = false;
-                    if (c0 != 0 && K > 0) {
-                        // a later chunk changes nothing unless one of its candidates beats the K-th kept entry
-                        const int last = K - 1;
-                        const uint64_t thr_k = __shfl_sync(kFull, last >= 32 ? keep_key[KR - 1] : keep_key[0], last & 31);
-                        skip = thr_k != 0 && __ballot_sync(kFull, ckey > thr_k) == 0u;
-                    }
-                    if (!skip) {
-                        uint64_t bk = ckey;
-                        uint32_t bp = cpay;
-                        #pragma unroll
-                        for (int size = 2; size <= 32; size <<= 1) {
-                            #pragma unroll
-                            for (int stride = size >> 1; stride > 0; stride >>= 1) {
-                                const uint64_t ok = __shfl_xor_sync(kFull, bk, stride);
-                                const uint32_t op = __shfl_xor_sync(kFull, bp, stride);
-                                const bool mine_first = first_of(bk, bp, ok, op);
-                                const bool lower = (lane & stride) == 0;
-                                const bool descending = (lane & size) == 0;
-                                const bool keep_mine = (lower == descending) ? mine_first : !mine_first;
-                                if (!keep_mine) { bk = ok; bp = op; }
-                            }
-                        }
-                        if (c0 == 0) {
-                            keep_key[0] = bk;
-                            keep_pay[0] = bp;
-                            #pragma unroll
-                            for (int r = 1; r < KR; ++r) { keep_key[r] = 0; keep_pay[r] = 0; }
-                        } else {
-                            // run 0 against the reversed chunk: lane-wise winners = the best 32 of both, losers = the rest
-                            // (both bitonic); the losers then meet run 1 the same way
-                            #pragma unroll
-                            for (int r = 0; r < KR; ++r) {
-                                const uint64_t rk = __shfl_sync(kFull, bk, 31 - lane);
-                                const uint32_t rp = __shfl_sync(kFull, bp, 31 - lane);
-                                const bool theirs = first_of(rk, rp, keep_key[r], keep_pay[r]);
-                                bk = theirs ? keep_key[r] : rk;          // the loser of the pair moves on
-                                bp = theirs ? keep_pay[r] : rp;
-                                if (theirs) { keep_key[r] = rk; keep_pay[r] = rp; }
-                                clean(keep_key[r], keep_pay[r]);
-                                if (r + 1 < KR) clean(bk, bp);
-                            }
-                        }
-                        #pragma unroll
-                        for (int r = 0; r < KR; ++r)
-                            if (r * 32 + lane >= K) { keep_key[r] = 0; keep_pay[r] = 0; }
-                    }
-                }
-            }
-
-            // ---- 5. survivors -> ring entries + trail ----
-            int nl = 0, nn = 0;
-            #pragma unroll
-            for (int r = 0; r < KR; ++r) {
-                const bool have = keep_key[r] != 0;
-                uint32_t tag0 = LT_TAG_UNK;
-                if (have) {
-                    const int rank = r * 32 + lane;
-                    const uint32_t kp = keep_pay[r];
-                    const int j = LT_WINDOW - (int)((kp >> 27) & 0xFu);
-                    const uint32_t prank = (kp >> 20) & 0x7Fu;
-                    const uint32_t bidx = kp & 0xFFFFFu;
-                    const bool unk_edge = (s_cnt[j] == 0);
-                    const int pslot = ((e - j) % kRing) * K + (int)prank;
-                    // the survivor's edge was prepared for this position: its word / morph products with M0
-                    // are in the cache, and x * M0 -> x * M1 is one multiplication by M1 / M0
-                    const bool cached = unk_edge || bidx < (uint32_t)kBucketCached;
-                    H2 wk1, wk2, mk1;
-                    uint32_t len, eref = kTrailUnk;
-                    if (!unk_edge) eref = es + bidx;
-                    if (cached) {
-                        const uint32_t cslot = unk_edge ? unk_base + (uint32_t)j : (eref & (kEdgeRing - 1));
-                        const H2 e0 = C.e0[cslot], g0 = unk_edge ? e0 : C.g0[cslot];
-                        const uint32_t em = C.meta[cslot];
-                        tag0 = em & 0xFFu;
-                        len = (em >> 8) & 0xFFFFu;
-                        wk1 = h2_mul(e0, kM1over0a, kM1over0b);
-                        wk2 = h2_mul(e0, kM2over0a, kM2over0b);
-                        mk1 = h2_mul(g0, kM1over0a, kM1over0b);
-                    } else {
-                        EdgeView k;
-                        unpack_edge(ldg16(A.edges + eref), k);
-                        edge_hashes<KB>(T, v, k, false);
-                        tag0 = k.tag0;
-                        len = k.len;
-                        wk1 = h2_mul(k.wk, kM1a, kM1b);
-                        wk2 = h2_mul(k.wk, kM2a, kM2b);
-                        mk1 = h2_mul(k.mk, kM1a, kM1b);
-                    }
-                    const uint32_t pmeta = e_meta[pslot];
-                    const uint32_t tj = pmeta & kMetaTagMask;
-                    const bool k_ctx = (tag0 < 32) && ((kCtxMask >> tag0) & 1u);
-                    const bool j_ctx = (tj < 32) && ((kCtxMask >> tj) & 1u);
-                    const int dst = slot_e * K + rank;
-                    e_score[dst] = unsortable(keep_key[r]);
-                    e_p1[dst] = wk1;
-                    e_pp[dst] = h2_add(wk1, h2_mul(e_p1[pslot], kM2over1a, kM2over1b));     // wk * M1 + wj * M2
-                    e_c1[dst] = k_ctx ? mk1 : (j_ctx ? e_c1[pslot] : H2{0, 0});
-                    const uint32_t ul = len < 8u ? len : 8u;
-                    e_meta[dst] = tag0 | kMetaHasI | ((k_ctx || j_ctx) ? kMetaHasCtx : 0u) | (ul << kMetaUnkLenShift);
-                    if (trail_smem) s_trail[(e - 1) * K + rank] = kp;
-                    else A.trail[(size_t)(s0 + e - 1) * K + rank] = (uint64_t)eref | ((uint64_t)j << 32) | ((uint64_t)prank << 40);
-                }
-                // ranks of the entries that may be followed by an unknown word, ascending
-                const unsigned m_have = __ballot_sync(kFull, have);
-                const unsigned m_non = __ballot_sync(kFull, have && tag0 != LT_TAG_UNK);
-                if (have && tag0 != LT_TAG_UNK) s_nonunk[slot_e * K + nn + __popc(m_non & lt_mask)] = (uint8_t)(r * 32 + lane);
-                nl += __popc(m_have);
-                nn += __popc(m_non);
-            }
-            if (lane == 0) { s_nbeam[slot_e] = (uint32_t)nl; s_nnon[slot_e] = (uint32_t)nn; s_acc[2] += (uint32_t)nl; }
-            __syncwarp();
+        } else {
+            constexpr bool kBig = true;
+#include "beam_positions.inc"
         }
 
         // ---- best path: matures[0] (tagger.py:78); with A.kbest every survivor (beam.py:59-61) ----

@@ -110,11 +110,33 @@ __device__ __forceinline__ H2 sub_hash(const DevTables& T, const SentView& v, in
     return h2_sub(H2{v.ha[b], v.hb[b]}, H2{v.ha[e], v.hb[e]}, pow_at(T, (uint32_t)(e - b)));
 }
 
-// q / d for the small flat item indices of the enumeration loops: exact through a float reciprocal
-// while q * 1 < 2^22 (the rounding error of (q + 0.5) * (1 / d) stays below the 0.5 / d margin), an
-// integer division otherwise.  `inv` = 1.0f / d, computed once per loop.
+// q / d for the small flat item indices of the enumeration loops: exact through a float reciprocal while
+// q < 2^20, an integer division otherwise.  `inv` = small_rcp(d), once per loop: the hardware's approximate
+// reciprocal (one instruction; the IEEE-rounded 1.0f / d carries an out-of-line slow path, and a call inside
+// these loops costs more than it looks, see beam_positions.inc).  Error budget: rcp.approx is within one ulp
+// (2^-23 relative), the multiply rounds once more (2^-24): |(q + 0.5) * inv - (q + 0.5) / d| < (q + 0.5) / d *
+// 1.5 * 2^-23, which stays below the 0.5 / d distance to the next integer boundary while q + 0.5 < 2^21.4.
+__device__ __forceinline__ float small_rcp(int d) {
+#if defined(LT_SIMT_EMU)
+    return 1.0f / (float)d;
+#else
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"((float)d));
+    return r;
+#endif
+}
 __device__ __forceinline__ int small_div(int q, int d, float inv) {
-    return q < (1 << 22) ? __float2int_rz(((float)q + 0.5f) * inv) : q / d;
+    return q < (1 << 20) ? __float2int_rz(((float)q + 0.5f) * inv) : q / d;
+}
+// sqrt for the triangular item decode (the caller corrects the result by one either way)
+__device__ __forceinline__ float approx_sqrt(float x) {
+#if defined(LT_SIMT_EMU)
+    return sqrtf(x);
+#else
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#endif
 }
 
 // A shared-memory word as ONE lane reads it between two warp barriers: warp-uniform by construction, whatever
@@ -177,7 +199,10 @@ __device__ __forceinline__ void prefix_hashes_inline(const uint16_t* ch, int L, 
 }
 
 // (out of line in the lattice kernel, whose instruction footprint is the tighter one; the beam kernel inlines it)
-__device__ __noinline__ void prefix_hashes(const uint16_t* ch, int L, int lane, uint64_t* ha, uint64_t* hb) {
+#ifndef LT_PH_ATTR
+#define LT_PH_ATTR __forceinline__        // (r2y: 2.7 us per C2 batch faster than out of line)
+#endif
+__device__ LT_PH_ATTR void prefix_hashes(const uint16_t* ch, int L, int lane, uint64_t* ha, uint64_t* hb) {
     prefix_hashes_inline(ch, L, lane, ha, hb);
 }
 
@@ -296,7 +321,7 @@ __device__ __forceinline__ uint64_t hit_key(int e, int b, uint32_t cls, uint32_t
 #define LT_STAGE_ATTR __forceinline__
 #endif
 #ifndef LT_FLUSH_ATTR
-#define LT_FLUSH_ATTR __noinline__
+#define LT_FLUSH_ATTR __forceinline__     // (r2y: 5 us per C2 batch faster than out of line; drain_rules is the opposite, +80 us inline)
 #endif
 __device__ LT_STAGE_ATTR void stage_hit(const Enum& E, const lt_edge& rec, uint64_t key, uint32_t task) {
     const uint32_t slot = atomicAdd(E.nh, 1u);
@@ -346,8 +371,11 @@ __device__ __forceinline__ void rule_candidate(const DevTables& T, const Enum& E
 // (Out of line; its arguments are the warp's shared-memory base and sizes by value, from which it
 // rebuilds the array views — passing the views by reference would force the caller's copies into
 // local memory for the whole kernel.)
+#ifndef LT_DRAIN_ATTR
+#define LT_DRAIN_ATTR __noinline__
+#endif
 template <int UC, int HCT>
-__device__ __noinline__ void drain_rules(const DevTables& T, unsigned char* base, int units_rt, int hcap_rt, int max_str, int lane) {
+__device__ LT_DRAIN_ATTR void drain_rules(const DevTables& T, unsigned char* base, int units_rt, int hcap_rt, int max_str, int lane) {
     const LatticeViews W = lattice_views<UC, HCT>(base, units_rt, hcap_rt, max_str);
     const SentView v = W.v;
     const Enum E = W.E;
@@ -648,7 +676,7 @@ __global__ void __launch_bounds__(lattice_max_threads(UC, HCT, LM), lattice_min_
             rref[3 * p + 2] = r3;
         }
         // substring table: every substring of at most max_str syllables, one wave of probes
-        const float inv_dm = 1.0f / (float)DM;
+        const float inv_dm = small_rcp(DM);
         for (int q = lane; q < L * DM; q += 32) {
             const int x = small_div(q, DM, inv_dm), len = q - x * DM + 1;
             uint32_t payload = 0;
@@ -689,7 +717,7 @@ __global__ void __launch_bounds__(lattice_max_threads(UC, HCT, LM), lattice_min_
                 for (int u = lane; u < 2 * n; u += 32) tcnt[u] = 0;
                 __syncwarp();
                 uint32_t ncand_try = 0;
-                const float inv_n = 1.0f / (float)n;
+                const float inv_n = small_rcp(n);
                 // (word_lookup starts with the whole-eojeol lookup alone: the items of task 0, lookup.py:157)
                 const int n_items1 = word_mode ? n : n * n;
                 for (int q0 = 0; q0 < n_items1; q0 += 32) {
@@ -765,7 +793,7 @@ __global__ void __launch_bounds__(lattice_max_threads(UC, HCT, LM), lattice_min_
                     __syncwarp();
                     const int tri = M * (M + 1) / 2;
                     const int items = (n - bl0) * tri;
-                    const float inv_tri = 1.0f / (float)tri;
+                    const float inv_tri = small_rcp(tri);
                     // stand-alone tags in list order (lookup.py:104-105), then Josa after a Noun
                     constexpr uint32_t standalone_tags = (1u << LT_TAG_NOUN) | (1u << LT_TAG_ADVERB) | (1u << LT_TAG_EXCLAMATION) |
                                                          (1u << LT_TAG_DETERMINER) | (1u << LT_TAG_NUMBER);
@@ -781,7 +809,7 @@ __global__ void __launch_bounds__(lattice_max_threads(UC, HCT, LM), lattice_min_
                             const int bl = bl0 + blq;
                             int t = qq - blq * tri;
                             // t -> (span, split offset inside the span): span (span - 1) / 2 <= t < span (span + 1) / 2
-                            int span = (int)((1.0f + sqrtf(8.0f * (float)t + 1.0f)) * 0.5f);
+                            int span = (int)((1.0f + approx_sqrt(8.0f * (float)t + 1.0f)) * 0.5f);
                             span -= (span * (span - 1) / 2 > t) ? 1 : 0;
                             span += (span * (span + 1) / 2 <= t) ? 1 : 0;
                             t -= span * (span - 1) / 2;

@@ -745,11 +745,12 @@ static int beam_plan(lt_batch* b, int lcap, int beam_size, bool kbest, const Bea
     // common beam sizes, sentence-array sizes and the (RegularizationScore, SimpleTrigramFeatureScore)
     // score program get their own instantiation (compile-time array offsets, unrolled scorer loop)
     if (kbest) P.fn = beam_size <= kRankMaxBeam ? beam_kernel<2, 0, 0, 0, 1> : (beam_size <= 32 ? beam_kernel<1, 0, 0, 0, 1> : beam_kernel<0, 0, 0, 0, 1>);
-    else if (beam_size == 5 && uclass == 64) P.fn = reg_tri ? beam_kernel<2, 5, 64, 1> : beam_kernel<2, 5, 64, 0>;
-    else if (beam_size == 5 && uclass == 128) P.fn = reg_tri ? beam_kernel<2, 5, 128, 1> : beam_kernel<2, 5, 128, 0>;
+    // (the specialised kernels also know at compile time where the back-pointers live)
+    else if (beam_size == 5 && uclass == 64) P.fn = reg_tri ? (P.trail_smem ? beam_kernel<2, 5, 64, 1, 0, 1> : beam_kernel<2, 5, 64, 1, 0, 0>) : beam_kernel<2, 5, 64, 0>;
+    else if (beam_size == 5 && uclass == 128) P.fn = reg_tri ? (P.trail_smem ? beam_kernel<2, 5, 128, 1, 0, 1> : beam_kernel<2, 5, 128, 1, 0, 0>) : beam_kernel<2, 5, 128, 0>;
     else if (beam_size == 5) P.fn = reg_tri ? beam_kernel<2, 5, 0, 1> : beam_kernel<2, 5, 0, 0>;
-    else if (beam_size == 10 && uclass == 64) P.fn = reg_tri ? beam_kernel<2, 10, 64, 1> : beam_kernel<2, 10, 64, 0>;
-    else if (beam_size == 10 && uclass == 128) P.fn = reg_tri ? beam_kernel<2, 10, 128, 1> : beam_kernel<2, 10, 128, 0>;
+    else if (beam_size == 10 && uclass == 64) P.fn = reg_tri ? (P.trail_smem ? beam_kernel<2, 10, 64, 1, 0, 1> : beam_kernel<2, 10, 64, 1, 0, 0>) : beam_kernel<2, 10, 64, 0>;
+    else if (beam_size == 10 && uclass == 128) P.fn = reg_tri ? (P.trail_smem ? beam_kernel<2, 10, 128, 1, 0, 1> : beam_kernel<2, 10, 128, 1, 0, 0>) : beam_kernel<2, 10, 128, 0>;
     else if (beam_size == 10) P.fn = reg_tri ? beam_kernel<2, 10, 0, 1> : beam_kernel<2, 10, 0, 0>;
     else if (beam_size <= kRankMaxBeam) P.fn = reg_tri ? beam_kernel<2, 0, 0, 1> : beam_kernel<2, 0, 0, 0>;
     else if (beam_size == 32) P.fn = reg_tri ? beam_kernel<1, 32, 0, 1> : beam_kernel<1, 32, 0, 0>;

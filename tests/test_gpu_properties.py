@@ -115,3 +115,22 @@ def test_other_beam_sizes_keep_invariants(workload):
         assert (status == 0).all()
         assert (edges['e'][path_off[1:] - 1] == lengths).all()
         assert (edges['b'][path_off[:-1]] == 0).all()
+
+
+def test_small_div_exhaustive(tmp_path):
+    """The lattice kernel splits flat item indices with a float multiply by the hardware's approximate reciprocal
+    (lattice.cuh: small_div / small_rcp) and decodes triangular indices through an approximate square root: both
+    are checked against integer arithmetic over their whole range on the device they run on."""
+    import os
+    import shutil
+    import subprocess
+    nvcc = shutil.which('nvcc') or '/usr/local/cuda/bin/nvcc'
+    if not os.path.exists(nvcc):
+        pytest.skip('no nvcc on this box')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / 'check_small_div')
+    subprocess.run([nvcc, '-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-std=c++17',
+                    '-I', os.path.join(root, 'lattice_based_tagger_b200', 'csrc'), '-o', exe,
+                    os.path.join(root, 'tests', 'cuda', 'check_small_div.cu')], check=True)
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and 'mismatches 0' in out.stdout, out.stdout + out.stderr

@@ -720,7 +720,10 @@ __global__ void __launch_bounds__(lattice_max_threads(UC, HCT, LM), lattice_min_
                 const float inv_n = small_rcp(n);
                 // (word_lookup starts with the whole-eojeol lookup alone: the items of task 0, lookup.py:157)
                 const int n_items1 = word_mode ? n : n * n;
-                for (int q0 = 0; q0 < n_items1; q0 += 32) {
+                // (the passes run in an inner loop without any call; it is left for drain_rules when the queue fills up
+                // and when the items are done)
+                for (int q0 = 0; q0 < n_items1;) {
+                  for (bool room = true; room && q0 < n_items1; q0 += 32) {
                     const int q = q0 + lane;
                     {
                         const bool valid = q < n_items1;
@@ -743,9 +746,10 @@ __global__ void __launch_bounds__(lattice_max_threads(UC, HCT, LM), lattice_min_
                     }
                     // (read by one lane between two barriers: a lane that ran ahead into the next pass must not be able
                     // to change what the others see here)
-                    if (warp_read(rqn) > (uint32_t)kRuleDrainAt) drain_rules<UC, HCT>(T, base, units, HC, DM, lane);     // a pass queues at most 3 per lane
+                    room = warp_read(rqn) <= (uint32_t)kRuleDrainAt;      // a pass queues at most 3 per lane
+                  }
+                  drain_rules<UC, HCT>(T, base, units, HC, DM, lane);
                 }
-                drain_rules<UC, HCT>(T, base, units, HC, DM, lane);
                 // ---- a split survives only when both sides found something (lookup.py:205-209) ----
                 uint32_t nstaged = *nh;
                 bool too_many = nstaged > (uint32_t)HC;
@@ -800,7 +804,8 @@ __global__ void __launch_bounds__(lattice_max_threads(UC, HCT, LM), lattice_min_
                     constexpr uint64_t standalone_order = (0ull << (4 * LT_TAG_NOUN)) | (1ull << (4 * LT_TAG_ADVERB)) |
                                                           (2ull << (4 * LT_TAG_EXCLAMATION)) | (3ull << (4 * LT_TAG_DETERMINER)) |
                                                           (4ull << (4 * LT_TAG_NUMBER)) | (5ull << (4 * LT_TAG_JOSA));
-                    for (int q0 = 0; q0 < items; q0 += 32) {
+                    for (int q0 = 0; q0 < items;) {
+                      for (bool room = true; room && q0 < items; q0 += 32) {
                         const int q = q0 + lane;
                         {
                             const bool in_range = q < items;
@@ -827,9 +832,10 @@ __global__ void __launch_bounds__(lattice_max_threads(UC, HCT, LM), lattice_min_
                             ncand_try += emit_pass<UC, HCT>(T, v, E, base, units, lane, valid, b, e, p, 0u, first, tagbits, (uint32_t)span, first,
                                                    word_mode ? ~0ull : standalone_order, true, pass);
                         }
-                        if (warp_read(rqn) > (uint32_t)kRuleDrainAt) drain_rules<UC, HCT>(T, base, units, HC, DM, lane);
+                        room = warp_read(rqn) <= (uint32_t)kRuleDrainAt;
+                      }
+                      drain_rules<UC, HCT>(T, base, units, HC, DM, lane);
                     }
-                    drain_rules<UC, HCT>(T, base, units, HC, DM, lane);
                     nstaged = *nh;
                     too_many = nstaged > (uint32_t)HC;
                     alive_here = nstaged - slots;             // every stage-2 hit survives
@@ -861,12 +867,15 @@ __global__ void __launch_bounds__(lattice_max_threads(UC, HCT, LM), lattice_min_
                 {
                     const uint32_t H = nstaged - slots;
                     uint32_t P = 0;                      // padded size when the eojeol is ranked by sorting
-                    if (H >= (uint32_t)A.sort_min) {
+                    // (the instantiation for short sentences with the small staging area goes without: the call alone costs
+                    // it 1.5 % and its eojeols hardly ever reach the threshold; LT_SORT_MIN does not apply there)
+                    constexpr bool kCanSort = !(UC == 64 && HCT == kLatDefaultHcap);
+                    if (kCanSort && H >= (uint32_t)A.sort_min) {
                         P = 32;
                         while (P < H) P <<= 1;
                         if (slots + P > (uint32_t)HC) P = 0;
                     }
-                    if (P) {
+                    if (kCanSort && P) {
                         rank_by_sort(hkey, htask, slots, H, P, alive, alive_here, lane);
                     } else {
                         for (uint32_t h = slots + lane; h < nstaged; h += 32) {

@@ -73,11 +73,12 @@ def test_many_sentences_across_ctas(monkeypatch, block_order):
             assert [tuple(w) for w in seq.sequences] == want[sent].words and seq.score == want[sent].score
 
 
-@pytest.mark.parametrize('hit_cap', [None, '32'])
+@pytest.mark.parametrize('hit_cap', ['64', '32'])
 def test_rank_by_sorting(monkeypatch, hit_cap):
     """The lattice kernel ranks the hits of large eojeols with an in-place sort instead of the counting loop;
-    LT_SORT_MIN=1 sends every eojeol through it (with a small staging area: next to flushes, retries and the
-    fallback for eojeols whose padding does not fit)."""
+    LT_SORT_MIN=1 sends every eojeol through it (staging areas other than the default one: the instantiation for
+    short sentences with the default area carries no sort; small areas add flushes, retries and the fallback for
+    eojeols whose padding does not fit)."""
     monkeypatch.setenv('LT_SORT_MIN', '1')
     if hit_cap:
         monkeypatch.setenv('LT_HIT_CAP', hit_cap)

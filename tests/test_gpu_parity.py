@@ -314,7 +314,7 @@ def test_retry_pass_and_adaptive_staging(monkeypatch):
         _check_against_oracle(tagger, oracle, sents, (5,))
 
 
-@pytest.mark.parametrize('hit_cap', [None, '32'])
+@pytest.mark.parametrize('hit_cap', ['64', '32'])
 def test_rank_by_sorting(monkeypatch, hit_cap):
     """Large eojeols are ranked by an in-place sort (lattice.cuh: rank_staged); LT_SORT_MIN=1 sends every eojeol
     through it: same lattices (edge order included), same paths, same scores."""

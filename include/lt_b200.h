@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define LT_ABI_VERSION 2
+#define LT_ABI_VERSION 3
 
 /* return codes */
 #define LT_OK            0

@@ -452,6 +452,7 @@ struct BeamPlan {
 struct lt_batch {
     lt_tables* tables = nullptr;
     cudaStream_t own_stream = nullptr;
+    unsigned int* h_ctl = nullptr;   // pinned: the control words come back with the results without stalling the copies queued behind them
     cudaStream_t last_stream = nullptr;
     // inputs (host entry point) and per-unit / per-sentence arrays
     DevBuf text, sent_off, pos, scan_tmp;
@@ -573,6 +574,7 @@ extern "C" int lt_batch_create(lt_tables* tables, lt_batch** out) {
     lt_batch* b = new lt_batch();
     b->tables = tables;
     CU(cudaStreamCreateWithFlags(&b->own_stream, cudaStreamNonBlocking));
+    CU(cudaMallocHost(reinterpret_cast<void**>(&b->h_ctl), kCtlWords * sizeof(unsigned int)));
     for (auto& e : b->ev) CU(cudaEventCreate(&e));
     // debugging / test knobs, read once here: tiny initial capacities exercise the grow-and-rerun path
     if (const char* env = getenv("LT_HIT_CAP")) b->hcap = std::max(8, atoi(env));
@@ -600,6 +602,7 @@ extern "C" void lt_batch_destroy(lt_batch* b) {
         if (x->p) cudaFree(x->p);
     for (auto& e : b->ev)
         if (e) cudaEventDestroy(e);
+    if (b->h_ctl) cudaFreeHost(b->h_ctl);
     if (b->own_stream) cudaStreamDestroy(b->own_stream);
     delete b;
 }
@@ -1057,8 +1060,8 @@ static int resolve(lt_batch* b) {
     if (!b->have_lattice || b->resolved) return LT_OK;
     cudaStream_t st = b->last_stream;
     for (int round = 0; round < 12; ++round) {
-        unsigned int ctl[kCtlWords];
-        CU(cudaMemcpyAsync(ctl, b->ctl.p, sizeof ctl, cudaMemcpyDeviceToHost, st));
+        unsigned int* ctl = b->h_ctl;
+        CU(cudaMemcpyAsync(ctl, b->ctl.p, kCtlWords * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
         const int r = check_and_rerun(b, ctl, st);
         if (r < 0) return -r;
@@ -1172,13 +1175,13 @@ static int fetch_paths(lt_batch* b, int32_t* path_off, lt_edge* path_edges, int6
         path_off[0] = 0;
         return LT_OK;
     }
-    unsigned int ctl[kCtlWords];
+    unsigned int* ctl = b->h_ctl;
     int64_t copied = 0;
     for (int round = 0; round < 12; ++round) {
         int64_t guess = b->words_hint < 0 ? b->n_units / 2 + 64 : b->words_hint + b->words_hint / 8 + 64;
         guess = std::min<int64_t>(std::min<int64_t>(guess, path_cap), b->n_units);
         if (!path_edges) guess = 0;
-        CU(cudaMemcpyAsync(ctl, b->ctl.p, sizeof ctl, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(ctl, b->ctl.p, kCtlWords * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
         CU(cudaMemcpyAsync(path_off, b->path_off.p, (size_t)(n + 1) * 4, cudaMemcpyDeviceToHost, st));
         CU(cudaMemcpyAsync(scores, b->scores.p, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
         CU(cudaMemcpyAsync(status, b->status.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));

@@ -336,10 +336,13 @@ __device__ __forceinline__ double unsortable(uint64_t key) {
 }
 
 #ifndef LT_BEAM_MINB
-#define LT_BEAM_MINB 2
+#define LT_BEAM_MINB 1
 #endif
 #ifndef LT_BEAM_MAXW
-#define LT_BEAM_MAXW 8         // largest CTA in warps (with LT_BEAM_MINB: the register budget the kernels are compiled for)
+#define LT_BEAM_MAXW 16        // largest CTA in warps (with LT_BEAM_MINB: the register budget the kernels are compiled for:
+                               // 512 threads x 1 CTA = 128 registers, as 256 x 2 before).  One CTA of 13 warps is what fits an SM
+                               // when a warp takes 16.5 KB of shared memory (beam 10, 128-element arrays): 13 resident warps
+                               // instead of 3 x 4 — C3 sample 3.34 -> 3.19 ms, C5 sample 4.14 -> 3.96 ms (r3f)
 #endif
 #ifndef LT_BEAM_REG_WARPS
 #define LT_BEAM_REG_WARPS 16   // warps per SM that budget allows (the host's residency estimate)
@@ -354,7 +357,7 @@ constexpr int kBeamMaxWarpsC = LT_BEAM_MAXW;
 constexpr int beam_max_threads(int, int, int, int) { return kBeamMaxWarpsC * 32; }
 constexpr int beam_min_blocks(int, int, int, int) { return LT_BEAM_MINB; }
 constexpr int kBeamWarps = 4;                 // preferred warps per CTA of the beam kernel
-constexpr int kBeamMaxWarps = kBeamMaxWarpsC;              // largest CTA (128 registers per thread either way: 8 warps x 2 CTAs = 4 warps x 4 CTAs)
+constexpr int kBeamMaxWarps = kBeamMaxWarpsC;              // largest CTA (128 registers per thread whatever the shape)
 
 // Edge prep: hash products and the edge-only part of the score program into cache slot `slot`.
 template <int PROG, int IMP, bool LEAN = false>

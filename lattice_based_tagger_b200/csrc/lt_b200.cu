@@ -430,6 +430,7 @@ enum { kCtlLatticeQueue = 0, kCtlBeamQueue = 1, kCtlCursor = 2 /* 2 words */, kC
        kCtlRetryCount = 7, kCtlWords = 8 };
 
 static const size_t kSmemBudget = 200 * 1024;
+static const size_t kBeamCtaSmemMax = 226 * 1024;    // one large beam CTA may take (nearly) all the shared memory an SM has
 
 // Launch shapes are decided once per (array size, capacity) and kept: kernel instantiation, CTA shape,
 // shared memory, resident CTAs per SM.  Nothing of this is recomputed (or asked of the driver) per batch.
@@ -719,12 +720,13 @@ static int beam_plan(lt_batch* b, int lcap, int beam_size, bool kbest, const Bea
     // 128 registers per thread (16 warps) and the per-warp shared memory; ties go to 4-warp CTAs
     auto resident_warps = [&](size_t warp_smem, int w) -> int {
         const size_t cta = dense_bytes + warp_smem * w;
-        if (cta > kSmemBudget) return 0;
+        if (cta > (w > 8 ? kBeamCtaSmemMax : kSmemBudget)) return 0;
         return w * (int)std::min<size_t>(LT_BEAM_REG_WARPS / w, (size_t)228 * 1024 / (cta + 1024));
     };
     auto best_warps = [&](size_t warp_smem) -> int {
         int best = 0, best_res = 0;
-        for (int w : {kBeamWarps, 8, 6, 5, 3, 2, 1}) {
+        // (ties go to the earlier entry: 4-warp CTAs first, then the larger shapes)
+        for (int w : {kBeamWarps, 8, 6, 5, 3, 2, 1, 7, 9, 10, 11, 12, 13, 14, 15, 16}) {
             if (w > kBeamMaxWarps) continue;
             const int r = resident_warps(warp_smem, w);
             if (r > best_res) { best_res = r; best = w; }

@@ -25,8 +25,8 @@
 //      (a cuckoo table: both slots of a key loaded at once), template 3/6 come from shared memory;
 //   4. keeps the best `beam` candidates on the order-preserving integer image of the fp64 score
 //      with ties resolved towards the earlier candidate, which is exactly the stable sort of
-//      Beam.append (beam.py:83-86): rank counting (beam <= 16), a sorting network (<= 32) or
-//      arg-max rounds (<= 64);
+//      Beam.append (beam.py:83-86): rank counting (beam <= 16), a sorting network (<= 32) or two
+//      sorted runs of 32 merged by sorting networks (<= 64);
 //   5. writes the survivors as new ring entries and one back-pointer each (shared memory when the
 //      host finds room, HBM otherwise).
 // The best path is recovered from the back-pointers and written as 16-byte edge records.
@@ -35,6 +35,9 @@
 // (beam_kernel<MODE, KT, UC, PROG>): with those fixed every shared-memory array sits at a constant
 // offset and the scorer loop unrolls with its template seeds as immediates — in this latency-bound
 // kernel dynamically indexed constant loads and spilled address arithmetic were the largest costs.
+// Steps 1-5, the position loop, live in beam_positions.inc and are compiled into the kernel TWICE: once for any
+// sentence, once without the code (and the out-of-line calls) that only buckets beyond the edge cache need —
+// see the note at the top of that file.
 #pragma once
 #include "lattice.cuh"
 #include "tables.cuh"
@@ -399,7 +402,7 @@ __device__ __forceinline__ void prep_edge(const DevTables& T, const SentView& v,
 // MODE selects the top-K of a position's candidates:
 //   2  rank by counting (beam <= kRankMaxBeam): every candidate counts the pool entries that beat it
 //   1  32-lane bitonic sorting network per chunk + bitonic merge with the kept list (beam <= 32)
-//   0  rounds of warp arg-max with two kept entries per lane (beam 33..64)
+//   0  two kept entries per lane = two sorted runs of 32, chunks merged into them by sorting networks (beam 33..64)
 // KT: the beam size, UC: the sentence-array size when known at compile time (array offsets become
 // constants, which is what keeps the kernel's address arithmetic out of registers); 0 = A.beam / A.units.
 // PROG: 1 = the score program is exactly (RegularizationScore, SimpleTrigramFeatureScore) — the

@@ -23,8 +23,10 @@
 //      shared memory with a sort key (end, begin, class, split, candidate order) that encodes the
 //      reference's emission order.
 //   5. the eojeol's hits are filtered (lr_lookup keeps a split only when both sides are non-empty,
-//      lookup.py:205-209) and ranked by key; staged edges go to HBM at their rank with one atomic
-//      reservation per flush (normally one per sentence).
+//      lookup.py:205-209) and ranked by key (a counting loop, or an in-place bitonic sort for eojeols with many
+//      hits); staged edges go to HBM in rank order with one atomic reservation per flush (normally one per
+//      sentence).  An eojeol whose hits outgrow the staging area goes, alone, to a retry pass with a larger one
+//      (the RP = 1 instantiation); the sentence's other eojeols are finished here.
 // Output is CSR keyed by END position: pos[sent_off[s]+e-1] = (first edge, count) of the edges of
 // sentence s ending at syllable e, ordered by begin and, within one (b, e) span, in the reference's
 // emission order (the only order beam_search can observe).

@@ -144,3 +144,44 @@ def check_host_api(case):
         want_nodes, want_links = lo.lattice_graph(sent, edges)
         assert [tuple(w) for w in nodes] == want_nodes
         assert [[tuple(a), tuple(b), w] for a, b, w in links] == want_links
+
+
+def dense_case(seed, syllables=14):
+    """One long eojeol whose every prefix and suffix is a dictionary word under many tags: the
+    bucket of the eojeol's last syllable holds more edges than the beam kernel caches per end position,
+    and most of them span more than the 8-syllable window."""
+    import random
+    rng = random.Random(seed)
+    alphabet = ['가', '나', '다']
+    word = ''.join(rng.choice(alphabet) for _ in range(syllables))
+    tags = ['Noun', 'Adverb', 'Exclamation', 'Determiner', 'Number', 'Pronoun', 'Josa', 'Eomi', 'Verb', 'Adjective']
+    tag_to_morphs = {t: set() for t in tags}
+    for i in range(1, len(word)):
+        for piece in (word[:i], word[i:]):
+            for t in rng.sample(tags[:6], 5):
+                tag_to_morphs[t].add(piece)
+    for t in ('Josa', 'Eomi', 'Verb', 'Adjective'):
+        tag_to_morphs[t].update({word[-1], word[-2:], word[:2]})
+    case = {'seed': seed, 'tags': tags, 'tag_to_morphs': {t: sorted(m) for t, m in tag_to_morphs.items()},
+            'rules': {word[3]: [(word[3], word[-1])], word[5:7]: [(word[5], word[-2:])]},
+            'sentences': [word, word + ' ' + word[:5], word[2:] + word, word[:9] + ' ' + word[4:]],
+            'funcs': [{'kind': 'reg', 'unknown_penalty': -0.5, 'known_preference': 0.5, 'syllable_penalty': -0.2},
+                      {'kind': 'trigram'}],
+            'feature_keys': [], 'coefficients': []}
+    return case
+
+
+def check_dense_case(seed, syllables, beams, min_bucket):
+    """Lattice order, paths and scores of the dense case against the oracle; the case must hold a bucket of at
+    least `min_bucket` edges with spans beyond the window."""
+    import lattice_based_tagger_b200 as pkg
+    case = dense_case(seed, syllables)
+    _cases.add_features(case, _cases.observed_features(case, lo, seed=seed), seed)
+    dictionary, funcs = _cases.build_objects(case, pkg)
+    tagger = pkg.Tagger(dictionary, score_funcs=funcs)
+    oracle = lo.OracleTagger(dictionary, funcs)
+    sents = case['sentences']
+    words, bindex = tagger.lattice_batch(sents[:1])[0]
+    last = [w for w in words[1:-1] if w.e == len(sents[0])]
+    assert len(last) >= min_bucket and max(w.e - w.b for w in last) > 8       # the case does what it is built for
+    check_against_oracle(tagger, oracle, sents, beams)

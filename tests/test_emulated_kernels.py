@@ -89,6 +89,13 @@ def test_rank_by_sorting(monkeypatch, hit_cap):
     _checks.check_against_oracle(tagger, oracle, case['sentences'], (5,), counters=True)
 
 
+@pytest.mark.parametrize('seed,syllables', [(7, 14), (9, 22)])
+def test_buckets_beyond_the_edge_cache(seed, syllables):
+    """The beam kernel's any-sentence copy of the position loop: buckets of more edges than the edge cache holds
+    (a second prep pass up to 64 edges, edges beyond prepared on the fly), spans beyond the window."""
+    _checks.check_dense_case(seed, syllables, (5, 10, 33), min_bucket=90 if syllables > 14 else 41)
+
+
 def test_kbest_survivors():
     case = _checks.make_case(3001, n_sent=10, max_sent_len=24)
     dictionary, funcs = _cases.build_objects(case, pkg)

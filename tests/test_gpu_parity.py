@@ -223,43 +223,11 @@ def _check_against_oracle(tagger, oracle, sents, beams):
             assert seq.score == want.score, (sent, k)
 
 
-def _dense_case(seed):
-    """One long eojeol whose every prefix and suffix is a dictionary word under many tags: the
-    bucket of the eojeol's last syllable holds far more than the 32 edges the beam kernel caches,
-    and most of them span more than the 8-syllable window."""
-    import random
-    rng = random.Random(seed)
-    alphabet = ['가', '나', '다']
-    word = ''.join(rng.choice(alphabet) for _ in range(14))
-    tags = ['Noun', 'Adverb', 'Exclamation', 'Determiner', 'Number', 'Pronoun', 'Josa', 'Eomi', 'Verb', 'Adjective']
-    tag_to_morphs = {t: set() for t in tags}
-    for i in range(1, len(word)):
-        for piece in (word[:i], word[i:]):
-            for t in rng.sample(tags[:6], 5):
-                tag_to_morphs[t].add(piece)
-    for t in ('Josa', 'Eomi', 'Verb', 'Adjective'):
-        tag_to_morphs[t].update({word[-1], word[-2:], word[:2]})
-    case = {'seed': seed, 'tags': tags, 'tag_to_morphs': {t: sorted(m) for t, m in tag_to_morphs.items()},
-            'rules': {word[3]: [(word[3], word[-1])], word[5:7]: [(word[5], word[-2:])]},
-            'sentences': [word, word + ' ' + word[:5], word[2:] + word, word[:9] + ' ' + word[4:]],
-            'funcs': [{'kind': 'reg', 'unknown_penalty': -0.5, 'known_preference': 0.5, 'syllable_penalty': -0.2},
-                      {'kind': 'trigram'}],
-            'feature_keys': [], 'coefficients': []}
-    return case
-
-
-@pytest.mark.parametrize('seed', [7, 8])
-def test_buckets_beyond_the_edge_cache(seed):
-    case = _dense_case(seed)
-    _cases.add_features(case, _cases.observed_features(case, lo, seed=seed), seed)
-    dictionary, funcs = _cases.build_objects(case, pkg)
-    tagger = pkg.Tagger(dictionary, score_funcs=funcs)
-    oracle = lo.OracleTagger(dictionary, funcs)
-    sents = case['sentences']
-    words, bindex = tagger.lattice_batch(sents[:1])[0]
-    last = [w for w in words[1:-1] if w.e == len(sents[0])]
-    assert len(last) > 40 and max(w.e - w.b for w in last) > 8       # the case does what it is built for
-    _check_against_oracle(tagger, oracle, sents, (1, 5, 10, 20, 32, 40))
+@pytest.mark.parametrize('seed,syllables', [(7, 14), (8, 14), (9, 22)])
+def test_buckets_beyond_the_edge_cache(seed, syllables):
+    """Buckets beyond the 64 edges the beam kernel caches per end position: the 14-syllable cases sit around that
+    size (one second prep pass, a handful of edges scored on the fly), the 22-syllable one far beyond it."""
+    _checks.check_dense_case(seed, syllables, (1, 5, 10, 20, 32, 40), min_bucket=90 if syllables > 14 else 41)
 
 
 def test_trail_in_hbm_and_generic_array_sizes(monkeypatch):

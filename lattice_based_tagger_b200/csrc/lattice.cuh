@@ -544,7 +544,7 @@ __device__ LT_FLUSH_ATTR void flush_staged(const LatticeArgs& A, int lane, uint3
 //   larger ones (here): bitonic sort of (key, slot) pairs in place, padded to P = a power of two with dead keys — taken
 //                  when the padding fits the staging area (a 1 000-hit eojeol ranks in ~14 k warp instructions instead
 //                  of ~160 k; the counting loop was 12 % of C3's main pass and most of its retry pass).
-constexpr int kSortMin = 96;                // entries from which the sort pays (LatticeArgs::sort_min; LT_SORT_MIN overrides)
+constexpr int kSortMin = 160;               // entries from which the sort pays (C3 sample, r3i: 48 / 96 / 160 -> lattice 1.859 / 1.836 / 1.829 ms) (LatticeArgs::sort_min; LT_SORT_MIN overrides)
 #ifndef LT_RANK_UNROLL
 #define LT_RANK_UNROLL 4
 #endif

@@ -848,53 +848,13 @@ def strong_scaling(args, W_headline, dev, rank, world, local_rank, flush):
     reps = 3
     t_shard, local = timed(lambda: tag_indices(mine), reps)
 
-    # gather of the packed results on rank 0: counts first, then every rank's arrays straight into their place in ONE
-    # device buffer per array (point-to-point over NCCL / NVLink, exact sizes: contiguous shards need no reordering and
-    # no padding), and one copy per array into pinned host memory
+    # gather of the packed results on rank 0 (sharding.gather_packed_contiguous: contiguous shards need no reordering
+    # and no padding — every rank's arrays go point to point into their place in one device buffer per array, then
+    # one copy per array into pinned host memory)
     pinned_cache = {}
 
-    def pinned(name, size, dtype):
-        buf = pinned_cache.get(name)
-        if buf is None or buf.numel() < size:
-            buf = pinned_cache[name] = torch.empty(max(1, size), dtype=dtype).pin_memory()
-        return buf[:size]
-
     def gather():
-        plen, edges, scores, status = local
-        counts = torch.tensor([plen.size, edges.size], dtype=torch.int64, device=dev)
-        all_counts = [torch.zeros_like(counts) for _ in range(world)]
-        dist.all_gather(all_counts, counts)
-        sizes = [(int(c[0]), int(c[1])) for c in all_counts]
-        mine_arrays = [(plen.astype(np.int32), torch.int32, 0, 1), (status.astype(np.int32), torch.int32, 0, 1),
-                       (np.ascontiguousarray(scores, dtype=np.float64), torch.float64, 0, 1),
-                       (np.ascontiguousarray(edges).view(np.uint8).reshape(-1, 16).view(np.int64).reshape(-1), torch.int64, 1, 2)]
-        if rank != 0:
-            for arr, dtype, _, _ in mine_arrays:
-                if arr.size:
-                    dist.send(torch.from_numpy(arr).to(dev), 0)
-            return None
-        out = []
-        for k, (arr, dtype, which, mult) in enumerate(mine_arrays):
-            total = sum(sz[which] for sz in sizes) * mult
-            buf = torch.empty(max(1, total), dtype=dtype, device=dev)
-            off = 0
-            for r, sz in enumerate(sizes):
-                cnt = sz[which] * mult
-                if cnt:
-                    if r == 0:
-                        buf[off:off + cnt] = torch.from_numpy(arr).to(dev)
-                    else:
-                        dist.recv(buf[off:off + cnt], r)
-                off += cnt
-            host = pinned(k, total, dtype)
-            host.copy_(buf[:total], non_blocking=True)
-            out.append(host)
-        torch.cuda.synchronize(dev)
-        plen_all, status_all, scores_all = out[0].numpy(), out[1].numpy(), out[2].numpy()
-        out_edges = out[3].numpy().view(np.uint8).reshape(-1, 16).view(_native.EDGE_DTYPE).reshape(-1)
-        path_off = np.zeros(n + 1, dtype=np.int64)
-        np.cumsum(plen_all, out=path_off[1:])
-        return path_off, out_edges, scores_all, status_all
+        return sharding.gather_packed_contiguous(local, rank, world, device=dev, pinned=pinned_cache)
 
     gather()                              # (first use of the collective: communicator set-up is not part of a gather)
     torch.cuda.synchronize(dev)

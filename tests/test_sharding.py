@@ -125,3 +125,45 @@ def test_two_ranks_packed_gather(tmp_path):
     mp.spawn(_packed_worker, args=(world, _free_port(), 91, str(tmp_path)), nprocs=world, join=True)
     for rank in range(world):
         assert (tmp_path / ('rank%d' % rank)).read_text() == 'ok'
+
+
+def _worker_packed(rank, world, port, out_dir):
+    """Contiguous shards of synthetic packed results through gather_packed_contiguous (gloo, host tensors)."""
+    from lattice_based_tagger_b200 import _native
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    rng = np.random.default_rng(5)
+    n = 57
+    plen = rng.integers(0, 9, size=n).astype(np.int32)
+    plen[10:14] = 0                                          # sentences without a path
+    off = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(plen, out=off[1:])
+    edges = np.zeros(int(off[-1]), dtype=_native.EDGE_DTYPE)
+    edges['b'] = np.arange(edges.size) % 50
+    edges['e'] = edges['b'] + 1
+    edges['rule'] = np.arange(edges.size)
+    scores = rng.standard_normal(n)
+    status = (plen == 0).astype(np.int32)
+    bounds = sharding.shard_bounds(rng.integers(1, 40, size=n), world)
+    a, b = bounds[rank], bounds[rank + 1]
+    local = (plen[a:b], edges[off[a]:off[b]], scores[a:b], status[a:b])
+    got = sharding.gather_packed_contiguous(local, rank, world)
+    ok = True
+    if rank == 0:
+        path_off, out_edges, out_scores, out_status = got
+        ok = (np.array_equal(path_off, off) and np.array_equal(out_edges, edges) and np.array_equal(out_scores, scores)
+              and np.array_equal(out_status, status))
+    else:
+        ok = got is None
+    with open(os.path.join(out_dir, 'rank%d' % rank), 'w') as f:
+        f.write('ok' if ok else 'mismatch')
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('world', [2, 3])
+def test_gather_packed_contiguous(tmp_path, world):
+    mp.spawn(_worker_packed, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    for rank in range(world):
+        assert (tmp_path / ('rank%d' % rank)).read_text() == 'ok'

@@ -96,10 +96,12 @@ def _packed_worker(rank, world, port, seed, out_dir):
         tagger = pkg.Tagger(dictionary, score_funcs=funcs)
         sents = case['sentences']
         merged = sharding.tag_sharded_packed(tagger, sents, 5, rank, world)
+        merged_c = sharding.tag_sharded_packed(tagger, sents, 5, rank, world, contiguous=True)
         ok = True
         if rank == 0:
             whole = tagger.tag_batch_packed(sents, 5)
             ok = all(np.array_equal(a, b) for a, b in zip(merged, whole))
+            ok = ok and all(np.array_equal(a, b) for a, b in zip(merged_c, whole))      # contiguous shards, fast gather
             oracle = lo.OracleTagger(dictionary, funcs)
             seqs = tagger.unpack(sents, merged, errors='none')
             for sent, seq in zip(sents, seqs):
@@ -110,7 +112,7 @@ def _packed_worker(rank, world, port, seed, out_dir):
                     continue
                 ok = ok and [tuple(w) for w in seq.sequences] == want.words and seq.score == want.score
         else:
-            ok = merged is None
+            ok = merged is None and merged_c is None
         tagger.close()
     with open(os.path.join(out_dir, 'rank%d' % rank), 'w') as f:
         f.write('ok' if ok else 'mismatch')

@@ -3,6 +3,11 @@
 #include "simt.h"
 
 #include <deque>
+#include <unordered_map>
+
+#include <signal.h>
+#include <sys/mman.h>
+#include <unistd.h>
 
 namespace simt {
 
@@ -156,6 +161,65 @@ void block_barrier() {
     }
 }
 
+// ---- LT_SIMT_MEMCHECK=1: device buffers and the dynamic shared memory of a launch end at a guard page ----------
+// (what compute-sanitizer's memcheck finds on the device, for accesses past the END of a buffer: the buffer is
+// placed so that its last 16-byte unit touches an inaccessible page, and the page before the mapping is
+// inaccessible as well; the fault is reported with the block and thread that made the access)
+static bool memcheck() {
+    static const bool on = [] { const char* e = getenv("LT_SIMT_MEMCHECK"); return e && e[0] == '1'; }();
+    return on;
+}
+struct Guarded { void* base; size_t len; };
+static std::unordered_map<void*, Guarded> g_guarded;
+
+static void on_fault(int, siginfo_t* info, void*) {
+    State& S = g_state;
+    char msg[200];
+    const int n = snprintf(msg, sizeof msg, "[simt] memcheck: invalid access at %p (block %u, thread %u)\n", info->si_addr, S.bid.x,
+                           S.cur ? S.cur->tid.x : 0u);
+    if (n > 0 && write(2, msg, (size_t)n) < 0) {}
+    abort();
+}
+
+static void* guarded_alloc(size_t n, int fill) {
+    static const bool installed = [] {
+        struct sigaction sa;
+        memset(&sa, 0, sizeof sa);
+        sa.sa_sigaction = on_fault;
+        sa.sa_flags = SA_SIGINFO;
+        sigaction(SIGSEGV, &sa, nullptr);
+        return true;
+    }();
+    (void)installed;
+    const size_t page = (size_t)sysconf(_SC_PAGESIZE);
+    const size_t body = (n + 15) & ~(size_t)15;
+    const size_t pages = (body + page - 1) / page + 2;               // guard | data ... | guard
+    unsigned char* base = static_cast<unsigned char*>(mmap(nullptr, pages * page, PROT_NONE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0));
+    if (base == MAP_FAILED) return nullptr;
+    if (mprotect(base + page, (pages - 2) * page, PROT_READ | PROT_WRITE) != 0) { munmap(base, pages * page); return nullptr; }
+    unsigned char* p = base + (pages - 1) * page - body;
+    memset(p, fill, body);
+    g_guarded[p] = Guarded{base, pages * page};
+    return p;
+}
+static void guarded_free(void* p) {
+    auto it = g_guarded.find(p);
+    if (it == g_guarded.end()) { fprintf(stderr, "[simt] memcheck: free of %p, which is no live device buffer\n", p); abort(); }
+    munmap(it->second.base, it->second.len);
+    g_guarded.erase(it);
+}
+
+void* dev_alloc(size_t n) {
+    if (memcheck()) return guarded_alloc(n ? n : 1, 0xCD);
+    void* p = aligned_alloc(256, (n + 255) & ~(size_t)255);
+    if (p) memset(p, 0xCD, n);
+    return p;
+}
+void dev_free(void* p) {
+    if (!p) return;
+    if (memcheck()) guarded_free(p); else free(p);
+}
+
 static std::vector<unsigned char> g_smem;
 
 void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()>& body) {
@@ -163,8 +227,15 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()
     if (S.cur) die("nested launch");
     const unsigned nthreads = block.x;
     if (nthreads == 0 || grid.x == 0) return;
-    if (g_smem.size() < smem_bytes + 64) g_smem.resize(smem_bytes + 64);
-    S.smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(g_smem.data()) + 63) & ~(uintptr_t)63);
+    void* guarded_smem = nullptr;
+    if (memcheck()) {
+        guarded_smem = guarded_alloc(smem_bytes ? smem_bytes : 1, 0xA5);
+        if (!guarded_smem) die("memcheck: no memory for the shared-memory mapping");
+        S.smem = static_cast<unsigned char*>(guarded_smem);
+    } else {
+        if (g_smem.size() < smem_bytes + 64) g_smem.resize(smem_bytes + 64);
+        S.smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(g_smem.data()) + 63) & ~(uintptr_t)63);
+    }
     S.bdim = block;
     S.gdim = grid;
     S.body = &body;
@@ -212,6 +283,7 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()
     }
     S.cur = nullptr;
     S.body = nullptr;
+    if (guarded_smem) guarded_free(guarded_smem);
 }
 
 }  // namespace simt

@@ -13,6 +13,10 @@
 // may be pending in one warp at the same time (divergent code).  Memory is sequentially
 // consistent by construction, atomics are plain read-modify-writes.  A deadlock (every live fiber
 // waiting) aborts with a message.
+// LT_SIMT_MEMCHECK=1: every device buffer and the dynamic shared memory of every launch end at an
+// inaccessible page (simt.cpp), so an access past the end of either faults at the access and is
+// reported with its block and thread — the pool's GPU boxes refuse compute-sanitizer, this is the
+// memory check the kernels get.
 #pragma once
 #ifndef LT_SIMT_EMU
 #error "simt.h is only for -DLT_SIMT_EMU builds (tests)"
@@ -107,6 +111,8 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()
 uint64_t collective(int op, uint32_t mask, uint64_t value, int arg, const char* file, int line);
 void block_barrier();
 inline unsigned char* dyn_smem() { return state().smem; }
+void* dev_alloc(size_t n);
+void dev_free(void* p);
 
 struct TidProxy { operator uint3() const { return state().cur->tid; } };
 
@@ -205,8 +211,10 @@ static inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
 static inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) { const char* sms_ = getenv("LT_SIMT_SMS"); p->multiProcessorCount = sms_ ? atoi(sms_) : 2; strcpy(p->name, "simt-emu"); return cudaSuccess; }
 static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 static inline const char* cudaGetErrorString(cudaError_t) { return "simt-emu error"; }
-static inline cudaError_t cudaMalloc(void** p, size_t n) { *p = aligned_alloc(256, (n + 255) & ~(size_t)255); if (*p) memset(*p, 0xCD, n); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
-static inline cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
+// (simt::dev_alloc: plain aligned memory filled with 0xCD, or — LT_SIMT_MEMCHECK=1 — a mapping that ends at an
+// inaccessible guard page, so that a kernel reading or writing past a device buffer faults at the access)
+static inline cudaError_t cudaMalloc(void** p, size_t n) { *p = simt::dev_alloc(n); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+static inline cudaError_t cudaFree(void* p) { simt::dev_free(p); return cudaSuccess; }
 static inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { memcpy(d, s, n); return cudaSuccess; }
 static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t = nullptr) { memcpy(d, s, n); return cudaSuccess; }
 static inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t = nullptr) { memset(d, v, n); return cudaSuccess; }

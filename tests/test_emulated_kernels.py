@@ -155,3 +155,35 @@ def test_update_weights_and_trainer():
     tri.coefficients = np.random.default_rng(0).standard_normal(len(tri.coefficients))
     tagger.update_weights()
     _checks.check_against_oracle(tagger, lo.OracleTagger(dictionary, funcs), case['sentences'], (1, 5))
+
+
+def test_memcheck_self_test(tmp_path):
+    """LT_SIMT_MEMCHECK=1 places device buffers and a launch's dynamic shared memory against guard pages: the
+    emulator's own check that an access one element past either is caught (and that a clean kernel is not)."""
+    import os
+    import subprocess
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'simt')
+    exe = str(tmp_path / 'selftest_memcheck')
+    subprocess.run(['g++', '-std=c++17', '-O1', '-DLT_SIMT_EMU', '-I', here, '-o', exe,
+                    os.path.join(here, 'selftest_memcheck.cpp'), os.path.join(here, 'simt.cpp')], check=True)
+    env = dict(os.environ, LT_SIMT_MEMCHECK='1')
+    clean = subprocess.run([exe, 'ok'], env=env, capture_output=True, text=True)
+    assert clean.returncode == 0 and 'clean' in clean.stdout
+    for what in ('global', 'shared'):
+        out = subprocess.run([exe, what], env=env, capture_output=True, text=True)
+        assert out.returncode != 0 and 'memcheck: invalid access' in out.stderr, (what, out.stderr)
+    assert subprocess.run([exe, 'global'], capture_output=True).returncode == 0      # off without the switch
+
+
+def test_kernels_under_memcheck():
+    """The kernels over random cases with every device buffer and the shared memory of every launch ending at a
+    guard page (a fresh process: the switch is read once), small staging areas included — the retry pass and the
+    grow-and-rerun path index the buffers closest to their ends."""
+    import os
+    import subprocess
+    import sys
+    script = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'fuzz_emulated.py')
+    for extra in ({}, {'LT_HIT_CAP': '8', 'LT_EDGE_CAP': '16'}):
+        env = dict(os.environ, LT_SIMT_MEMCHECK='1', **extra)
+        out = subprocess.run([sys.executable, script, '2001', '2004'], env=env, capture_output=True, text=True)
+        assert out.returncode == 0 and '0 failures' in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]

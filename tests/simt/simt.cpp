@@ -169,6 +169,13 @@ static bool memcheck() {
     static const bool on = [] { const char* e = getenv("LT_SIMT_MEMCHECK"); return e && e[0] == '1'; }();
     return on;
 }
+// LT_SIMT_FILL=<byte>: what fresh device buffers and a block's shared memory hold before the kernels write them
+// (default 0xCD / 0xA5).  On the GPU that is whatever the previous owner left: a result that changes with the
+// fill depends on uninitialised memory (compute-sanitizer's initcheck, by differential runs).
+static int fill_byte(int dflt) {
+    static const int v = [] { const char* e = getenv("LT_SIMT_FILL"); return e ? (int)strtol(e, nullptr, 0) & 0xFF : -1; }();
+    return v < 0 ? dflt : v;
+}
 struct Guarded { void* base; size_t len; };
 static std::unordered_map<void*, Guarded> g_guarded;
 
@@ -210,9 +217,9 @@ static void guarded_free(void* p) {
 }
 
 void* dev_alloc(size_t n) {
-    if (memcheck()) return guarded_alloc(n ? n : 1, 0xCD);
+    if (memcheck()) return guarded_alloc(n ? n : 1, fill_byte(0xCD));
     void* p = aligned_alloc(256, (n + 255) & ~(size_t)255);
-    if (p) memset(p, 0xCD, n);
+    if (p) memset(p, fill_byte(0xCD), n);
     return p;
 }
 void dev_free(void* p) {
@@ -229,7 +236,7 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()
     if (nthreads == 0 || grid.x == 0) return;
     void* guarded_smem = nullptr;
     if (memcheck()) {
-        guarded_smem = guarded_alloc(smem_bytes ? smem_bytes : 1, 0xA5);
+        guarded_smem = guarded_alloc(smem_bytes ? smem_bytes : 1, fill_byte(0xA5));
         if (!guarded_smem) die("memcheck: no memory for the shared-memory mapping");
         S.smem = static_cast<unsigned char*>(guarded_smem);
     } else {
@@ -249,7 +256,7 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()
         const unsigned b = reverse ? grid.x - 1 - bi : bi;
         S.bid = uint3{b, 0, 0};
         // poison shared memory: a kernel that relies on stale contents fails the same way everywhere
-        memset(S.smem, 0xA5, smem_bytes);
+        memset(S.smem, fill_byte(0xA5), smem_bytes);
         S.warps.assign(nwarps, Warp());
         g_pending.assign(nwarps, std::deque<Pending>());
         S.block_arrived = 0;

@@ -685,15 +685,23 @@ def run_gpu(args):
             line['strong'] = strong
         if world == 1 and not args.no_cpu_baseline:
             line.update(cpu_baseline(W, B))
+        # (the sections after the headline are additions to it: a failure in one of them is reported in its place
+        # and must not cost the line)
         if world == 1 and not args.no_api:
-            line['api'] = api_numbers(W, local_rank)
+            try:
+                line['api'] = api_numbers(W, local_rank)
+            except Exception as exc:
+                line['api'] = {'error': '%s: %s' % (type(exc).__name__, exc)}
         if world == 1 and args.other_configs:
             W.tagger.close()
             W.reg_tagger.close()
             del B
             line['other_configs'] = {}
             for name in args.other_configs:
-                line['other_configs'][name] = other_config(name, args, dev, local_rank, barrier, flush, peak, peak_kind)
+                try:
+                    line['other_configs'][name] = other_config(name, args, dev, local_rank, barrier, flush, peak, peak_kind)
+                except Exception as exc:
+                    line['other_configs'][name] = {'error': '%s: %s' % (type(exc).__name__, exc)}
         emit(line)
     if world > 1:
         dist.barrier()
